@@ -1,0 +1,238 @@
+#!/usr/bin/env python
+"""bench.py — step-2 K=60 graph build throughput (Gbases/s) on N B200s; see DESIGN.md §Measurement.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--genome-mbp G] [--coverage C] [--impl reference]
+
+One step = one whole pass of step 2 (count -> adjacency -> unipaths -> HBV -> read pathing) over one synthetic read set.
+`value` = bases / device time with the read stores already resident in HBM; `e2e` = the same through w2rap_step2_run()
+with pinned HOST buffers (H2D of the stores and D2H of graph + paths inside the timed region).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "step-2 K=60 graph build Gbases/s"
+
+
+def clocks_sampler(stop, out):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", os.environ.get("LOCAL_RANK", "0")],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    reasons = []
+    for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+        if any(s[2 + i].lower().startswith("active") for s in samples):
+            reasons.append(name)
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference_arm(args):
+    """The reference's own CPU step 2 (oracle/_ref/w2rap-contigger, all host threads) on a bounded sample of the same workload."""
+    import numpy as np
+    import w2r_testlib as T
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    genome = int(args.ref_genome_mbp * 1e6)
+    rng = np.random.default_rng(1)
+    g = T.make_genome(rng, genome, max(1, genome // 50000))
+    n_pairs = genome * args.coverage // 500
+    rs = T.flatten_reads(*T.simulate_reads(rng, [(g, False, 1.0)], n_pairs, 250))
+    kind = "reference" if os.path.exists(T.REF_BIN) else "port"
+    times = []
+    for it in range(args.warmup + args.steps):
+        if kind == "reference":
+            d = tempfile.mkdtemp(prefix="w2rap_ref_")
+            T.write_fastb_qualp(d, rs)
+            _, perf = T.run_reference_step2(d, threads=cores)
+            t = perf.get("buildReadQGraph", 0.0) + perf.get("FixPaths", 0.0)
+            subprocess.run(["rm", "-rf", d])
+        else:
+            t0 = time.time()
+            T.run_oracle(rs, T.default_params(apply_fixpaths=1))
+            t = time.time() - t0
+        if it >= args.warmup:
+            times.append(t)
+    t = sum(times) / len(times)
+    v = rs.n_bases / t / 1e9
+    sample = "%.1f Mbp random genome + repeats, 2x250 PE at %dx (%d reads, %.0f Mbases); %s" % (
+        args.ref_genome_mbp, args.coverage, rs.n, rs.n_bases / 1e6,
+        "oracle/_ref/w2rap-contigger --from_step 2 --to_step 2, TIME buildReadQGraph+FixPaths" if kind == "reference" else "oracle/step2_oracle.c")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "bounded sample of the bench workload: " + sample},
+            "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--genome-mbp", type=float, default=135.0, help="Arabidopsis-sized (BASELINE.json configs[1])")
+    ap.add_argument("--coverage", type=int, default=60)
+    ap.add_argument("--read-len", type=int, default=250)
+    ap.add_argument("--ref-genome-mbp", type=float, default=1.0, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import w2r_testlib as T
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = T.product_lib()
+    if lib.w2rap_step2_device_count() <= local:
+        raise SystemExit("no B200 visible: this benchmark has no CPU path")
+    err = C.create_string_buffer(1024)
+    genome = int(args.genome_mbp * 1e6)
+    # weak scaling: every rank builds the graph of its own read shard (replica genomes, different seeds)
+    sp = T.SynthParams(genome, args.read_len, args.coverage, 1000 + rank, 0, 0, 0)
+    h = C.c_void_p()
+    if lib.w2rap_step2_synth(C.byref(sp), local, C.byref(h), err, 1024):
+        raise SystemExit("synth failed: " + err.value.decode())
+    p = T.default_params(apply_fixpaths=1, device=local)
+    hr = T.Reads()
+    if lib.w2rap_step2_download_reads(h, C.byref(hr), err, 1024):
+        raise SystemExit("download failed: " + err.value.decode())
+    n_reads = int(hr.n_reads)
+    n_bases = n_reads * args.read_len
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def step_resident():
+        g = T.Graph()
+        if lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 1024):
+            raise SystemExit("run failed: " + err.value.decode())
+        t = {n: getattr(g.timings, n) for n, _ in T.Timings._fields_}
+        info = (int(g.n_kmer_instances), int(g.n_distinct), int(g.n_solid), int(g.n_edges), int(g.n_edge_bases), int(g.n_pathed), int(g.n_path_edges))
+        lib.w2rap_step2_free(C.byref(g))
+        return t, info
+
+    def step_e2e():
+        g = T.Graph()
+        if lib.w2rap_step2_run(C.byref(hr), C.byref(p), C.byref(g), err, 1024):
+            raise SystemExit("run failed: " + err.value.decode())
+        t = {n: getattr(g.timings, n) for n, _ in T.Timings._fields_}
+        d2h = 8 * (int(g.n_edges) + 1) + 4 * int(g.n_edges) * 7 + int(g.n_edge_bases) // 4 + 4 * int(g.n_paths) + 8 * (int(g.n_paths) + 1) + 4 * int(g.n_path_edges)
+        lib.w2rap_step2_free(C.byref(g))
+        return t, d2h
+
+    for _ in range(args.warmup):
+        step_resident()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True)
+    th.start()
+    barrier()
+    tt, info = [], None
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        t, info = step_resident()
+        tt.append(t)
+    barrier()
+    wall_resident = time.time() - t_wall0
+    dev_ms = sum(t["total_ms"] - t["d2h_ms"] for t in tt) / len(tt)      # device time, results left on the device side of the copy
+    full_ms = sum(t["total_ms"] for t in tt) / len(tt)
+    # end to end through the host-buffer entry point
+    step_e2e()
+    barrier()
+    t0 = time.time()
+    e2e_d2h = 0
+    for _ in range(args.steps):
+        _, e2e_d2h = step_e2e()
+    barrier()
+    e2e_ms = (time.time() - t0) / args.steps * 1e3
+    stop.set()
+    th.join(timeout=2)
+    if dist is not None:
+        import torch
+        v = torch.tensor([dev_ms, e2e_ms, full_ms], device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, full_ms = [float(x) for x in v.tolist()]
+    if rank != 0:
+        return
+    I, D, S, E, EB, pathed, npe = info
+    h2d = int(hr.base_off and 0) + n_reads * ((args.read_len + 3) // 4) + 0
+    qbytes = int(T._arr(hr.qual_off, n_reads + 1, "<u8")[-1])
+    b_in = n_reads * ((args.read_len + 3) // 4) + qbytes + 12 * n_reads
+    b_path = 6 * n_reads + 4 * npe
+    alg_bytes_total = 2 * b_in + 34 * I + 48 * S + EB // 2 + b_path
+    count_ms = sum(t["count_kernel_ms"] for t in tt) / len(tt)
+    count_launches = tt[-1]["count_launches"]
+    alg_bytes_count = b_in + 34 * I                                                  # the extract+count kernel's share of the model
+    peak, peak_src = peaks()
+    achieved = alg_bytes_count / (count_ms * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                "--coverage", str(args.coverage), "--ref-genome-mbp", str(args.ref_genome_mbp)], capture_output=True, text=True, timeout=900)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:   # the baseline is reported, never required
+            cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)[:200]}
+    line = {
+        "metric": METRIC, "value": world * n_bases / (dev_ms * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "%.0f Mbp synthetic genome + repeat families, 2x%d bp PE at %dx per GPU (%d reads, %.2f Gbases per GPU), min_qual 7, min_freq 4; whole step 2 incl. read pathing + FixPaths" % (
+                       args.genome_mbp, args.read_len, args.coverage, n_reads, n_bases / 1e9),
+                   "cache": "inputs (%.1f GB) and counting table larger than the 126 MB L2" % (b_in / 1e9),
+                   "kmer_instances": I, "distinct": D, "solid": S, "edges": E, "reads_pathed": pathed,
+                   "parallelism": "one process per GPU; read shards are independent graphs in this round (see DESIGN.md §Multi-GPU)"},
+        "e2e": {"value": world * n_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": int(tt[-1]["kernel_launches"]) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "k_extract_count", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_count / max(1, count_launches), "launches_per_step": count_launches,
+                     "kernel_ms_per_step": count_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
+        "stage_ms": {k: sum(t[k] for t in tt) / len(tt) for k in ("count_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
+        "clocks": summarize_clocks(samples),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    lib.w2rap_step2_free_host_reads(C.byref(hr))
+    lib.w2rap_step2_release(h)
+
+
+if __name__ == "__main__":
+    main()

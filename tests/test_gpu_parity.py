@@ -1,0 +1,189 @@
+"""Parity of the CUDA path (through the C ABI, host buffers) with the oracle — bit-exact, every stage.
+
+Both sides emit canonical edges sorted by sequence, so every array must be identical: counters, histogram, the distinct
+k-mer set with counts and contexts (dump level 2), the solid dictionary with pruned contexts and (edge, offset) (level 1),
+edge sequences, vertex ids, hbv ids and every read path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def both(T, rs, **kw):
+    got = T.run_product(rs, T.default_params(**kw))
+    want = T.run_oracle(rs, T.default_params(**{k: v for k, v in kw.items() if k not in ("table_slots", "device")}))
+    return want, got
+
+
+def test_smoke_set(T):
+    want, got = both(T, T.smoke_set(seed=1, genome=20000, cov=40), dump_kmers=1)
+    T.assert_graph_equal(want, got)
+    assert got["timings"]["kernel_launches"] > 20
+
+
+def test_distinct_kmers_counts_contexts(T):
+    rs = T.rich_set(seed=2, genome=60000, cov=50, pq_mode=1)
+    want, got = both(T, rs, dump_kmers=2, want_paths=0)
+    T.assert_graph_equal(want, got, check_paths=False)
+    assert len(got["dump"]) == got["n_distinct"] and got["dump"]["count"].max() <= 255
+
+
+def test_rich_set_all_stages(T):
+    rs = T.rich_set(seed=2, genome=100000, cov=60, pq_mode=1)
+    want, got = both(T, rs, dump_kmers=1)
+    T.assert_graph_equal(want, got)
+    assert got["n_edges"] > 1000 and got["n_multipathed"] > 1000
+
+
+def test_varlen_reads_fixpaths(T):
+    rs = T.rich_set(seed=5, genome=40000, cov=50, families=5, palindromes=4, plasmid=1500, vary_len=True)
+    want, got = both(T, rs, dump_kmers=1, apply_fixpaths=1)
+    T.assert_graph_equal(want, got)
+
+
+@pytest.mark.parametrize("case", ["circ", "rich"])
+def test_golden_reference_outputs(T, case):
+    """Straight against the files the UNMODIFIED reference wrote (tests/golden): modulo its racy edge numbering."""
+    d = os.path.join(GOLD, case)
+    rs = T.read_fastb_qualp(d)
+    got = T.run_product(rs, T.default_params(apply_fixpaths=1))
+    rep = T.compare_with_reference(got, T.graph_from_reference_files(d))
+    assert rep["edge_set_equal"] and rep["hist_equal"] and rep["vertices_equal"], rep
+    assert rep["path_mismatches"] == [] and rep["path_ties"] <= 3, rep
+
+
+def test_multi_pass_counting(T):
+    """A forced small counting table: several hash-range passes must give the same answer as one."""
+    rs = T.rich_set(seed=6, genome=50000, cov=40)
+    want, got = both(T, rs, dump_kmers=2, table_slots=60000)
+    assert got["timings"]["count_passes"] > 3
+    T.assert_graph_equal(want, got)
+
+
+def test_parameters(T):
+    rs = T.rich_set(seed=7, genome=30000, cov=12, families=4, palindromes=2, plasmid=800)
+    for mq, mf in ((7, 3), (10, 2), (20, 1), (0, 8)):
+        want, got = both(T, rs, dump_kmers=1, min_qual=mq, min_freq=mf)
+        T.assert_graph_equal(want, got, "min_qual=%d min_freq=%d" % (mq, mf))
+
+
+def test_edge_cases(T):
+    rng = np.random.default_rng(9)
+    empty = T.ReadSet(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    got = T.run_product(empty)
+    assert got["n_edges"] == 0 and got["n_paths"] == 0 and got["n_vertices"] == 0
+    g = rng.integers(0, 4, 400, dtype=np.uint8)
+    codes = np.zeros((40, 250), np.uint8)
+    quals = np.full((40, 250), 30, np.uint8)
+    lens = np.full(40, 250, np.uint32)
+    for i in range(40):
+        codes[i] = g[i:i + 250]
+    lens[0], lens[1] = 10, 59
+    quals[2, :] = 2
+    quals[3, 60:] = 2
+    quals[4, 61:] = 2
+    rs = T.flatten_reads(codes, quals, lens)
+    want, got = both(T, rs, dump_kmers=1, min_freq=1)
+    T.assert_graph_equal(want, got)
+    # nothing solid at all: no edges, every path empty
+    want, got = both(T, rs, min_freq=200)
+    T.assert_graph_equal(want, got)
+    assert got["n_solid"] == 0 and got["n_pathed"] == 0
+
+
+def test_saturating_counts(T):
+    """>255 copies of the same read: counts saturate at 255, histogram bin 100 collects them."""
+    rng = np.random.default_rng(10)
+    g = rng.integers(0, 4, 300, dtype=np.uint8)
+    codes = np.tile(g[:250], (400, 1))
+    rs = T.flatten_reads(codes, np.full((400, 250), 35, np.uint8), np.full(400, 250, np.uint32))
+    want, got = both(T, rs, dump_kmers=2)
+    T.assert_graph_equal(want, got)
+    assert got["dump"]["count"].max() == 255 and got["hist"][100] == got["n_distinct"]
+
+
+def test_resident_and_file_level_entry_points(T, tmp_path):
+    lib = T.product_lib()
+    rs = T.rich_set(seed=8, genome=30000, cov=40, families=3, palindromes=2, plasmid=1000)
+    want = T.run_oracle(rs, T.default_params(apply_fixpaths=1))
+    # device-resident variant
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    reads = rs.c()
+    assert lib.w2rap_step2_upload(C.byref(reads), -1, C.byref(h), err, 512) == 0, err.value
+    p = T.default_params(apply_fixpaths=1)
+    for _ in range(2):
+        g = T.Graph()
+        assert lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 512) == 0, err.value
+        got = T.graph_to_dict(g)
+        lib.w2rap_step2_free(C.byref(g))
+        T.assert_graph_equal(want, got, "resident run")
+    lib.w2rap_step2_release(h)
+    # file-level drop-in: .fastb/.qualp in, .hbv/.paths/.freqs out
+    T.write_fastb_qualp(str(tmp_path), rs)
+    assert lib.w2rap_step2_run_files(str(tmp_path).encode(), b"x", C.byref(T.default_params()), None, err, 512) == 0, err.value
+    ref = T.graph_from_reference_files(str(tmp_path))
+    rep = T.compare_with_reference(want, ref)
+    assert rep["edge_set_equal"] and rep["vertices_equal"] and rep["hist_equal"] and rep["path_mismatches"] == [] and rep["path_ties"] == 0
+
+
+def test_device_synth_reads_are_valid_and_path(T):
+    """The on-device generator emits valid read stores: the oracle decodes them and both sides agree on the result."""
+    lib = T.product_lib()
+    sp = T.SynthParams(150000, 250, 30, 42, 50, 0, 0)
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    assert lib.w2rap_step2_synth(C.byref(sp), -1, C.byref(h), err, 512) == 0, err.value
+    r = T.Reads()
+    assert lib.w2rap_step2_download_reads(h, C.byref(r), err, 512) == 0, err.value
+    n = int(r.n_reads)
+    assert n == 150000 * 30 // 250
+    boff, qoff = T._arr(r.base_off, n + 1, "<u8"), T._arr(r.qual_off, n + 1, "<u8")
+    rs = T.ReadSet(T._arr(r.bases, int(boff[-1]), "u1"), boff, T._arr(r.len, n, "<u4"), T._arr(r.quals, int(qoff[-1]), "u1"), qoff)
+    lib.w2rap_step2_free_host_reads(C.byref(r))
+    want = T.run_oracle(rs)
+    g = T.Graph()
+    p = T.default_params()
+    assert lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 512) == 0, err.value
+    got = T.graph_to_dict(g)
+    lib.w2rap_step2_free(C.byref(g))
+    lib.w2rap_step2_release(h)
+    T.assert_graph_equal(want, got, "device-generated reads")
+    assert got["n_pathed"] > 0.95 * n and 0.9 * 150000 < got["n_solid"] < 2.2 * 150000
+
+
+def test_size_independent_properties_at_scale(T):
+    """A few million reads (too slow for the oracle): structural invariants of the result."""
+    lib = T.product_lib()
+    sp = T.SynthParams(4_000_000, 250, 40, 7, 0, 0, 0)
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    assert lib.w2rap_step2_synth(C.byref(sp), -1, C.byref(h), err, 512) == 0, err.value
+    g = T.Graph()
+    p = T.default_params(apply_fixpaths=1, dump_kmers=1)
+    assert lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 512) == 0, err.value
+    d = T.graph_to_dict(g)
+    lib.w2rap_step2_free(C.byref(g))
+    lib.w2rap_step2_release(h)
+    # every solid k-mer lies on exactly one edge at a valid offset, and the edge k-mer count adds up
+    assert d["n_solid"] == len(d["dump"]) == int((d["edge_len"].astype(np.int64) - 59).sum())
+    assert (d["dump"]["edge"] < d["n_edges"]).all()
+    assert (d["dump"]["offset"] + 60 <= d["edge_len"][d["dump"]["edge"]]).all()
+    assert int(d["hist"][1:].sum()) == d["n_distinct"] and int(d["hist"][4:].sum()) == d["n_solid"]
+    # dump sorted strictly (no duplicate k-mers); edges sorted by sequence; vertex ids dense
+    w = d["dump"]
+    assert ((w["w0"][1:] > w["w0"][:-1]) | ((w["w0"][1:] == w["w0"][:-1]) & (w["w1"][1:] > w["w1"][:-1]))).all()
+    assert set(np.unique(d["edge_vertices"][d["edge_vertices"] >= 0])) == set(range(d["n_vertices"]))
+    # post-FixPaths paths are walks in the graph
+    seqs, left, right = T.hbv_view(d)
+    pe, po = d["path_edges"], d["path_off"]
+    inner = np.ones(len(pe), bool)
+    inner[(po[1:][po[1:] > po[:-1]] - 1).astype(np.int64)] = False
+    idx = np.nonzero(inner)[0]
+    assert (right[pe[idx]] == left[pe[idx + 1]]).all()
+    assert d["n_pathed"] > 0.97 * d["n_reads"]

@@ -1,0 +1,86 @@
+"""Host-side unit tests of the kernels' device functions (tests/hostcheck/hostcheck.cpp) against the oracle.
+
+The CUDA kernels are thin loops around host/device functions (csrc/{kmer,pqvec,extract,unipath,path}.cuh); hostcheck drives
+the same functions serially in kernel order.  This is where logic errors are caught without a GPU; the `-m gpu` tests then
+check the real kernels through the C ABI.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
+
+
+@pytest.fixture(scope="session")
+def hc(T):
+    src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, src], check=True)
+    lib = C.CDLL(SO)
+    lib.hc_count.argtypes = [C.POINTER(T.Reads), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.hc_graph.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(T.Reads), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(T.Graph)]
+    lib.hc_free.argtypes = [C.c_void_p]
+    lib.hc_graph_free.argtypes = [C.POINTER(T.Graph)]
+    return lib
+
+
+def run_hostcheck(T, hc, rs, min_qual=7, min_freq=4, apply_fixpaths=0, cap=24, left_cap=8):
+    ptr, n, ninst = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    reads = rs.c()
+    assert hc.hc_count(C.byref(reads), min_qual, C.byref(ptr), C.byref(n), C.byref(ninst)) == 0
+    allk = T._arr(ptr.value, n.value, T.KMER_REC_DTYPE)
+    g = T.Graph()
+    rc = hc.hc_graph(ptr, n, min_freq, C.byref(reads), 1, apply_fixpaths, cap, left_cap, C.byref(g))
+    hc.hc_free(ptr)
+    assert rc == 0, "hostcheck stage failure %d" % rc
+    d = T.graph_to_dict(g)
+    n_ovf = g.timings.reserved
+    hc.hc_graph_free(C.byref(g))
+    return allk, ninst.value, d, n_ovf
+
+
+def check_against_oracle(T, hc, rs, **kw):
+    allk, ninst, d, n_ovf = run_hostcheck(T, hc, rs, **kw)
+    pk = {k: v for k, v in kw.items() if k in ("min_qual", "min_freq", "apply_fixpaths")}
+    o2 = T.run_oracle(rs, T.default_params(dump_kmers=2, want_paths=0, **pk))
+    assert ninst == o2["n_kmer_instances"]
+    for f in ("w0", "w1", "count", "ctx"):
+        assert np.array_equal(allk[f], o2["dump"][f]), "distinct k-mer field %s differs" % f
+    o1 = T.run_oracle(rs, T.default_params(dump_kmers=1, **pk))
+    for k in ("n_kmer_instances", "n_bases", "n_reads", "hist"):      # not produced by hostcheck
+        d[k] = o1[k]
+    T.assert_graph_equal(o1, d, "hostcheck vs oracle")
+    return d, n_ovf
+
+
+def test_device_functions_smoke(T, hc):
+    check_against_oracle(T, hc, T.smoke_set(seed=1, genome=20000, cov=40))
+
+
+def test_device_functions_rich(T, hc):
+    d, _ = check_against_oracle(T, hc, T.rich_set(seed=2, genome=60000, cov=50, pq_mode=1))
+    assert d["n_edges"] > 500
+
+
+def test_device_functions_rich_varlen_fixpaths(T, hc):
+    check_against_oracle(T, hc, T.rich_set(seed=5, genome=40000, cov=50, families=5, palindromes=4, plasmid=1500, vary_len=True), apply_fixpaths=1)
+
+
+def test_device_functions_golden_circ(T, hc):
+    """Circles of both length parities, palindromes; tiny staging rows force the overflow path."""
+    rs = T.read_fastb_qualp(os.path.join(HERE, "golden", "circ"))
+    d, n_ovf = check_against_oracle(T, hc, rs, cap=3, left_cap=1)
+    assert n_ovf > 0
+    check_against_oracle(T, hc, rs, min_freq=2, min_qual=10)
+
+
+def test_device_functions_low_coverage_fragmented(T, hc):
+    """min_freq high relative to coverage: a shattered graph with many tips, gaps and short edges."""
+    check_against_oracle(T, hc, T.rich_set(seed=7, genome=30000, cov=12, families=4, palindromes=2, plasmid=800), min_freq=3)

@@ -1,0 +1,465 @@
+// kernels.cuh — the sm_100a kernels of the step-2 path (device code only).
+//
+// K1 k_good_len / k_extract_count : PQVec quality floor + canonical 60-mer/context extraction fused with the counting-table
+//                                   insert (one 128-bit CAS claims a 32-byte slot = one DRAM sector)
+// K2 k_count_stats / k_collect_solid / k_insert_solid : histogram, min-frequency filter, dictionary build
+// K3 k_adjacency                  : recomputeAdjacencies
+// K4 k_links / k_rank_* / k_cycle_* / k_strand_decide / k_collect_heads / k_assign_edges / k_emit_edges : unipaths
+// K5 k_edge_ends / k_vertex_* / k_hbv_edges / k_adj_* : HBV vertices + incidence
+// K6 k_path_reads / k_path_gather : read pathing (+FixPaths)
+#pragma once
+#include "extract.cuh"
+#include "kmer.cuh"
+#include "path.cuh"
+#include "pqvec.cuh"
+#include "rt.cuh"
+#include "unipath.cuh"
+
+namespace w2r {
+
+struct ReadsView {
+    uint64_t n;
+    const uint8_t* bases;
+    const uint64_t* base_off;
+    const uint32_t* len;
+    const uint8_t* quals;
+    const uint64_t* qual_off;
+};
+
+struct U128 { uint64_t lo, hi; };
+
+// 128-bit compare-and-swap on a 16-byte aligned global address (ATOMG.E.CAS.128 on sm_100a).
+__device__ __forceinline__ U128 cas128(void* addr, uint64_t cmp_lo, uint64_t cmp_hi, uint64_t val_lo, uint64_t val_hi) {
+    U128 old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.lo), "=l"(old.hi)
+        : "l"(cmp_lo), "l"(cmp_hi), "l"(val_lo), "l"(val_hi), "l"(addr)
+        : "memory");
+    return old;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append: every thread of the (converged) warp calls it; returns the slot index for threads with want.
+__device__ __forceinline__ uint64_t warp_append(unsigned long long* cursor, bool want) {
+    unsigned active = __activemask();
+    unsigned m = __ballot_sync(active, want);
+    if (!want) return 0;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+// Warp-reduced counter add (all threads of the converged warp call it).
+__device__ __forceinline__ void warp_add(unsigned long long* counter, unsigned long long v) {
+    unsigned active = __activemask();
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(active, v, d);
+    // with a partial mask the shuffle of an inactive lane returns the caller's own value, so only use this from full warps
+    if (lane_id() == 0 && v) atomicAdd(counter, v);
+}
+
+// ================================================================ K1: quality floor, extraction, counting
+
+__global__ void k_init_count_table(CountSlot* tab, uint64_t T) {
+    const uint4 key = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), zero = make_uint4(0, 0, 0, 0);
+    uint4* p = reinterpret_cast<uint4*>(tab);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * T; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (i & 1) ? zero : key;
+}
+
+// paths/long/BuildReadQGraph.cc:962-987: one thread decodes one read's PQVec stream and finds its good length.
+__global__ void k_good_len(ReadsView r, uint32_t min_qual, uint16_t* __restrict__ good, unsigned long long* __restrict__ n_inst, int* __restrict__ bad) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < r.n; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        unsigned long long mine = 0;
+        if (i < r.n) {
+            uint32_t nq = 0;
+            uint32_t gl = pq_good_length(r.quals + r.qual_off[i], min_qual, &nq);
+            if (nq != r.len[i]) atomicExch(bad, 1);              // a valid store has one quality per base
+            if (gl > r.len[i]) gl = r.len[i];
+            good[i] = (uint16_t)gl;
+            if (gl > (uint32_t)K) mine = gl - K + 1;
+        }
+        unsigned active = __activemask();
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(active, mine, d);
+        if (lane_id() == 0 && mine) atomicAdd(n_inst, mine);
+    }
+}
+
+constexpr uint32_t COUNT_MAX_PROBE = 1u << 14;
+
+struct CountParams {
+    CountSlot* tab;
+    uint64_t T;
+    uint32_t npass, pass;      // keep k-mers with (hash & 0xffff) % npass == pass
+    uint32_t sample;           // 1: keep only k-mers with ((hash >> 16) & 63) == 0 (distinct-count estimate)
+    int* overflow;
+};
+
+struct CountEmit {
+    const CountParams& cp;
+    __device__ __forceinline__ void operator()(Kmer k, uint32_t ctx) const {
+        const uint64_t h = kmer_hash(k);
+        if (cp.sample) { if (((h >> 16) & 63u) != 0) return; }
+        else if (cp.npass > 1 && (uint32_t)(h & 0xffffu) % cp.npass != cp.pass) return;
+        uint64_t s = mulhi64(h, cp.T);
+        for (uint32_t probe = 0; probe < COUNT_MAX_PROBE; ++probe) {
+            CountSlot* p = cp.tab + s;
+            ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(p));
+            bool hit = false;
+            if (cur.x == k.w0 && cur.y == k.w1) hit = true;
+            else if (cur.x == EMPTY_W0) {
+                U128 old = cas128(p, ~0ull, ~0ull, k.w0, k.w1);
+                hit = (old.lo == ~0ull && old.hi == ~0ull) || (old.lo == k.w0 && old.hi == k.w1);
+            }
+            if (hit) {
+                atomicAdd(&p->count, 1u);
+                uint32_t have = __ldcg(&p->ctx);
+                if ((have & ctx) != ctx) atomicOr(&p->ctx, ctx);
+                return;
+            }
+            if (++s == cp.T) s = 0;
+        }
+        atomicExch(cp.overflow, 1);
+    }
+};
+
+// paths/long/BuildReadQGraph.cc:1062-1080 fused with the sort/collapse of :1081-1082 (as a hash count): one thread per read.
+__global__ void __launch_bounds__(256) k_extract_count(ReadsView r, const uint16_t* __restrict__ good, CountParams cp) {
+    CountEmit emit{cp};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t gl = good[i];
+        if (gl > (uint32_t)K) extract_read_kmers(r.bases + r.base_off[i], gl, emit);
+    }
+}
+
+// ================================================================ K2: histogram, filter, dictionary
+
+// hist[min(100,min(255,count))]++ (BuildReadQGraph.cc:1094-1097); hist[101] = k-mers with count >= min_freq; hist[102] = occupied.
+__global__ void k_count_stats(const CountSlot* __restrict__ tab, uint64_t T, uint32_t min_freq, unsigned long long* __restrict__ hist /*[104]*/) {
+    __shared__ unsigned int sh[104];
+    for (int j = threadIdx.x; j < 104; j += blockDim.x) sh[j] = 0;
+    __syncthreads();
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool occ = false;
+        uint32_t c = 0;
+        if (i < T) { ulonglong2 k = __ldcs(reinterpret_cast<const ulonglong2*>(tab + i)); if (k.x != EMPTY_W0) { occ = true; c = tab[i].count; if (c > 255u) c = 255u; } }
+        uint32_t bin = occ ? (c > 100u ? 100u : c) : 103u;
+        unsigned peers = __match_any_sync(__activemask(), bin);
+        if (occ && (peers & ((1u << lane_id()) - 1u)) == 0) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+        bool solid = occ && c >= min_freq;
+        unsigned ms = __ballot_sync(__activemask(), solid);
+        if (lane_id() == 0 && ms) atomicAdd(&sh[101], (unsigned)__popc(ms));
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 103; j += blockDim.x) if (sh[j]) atomicAdd(&hist[j], (unsigned long long)sh[j]);
+}
+
+// Appends every solid k-mer as a 16-byte record: w0, w1 | ctx (the low byte of w1 is free).
+__global__ void k_collect_solid(const CountSlot* __restrict__ tab, uint64_t T, uint32_t min_freq, ulonglong2* __restrict__ out, unsigned long long* cursor) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool want = false;
+        ulonglong2 k = make_ulonglong2(0, 0);
+        uint32_t ctx = 0;
+        if (i < T) {
+            k = __ldcs(reinterpret_cast<const ulonglong2*>(tab + i));
+            if (k.x != EMPTY_W0) { uint32_t c = tab[i].count; if (c > 255u) c = 255u; want = c >= min_freq; ctx = tab[i].ctx & 0xffu; }
+        }
+        uint64_t pos = warp_append(cursor, want);
+        if (want) out[pos] = make_ulonglong2(k.x, k.y | ctx);
+    }
+}
+// Test hook (dump level 2): every distinct k-mer with its saturated count and raw context.
+struct DumpRec { uint64_t w0, w1; uint32_t count, ctx, edge, off; };
+__global__ void k_collect_all(const CountSlot* __restrict__ tab, uint64_t T, DumpRec* __restrict__ out, unsigned long long* cursor) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool want = i < T && tab[i].w0 != EMPTY_W0;
+        uint64_t pos = warp_append(cursor, want);
+        if (want) { uint32_t c = tab[i].count; out[pos] = DumpRec{tab[i].w0, tab[i].w1, c > 255u ? 255u : c, tab[i].ctx & 0xffu, NIL, 0}; }
+    }
+}
+__global__ void k_dump_solid(SolidTable st, DumpRec* __restrict__ out, unsigned long long* cursor) {
+    const uint64_t T = st.size();
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool want = i < T && st.slots[i].w0 != EMPTY_W0;
+        uint64_t pos = warp_append(cursor, want);
+        if (want) { const SolidSlot& s = st.slots[i]; out[pos] = DumpRec{s.w0, s.w1, 0, s.ctx & 0xffu, s.edge, s.off}; }
+    }
+}
+
+// Dictionary build (BuildReadQGraph.cc:1096-1104 insertEntryNoLocking, in parallel): keys are unique, so a successful CAS owns the slot.
+__global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, SolidTable st) {
+    const uint64_t mask = st.size() - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 rec = __ldcs(recs + i);
+        Kmer k{rec.x, rec.y & ~0xffull};
+        uint32_t ctx = (uint32_t)rec.y & 0xffu;
+        uint64_t h = st.home(k);
+        for (;;) {
+            SolidSlot* p = st.slots + h;
+            U128 old = cas128(p, ~0ull, ~0ull, k.w0, k.w1);
+            if (old.lo == ~0ull && old.hi == ~0ull) { p->ctx = ctx; p->edge = NIL; p->off = 0; p->pad = 0; break; }
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+// ================================================================ K3: adjacency pruning (kmers/ReadPather.h:307-346)
+__global__ void k_adjacency(SolidTable st) {
+    const uint64_t T = st.size();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) {
+        SolidSlot* s = st.slots + i;
+        if (s->w0 == EMPTY_W0) continue;
+        uint32_t c = s->ctx & 0xffu;
+        uint32_t c2 = pruned_context(st, Kmer{s->w0, s->w1}, c);
+        if (c2 != c) s->ctx = c2;     // other threads only test membership (keys), never contexts, during this kernel
+    }
+}
+
+// ================================================================ K4: unipaths
+__global__ void k_links(SolidTable st, uint32_t* __restrict__ next0, int* __restrict__ missing) {
+    const uint64_t nn = 2 * st.size();
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nn; x += (uint64_t)gridDim.x * blockDim.x) {
+        int miss = 0;
+        next0[x] = unipath_succ_link(st, (uint32_t)x, &miss);
+        if (miss) atomicExch(missing, 1);
+    }
+}
+// Rank state per node: .x = pointer, .y = distance | RANK_RESOLVED.  Tails (no successor) are resolved fixed points.
+__global__ void k_rank_init(const uint32_t* __restrict__ next0, uint64_t nn, RankState* __restrict__ A) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nn; x += (uint64_t)gridDim.x * blockDim.x) A[x] = rank_init_node(next0, (uint32_t)x);
+}
+__global__ void k_rank_init_list(const uint32_t* __restrict__ list, uint64_t n, const uint32_t* __restrict__ next0, RankState* __restrict__ A) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) { uint32_t x = list[i]; A[x] = rank_init_node(next0, x); }
+}
+// One pointer-jumping round A -> B over all nodes (list == nullptr) or over a node list; counts unresolved nodes.
+__global__ void k_rank_step(const uint32_t* __restrict__ list, uint64_t n, const RankState* __restrict__ A, RankState* __restrict__ B, unsigned long long* __restrict__ unresolved) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool un = false;
+        if (i < n) {
+            uint32_t x = list ? list[i] : (uint32_t)i;
+            B[x] = rank_step_node(A, x, &un);
+        }
+        unsigned m = __ballot_sync(__activemask(), un);
+        if (lane_id() == 0 && m) atomicAdd(unresolved, (unsigned long long)__popc(m));
+    }
+}
+__global__ void k_copy_list(const uint32_t* __restrict__ list, uint64_t n, const RankState* __restrict__ src, RankState* __restrict__ dst) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[list[i]] = src[list[i]];
+}
+__global__ void k_collect_unresolved(const RankState* __restrict__ A, uint64_t nn, uint32_t* __restrict__ list, unsigned long long* cursor) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = base + threadIdx.x;
+        bool want = x < nn && !(A[x].y & RANK_RESOLVED);
+        uint64_t pos = warp_append(cursor, want);
+        if (want) list[pos] = (uint32_t)x;
+    }
+}
+// Smooth circles (BuildReadQGraph.cc:126-180): minimum canonical k-mer of every cycle by pointer doubling.
+__global__ void k_cycle_init(const uint32_t* __restrict__ list, uint64_t n, const uint32_t* __restrict__ next0, RankState* __restrict__ A) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t x = list[i];
+        A[x] = RankState{next0[x], x >> 1};
+    }
+}
+__global__ void k_cycle_step(const uint32_t* __restrict__ list, uint64_t n, SolidTable st, const RankState* __restrict__ A, RankState* __restrict__ B, int* __restrict__ changed) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t x = list[i];
+        bool ch;
+        B[x] = cycle_step_node(st, A, x, &ch);
+        if (ch) *changed = 1;
+    }
+}
+// Cut both strand cycles at the minimum k-mer: (kmin,+) becomes a head, (kmin,-) a tail.
+__global__ void k_cycle_cut(const uint32_t* __restrict__ list, uint64_t n, const RankState* __restrict__ A, uint32_t* __restrict__ next0) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        cycle_cut_node(A, next0, list[i]);
+    }
+}
+// Per strand path: keep it iff its sequence is FWD or PALINDROME (dna/CanonicalForm.h:34-46, BuildReadQGraph.cc:247-258).
+// R[x] = (tail(x), dist to tail | RESOLVED).  keep[] is indexed by the head node of the strand.
+__global__ void k_strand_decide(SolidTable st, const RankState* __restrict__ R, uint8_t* __restrict__ keep, int* __restrict__ too_long) {
+    const uint64_t nn = 2 * st.size();
+    for (uint64_t xi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; xi < nn; xi += (uint64_t)gridDim.x * blockDim.x) {
+        if (strand_decide_node(st, R, (uint32_t)xi, keep)) atomicExch(too_long, 1);
+    }
+}
+__global__ void k_collect_heads(SolidTable st, const RankState* __restrict__ R, const uint8_t* __restrict__ keep, uint32_t* __restrict__ h_node,
+                                uint64_t* __restrict__ h_w0, uint64_t* __restrict__ h_w1, uint32_t* __restrict__ h_n, unsigned long long* cursor, uint64_t cap) {
+    const uint64_t nn = 2 * st.size();
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t xi = base + threadIdx.x;
+        bool want = false;
+        uint32_t x = (uint32_t)xi;
+        if (xi < nn) want = head_is_kept(st, R, keep, x);
+        uint64_t pos = warp_append(cursor, want);
+        if (want && pos < cap) {
+            Kmer k = node_kmer(st, x);
+            h_node[pos] = x; h_w0[pos] = k.w0; h_w1[pos] = k.w1; h_n[pos] = (R[x].y & ~RANK_RESOLVED) + 1u;
+        }
+    }
+}
+__global__ void k_assign_edges(const uint32_t* __restrict__ perm, uint64_t E, const uint32_t* __restrict__ h_node, const uint32_t* __restrict__ h_n,
+                               uint32_t* __restrict__ edge_of_head, uint32_t* __restrict__ edge_len, uint32_t* __restrict__ edge_nbytes) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t j = perm[i];
+        edge_of_head[h_node[j]] = (uint32_t)i;
+        uint32_t len = h_n[j] + K - 1;
+        edge_len[i] = len;
+        edge_nbytes[i] = (len + 3) / 4;
+    }
+}
+struct OrBase {
+    uint8_t* bases;   // zeroed, 4-byte aligned
+    __device__ __forceinline__ void operator()(uint64_t byte_off, uint64_t pos, uint32_t b) const {
+        uint64_t addr = byte_off + (pos >> 2);
+        atomicOr(reinterpret_cast<uint32_t*>(bases + (addr & ~3ull)), b << (8 * (uint32_t)(addr & 3ull) + 2 * (uint32_t)(pos & 3ull)));
+    }
+};
+// Every k-mer of a kept strand writes its first base (the tail also its other 59) and its KDef (edge id, offset).
+__global__ void k_emit_edges(SolidTable st, const RankState* __restrict__ R, const uint32_t* __restrict__ edge_of_head, const uint64_t* __restrict__ edge_off,
+                             uint8_t* __restrict__ edge_bases) {
+    const uint64_t nn = 2 * st.size();
+    OrBase put{edge_bases};
+    for (uint64_t xi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; xi < nn; xi += (uint64_t)gridDim.x * blockDim.x) emit_node(st, R, edge_of_head, edge_off, (uint32_t)xi, put);
+}
+
+// ================================================================ K5: HBV vertices (paths/long/HBVFromEdges.cc:76-154)
+// End w of edge e: 0 fwd-left, 1 fwd-right, 2 rc-left, 3 rc-right.  Key = (FNV-1a 64 over the 59 base codes as bytes
+// (math/Hash.h:26-35), then the bases) — the order EdgeEnd::operator< defines (:34-38).
+__global__ void k_edge_ends(const uint8_t* __restrict__ edge_bases, const uint64_t* __restrict__ edge_off, const uint32_t* __restrict__ edge_len, uint64_t E,
+                            uint64_t* __restrict__ kh, uint64_t* __restrict__ k0, uint64_t* __restrict__ k1, uint8_t* __restrict__ is_pal) {
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * E; idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = idx >> 2;
+        uint32_t w = (uint32_t)idx & 3u;
+        bool pal; EndKey key;
+        edge_end_key(edge_bases + edge_off[e], edge_len[e], w, &pal, &key);
+        if (w == 0) is_pal[e] = pal ? 1 : 0;
+        kh[idx] = key.h; k0[idx] = key.k0; k1[idx] = key.k1;
+    }
+}
+__global__ void k_vertex_flags(const uint32_t* __restrict__ perm, uint64_t n4, const uint64_t* __restrict__ kh, const uint64_t* __restrict__ k0,
+                               const uint64_t* __restrict__ k1, uint32_t* __restrict__ flag) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t j = perm[i];
+        bool valid = !(kh[j] == ~0ull && k0[j] == ~0ull && k1[j] == ~0ull);
+        uint32_t fl = 0;
+        if (valid) {
+            if (i == 0) fl = 1;
+            else { uint32_t q = perm[i - 1]; fl = (kh[q] != kh[j] || k0[q] != k0[j] || k1[q] != k1[j]) ? 1u : 0u; }
+        }
+        flag[i] = fl;
+    }
+}
+__global__ void k_scatter_vids(const uint32_t* __restrict__ perm, uint64_t n4, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ excl,
+                               const uint64_t* __restrict__ kh, const uint64_t* __restrict__ k0, const uint64_t* __restrict__ k1, int32_t* __restrict__ edge_vertices) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t j = perm[i];
+        bool valid = !(kh[j] == ~0ull && k0[j] == ~0ull && k1[j] == ~0ull);
+        edge_vertices[j] = valid ? (int32_t)(excl[i] + flag[i]) - 1 : -1;
+    }
+}
+__global__ void k_pal_widths(const uint8_t* __restrict__ is_pal, uint64_t E, uint32_t* __restrict__ width) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) width[i] = is_pal[i] ? 1u : 2u;
+}
+// HBV edge ids: canonical edge i -> fwd id, then rc id (one id for a palindrome) (HBVFromEdges.cc:137-151).
+__global__ void k_hbv_edges(uint64_t E, const uint8_t* __restrict__ is_pal, const uint32_t* __restrict__ xl, const int32_t* __restrict__ edge_vertices,
+                            int32_t* __restrict__ fwd_xlat, int32_t* __restrict__ rev_xlat, uint32_t* __restrict__ hcanon, int32_t* __restrict__ hleft, int32_t* __restrict__ hright) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t f = xl[i];
+        fwd_xlat[i] = (int32_t)f;
+        hcanon[f] = (uint32_t)(i << 1); hleft[f] = edge_vertices[4 * i]; hright[f] = edge_vertices[4 * i + 1];
+        if (is_pal[i]) rev_xlat[i] = (int32_t)f;
+        else { rev_xlat[i] = (int32_t)f + 1; hcanon[f + 1] = (uint32_t)(i << 1) | 1u; hleft[f + 1] = edge_vertices[4 * i + 2]; hright[f + 1] = edge_vertices[4 * i + 3]; }
+    }
+}
+__global__ void k_adj_fill(uint64_t nh, const int32_t* __restrict__ hleft, const int32_t* __restrict__ hright, int32_t* __restrict__ from_e, int32_t* __restrict__ to_e,
+                           uint32_t* __restrict__ from_cnt, uint32_t* __restrict__ to_cnt, int* __restrict__ bad) {
+    for (uint64_t he = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; he < nh; he += (uint64_t)gridDim.x * blockDim.x) {
+        int32_t l = hleft[he], r = hright[he];
+        uint32_t a = atomicAdd(&from_cnt[l], 1u);
+        if (a < 4) from_e[4 * (int64_t)l + a] = (int32_t)he; else atomicExch(bad, 1);
+        uint32_t b = atomicAdd(&to_cnt[r], 1u);
+        if (b < 4) to_e[4 * (int64_t)r + b] = (int32_t)he; else atomicExch(bad, 1);
+    }
+}
+// graph/DigraphTemplate.h:1829-1839: lists are ordered by (neighbour vertex, edge id) when edges are added in id order.
+__global__ void k_adj_sort(uint64_t nv, const int32_t* __restrict__ hleft, const int32_t* __restrict__ hright, int32_t* __restrict__ from_e, int32_t* __restrict__ to_e,
+                           const uint32_t* __restrict__ from_cnt, const uint32_t* __restrict__ to_cnt, uint8_t* __restrict__ from_n, uint8_t* __restrict__ to_n) {
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (uint64_t)gridDim.x * blockDim.x) {
+        for (int dir = 0; dir < 2; ++dir) {
+            int32_t* lst = (dir ? to_e : from_e) + 4 * v;
+            const int32_t* nb = dir ? hleft : hright;
+            uint32_t n = dir ? to_cnt[v] : from_cnt[v];
+            if (n > 4) n = 4;
+            for (uint32_t i = 1; i < n; ++i) {
+                int32_t e = lst[i]; int32_t ke = nb[e];
+                int j = (int)i - 1;
+                while (j >= 0 && (nb[lst[j]] > ke || (nb[lst[j]] == ke && lst[j] > e))) { lst[j + 1] = lst[j]; --j; }
+                lst[j + 1] = e;
+            }
+            (dir ? to_n : from_n)[v] = (uint8_t)n;
+        }
+    }
+}
+
+// ================================================================ K6: read pathing
+struct alignas(8) PathMeta { uint32_t x, y; };   // x = first id in the staging row, y = path length | overflow << 31
+// One thread per read.  stage: [n_rows][cap] ints; meta: per row (start, len | overflow<<31).
+__global__ void __launch_bounds__(128) k_path_reads(ReadsView r, GraphView g, const uint32_t* __restrict__ list, uint64_t n_rows, uint8_t* __restrict__ qscratch,
+                                                    uint32_t qstride, int32_t* __restrict__ stage, uint32_t cap, uint32_t left_cap, int32_t* __restrict__ out_offset,
+                                                    PathMeta* __restrict__ out_meta, uint32_t apply_fixpaths) {
+    uint8_t* myq = qscratch + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * qstride;
+    for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = list ? list[row] : row;
+        PathResult pr = path_one_read(g, r.bases + r.base_off[i], r.len[i], r.quals + r.qual_off[i], myq, stage + row * cap, cap, left_cap, apply_fixpaths != 0);
+        out_offset[row] = pr.offset;
+        out_meta[row] = PathMeta{pr.start, pr.overflow ? 0x80000000u : pr.len};
+    }
+}
+// lens[target] = path length (0 for overflowed rows); counters: pathed (>0 edges), multipathed (>2 edges), overflowed rows.
+__global__ void k_path_lens(const PathMeta* __restrict__ meta, const uint32_t* __restrict__ list, uint64_t n, uint32_t* __restrict__ lens,
+                            unsigned long long* __restrict__ counters /*pathed, multipathed, overflow*/) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        uint32_t len = 0; bool ovf = false;
+        if (i < n) { uint32_t m = meta[i].y; ovf = m >> 31; len = ovf ? 0 : m; lens[list ? list[i] : i] = len; }
+        unsigned act = __activemask();
+        unsigned a = __ballot_sync(act, len > 0), b = __ballot_sync(act, len > 2), c = __ballot_sync(act, ovf);
+        if (lane_id() == 0) { if (a) atomicAdd(&counters[0], (unsigned long long)__popc(a)); if (b) atomicAdd(&counters[1], (unsigned long long)__popc(b)); if (c) atomicAdd(&counters[2], (unsigned long long)__popc(c)); }
+    }
+}
+__global__ void k_path_gather(const int32_t* __restrict__ stage, uint32_t cap, const PathMeta* __restrict__ meta, const uint32_t* __restrict__ list,
+                              const int32_t* __restrict__ row_offset, const uint64_t* __restrict__ path_off, uint64_t n, int32_t* __restrict__ path_edges,
+                              int32_t* __restrict__ path_offset) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        PathMeta m = meta[i];
+        if (m.y >> 31) continue;
+        uint64_t rd = list ? list[i] : i;
+        const int32_t* src = stage + i * cap + m.x;
+        int32_t* dst = path_edges + path_off[rd];
+        for (uint32_t j = 0; j < m.y; ++j) dst[j] = src[j];
+        path_offset[rd] = row_offset[i];
+    }
+}
+// Second-chance pathing for the (rare) reads whose path overflowed the staging row: results are patched into the big arrays.
+__global__ void k_collect_overflow(const PathMeta* __restrict__ meta, uint64_t n, uint32_t* __restrict__ list, unsigned long long* cursor) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool want = i < n && (meta[i].y >> 31);
+        uint64_t pos = warp_append(cursor, want);
+        if (want) list[pos] = (uint32_t)i;
+    }
+}
+
+}  // namespace w2r

@@ -1,0 +1,141 @@
+// kmer.cuh — 60-mer arithmetic, context bytes, hashing and the two open-addressing tables.
+//
+// Everything here is W2R_HD (host + device) so that the same code the kernels run can be unit-tested on the host
+// (tests/hostcheck) against the oracle.  The product library only ever runs it on the device.
+//
+// K-mer layout = the reference's KMer<60> (kmers/KMer.h:155-162): two u64 words, base 0 in bits 63-62 of w0,
+// bases 32..59 in bits 63..8 of w1, low 8 bits of w1 zero.  Unsigned (w0,w1) order == the reference's operator<
+// (kmers/KMer.h:312-319) == lexicographic order with A<C<G<T.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define W2R_HD __host__ __device__ __forceinline__
+#else
+#define W2R_HD inline
+#endif
+
+namespace w2r {
+
+constexpr int K = 60;
+constexpr uint32_t NIL = 0xffffffffu;
+constexpr uint64_t EMPTY_W0 = ~0ull;   // a canonical 60-mer never has 32 leading T's (its RC would start with 28+ A's and be smaller)
+
+struct Kmer { uint64_t w0, w1; };
+
+W2R_HD bool operator==(Kmer a, Kmer b) { return a.w0 == b.w0 && a.w1 == b.w1; }
+W2R_HD bool kmer_less(Kmer a, Kmer b) { return a.w0 < b.w0 || (a.w0 == b.w0 && a.w1 < b.w1); }
+
+// kmers/KMer.h:191-203 toSuccessor / :176-189 toPredecessor
+W2R_HD Kmer kmer_succ(Kmer k, uint32_t b) { return Kmer{(k.w0 << 2) | (k.w1 >> 62), (k.w1 << 2) | ((uint64_t)b << 8)}; }
+W2R_HD Kmer kmer_pred(Kmer k, uint32_t b) { return Kmer{(k.w0 >> 2) | ((uint64_t)b << 62), ((k.w1 >> 2) | (k.w0 << 62)) & ~0xffull}; }
+
+// reverse the order of the 32 two-bit groups of a word
+W2R_HD uint64_t rev2(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    x = __brevll(x);
+    return ((x & 0xaaaaaaaaaaaaaaaaull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+#else
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+    x = ((x >> 8) & 0x00ff00ff00ff00ffull) | ((x & 0x00ff00ff00ff00ffull) << 8);
+    x = ((x >> 16) & 0x0000ffff0000ffffull) | ((x & 0x0000ffff0000ffffull) << 16);
+    return (x >> 32) | (x << 32);
+#endif
+}
+// kmers/KMer.h:205-227 rc(): complement, reverse the 60 bases, re-align to the top.
+W2R_HD Kmer kmer_rc(Kmer k) {
+    // 128-bit value V = w0:w1 holds 60 bases then 8 zero bits.  Reverse all 64 groups of ~V: the 4 pad groups come first.
+    uint64_t a = rev2(~k.w1);          // groups 63..32 reversed -> becomes the high word of the reversed value
+    uint64_t b = rev2(~k.w0);
+    // reversed value R = a:b, whose top 4 groups are the complemented padding (all ones); shift left by 8 bits.
+    return Kmer{(a << 8) | (b >> 56), b << 8};
+}
+// dna/CanonicalForm.h:51-63, K even: FWD (0) iff kmer < rc, REV (1) iff rc < kmer, PALINDROME (2)
+W2R_HD int kmer_form(Kmer k, Kmer rc) { return kmer_less(k, rc) ? 0 : (kmer_less(rc, k) ? 1 : 2); }
+W2R_HD bool kmer_is_palindrome(Kmer k) { return kmer_rc(k) == k; }
+W2R_HD uint32_t kmer_base(Kmer k, int i) { return i < 32 ? (uint32_t)(k.w0 >> (62 - 2 * i)) & 3u : (uint32_t)(k.w1 >> (62 - 2 * (i - 32))) & 3u; }
+W2R_HD uint32_t kmer_first(Kmer k) { return (uint32_t)(k.w0 >> 62); }
+W2R_HD uint32_t kmer_last(Kmer k) { return (uint32_t)(k.w1 >> 8) & 3u; }
+
+// kmers/KMerContext.h: high nibble = predecessor mask, low nibble = successor mask; RC = bit reversal (KMerContext.cc:19-37)
+W2R_HD uint32_t ctx_rc(uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __brev(c) >> 24;
+#else
+    c = ((c >> 4) | (c << 4)) & 0xff; c = ((c & 0xcc) >> 2) | ((c & 0x33) << 2); c = ((c & 0xaa) >> 1) | ((c & 0x55) << 1);
+    return c & 0xff;
+#endif
+}
+W2R_HD int nib_count(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __popc(m & 15u);
+#else
+    m &= 15u; return (int)((m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1));
+#endif
+}
+W2R_HD uint32_t nib_single(uint32_t m) { m &= 15u; return m == 1 ? 0u : (m == 2 ? 1u : (m == 4 ? 2u : 3u)); }
+
+// 64-bit mixing hash of a k-mer (any mixing hash will do; the reference's FNV over the k-mer bytes is only used for
+// its own HashSet placement, kmers/KMer.h:229-232).  Low 16 bits select the counting pass / owner GPU, the slot comes
+// from the high bits.
+W2R_HD uint64_t kmer_hash(Kmer k) {
+    uint64_t a = k.w0 * 0x9e3779b97f4a7c15ull;
+    a ^= a >> 32;
+    a += k.w1 * 0xc2b2ae3d27d4eb4full;
+    a ^= a >> 29;
+    a *= 0xbf58476d1ce4e5b9ull;
+    a ^= a >> 32;
+    a *= 0x94d049bb133111ebull;
+    a ^= a >> 31;
+    return a;
+}
+W2R_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// ---------------------------------------------------------------- packed reads / edges (feudal/FieldVec.h:765-769)
+W2R_HD uint32_t packed_base(const uint8_t* p, uint64_t i) { return (p[i >> 2] >> ((i & 3) * 2)) & 3u; }
+
+// ---------------------------------------------------------------- tables
+// Counting table slot: one 32-byte sector.  {w0,w1} is claimed with a single 128-bit CAS.
+struct __attribute__((aligned(32))) CountSlot { uint64_t w0, w1; uint32_t count, ctx; uint64_t pad; };
+// Solid (dictionary) slot = the reference's KmerDictEntry (kmers/ReadPather.h:149-169): k-mer + KDef{edge, offset, context}.
+struct __attribute__((aligned(32))) SolidSlot { uint64_t w0, w1; uint32_t ctx, edge, off, pad; };
+
+struct SolidTable {
+    SolidSlot* slots;
+    uint32_t log2n;            // slots = 1 << log2n  (<= 2^31 so that oriented node ids 2*slot+o fit in 32 bits)
+    W2R_HD uint64_t size() const { return 1ull << log2n; }
+    W2R_HD uint64_t home(Kmer k) const { return kmer_hash(k) >> (64 - log2n); }
+};
+
+// Canonical lookup; returns slot or -1.
+W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) {
+    uint64_t mask = t.size() - 1, h = t.home(k);
+    for (;;) {
+        const SolidSlot* s = t.slots + h;
+#if defined(__CUDA_ARCH__)
+        ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(s));
+        uint64_t a = kk.x, b = kk.y;
+#else
+        uint64_t a = s->w0, b = s->w1;
+#endif
+        if (a == k.w0 && b == k.w1) return (int64_t)h;
+        if (a == EMPTY_W0) return -1;
+        h = (h + 1) & mask;
+    }
+}
+// kmers/ReadPather.h:196-199 findEntry: canonicalise then look up.  *rev = query was in REV form (rc < query).
+W2R_HD int64_t solid_find_any(const SolidTable& t, Kmer k, bool* rev) {
+    Kmer r = kmer_rc(k);
+    bool isrev = kmer_less(r, k);
+    if (rev) *rev = isrev;
+    return solid_find(t, isrev ? r : k);
+}
+
+}  // namespace w2r

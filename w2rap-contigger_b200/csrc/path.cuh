@@ -1,0 +1,248 @@
+// path.cuh — read pathing for one read (path_reads_OMP body, paths/long/BuildReadQGraph.cc:829-929) as a
+// host/device function over device-format graph arrays.  One thread paths one read.
+//
+// The reference materialises a vector<PathPart> and edits it; here the same rules are evaluated in streaming form with
+// O(1) state (at most the two most recent seeds can still be dropped by the captured-gap rule and the short-tail rule).
+// Every rule cites the reference lines it restates; quirks are kept.
+#pragma once
+#include "extract.cuh"
+#include "kmer.cuh"
+#include "pqvec.cuh"
+
+namespace w2r {
+
+struct GraphView {
+    SolidTable solid;
+    const uint8_t* edge_bases;     // canonical edges, bvec packing, byte aligned per edge
+    const uint64_t* edge_off;      // byte offsets
+    const uint32_t* edge_len;      // bases
+    const int32_t* fwd_xlat;       // canonical edge -> hbv edge id (paths/long/HBVFromEdges.cc:137-151)
+    const int32_t* rev_xlat;
+    const uint32_t* hcanon;        // hbv edge -> (canonical edge << 1) | is_rc
+    const int32_t* hleft;          // hbv edge -> source vertex
+    const int32_t* hright;         // hbv edge -> target vertex
+    const int32_t* from_e;         // [4*v + i] FromEdgeObj(v) in the reference's list order (graph/DigraphTemplate.h:1829-1839)
+    const int32_t* to_e;           // [4*v + i] ToEdgeObj(v)
+    const uint8_t* from_n;         // FromSize(v)  (<= 4: the edges leaving a (K-1)-mer start with distinct k-mers)
+    const uint8_t* to_n;           // ToSize(v)
+};
+
+// staging row of `cap` ints: [0,left_cap) left extensions (stored backwards), [left_cap,cap) seeds + right extensions
+
+struct PathPart { uint32_t edge, rc, off, len, elen; bool after_gap; };
+
+W2R_HD uint32_t edge_base_oriented(const GraphView& g, uint32_t canon, uint32_t rc, uint64_t pos) {
+    const uint8_t* p = g.edge_bases + g.edge_off[canon];
+    return rc ? 3u - packed_base(p, (uint64_t)g.edge_len[canon] - 1 - pos) : packed_base(p, pos);
+}
+W2R_HD uint32_t hbv_edge_base(const GraphView& g, int32_t he, uint64_t pos) { uint32_t hc = g.hcanon[he]; return edge_base_oriented(g, hc >> 1, hc & 1u, pos); }
+W2R_HD uint32_t hbv_edge_len(const GraphView& g, int32_t he) { return g.edge_len[g.hcanon[he] >> 1]; }
+W2R_HD bool part_same_edge(const PathPart& a, const PathPart& b) { return a.edge == b.edge && a.rc == b.rc; }
+
+// BuildReadQGraph.cc:552-558 isJoinable: same edge id, or equal LAST (K-1)-mers of the two oriented edges.
+W2R_HD bool part_joinable(const GraphView& g, const PathPart& a, const PathPart& b) {
+    if (a.edge == b.edge) return true;
+    uint64_t la = g.edge_len[a.edge], lb = g.edge_len[b.edge];
+    for (int i = 0; i < K - 1; ++i)
+        if (edge_base_oriented(g, a.edge, a.rc, la - (K - 1) + i) != edge_base_oriented(g, b.edge, b.rc, lb - (K - 1) + i)) return false;
+    return true;
+}
+
+// paths/long/ExtendReadPath.cc:15-109.  penalty -= 0.2*penalty (unsigned -= double) == 4*penalty/5 in integers.
+W2R_HD uint32_t score_left_overlap(const GraphView& g, const uint8_t* bases, const uint8_t* quals, uint32_t start, int32_t he) {
+    uint32_t qsum = 0, pen = 0;
+    int64_t b = (int64_t)start - 1, e = (int64_t)hbv_edge_len(g, he) - K;
+    while (b >= 0 && e >= 0) {
+        if (packed_base(bases, (uint64_t)b) != hbv_edge_base(g, he, (uint64_t)e)) { uint32_t q = quals[b] == 2 ? 20u : quals[b]; pen += q; qsum += pen; }
+        else if (pen > 0) pen = 4u * pen / 5u;
+        --b; --e;
+    }
+    if (b >= 0) qsum += 10u * (uint32_t)(b + 1);
+    return qsum;
+}
+W2R_HD uint32_t score_right_overlap(const GraphView& g, const uint8_t* bases, const uint8_t* quals, uint32_t rlen, uint32_t start, int32_t he) {
+    uint32_t qsum = 0, pen = 0;
+    uint64_t b = rlen - start, e = K - 1, elen = hbv_edge_len(g, he);
+    while (b < rlen && e < elen) {
+        if (packed_base(bases, b) != hbv_edge_base(g, he, e)) { uint32_t q = quals[b] == 2 ? 20u : quals[b]; pen += q; qsum += pen; }
+        else if (pen > 0) pen = 4u * pen / 5u;
+        ++b; ++e;
+    }
+    if (b < rlen) qsum += 10u * (uint32_t)(rlen - b);
+    return qsum;
+}
+
+// ExtendReadPath.cc:150-212 (left) / :262-318 (right): classify candidates, then score.  Returns the chosen hbv edge or -1.
+W2R_HD int32_t choose_extension(const GraphView& g, int32_t v, bool leftward, uint32_t last_gap, const uint8_t* bases, const uint8_t* quals, uint32_t rlen) {
+    const int32_t* cand = (leftward ? g.to_e : g.from_e) + 4 * (int64_t)v;
+    const uint32_t nc = leftward ? g.to_n[v] : g.from_n[v];
+    const bool solo = nc == 1;
+    uint32_t hanging = 0, nlong = 0, nshort = 0;
+    int32_t short_v = -1;
+    bool short_multi = false;
+    for (uint32_t i = 0; i < nc; ++i) {
+        int32_t e = cand[i];
+        int32_t d = leftward ? g.hleft[e] : g.hright[e];
+        bool hang = leftward ? (g.to_n[d] == 0 && g.from_n[d] == 1) : (g.from_n[d] == 0 && g.to_n[d] == 1);
+        if (hang) hanging |= 1u << i;
+        bool is_long = hbv_edge_len(g, e) - (uint32_t)(K - 1) >= last_gap;
+        if (is_long) ++nlong;
+        if (!is_long && !hang) { if (!nshort) short_v = d; else if (d != short_v) short_multi = true; ++nshort; }
+    }
+    if (!solo && nshort > 0) {
+        if (nlong > 0 || short_multi) return -1;
+        if ((leftward ? g.to_n[short_v] : g.from_n[short_v]) != 1) return -1;
+    }
+    int32_t least_edge = -1;
+    uint32_t least = 0xffffffffu;
+    for (uint32_t i = 0; i < nc; ++i) {
+        if (!((hanging >> i) & 1u) || solo) {
+            uint32_t s = leftward ? score_left_overlap(g, bases, quals, last_gap, cand[i]) : score_right_overlap(g, bases, quals, rlen, last_gap, cand[i]);
+            if (s < least) { least = s; least_edge = cand[i]; }
+        }
+    }
+    if (least_edge == -1 || least > last_gap * 10u) return -1;
+    return least_edge;
+}
+
+struct PathResult { int32_t offset; uint32_t start, len; bool overflow; };
+
+// Paths one read.  `row` is this read's staging row of `cap` ints; `qscratch` holds >= rlen bytes for lazily decoded quals.
+W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32_t rlen, const uint8_t* qstream, uint8_t* qscratch,
+                                int32_t* row, uint32_t cap, uint32_t left_cap, bool apply_fixpaths) {
+    const uint32_t PATH_LEFT_CAP = left_cap;
+    PathResult res{0, left_cap, 0, false};
+    if (rlen < (uint32_t)K) return res;                     // :503-506 a single gap part: empty path
+    const uint32_t nk = rlen - K + 1;
+    const uint32_t right_cap = cap - PATH_LEFT_CAP;
+
+    PathPart pend[2];
+    int npend = 0;
+    bool last_kept_valid = false; uint32_t lk_edge = 0, lk_rc = 0;
+    uint32_t n_ids = 0, sum_kmers = 0, seeds = 0, nparts = 0;
+    bool first_is_gap = false, have_first_hit = false;
+    uint32_t gap0_len = 0, first_hit_off = 0;
+    bool last_is_gap = false, last2_is_gap = false;
+    bool pending_gap = false; uint32_t gap_len = 0, gap_index = 0;
+
+    auto commit = [&](const PathPart& h) {                  // :804-815 pathPartsToReadPath, one kept seed
+        if (last_kept_valid && lk_edge == h.edge && lk_rc == h.rc) return;
+        if (n_ids < right_cap) row[PATH_LEFT_CAP + n_ids] = h.rc ? g.rev_xlat[h.edge] : g.fwd_xlat[h.edge]; else res.overflow = true;
+        ++n_ids; sum_kmers += h.elen;
+        last_kept_valid = true; lk_edge = h.edge; lk_rc = h.rc;
+    };
+
+    uint32_t itr = 0;
+    while (itr < nk) {                                      // :500-550 BRQ_Pather::path
+        Kmer f = kmer_at(bases, itr);
+        Kmer r = kmer_rc(f);
+        int64_t slot = solid_find(g.solid, kmer_less(r, f) ? r : f);
+        if (slot < 0) {
+            uint32_t gl = 1;
+            ++itr;
+            while (itr < nk) {
+                uint32_t nb = packed_base(bases, itr + K - 1);
+                f = kmer_succ(f, nb); r = kmer_pred(r, 3u - nb);
+                slot = solid_find(g.solid, kmer_less(r, f) ? r : f);
+                if (slot >= 0) break;
+                ++gl; ++itr;
+            }
+            if (nparts == 0) { first_is_gap = true; gap0_len = gl; }
+            gap_len = gl; gap_index = nparts; ++nparts;
+            last2_is_gap = last_is_gap; last_is_gap = true;
+            pending_gap = true;
+            if (slot < 0) break;
+        }
+        const SolidSlot& ss = g.solid.slots[slot];
+        PathPart h;
+        h.edge = ss.edge;
+        const uint32_t elen = g.edge_len[h.edge];
+        uint32_t o = ss.off;
+        const uint8_t* ep = g.edge_bases + g.edge_off[h.edge];
+        // dna/CanonicalForm.h:85-92 isRC: the read k-mer is the reverse complement of the edge k-mer at that offset
+        Kmer ek = kmer_at(ep, o);
+        h.rc = !(ek == f);
+        h.elen = elen - K + 1;
+        uint32_t len = 1;
+        if (!h.rc) {
+            uint64_t rp = (uint64_t)itr + K, e2 = (uint64_t)o + K;
+            while (rp < rlen && e2 < elen && packed_base(bases, rp) == packed_base(ep, e2)) { ++len; ++rp; ++e2; }
+            h.off = o;
+        } else {
+            uint64_t ro = (uint64_t)elen - o;               // position in rc(edge) just past the k-mer
+            uint64_t rp = (uint64_t)itr + K, e2 = ro;
+            while (rp < rlen && e2 < elen && packed_base(bases, rp) == 3u - packed_base(ep, (uint64_t)elen - 1 - e2)) { ++len; ++rp; ++e2; }
+            h.off = (uint32_t)(ro - K);
+        }
+        h.len = len;
+        h.after_gap = pending_gap;
+        // :875-898 captured-gap consistency, evaluated when the seed after an interior gap arrives
+        if (pending_gap && gap_index >= 1) {
+            const PathPart& pv = pend[npend - 1];
+            uint32_t gd = h.off - (pv.off + pv.len);        // :470 unsigned arithmetic
+            if (!part_same_edge(pv, h)) gd += pv.elen;
+            int32_t diff = (int32_t)(gap_len - gd);
+            uint32_t ad = (uint32_t)(diff < 0 ? -diff : diff);
+            if (!(ad <= 3u) || !part_joinable(g, pv, h)) {
+                if (seeds > 1) { last2_is_gap = pv.after_gap; --npend; }   // drop the seed before the gap and everything after it
+                else { last2_is_gap = false; }                             // the gap absorbs everything after it
+                last_is_gap = true;
+                break;
+            }
+        }
+        pending_gap = false;
+        if (npend == 2) { commit(pend[0]); pend[0] = pend[1]; npend = 1; }
+        pend[npend++] = h;
+        ++seeds;
+        if (!have_first_hit) { have_first_hit = true; first_hit_off = h.off; }
+        ++nparts; last2_is_gap = last_is_gap; last_is_gap = false;
+        itr += len;
+    }
+    // :904-918 a trailing seed that only reached <= 5 k-mers into an edge from its very start is dropped
+    if (last_is_gap) {
+        if (nparts > 1 && !last2_is_gap && npend > 0) { const PathPart& l2 = pend[npend - 1]; if (l2.off == 0 && l2.len <= 5) --npend; }
+    } else if (npend > 0) {
+        const PathPart& l = pend[npend - 1];
+        if (l.off == 0 && l.len <= 5) --npend;
+    }
+    for (int i = 0; i < npend; ++i) commit(pend[i]);
+    if (n_ids == 0 || res.overflow) return res;
+    int32_t offset = first_is_gap ? (int32_t)first_hit_off - (int32_t)gap0_len : (int32_t)first_hit_off;   // :816-826
+
+    // :922-923 quality-aware extension (ExtendReadPath.cc:115-348); all left extensions first, then right
+    bool have_quals = false;
+    uint32_t nl = 0;
+    int32_t front = row[PATH_LEFT_CAP], back = row[PATH_LEFT_CAP + n_ids - 1];
+    while (offset < 0 && (uint32_t)(-offset) >= 10u) {
+        if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
+        int32_t e = choose_extension(g, g.hleft[front], true, (uint32_t)(-offset), bases, qscratch, rlen);
+        if (e < 0) break;
+        uint32_t ek = hbv_edge_len(g, e) - K + 1;
+        offset += (int32_t)ek; sum_kmers += ek;
+        if (nl < PATH_LEFT_CAP) row[PATH_LEFT_CAP - 1 - nl] = e; else res.overflow = true;
+        ++nl; front = e;
+    }
+    for (;;) {
+        int32_t lastg = (int32_t)rlen + offset - (int32_t)sum_kmers - (K - 1);
+        if (lastg < 10) break;
+        if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
+        // the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
+        int32_t e = choose_extension(g, g.hleft[back], false, (uint32_t)lastg, bases, qscratch, rlen);
+        if (e < 0) break;
+        sum_kmers += hbv_edge_len(g, e) - K + 1;
+        if (n_ids < right_cap) row[PATH_LEFT_CAP + n_ids] = e; else res.overflow = true;
+        ++n_ids; back = e;
+    }
+    if (res.overflow) return res;
+    res.offset = offset;
+    res.start = PATH_LEFT_CAP - nl;
+    res.len = nl + n_ids;
+    if (apply_fixpaths) {                                    // large/GapToyTools.cc:322-335
+        const int32_t* p = row + res.start;
+        for (uint32_t i = 0; i + 1 < res.len; ++i)
+            if (g.hright[p[i]] != g.hleft[p[i + 1]]) { res.len = i + 1; break; }
+    }
+    return res;
+}
+
+}  // namespace w2r

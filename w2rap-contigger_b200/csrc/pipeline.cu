@@ -1,0 +1,640 @@
+// pipeline.cu — host orchestration of the step-2 path on one B200 and the C ABI over it (include/w2rap_step2.h).
+//
+// Mirrors buildReadQGraph (paths/long/BuildReadQGraph.cc:1253-1327) stage by stage:
+//   createDictOMPRecursive  -> count_stage()      (k_good_len, k_extract_count, k_count_stats, k_collect_solid, k_insert_solid)
+//   recomputeAdjacencies    -> k_adjacency
+//   buildEdges              -> unipath_stage()    (k_links, pointer-jumping list ranking, circles, edge emission)
+//   buildHBVFromEdges       -> hbv_stage()        (end keys, radix sort, vertex ids, incidence)
+//   path_reads_OMP(+FixPaths)-> path_stage()
+// No CPU fallback: without a usable sm_100 device every compute entry point fails with W2RAP_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <mutex>
+
+#include "../../include/w2rap_step2.h"
+#include "device_reads.cuh"
+#include "kernels.cuh"
+#include "prims.cuh"
+
+namespace w2r {
+
+// Output arrays live in plain pinned allocations owned by the graph.
+struct GraphOwner {
+    std::vector<void*> pinned;
+    ~GraphOwner() { for (void* p : pinned) cudaFreeHost(p); }
+};
+template <class T>
+static T* out_alloc(GraphOwner* o, size_t n) {
+    void* p = nullptr;
+    W2R_CUDA(cudaMallocHost(&p, (n ? n : 1) * sizeof(T)));
+    o->pinned.push_back(p);
+    return (T*)p;
+}
+
+static void check_device(int device, Ctx& c) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); W2R_FAIL(W2RAP_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path"); }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d does not exist (%d visible)", device, n);
+    cudaDeviceProp pr;
+    W2R_CUDA(cudaGetDeviceProperties(&pr, device));
+    if (pr.major < 10) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100; this library only carries sm_100a code", device, pr.name, pr.major, pr.minor);
+    W2R_CUDA(cudaSetDevice(device));
+    c.device = device;
+    c.sm_count = pr.multiProcessorCount;
+    static std::once_flag pool_once[16];
+    std::call_once(pool_once[device & 15], [&] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+    });
+}
+
+// stream-ordered device buffer (memory comes back from the pool on the next call, so steady-state steps do not hit the driver)
+template <class T>
+struct SBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    SBuf() {}
+    SBuf(Ctx& c, size_t n_) { alloc(c, n_); }
+    SBuf(const SBuf&) = delete;
+    SBuf& operator=(const SBuf&) = delete;
+    SBuf(SBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    SBuf& operator=(SBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; } return *this; }
+    ~SBuf() { release(); }
+    void alloc(Ctx& c, size_t n_) {
+        release();
+        s = c.stream; n = n_;
+        if (n) W2R_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+    }
+    void release() { if (p) cudaFreeAsync(p, s); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+    void zero() { if (n) W2R_CUDA(cudaMemsetAsync(p, 0, bytes(), s)); }
+    void fill_ff() { if (n) W2R_CUDA(cudaMemsetAsync(p, 0xff, bytes(), s)); }
+};
+
+static size_t device_budget(const Ctx& c) {
+    size_t fr = 0, tot = 0;
+    W2R_CUDA(cudaMemGetInfo(&fr, &tot));
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+        uint64_t reserved = 0, used = 0;
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        if (reserved > used) fr += (size_t)(reserved - used);
+    }
+    return fr;
+}
+
+struct StageTimer {
+    Ctx& c;
+    cudaEvent_t ev[2];
+    explicit StageTimer(Ctx& c_) : c(c_) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+    ~StageTimer() { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); }
+    void start() { cudaEventRecord(ev[0], c.stream); }
+    float stop() { cudaEventRecord(ev[1], c.stream); cudaEventSynchronize(ev[1]); float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); return ms; }
+};
+
+static void say(const Ctx& c, const char* fmt, ...) {
+    if (!c.verbose) return;
+    va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap); printf("\n"); fflush(stdout);
+}
+
+// ---------------------------------------------------------------- the pipeline
+struct Pipeline {
+    Ctx c;
+    const DeviceReads& dr;
+    const w2rap_params& prm;
+    w2rap_graph* out;
+    GraphOwner* owner;
+    std::vector<DumpRec> dump_host;
+
+    // persistent device state between stages
+    SBuf<uint16_t> good;
+    SBuf<SolidSlot> solid_slots;
+    SolidTable st{nullptr, 0};
+    uint64_t E = 0, nv = 0, nh = 0;
+    SBuf<uint8_t> edge_bases; SBuf<uint64_t> edge_off; SBuf<uint32_t> edge_len;
+    SBuf<int32_t> edge_vertices, fwd_xlat, rev_xlat, hleft, hright, from_e, to_e;
+    SBuf<uint32_t> hcanon;
+    SBuf<uint8_t> from_n, to_n;
+    uint64_t edge_bytes = 0;
+
+    Pipeline(const DeviceReads& dr_, const w2rap_params& p_, w2rap_graph* out_, GraphOwner* ow) : dr(dr_), prm(p_), out(out_), owner(ow) {}
+
+    unsigned grid(uint64_t n, unsigned block, unsigned per_sm = 16) const { return grid_for(c, n, block, per_sm); }
+
+    // ---- createDictOMPRecursive (BuildReadQGraph.cc:1015-1117)
+    void count_stage() {
+        const ReadsView rv = dr.view();
+        good.alloc(c, dr.n);
+        SBuf<unsigned long long> scal(c, 8);
+        scal.zero();
+        SBuf<int> flags(c, 4);
+        flags.zero();
+        if (dr.n) W2R_LAUNCH(c, k_good_len, grid(dr.n, 128), 128, 0, rv, prm.min_qual, good.p, scal.p, flags.p);
+        unsigned long long n_inst = d2h_scalar(c, scal.p);
+        if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
+        out->n_kmer_instances = n_inst;
+        say(c, "%llu k-mer instances in quality-floored reads", n_inst);
+
+        // estimate the number of distinct k-mers from a 1/64 hash sample so that the table is sized for the data, not for the worst case
+        double d_est = (double)n_inst;
+        EventTimer kt(c.stream);
+        float kernel_ms = 0;
+        if (n_inst > (1ull << 22) && !prm.table_slots) {
+            uint64_t Ts = n_inst / 24 + 4096;
+            SBuf<CountSlot> tab(c, Ts);
+            W2R_LAUNCH(c, k_init_count_table, grid(2 * Ts, 256), 256, 0, tab.p, Ts);
+            CountParams cp{tab.p, Ts, 1, 0, 1, flags.p + 1};
+            kt.start();
+            W2R_LAUNCH(c, k_extract_count, grid(dr.n, 256, 8), 256, 0, rv, good.p, cp); c.count_launches++;
+            kernel_ms += kt.stop();
+            SBuf<unsigned long long> h(c, 104); h.zero();
+            W2R_LAUNCH(c, k_count_stats, grid(Ts, 256), 256, 0, tab.p, Ts, prm.min_freq, h.p);
+            std::vector<unsigned long long> hh(104);
+            W2R_CUDA(cudaMemcpyAsync(hh.data(), h.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            unsigned long long occ = 0; for (int i = 1; i <= 100; ++i) occ += hh[i];
+            if (!d2h_scalar(c, flags.p + 1)) d_est = std::min((double)n_inst, (double)occ * 64.0 * 1.08 + 65536.0);
+            else W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
+            say(c, "sampled distinct estimate: %.0f", d_est);
+        }
+        uint64_t T_total = (uint64_t)(d_est / 0.6) + 1024;
+        size_t budget = (size_t)(device_budget(c) * 0.70);
+        uint64_t T_max = std::max<uint64_t>(1024, budget / sizeof(CountSlot));
+        uint32_t npass = 1;
+        uint64_t T = T_total;
+        if (prm.table_slots) { T = std::max<uint64_t>(prm.table_slots, 64); npass = (uint32_t)std::max<uint64_t>(1, (T_total + T - 1) / T); }
+        else if (T_total > T_max) { npass = (uint32_t)((T_total + T_max - 1) / T_max); T = T_total / npass + 1024; }
+
+        std::vector<unsigned long long> hist(104, 0);
+        std::vector<SBuf<ulonglong2>> staged;
+        std::vector<uint64_t> staged_n;
+        for (int attempt = 0;; ++attempt) {
+            if (attempt > 6) W2R_FAIL(W2RAP_ERR_INTERNAL, "counting table overflowed repeatedly");
+            bool overflow = false;
+            std::fill(hist.begin(), hist.end(), 0ull);
+            staged.clear(); staged_n.clear(); dump_host.clear();
+            SBuf<CountSlot> tab(c, T);
+            for (uint32_t pass = 0; pass < npass && !overflow; ++pass) {
+                W2R_LAUNCH(c, k_init_count_table, grid(2 * T, 256), 256, 0, tab.p, T);
+                if (n_inst) {
+                    CountParams cp{tab.p, T, npass, pass, 0, flags.p + 1};
+                    kt.start();
+                    W2R_LAUNCH(c, k_extract_count, grid(dr.n, 256, 8), 256, 0, rv, good.p, cp); c.count_launches++;
+                    kernel_ms += kt.stop();
+                }
+                if (d2h_scalar(c, flags.p + 1)) { overflow = true; break; }
+                SBuf<unsigned long long> h(c, 104); h.zero();
+                W2R_LAUNCH(c, k_count_stats, grid(T, 256), 256, 0, tab.p, T, prm.min_freq, h.p);
+                std::vector<unsigned long long> hh(104);
+                W2R_CUDA(cudaMemcpyAsync(hh.data(), h.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+                W2R_CUDA(cudaStreamSynchronize(c.stream));
+                unsigned long long occ = 0;
+                for (int i = 0; i < 104; ++i) hist[i] += hh[i];
+                for (int i = 1; i <= 100; ++i) occ += hh[i];
+                if ((double)occ > 0.92 * (double)T) { overflow = true; break; }   // too dense to trust the probe bound next time; resize
+                uint64_t ns = hh[101];
+                staged.emplace_back(c, ns);
+                staged_n.push_back(ns);
+                W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 8, c.stream));
+                if (ns) W2R_LAUNCH(c, k_collect_solid, grid(T, 256), 256, 0, tab.p, T, prm.min_freq, staged.back().p, scal.p + 1);
+                if (prm.dump_kmers == 2 && occ) {
+                    SBuf<DumpRec> dd(c, occ);
+                    W2R_CUDA(cudaMemsetAsync(scal.p + 2, 0, 8, c.stream));
+                    W2R_LAUNCH(c, k_collect_all, grid(T, 256), 256, 0, tab.p, T, dd.p, scal.p + 2);
+                    size_t o = dump_host.size(); dump_host.resize(o + occ);
+                    W2R_CUDA(cudaMemcpyAsync(dump_host.data() + o, dd.p, occ * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
+                }
+            }
+            if (!overflow) break;
+            W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
+            if (prm.table_slots || T * 2 > T_max) npass *= 2; else T *= 2;
+            say(c, "counting table too small; retrying with %llu slots x %u passes", (unsigned long long)T, npass);
+        }
+        out->timings.count_kernel_ms = kernel_ms;
+        out->timings.count_passes = npass;
+        uint64_t n_distinct = 0, n_solid = 0;
+        for (int i = 1; i <= 100; ++i) { out->hist[i] = hist[i]; n_distinct += hist[i]; }
+        for (uint64_t v : staged_n) n_solid += v;
+        out->n_distinct = n_distinct; out->n_solid = n_solid;
+        say(c, "%llu kmers counted, filtering...", (unsigned long long)n_distinct);
+        say(c, "%llu / %llu kmers with Freq >= %u", (unsigned long long)n_solid, (unsigned long long)n_distinct, prm.min_freq);
+
+        // dictionary (kmers/ReadPather.h:176-349) as an open-addressing table at load <= 0.5
+        uint32_t lg = 10;
+        while ((1ull << lg) < 2 * n_solid) ++lg;
+        if (lg > 31) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^30 solid k-mers on one device");
+        solid_slots.alloc(c, 1ull << lg);
+        solid_slots.fill_ff();
+        st = SolidTable{solid_slots.p, lg};
+        for (size_t i = 0; i < staged.size(); ++i)
+            if (staged_n[i]) W2R_LAUNCH(c, k_insert_solid, grid(staged_n[i], 256), 256, 0, staged[i].p, staged_n[i], st);
+    }
+
+    // ---- buildEdges (BuildReadQGraph.cc:314-339)
+    void unipath_stage() {
+        const uint64_t T = st.size(), nn = 2 * T;
+        SBuf<uint32_t> next0(c, nn);
+        SBuf<int> flags(c, 4); flags.zero();
+        SBuf<unsigned long long> scal(c, 4); scal.zero();
+        W2R_LAUNCH(c, k_links, grid(nn, 256), 256, 0, st, next0.p, flags.p);
+        SBuf<RankState> A(c, nn), B(c, nn);
+        W2R_LAUNCH(c, k_rank_init, grid(nn, 256), 256, 0, next0.p, nn, A.p);
+        RankState* cur = A.p; RankState* oth = B.p;
+        unsigned long long prev_un = ~0ull;
+        for (int round = 0; round < 40; ++round) {
+            W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_rank_step, grid(nn, 256), 256, 0, (const uint32_t*)nullptr, nn, cur, oth, scal.p);
+            std::swap(cur, oth);
+            unsigned long long un = d2h_scalar(c, scal.p);
+            if (un == 0 || un == prev_un) { prev_un = un; break; }
+            prev_un = un;
+        }
+        if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a neighbour k-mer promised by a pruned context is missing (reference: ForceAssert in EdgeBuilder::lookup)");
+        if (prev_un) {   // smooth circles (:332-335)
+            uint64_t ncyc = prev_un;
+            SBuf<uint32_t> list(c, ncyc);
+            W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_collect_unresolved, grid(nn, 256), 256, 0, cur, nn, list.p, scal.p + 1);
+            if (d2h_scalar(c, scal.p + 1) != ncyc) W2R_FAIL(W2RAP_ERR_INTERNAL, "unresolved node count changed between kernels");
+            // minimum canonical k-mer per cycle by pointer doubling.  `cur` holds the final ranks of the path nodes and is
+            // preserved; the cycle work ping-pongs between `oth` and D, touching only cycle entries.
+            SBuf<RankState> D(c, nn);   // second buffer for cycle work (only cycle entries are touched)
+            RankState* x0 = oth; RankState* x1 = D.p;
+            W2R_LAUNCH(c, k_cycle_init, grid(ncyc, 256), 256, 0, list.p, ncyc, next0.p, x0);
+            for (int round = 0; round < 40; ++round) {
+                W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
+                W2R_LAUNCH(c, k_cycle_step, grid(ncyc, 256), 256, 0, list.p, ncyc, st, x0, x1, flags.p + 1);
+                std::swap(x0, x1);
+                if (!d2h_scalar(c, flags.p + 1)) break;
+            }
+            W2R_LAUNCH(c, k_cycle_cut, grid(ncyc, 256), 256, 0, list.p, ncyc, x0, next0.p);
+            // the cycles are now paths: rank them
+            W2R_LAUNCH(c, k_rank_init_list, grid(ncyc, 256), 256, 0, list.p, ncyc, next0.p, x0);
+            for (int round = 0; round < 40; ++round) {
+                W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+                W2R_LAUNCH(c, k_rank_step, grid(ncyc, 256), 256, 0, list.p, ncyc, x0, x1, scal.p);
+                std::swap(x0, x1);
+                unsigned long long un = d2h_scalar(c, scal.p);
+                if (un == 0) break;
+                if (round == 39) W2R_FAIL(W2RAP_ERR_INTERNAL, "circle ranking did not converge");
+            }
+            W2R_LAUNCH(c, k_copy_list, grid(ncyc, 256), 256, 0, list.p, ncyc, x0, cur);
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        const RankState* R = cur;
+        SBuf<uint8_t> keep(c, nn); keep.zero();
+        W2R_LAUNCH(c, k_strand_decide, grid(nn, 256), 256, 0, st, R, keep.p, flags.p + 2);
+        if (d2h_scalar(c, flags.p + 2)) W2R_FAIL(W2RAP_ERR_EDGE_TOO_LONG, "an edge is longer than 2^24 k-mers (reference: KDef offset is 24 bits)");
+        // heads of kept strands = edges.  Upper bound: one per solid k-mer.
+        uint64_t cap = out->n_solid;
+        SBuf<uint32_t> h_node(c, cap), h_n(c, cap);
+        SBuf<uint64_t> h_w0(c, cap), h_w1(c, cap);
+        W2R_CUDA(cudaMemsetAsync(scal.p + 2, 0, 8, c.stream));
+        W2R_LAUNCH(c, k_collect_heads, grid(nn, 256), 256, 0, st, R, keep.p, h_node.p, h_w0.p, h_w1.p, h_n.p, scal.p + 2, cap);
+        E = d2h_scalar(c, scal.p + 2);
+        if (E > cap) W2R_FAIL(W2RAP_ERR_INTERNAL, "more edges than solid k-mers");
+        // deterministic edge order: sorted by sequence == sorted by the first 60 bases (each oriented k-mer heads at most one edge)
+        SBuf<uint32_t> perm(c, E), tmp(c, E);
+        if (E) {
+            W2R_LAUNCH(c, k_rs_iota, grid(E, 256), 256, 0, perm.p, (uint32_t)E);
+            SortWord words[2] = {{h_w1.p, 8, 64}, {h_w0.p, 0, 64}};
+            radix_sort_perm(c, perm.p, tmp.p, (uint32_t)E, words, 2);
+        }
+        SBuf<uint32_t> edge_of_head(c, nn); edge_of_head.fill_ff();
+        edge_len.alloc(c, E);
+        SBuf<uint32_t> nbytes(c, E);
+        if (E) W2R_LAUNCH(c, k_assign_edges, grid(E, 256), 256, 0, perm.p, E, h_node.p, h_n.p, edge_of_head.p, edge_len.p, nbytes.p);
+        edge_off.alloc(c, E + 1);
+        SBuf<unsigned long long> tot(c, 1);
+        exclusive_scan<uint32_t, unsigned long long>(c, nbytes.p, E, (unsigned long long*)edge_off.p, tot.p);
+        edge_bytes = E ? d2h_scalar(c, tot.p) : 0;
+        W2R_CUDA(cudaMemcpyAsync(edge_off.p + E, &edge_bytes, 8, cudaMemcpyHostToDevice, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        edge_bases.alloc(c, (edge_bytes + 3 + 16) & ~3ull);
+        edge_bases.zero();
+        W2R_LAUNCH(c, k_emit_edges, grid(nn, 256), 256, 0, st, R, edge_of_head.p, edge_off.p, edge_bases.p);
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+    }
+
+    // ---- buildHBVFromEdges (paths/long/HBVFromEdges.cc:76-154)
+    void hbv_stage() {
+        edge_vertices.alloc(c, 4 * E); fwd_xlat.alloc(c, E); rev_xlat.alloc(c, E);
+        if (!E) { nv = nh = 0; return; }
+        const uint64_t n4 = 4 * E;
+        if (n4 >= (1ull << 32)) W2R_FAIL(W2RAP_ERR_OOM, "too many edges for 32-bit end indices");
+        SBuf<uint64_t> kh(c, n4), k0(c, n4), k1(c, n4);
+        SBuf<uint8_t> is_pal(c, E);
+        W2R_LAUNCH(c, k_edge_ends, grid(n4, 128), 128, 0, edge_bases.p, edge_off.p, edge_len.p, E, kh.p, k0.p, k1.p, is_pal.p);
+        SBuf<uint32_t> perm(c, n4), tmp(c, n4);
+        W2R_LAUNCH(c, k_rs_iota, grid(n4, 256), 256, 0, perm.p, (uint32_t)n4);
+        SortWord words[3] = {{k1.p, 10, 64}, {k0.p, 0, 64}, {kh.p, 0, 64}};
+        radix_sort_perm(c, perm.p, tmp.p, (uint32_t)n4, words, 3);
+        SBuf<uint32_t> flag(c, n4), excl(c, n4), tot(c, 1);
+        W2R_LAUNCH(c, k_vertex_flags, grid(n4, 256), 256, 0, perm.p, n4, kh.p, k0.p, k1.p, flag.p);
+        exclusive_scan<uint32_t, uint32_t>(c, flag.p, n4, excl.p, tot.p);
+        nv = d2h_scalar(c, tot.p);
+        W2R_LAUNCH(c, k_scatter_vids, grid(n4, 256), 256, 0, perm.p, n4, flag.p, excl.p, kh.p, k0.p, k1.p, edge_vertices.p);
+        SBuf<uint32_t> width(c, E), xl(c, E);
+        W2R_LAUNCH(c, k_pal_widths, grid(E, 256), 256, 0, is_pal.p, E, width.p);
+        exclusive_scan<uint32_t, uint32_t>(c, width.p, E, xl.p, tot.p);
+        nh = d2h_scalar(c, tot.p);
+        hcanon.alloc(c, nh); hleft.alloc(c, nh); hright.alloc(c, nh);
+        W2R_LAUNCH(c, k_hbv_edges, grid(E, 256), 256, 0, E, is_pal.p, xl.p, edge_vertices.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p);
+        from_e.alloc(c, 4 * nv); to_e.alloc(c, 4 * nv); from_n.alloc(c, nv); to_n.alloc(c, nv);
+        SBuf<uint32_t> fc(c, nv), tc(c, nv); fc.zero(); tc.zero();
+        SBuf<int> bad(c, 1); bad.zero();
+        W2R_LAUNCH(c, k_adj_fill, grid(nh, 256), 256, 0, nh, hleft.p, hright.p, from_e.p, to_e.p, fc.p, tc.p, bad.p);
+        if (d2h_scalar(c, bad.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a vertex has more than four edges on one side");
+        W2R_LAUNCH(c, k_adj_sort, grid(nv, 128), 128, 0, nv, hleft.p, hright.p, from_e.p, to_e.p, fc.p, tc.p, from_n.p, to_n.p);
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+    }
+
+    // ---- path_reads_OMP (+FixPaths)  (BuildReadQGraph.cc:829-929; large/GapToyTools.cc:322-335)
+    void path_stage(SBuf<int32_t>& d_offset, SBuf<uint64_t>& d_path_off, SBuf<int32_t>& d_path_edges, uint64_t* n_path_edges, unsigned long long* pathed,
+                    unsigned long long* multipathed) {
+        const uint64_t n = dr.n;
+        d_offset.alloc(c, n); d_path_off.alloc(c, n + 1);
+        *n_path_edges = 0; *pathed = 0; *multipathed = 0;
+        if (!n) { W2R_CUDA(cudaMemsetAsync(d_path_off.p, 0, 8, c.stream)); return; }
+        GraphView g{st, edge_bases.p, edge_off.p, edge_len.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, from_e.p, to_e.p, from_n.p, to_n.p};
+        const ReadsView rv = dr.view();
+        const unsigned block = 128;
+        const unsigned gr = grid(n, block, 12);
+        const uint32_t qstride = (dr.max_len + 15) & ~15u;
+        SBuf<uint8_t> qscratch(c, (size_t)gr * block * std::max<uint32_t>(qstride, 16));
+        const uint32_t cap = 24, left_cap = 8;
+        SBuf<int32_t> stage(c, n * cap), row_off(c, n);
+        SBuf<PathMeta> meta(c, n);
+        SBuf<uint32_t> lens(c, n);
+        SBuf<unsigned long long> counters(c, 4); counters.zero();
+        W2R_LAUNCH(c, k_path_reads, gr, block, 0, rv, g, (const uint32_t*)nullptr, n, qscratch.p, qstride, stage.p, cap, left_cap, row_off.p, meta.p, prm.apply_fixpaths);
+        W2R_LAUNCH(c, k_path_lens, grid(n, 256), 256, 0, meta.p, (const uint32_t*)nullptr, n, lens.p, counters.p);
+        unsigned long long cnt[3];
+        W2R_CUDA(cudaMemcpyAsync(cnt, counters.p, 24, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        // rows that overflowed the small staging row are pathed again with a row that always suffices
+        uint64_t n_ovf = cnt[2];
+        SBuf<uint32_t> olist(c, n_ovf);
+        const uint32_t cap2 = 3 * dr.max_len + 32, left2 = dr.max_len + 16;
+        SBuf<int32_t> stage2(c, n_ovf * cap2), row_off2(c, n_ovf);
+        SBuf<PathMeta> meta2(c, n_ovf);
+        if (n_ovf) {
+            W2R_CUDA(cudaMemsetAsync(counters.p + 3, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_collect_overflow, grid(n, 256), 256, 0, meta.p, n, olist.p, counters.p + 3);
+            W2R_LAUNCH(c, k_path_reads, grid(n_ovf, block, 12), block, 0, rv, g, (const uint32_t*)olist.p, n_ovf, qscratch.p, qstride, stage2.p, cap2, left2, row_off2.p, meta2.p,
+                       prm.apply_fixpaths);
+            W2R_CUDA(cudaMemsetAsync(counters.p + 2, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_path_lens, grid(n_ovf, 256), 256, 0, meta2.p, (const uint32_t*)olist.p, n_ovf, lens.p, counters.p);
+            W2R_CUDA(cudaMemcpyAsync(cnt, counters.p, 24, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            if (cnt[2]) W2R_FAIL(W2RAP_ERR_INTERNAL, "a read path overflowed the worst-case staging row");
+        }
+        *pathed = cnt[0]; *multipathed = cnt[1];
+        SBuf<unsigned long long> tot(c, 1);
+        exclusive_scan<uint32_t, unsigned long long>(c, lens.p, n, (unsigned long long*)d_path_off.p, tot.p);
+        *n_path_edges = d2h_scalar(c, tot.p);
+        W2R_CUDA(cudaMemcpyAsync(d_path_off.p + n, n_path_edges, 8, cudaMemcpyHostToDevice, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        d_path_edges.alloc(c, *n_path_edges);
+        W2R_LAUNCH(c, k_path_gather, grid(n, 256), 256, 0, stage.p, cap, meta.p, (const uint32_t*)nullptr, row_off.p, d_path_off.p, n, d_path_edges.p, d_offset.p);
+        if (n_ovf) W2R_LAUNCH(c, k_path_gather, grid(n_ovf, 256), 256, 0, stage2.p, cap2, meta2.p, (const uint32_t*)olist.p, row_off2.p, d_path_off.p, n_ovf, d_path_edges.p, d_offset.p);
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+    }
+
+    template <class T>
+    T* to_host(const T* dptr, size_t n) {
+        T* h = out_alloc<T>(owner, n);
+        if (n) W2R_CUDA(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+        return h;
+    }
+
+    void run() {
+        W2R_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.verbose = prm.verbose != 0;
+        StageTimer total(c), st_t(c);
+        total.start();
+        out->n_reads = dr.n; out->n_bases = dr.n_bases;
+        say(c, "creating kmers from reads...");
+        st_t.start(); count_stage(); out->timings.count_ms = st_t.stop();
+        good.release();
+        say(c, "updating adjacencies");
+        st_t.start();
+        W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st);
+        out->timings.adjacency_ms = st_t.stop();
+        say(c, "finding edges (unique paths)");
+        st_t.start(); unipath_stage(); out->timings.unipath_ms = st_t.stop();
+        say(c, "building graph...");
+        st_t.start(); hbv_stage(); out->timings.hbv_ms = st_t.stop();
+        SBuf<int32_t> d_offset, d_path_edges; SBuf<uint64_t> d_path_off;
+        uint64_t npe = 0; unsigned long long pathed = 0, multi = 0;
+        if (prm.want_paths) {
+            say(c, "pathing reads into graph...");
+            st_t.start(); path_stage(d_offset, d_path_off, d_path_edges, &npe, &pathed, &multi); out->timings.path_ms = st_t.stop();
+            say(c, "%llu / %llu reads pathed, %llu spanning junctions", pathed, (unsigned long long)dr.n, multi);
+        }
+        // ---- results to the host
+        st_t.start();
+        out->n_edges = E; out->n_vertices = nv; out->n_hbv_edges = nh;
+        out->edge_off = to_host<uint64_t>(edge_off.p, E + 1);
+        out->edge_len = to_host<uint32_t>(edge_len.p, E);
+        out->edge_bases = to_host<uint8_t>(edge_bases.p, edge_bytes);
+        out->edge_vertices = to_host<int32_t>(edge_vertices.p, 4 * E);
+        out->fwd_xlat = to_host<int32_t>(fwd_xlat.p, E);
+        out->rev_xlat = to_host<int32_t>(rev_xlat.p, E);
+        if (prm.want_paths) {
+            out->n_paths = dr.n; out->n_path_edges = npe; out->n_pathed = pathed; out->n_multipathed = multi;
+            out->path_offset = to_host<int32_t>(d_offset.p, dr.n);
+            out->path_off = to_host<uint64_t>(d_path_off.p, dr.n + 1);
+            out->path_edges = to_host<int32_t>(d_path_edges.p, npe);
+        }
+        if (prm.dump_kmers == 1 && out->n_solid) {
+            SBuf<DumpRec> dd(c, out->n_solid);
+            SBuf<unsigned long long> cur(c, 1); cur.zero();
+            W2R_LAUNCH(c, k_dump_solid, grid(st.size(), 256), 256, 0, st, dd.p, cur.p);
+            dump_host.resize(out->n_solid);
+            W2R_CUDA(cudaMemcpyAsync(dump_host.data(), dd.p, out->n_solid * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        out->timings.d2h_ms = st_t.stop();
+        if (E == 0 && out->edge_off) out->edge_off[0] = 0;
+        uint64_t neb = 0;
+        for (uint64_t i = 0; i < E; ++i) neb += out->edge_len[i];
+        out->n_edge_bases = neb;
+        if (prm.dump_kmers && !dump_host.empty()) {
+            std::sort(dump_host.begin(), dump_host.end(), [](const DumpRec& a, const DumpRec& b) { return a.w0 < b.w0 || (a.w0 == b.w0 && a.w1 < b.w1); });
+            out->n_dump = dump_host.size();
+            out->dump = out_alloc<w2rap_kmer_rec>(owner, dump_host.size());
+            static_assert(sizeof(DumpRec) == sizeof(w2rap_kmer_rec), "dump record layout");
+            memcpy(out->dump, dump_host.data(), dump_host.size() * sizeof(DumpRec));
+        }
+        out->timings.total_ms = total.stop();
+        out->timings.kernel_launches = c.launches;
+        out->timings.count_launches = c.count_launches;
+        say(c, "%llu edges of total length %llu; %llu vertices", (unsigned long long)E, (unsigned long long)neb, (unsigned long long)nv);
+    }
+
+    ~Pipeline() {
+        // free stream-ordered buffers before the stream goes away
+        good.release(); solid_slots.release(); edge_bases.release(); edge_off.release(); edge_len.release();
+        edge_vertices.release(); fwd_xlat.release(); rev_xlat.release(); hleft.release(); hright.release(); from_e.release(); to_e.release();
+        hcanon.release(); from_n.release(); to_n.release();
+        if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+    }
+};
+
+static void validate_reads(const w2rap_reads* in) {
+    if (!in) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null read store");
+    if (in->n_reads && (!in->bases || !in->base_off || !in->len || !in->quals || !in->qual_off)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null pointer in read store");
+    if (in->n_reads >= (1ull << 32)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "more than 2^32-1 reads on one device");
+}
+
+static void upload(const w2rap_reads* in, int device, DeviceReads* d, cudaStream_t s) {
+    d->device = device;
+    d->n = in->n_reads;
+    const uint64_t n = d->n;
+    d->bases_bytes = n ? in->base_off[n] : 0;
+    d->quals_bytes = n ? in->qual_off[n] : 0;
+    uint64_t nb = 0; uint32_t mx = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t L = in->len[i];
+        nb += L; if (L > mx) mx = L;
+        if (in->base_off[i + 1] < in->base_off[i] || in->base_off[i + 1] - in->base_off[i] < (uint64_t)(L + 3) / 4) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: base offsets do not hold its %u bases", (unsigned long long)i, L);
+        if (in->qual_off[i + 1] <= in->qual_off[i]) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: empty quality stream (at least the terminator byte is required)", (unsigned long long)i);
+    }
+    if (mx > 65535u) W2R_FAIL(W2RAP_ERR_BAD_ARG, "reads longer than 65535 bases are not supported (the reference stores good lengths in uint16_t)");
+    d->n_bases = nb; d->max_len = mx;
+    // +32 bytes of padding: the extraction loop may look one byte past a read, and the last stream must end inside the buffer
+    W2R_CUDA(cudaMalloc((void**)&d->bases, d->bases_bytes + 32));
+    W2R_CUDA(cudaMalloc((void**)&d->quals, d->quals_bytes + 32));
+    W2R_CUDA(cudaMalloc((void**)&d->base_off, (n + 1) * 8));
+    W2R_CUDA(cudaMalloc((void**)&d->qual_off, (n + 1) * 8));
+    W2R_CUDA(cudaMalloc((void**)&d->len, (n + 1) * 4));
+    W2R_CUDA(cudaMemsetAsync(d->bases + d->bases_bytes, 0, 32, s));
+    W2R_CUDA(cudaMemsetAsync(d->quals + d->quals_bytes, 0, 32, s));
+    if (n) {
+        W2R_CUDA(cudaMemcpyAsync(d->bases, in->bases, d->bases_bytes, cudaMemcpyHostToDevice, s));
+        W2R_CUDA(cudaMemcpyAsync(d->quals, in->quals, d->quals_bytes, cudaMemcpyHostToDevice, s));
+        W2R_CUDA(cudaMemcpyAsync(d->base_off, in->base_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+        W2R_CUDA(cudaMemcpyAsync(d->qual_off, in->qual_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+        W2R_CUDA(cudaMemcpyAsync(d->len, in->len, n * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        uint64_t z = 0;
+        W2R_CUDA(cudaMemcpyAsync(d->base_off, &z, 8, cudaMemcpyHostToDevice, s));
+        W2R_CUDA(cudaMemcpyAsync(d->qual_off, &z, 8, cudaMemcpyHostToDevice, s));
+    }
+    W2R_CUDA(cudaStreamSynchronize(s));
+}
+
+static void check_params(const w2rap_params* p) {
+    if (!p) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null params");
+    if (p->abi_version != W2RAP_STEP2_ABI_VERSION) W2R_FAIL(W2RAP_ERR_BAD_ARG, "ABI version %u, library has %d", p->abi_version, W2RAP_STEP2_ABI_VERSION);
+    if (p->K != W2RAP_K) W2R_FAIL(W2RAP_ERR_BAD_ARG, "K=%u: only K=60 is built (the reference hard-wires it, BuildReadQGraph.cc:51)", p->K);
+    if (p->min_freq == 0 || p->min_freq > 255) W2R_FAIL(W2RAP_ERR_BAD_ARG, "min_freq must be in 1..255 (counts saturate at 255)");
+}
+
+static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* out, float h2d_ms) {
+    GraphOwner* owner = new GraphOwner();
+    memset(out, 0, sizeof(*out));
+    out->_owner = owner;
+    try {
+        Pipeline pl(dr, *p, out, owner);
+        check_device(dr.device, pl.c);
+        pl.run();
+        out->timings.h2d_ms = h2d_ms;
+        out->timings.total_ms += h2d_ms;
+    } catch (...) {
+        delete owner;
+        memset(out, 0, sizeof(*out));
+        throw;
+    }
+}
+
+}  // namespace w2r
+
+// ================================================================ C ABI
+using namespace w2r;
+
+static int fail(const Error& e, char* err, size_t errlen) {
+    if (err && errlen) { snprintf(err, errlen, "%s", e.msg.c_str()); }
+    return e.code;
+}
+#define W2R_API_BEGIN try {
+#define W2R_API_END                                                                                                  \
+    }                                                                                                                \
+    catch (const Error& e) { return fail(e, err, errlen); }                                                          \
+    catch (const std::exception& e) { return fail(Error{W2RAP_ERR_INTERNAL, e.what()}, err, errlen); }               \
+    return W2RAP_OK;
+
+extern "C" {
+
+int w2rap_step2_abi_version(void) { return W2RAP_STEP2_ABI_VERSION; }
+const char* w2rap_step2_build_info(void) { return "w2rap step2 B200 (sm_100a), K=60, built " __DATE__ " " __TIME__; }
+
+int w2rap_step2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major >= 10) ++ok; }
+    return ok;
+}
+
+int w2rap_step2_upload(const w2rap_reads* in, int device, w2rap_device_reads** handle, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!handle) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null handle");
+    validate_reads(in);
+    Ctx c; check_device(device, c);
+    w2rap_device_reads* h = new w2rap_device_reads();
+    try { upload(in, c.device, &h->d, 0); } catch (...) { h->d.release(); delete h; throw; }
+    *handle = h;
+    W2R_API_END
+}
+
+void w2rap_step2_release(w2rap_device_reads* handle) {
+    if (!handle) return;
+    cudaSetDevice(handle->d.device);
+    handle->d.release();
+    delete handle;
+}
+
+int w2rap_step2_run_resident(w2rap_device_reads* handle, const w2rap_params* p, w2rap_graph* out, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!handle || !out) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null argument");
+    check_params(p);
+    run_on_device(handle->d, p, out, 0.f);
+    if (p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
+    W2R_API_END
+}
+
+int w2rap_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* out, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!out) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null output");
+    check_params(p);
+    validate_reads(in);
+    Ctx c; check_device(p->device, c);
+    DeviceReads d;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float h2d = 0;
+    try {
+        cudaEventRecord(e0, 0);
+        upload(in, c.device, &d, 0);
+        cudaEventRecord(e1, 0); cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
+        run_on_device(d, p, out, h2d);
+    } catch (...) { d.release(); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    d.release(); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
+    W2R_API_END
+}
+
+void w2rap_step2_free(w2rap_graph* out) {
+    if (!out) return;
+    delete (GraphOwner*)out->_owner;
+    memset(out, 0, sizeof(*out));
+}
+
+}  // extern "C"

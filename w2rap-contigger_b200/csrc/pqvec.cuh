@@ -1,0 +1,73 @@
+// pqvec.cuh — streaming decode of the reference's block-compressed quality vectors (PQVec).
+//
+// Format (feudal/PQVec.cc:87-120 encoder, :122-188 decoder): a stream of blocks
+//   u8 nQs (1..255) ; then LSB-first bits: 3 bits nBits, 6 bits minQ, nQs x nBits-bit deltas ; padded to a byte
+// terminated by a 0 byte.  quality = minQ + delta.
+#pragma once
+#include "kmer.cuh"
+
+namespace w2r {
+
+// Sequential reader over one PQVec stream.  next() returns the next quality or -1 at the terminator.
+struct PQReader {
+    const uint8_t* p;
+    uint64_t acc;      // bit accumulator (LSB = next bit)
+    uint32_t have;     // valid bits in acc
+    uint32_t left;     // quals left in the current block
+    uint32_t nbits, minq;
+    bool done;
+
+    W2R_HD explicit PQReader(const uint8_t* stream) : p(stream), acc(0), have(0), left(0), nbits(0), minq(0), done(false) {}
+
+    W2R_HD void fill(uint32_t need) { while (have < need) { acc |= (uint64_t)(*p++) << have; have += 8; } }
+
+    W2R_HD int next() {
+        if (left == 0) {
+            if (done) return -1;
+            uint32_t nq = *p++;           // block header byte (always byte aligned: acc is empty here)
+            if (nq == 0) { done = true; return -1; }
+            acc = 0; have = 0;
+            fill(9);
+            nbits = (uint32_t)acc & 7u; minq = (uint32_t)(acc >> 3) & 63u;
+            acc >>= 9; have -= 9;
+            left = nq;
+        }
+        uint32_t v = 0;
+        if (nbits) { fill(nbits); v = (uint32_t)acc & ((1u << nbits) - 1u); acc >>= nbits; have -= nbits; }
+        if (--left == 0) { acc = 0; have = 0; }   // the rest of the last byte is padding; p already points past it
+        return (int)(minq + v);
+    }
+};
+
+// paths/long/BuildReadQGraph.cc:962-987 count_good_lengths, evaluated in one forward pass: the reference scans from the END
+// and stops at the first position where K consecutive quals >= minQual have been seen; that is the end of the right-most
+// maximal run of >= K good quals, which a forward scan finds as "the last position at which the current run is >= K".
+// The result is stored in a uint16_t by the reference.  *n_quals receives the number of qualities in the stream.
+W2R_HD uint32_t pq_good_length(const uint8_t* stream, uint32_t min_qual, uint32_t* n_quals) {
+    PQReader r(stream);
+    uint32_t run = 0, good = 0, i = 0;
+    for (;;) {
+        int q = r.next();
+        if (q < 0) break;
+        ++i;
+        if ((uint32_t)q < min_qual) run = 0;
+        else if (++run >= (uint32_t)K) good = i;
+    }
+    if (n_quals) *n_quals = i;
+    return good & 0xffffu;
+}
+
+// Decodes up to `cap` quals into out; returns the number of quals in the stream.
+W2R_HD uint32_t pq_decode(const uint8_t* stream, uint8_t* out, uint32_t cap) {
+    PQReader r(stream);
+    uint32_t i = 0;
+    for (;;) {
+        int q = r.next();
+        if (q < 0) break;
+        if (i < cap) out[i] = (uint8_t)q;
+        ++i;
+    }
+    return i;
+}
+
+}  // namespace w2r
