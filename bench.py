@@ -169,7 +169,10 @@ def main():
     tt, info = [], None
     t_wall0 = time.time()
     for _ in range(args.steps):
-        t, info = step_resident()
+        t, info2 = step_resident()
+        if info is not None and info2 != info:
+            raise SystemExit("non-deterministic result between steps: %r vs %r" % (info, info2))
+        info = info2
         tt.append(t)
     barrier()
     wall_resident = time.time() - t_wall0

@@ -88,17 +88,21 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     int missing = 0;
     for (uint64_t x = 0; x < nn; ++x) next0[x] = unipath_succ_link(st, (uint32_t)x, &missing);
     if (missing) return 101;
-    std::vector<RankState> A(nn), B(nn), D(nn);
-    for (uint64_t x = 0; x < nn; ++x) A[x] = rank_init_node(next0.data(), (uint32_t)x);
-    RankState* cur = A.data(); RankState* oth = B.data();
+    std::vector<RankState> A(nn, RankState{NIL, 0xffffffffu}), B(nn), D(nn);
+    // k_splitter_walk, k_rank_step_inplace, k_splitter_finish
+    std::vector<uint32_t> splist;
+    for (uint64_t x = 0; x < nn; ++x) if (node_is_splitter(next0.data(), (uint32_t)x)) { splist.push_back((uint32_t)x); splitter_walk(next0.data(), (uint32_t)x, A.data(), B.data()); }
     uint64_t prev_un = ~0ull;
-    for (int round = 0; round < 40; ++round) {
+    for (int round = 0; round < 48 && !splist.empty(); ++round) {
         uint64_t un = 0;
-        for (uint64_t x = 0; x < nn; ++x) { bool u; oth[x] = rank_step_node(cur, (uint32_t)x, &u); un += u; }
-        std::swap(cur, oth);
+        for (uint32_t x : splist) { bool u; B[x] = rank_step_node(B.data(), x, &u); un += u; }
         if (un == 0 || un == prev_un) { prev_un = un; break; }
         prev_un = un;
     }
+    prev_un = 0;
+    for (uint64_t x = 0; x < nn; ++x) { A[x] = splitter_finish_node(next0.data(), A.data(), B.data(), (uint32_t)x); prev_un += !(A[x].y & RANK_RESOLVED); }
+    RankState* cur = A.data(); RankState* oth = B.data();
+    out->timings.count_passes = (uint32_t)prev_un;   // reported to the test: nodes that went through the circle path
     if (prev_un) {
         std::vector<uint32_t> list;
         for (uint64_t x = 0; x < nn; ++x) if (!(cur[x].y & RANK_RESOLVED)) list.push_back((uint32_t)x);

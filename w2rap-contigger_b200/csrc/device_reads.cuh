@@ -12,9 +12,12 @@ struct DeviceReads {
     uint64_t* base_off = nullptr;
     uint64_t* qual_off = nullptr;
     uint32_t* len = nullptr;
+    bool pooled = false;            // true: buffers come from the stream-ordered pool (freed with cudaFreeAsync on pool_stream)
+    cudaStream_t pool_stream = nullptr;
     ReadsView view() const { return ReadsView{n, bases, base_off, len, quals, qual_off}; }
     void release() {
-        cudaFree(bases); cudaFree(quals); cudaFree(base_off); cudaFree(qual_off); cudaFree(len);
+        void* ps[5] = {bases, quals, base_off, qual_off, len};
+        for (void* q : ps) { if (!q) continue; if (pooled) cudaFreeAsync(q, pool_stream); else cudaFree(q); }
         bases = quals = nullptr; base_off = qual_off = nullptr; len = nullptr;
     }
 };

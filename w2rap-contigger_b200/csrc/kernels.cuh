@@ -254,6 +254,49 @@ __global__ void k_rank_step(const uint32_t* __restrict__ list, uint64_t n, const
         if (lane_id() == 0 && m) atomicAdd(unresolved, (unsigned long long)__popc(m));
     }
 }
+// In-place pointer jumping over a node list (used for the splitters): every state (p, d) says "p is d steps ahead of me";
+// composing it with ANY valid state of p (old or new) gives a valid state, so no double buffer is needed as long as the
+// 8-byte state is read and written in one transaction (L2-coherent __ldcg/__stcg).
+__global__ void k_rank_step_inplace(const uint32_t* __restrict__ list, uint64_t n, unsigned long long* S, unsigned long long* __restrict__ unresolved) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool un = false;
+        if (i < n) {
+            uint32_t x = list[i];
+            unsigned long long a = __ldcg(S + x);
+            uint32_t ax = (uint32_t)a, ay = (uint32_t)(a >> 32);
+            if (!(ay & RANK_RESOLVED)) {
+                unsigned long long b = __ldcg(S + ax);
+                uint32_t bx = (uint32_t)b, by = (uint32_t)(b >> 32);
+                ay = (ay + (by & ~RANK_RESOLVED)) | (by & RANK_RESOLVED);
+                __stcg(S + x, (unsigned long long)bx | ((unsigned long long)ay << 32));
+                un = !(ay & RANK_RESOLVED);
+            }
+        }
+        unsigned m = __ballot_sync(__activemask(), un);
+        if (lane_id() == 0 && m) atomicAdd(unresolved, (unsigned long long)__popc(m));
+    }
+}
+// Splitter-based list ranking (see unipath.cuh).
+__global__ void k_splitter_walk(const uint32_t* __restrict__ next0, uint64_t nn, RankState* __restrict__ label, RankState* __restrict__ S,
+                                uint32_t* __restrict__ list, unsigned long long* cursor) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = base + threadIdx.x;
+        bool sp = x < nn && node_is_splitter(next0, (uint32_t)x);
+        uint64_t pos = warp_append(cursor, sp);
+        if (sp) { list[pos] = (uint32_t)x; splitter_walk(next0, (uint32_t)x, label, S); }
+    }
+}
+__global__ void k_splitter_finish(const uint32_t* __restrict__ next0, uint64_t nn, RankState* __restrict__ label_then_rank, const RankState* __restrict__ S,
+                                  unsigned long long* __restrict__ unresolved) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = base + threadIdx.x;
+        bool un = false;
+        if (x < nn) { RankState r = splitter_finish_node(next0, label_then_rank, S, (uint32_t)x); label_then_rank[x] = r; un = !(r.y & RANK_RESOLVED); }
+        unsigned m = __ballot_sync(__activemask(), un);
+        if (lane_id() == 0 && m) atomicAdd(unresolved, (unsigned long long)__popc(m));
+    }
+}
 __global__ void k_copy_list(const uint32_t* __restrict__ list, uint64_t n, const RankState* __restrict__ src, RankState* __restrict__ dst) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[list[i]] = src[list[i]];
 }

@@ -19,15 +19,43 @@
 
 namespace w2r {
 
-// Output arrays live in plain pinned allocations owned by the graph.
+// Output arrays live in pinned host memory.  cudaMallocHost is slow (it maps and locks pages), so blocks are kept in a
+// process-wide pool and reused by later calls: steady-state steps pay no allocation.
+struct PinnedPool {
+    struct Block { void* p; size_t bytes; bool used; };
+    std::mutex mu;
+    std::vector<Block> blocks;
+    void* acquire(size_t bytes) {
+        if (bytes < 64) bytes = 64;
+        std::lock_guard<std::mutex> g(mu);
+        int best = -1;
+        for (size_t i = 0; i < blocks.size(); ++i)
+            if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + 4096 && (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = (int)i;
+        if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+        void* p = nullptr;
+        size_t cap = bytes + bytes / 8;       // a little slack so that slightly larger results of the next step still fit
+        cudaError_t e = cudaMallocHost(&p, cap);
+        if (e != cudaSuccess) {               // drop idle blocks and retry once
+            cudaGetLastError();
+            for (auto& b : blocks) if (!b.used && b.p) { cudaFreeHost(b.p); b.p = nullptr; b.bytes = 0; }
+            W2R_CUDA(cudaMallocHost(&p, cap));
+        }
+        blocks.push_back(Block{p, cap, true});
+        return p;
+    }
+    void release(void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    static PinnedPool& get() { static PinnedPool* pool = new PinnedPool(); return *pool; }   // leaked on purpose: outlives the CUDA context teardown order
+};
 struct GraphOwner {
     std::vector<void*> pinned;
-    ~GraphOwner() { for (void* p : pinned) cudaFreeHost(p); }
+    ~GraphOwner() { for (void* p : pinned) PinnedPool::get().release(p); }
 };
 template <class T>
 static T* out_alloc(GraphOwner* o, size_t n) {
-    void* p = nullptr;
-    W2R_CUDA(cudaMallocHost(&p, (n ? n : 1) * sizeof(T)));
+    void* p = PinnedPool::get().acquire((n ? n : 1) * sizeof(T));
     o->pinned.push_back(p);
     return (T*)p;
 }
@@ -242,22 +270,33 @@ struct Pipeline {
         SBuf<int> flags(c, 4); flags.zero();
         SBuf<unsigned long long> scal(c, 4); scal.zero();
         W2R_LAUNCH(c, k_links, grid(nn, 256), 256, 0, st, next0.p, flags.p);
-        SBuf<RankState> A(c, nn), B(c, nn);
-        W2R_LAUNCH(c, k_rank_init, grid(nn, 256), 256, 0, next0.p, nn, A.p);
-        RankState* cur = A.p; RankState* oth = B.p;
-        unsigned long long prev_un = ~0ull;
-        for (int round = 0; round < 40; ++round) {
-            W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
-            W2R_LAUNCH(c, k_rank_step, grid(nn, 256), 256, 0, (const uint32_t*)nullptr, nn, cur, oth, scal.p);
-            std::swap(cur, oth);
-            unsigned long long un = d2h_scalar(c, scal.p);
-            if (un == 0 || un == prev_un) { prev_un = un; break; }
-            prev_un = un;
-        }
+        // list ranking: splitters walk to the next splitter, the splitters alone are ranked by pointer jumping (unipath.cuh)
+        SBuf<RankState> A(c, nn), B(c, nn);          // A: label, then the final (tail, distance) of every node; B: splitter states
+        SBuf<uint32_t> splist(c, nn / 16 + out->n_solid / 2 + 1024);
+        W2R_CUDA(cudaMemsetAsync(A.p, 0xff, A.bytes(), c.stream));     // label = {NIL, ...}
+        W2R_CUDA(cudaMemsetAsync(scal.p + 3, 0, 8, c.stream));
+        W2R_LAUNCH(c, k_splitter_walk, grid(nn, 256), 256, 0, next0.p, nn, A.p, B.p, splist.p, scal.p + 3);
         if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a neighbour k-mer promised by a pruned context is missing (reference: ForceAssert in EdgeBuilder::lookup)");
+        const uint64_t nsp = d2h_scalar(c, scal.p + 3);
+        if (nsp > splist.n) W2R_FAIL(W2RAP_ERR_INTERNAL, "splitter list overflow");
+        unsigned long long prev_un = ~0ull;
+        if (nsp) {
+            for (int round = 0; round < 48; ++round) {
+                W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+                W2R_LAUNCH(c, k_rank_step_inplace, grid(nsp, 256), 256, 0, (const uint32_t*)splist.p, nsp, (unsigned long long*)B.p, scal.p);
+                unsigned long long un = d2h_scalar(c, scal.p);
+                if (un == 0 || un == prev_un) { prev_un = un; break; }
+                prev_un = un;
+            }
+        }
+        W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+        W2R_LAUNCH(c, k_splitter_finish, grid(nn, 256), 256, 0, next0.p, nn, A.p, (const RankState*)B.p, scal.p);
+        prev_un = d2h_scalar(c, scal.p);
+        RankState* cur = A.p; RankState* oth = B.p;
         if (prev_un) {   // smooth circles (:332-335)
             uint64_t ncyc = prev_un;
             SBuf<uint32_t> list(c, ncyc);
+            splist.release();
             W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 8, c.stream));
             W2R_LAUNCH(c, k_collect_unresolved, grid(nn, 256), 256, 0, cur, nn, list.p, scal.p + 1);
             if (d2h_scalar(c, scal.p + 1) != ncyc) W2R_FAIL(W2RAP_ERR_INTERNAL, "unresolved node count changed between kernels");
@@ -494,6 +533,9 @@ static void validate_reads(const w2rap_reads* in) {
     if (in->n_reads >= (1ull << 32)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "more than 2^32-1 reads on one device");
 }
 
+static void dev_alloc(DeviceReads* d, void** p, size_t bytes, cudaStream_t s) {
+    if (d->pooled) W2R_CUDA(cudaMallocAsync(p, bytes, s)); else W2R_CUDA(cudaMalloc(p, bytes));
+}
 static void upload(const w2rap_reads* in, int device, DeviceReads* d, cudaStream_t s) {
     d->device = device;
     d->n = in->n_reads;
@@ -510,11 +552,11 @@ static void upload(const w2rap_reads* in, int device, DeviceReads* d, cudaStream
     if (mx > 65535u) W2R_FAIL(W2RAP_ERR_BAD_ARG, "reads longer than 65535 bases are not supported (the reference stores good lengths in uint16_t)");
     d->n_bases = nb; d->max_len = mx;
     // +32 bytes of padding: the extraction loop may look one byte past a read, and the last stream must end inside the buffer
-    W2R_CUDA(cudaMalloc((void**)&d->bases, d->bases_bytes + 32));
-    W2R_CUDA(cudaMalloc((void**)&d->quals, d->quals_bytes + 32));
-    W2R_CUDA(cudaMalloc((void**)&d->base_off, (n + 1) * 8));
-    W2R_CUDA(cudaMalloc((void**)&d->qual_off, (n + 1) * 8));
-    W2R_CUDA(cudaMalloc((void**)&d->len, (n + 1) * 4));
+    dev_alloc(d, (void**)&d->bases, d->bases_bytes + 32, s);
+    dev_alloc(d, (void**)&d->quals, d->quals_bytes + 32, s);
+    dev_alloc(d, (void**)&d->base_off, (n + 1) * 8, s);
+    dev_alloc(d, (void**)&d->qual_off, (n + 1) * 8, s);
+    dev_alloc(d, (void**)&d->len, (n + 1) * 4, s);
     W2R_CUDA(cudaMemsetAsync(d->bases + d->bases_bytes, 0, 32, s));
     W2R_CUDA(cudaMemsetAsync(d->quals + d->quals_bytes, 0, 32, s));
     if (n) {
@@ -618,15 +660,19 @@ int w2rap_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* o
     validate_reads(in);
     Ctx c; check_device(p->device, c);
     DeviceReads d;
+    d.pooled = true;
+    cudaStream_t us = nullptr;
+    W2R_CUDA(cudaStreamCreateWithFlags(&us, cudaStreamNonBlocking));
+    d.pool_stream = us;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float h2d = 0;
     try {
-        cudaEventRecord(e0, 0);
-        upload(in, c.device, &d, 0);
-        cudaEventRecord(e1, 0); cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
+        cudaEventRecord(e0, us);
+        upload(in, c.device, &d, us);
+        cudaEventRecord(e1, us); cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
         run_on_device(d, p, out, h2d);
-    } catch (...) { d.release(); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
-    d.release(); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
     W2R_API_END
 }

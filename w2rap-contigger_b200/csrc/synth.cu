@@ -3,6 +3,7 @@
 // dominate the run.  Model: i.i.d. ACGT genome with planted repeat families, optional SNP haplotype,
 // 2 x read_len PE reads from N(500,50) fragments on both strands, Q37 body with a U(0,60) low-quality tail (Q2-15),
 // 1% sporadic Q2-19, substitution errors drawn at 10^(-Q/10), no Ns.  Deterministic in (seed, read index).
+#include <algorithm>
 #include <cmath>
 #include <random>
 
@@ -161,6 +162,14 @@ int w2rap_step2_synth(const w2rap_synth_params* sp, int device, w2rap_device_rea
                 for (uint32_t k = 0; k < copies; ++k) jobs.push_back(RepeatJob{pool_len, rng() % (G - len), len, (uint32_t)(rng() & 1), rng()});
                 pool_len += len;
                 budget -= std::min<uint64_t>(budget, (uint64_t)len * copies);
+            }
+            // copies must not overlap: concurrent blocks write them, and the genome has to be deterministic in the seed
+            std::sort(jobs.begin(), jobs.end(), [](const RepeatJob& a, const RepeatJob& b) { return a.dst < b.dst; });
+            {
+                std::vector<RepeatJob> keep;
+                uint64_t end = 0;
+                for (const RepeatJob& j : jobs) if (keep.empty() || j.dst >= end) { keep.push_back(j); end = j.dst + j.len; }
+                jobs.swap(keep);
             }
             if (!jobs.empty()) {
                 DBuf<uint8_t> pool(pool_len);

@@ -16,6 +16,7 @@
 namespace w2r {
 
 constexpr uint32_t RANK_RESOLVED = 0x80000000u;
+constexpr uint32_t EMPTY_NODE = 0xfffffffeu;   // next0[] of a node whose slot holds no k-mer
 
 W2R_HD Kmer node_kmer(const SolidTable& t, uint32_t x) {
     const SolidSlot& s = t.slots[x >> 1];
@@ -27,7 +28,7 @@ W2R_HD Kmer node_kmer(const SolidTable& t, uint32_t x) {
 // (the reference would ForceAssert, :265).
 W2R_HD uint32_t unipath_succ_link(const SolidTable& t, uint32_t x, int* missing) {
     const SolidSlot& s = t.slots[x >> 1];
-    if (s.w0 == EMPTY_W0) return NIL;
+    if (s.w0 == EMPTY_W0) return EMPTY_NODE;
     Kmer k{s.w0, s.w1};
     Kmer rc = kmer_rc(k);
     if (rc == k) return NIL;                                   // :105 palindromes are one-k-mer edges
@@ -64,7 +65,37 @@ struct alignas(8) RankState { uint32_t x, y; };
 
 W2R_HD RankState rank_init_node(const uint32_t* next0, uint32_t x) {
     uint32_t nx = next0[x];
-    return nx == NIL ? RankState{x, RANK_RESOLVED} : RankState{nx, 1u};
+    return nx >= EMPTY_NODE ? RankState{x, RANK_RESOLVED} : RankState{nx, 1u};
+}
+
+// ---- list ranking with splitters (Helman-JaJa): O(N) work instead of O(N log N) pointer jumping over every node.
+// A node is a splitter if it heads a strand path or if a hash of its id says so (about 1 in 64).  Each splitter walks
+// its successors up to the next splitter, labelling every node it passes with (splitter, steps from it); the splitters
+// alone are then ranked by pointer jumping; finally every node derives (tail, distance to tail) from its splitter's.
+// Nodes of cycles that contain no splitter stay unlabelled; splitters on a cycle never resolve: both are "circle" nodes.
+constexpr uint32_t SPLITTER_MASK = 63u;
+W2R_HD bool hash_splitter(uint32_t x) { uint32_t h = x * 0x9e3779b1u; h ^= h >> 15; h *= 0x85ebca77u; h ^= h >> 13; return (h & SPLITTER_MASK) == 0; }
+W2R_HD bool node_is_splitter(const uint32_t* next0, uint32_t x) { return next0[x] != EMPTY_NODE && (next0[x ^ 1u] == NIL || hash_splitter(x)); }
+// label[] must be initialised to {NIL, 0}.  Writes label[y] for every node of the segment and the splitter's own state S[s].
+W2R_HD void splitter_walk(const uint32_t* next0, uint32_t s, RankState* label, RankState* S) {
+    uint32_t y = s, o = 0;
+    for (;;) {
+        label[y] = RankState{s, o};
+        uint32_t nx = next0[y];
+        if (nx == NIL) { S[s] = RankState{y, o | RANK_RESOLVED}; return; }          // reached the tail: resolved
+        ++o;
+        if (hash_splitter(nx) || nx == s) { S[s] = RankState{nx, o}; return; }       // next splitter (nx == s: a cycle with one splitter)
+        y = nx;
+    }
+}
+// After the splitters are ranked: node y -> (tail, distance to tail | RESOLVED), or unresolved if y lies on a circle.
+W2R_HD RankState splitter_finish_node(const uint32_t* next0, const RankState* label, const RankState* S, uint32_t y) {
+    if (next0[y] == EMPTY_NODE) return RankState{y, RANK_RESOLVED};
+    RankState l = label[y];
+    if (l.x == NIL) return RankState{y, 0};                                          // never labelled: a circle without splitter
+    RankState st = S[l.x];
+    if (!(st.y & RANK_RESOLVED)) return RankState{y, 0};                             // its splitter sits on a circle
+    return RankState{st.x, ((st.y & ~RANK_RESOLVED) - l.y) | RANK_RESOLVED};
 }
 W2R_HD RankState rank_step_node(const RankState* A, uint32_t x, bool* unresolved) {
     RankState a = A[x];
