@@ -202,9 +202,15 @@ def main():
     b_in = n_reads * ((args.read_len + 3) // 4) + qbytes + 12 * n_reads
     b_path = 6 * n_reads + 4 * npe
     alg_bytes_total = 2 * b_in + 34 * I + 48 * S + EB // 2 + b_path
-    count_ms = sum(t["count_kernel_ms"] for t in tt) / len(tt)
-    count_launches = tt[-1]["count_launches"]
-    alg_bytes_count = b_in + 34 * I                                                  # the extract+count kernel's share of the model
+    # dominant kernel: k_extract_partition (map: reads the packed bases, writes one record per instance) or the region count
+    # (reduce: reads every record back).  SURVEY 8(d) charges 34 B per instance for "written once and read once": 17 B each.
+    part_ms = sum(t["count_kernel_ms"] for t in tt) / len(tt)
+    region_ms = sum(t["region_ms"] for t in tt) / len(tt)
+    b_bases = n_reads * ((args.read_len + 3) // 4) + 14 * n_reads
+    if part_ms >= region_ms:
+        dom, count_ms, count_launches, alg_bytes_count = "k_extract_partition", part_ms, tt[-1]["count_launches"], b_bases + 17 * I
+    else:
+        dom, count_ms, count_launches, alg_bytes_count = "k_count_region+k_scan_region", region_ms, 2 * tt[-1]["count_passes"], 17 * I
     peak, peak_src = peaks()
     achieved = alg_bytes_count / (count_ms * 1e-3) / 1e9
     cpu = None
@@ -225,9 +231,9 @@ def main():
                    "parallelism": "one process per GPU; read shards are independent graphs in this round (see DESIGN.md §Multi-GPU)"},
         "e2e": {"value": world * n_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms},
         "gpu_launches": int(tt[-1]["kernel_launches"]) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_extract_count", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_count / max(1, count_launches), "launches_per_step": count_launches,
-                     "kernel_ms_per_step": count_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
+                     "kernel_ms_per_step": count_ms, "extract_partition_ms": part_ms, "region_count_ms": region_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
         "stage_ms": {k: sum(t[k] for t in tt) / len(tt) for k in ("count_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
         "clocks": summarize_clocks(samples),
         "cpu_baseline": cpu,

@@ -102,10 +102,11 @@ typedef struct w2rap_kmer_rec {
 /* Stage timings, device milliseconds from CUDA events on the stream the kernels run on. */
 typedef struct w2rap_timings {
     float h2d_ms, count_ms, solid_ms, adjacency_ms, unipath_ms, hbv_ms, path_ms, d2h_ms, total_ms;
-    float count_kernel_ms;        /* sum of the extract+count kernel launches only */
-    uint32_t count_launches;      /* launches of the extract+count kernel */
+    float count_kernel_ms;        /* the extract+partition kernel (k_extract_partition) launches only */
+    float region_ms;              /* the L2-resident count: all k_count_region + k_scan_region launches */
+    uint32_t count_launches;      /* launches of k_extract_partition */
     uint32_t kernel_launches;     /* all kernels launched by this call */
-    uint32_t count_passes;        /* hash-range passes used for counting */
+    uint32_t count_passes;        /* partition groups reduced through the counting region */
     uint32_t reserved;
 } w2rap_timings;
 

@@ -57,11 +57,20 @@ def test_golden_reference_outputs(T, case):
     assert rep["path_mismatches"] == [] and rep["path_ties"] <= 3, rep
 
 
-def test_multi_pass_counting(T):
-    """A forced small counting table: several hash-range passes must give the same answer as one."""
+def test_small_counting_region_many_groups(T):
+    """A forced small counting region: thousands of partitions / groups must give the same answer as one."""
     rs = T.rich_set(seed=6, genome=50000, cov=40)
     want, got = both(T, rs, dump_kmers=2, table_slots=60000)
     assert got["timings"]["count_passes"] > 3
+    T.assert_graph_equal(want, got)
+
+
+def test_tiny_counting_region_overflow_paths(T):
+    """A 64-slot region: group estimates are wrong all the time and some partitions exceed the region, so the per-partition
+    retry and the hash sub-range split (with roll-back of partial output) are exercised."""
+    rs = T.rich_set(seed=6, genome=12000, cov=30, families=2, palindromes=1, plasmid=600)
+    want, got = both(T, rs, dump_kmers=2, table_slots=64)
+    assert got["timings"]["count_passes"] > 1000
     T.assert_graph_equal(want, got)
 
 

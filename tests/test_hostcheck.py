@@ -19,7 +19,7 @@ SO = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
 @pytest.fixture(scope="session")
 def hc(T):
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh")]
+    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, src], check=True)

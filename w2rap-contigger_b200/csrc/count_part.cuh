@@ -1,0 +1,205 @@
+// count_part.cuh — k-mer counting as partition + L2-resident hash count.
+//
+// A global hash table ≫ L2 costs one random DRAM sector read and one write-back per k-mer INSTANCE (measured: 13 G inserts/s
+// on B200, 0.84 TB/s of 32-byte sector traffic).  Instead:
+//   pass A  k_extract_partition : every instance becomes a 16-byte record {w0, w1 | ctx} appended to the buffer of partition
+//                                 hash >> (64-logP).  Appends are one atomicAdd on the partition cursor + one 16-byte store;
+//                                 consecutive records of a partition fill whole sectors in L2 before they are evicted, so DRAM
+//                                 sees a streaming write of 16 B per instance.
+//   pass B  k_count_region      : the records of a group of partitions are streamed back (16 B per instance) and inserted into
+//                                 a 32 MB table REGION that stays resident in the 126 MB L2; all probing, the 128-bit CAS and
+//                                 the count/context REDs hit L2.
+//           k_scan_region       : histogram, min-frequency filter (solid records out), and the region is reset for the next group.
+// DRAM traffic: 16 B written + 16 B read per instance — the 34 B/instance of the SURVEY §8d model — and nothing else.
+// This is the MapReduceEngine shape (MapReduceEngine.h:288-358: map -> hash-partition -> reduce), on one device.
+#pragma once
+#include "kernels.cuh"
+
+namespace w2r {
+
+struct PartParams {
+    ulonglong2* recs;        // [P * nsub][cap]
+    uint32_t* cursor;        // [P * nsub] * cstride: records appended per sub-buffer, one cursor per L2 line
+    uint64_t cap;            // capacity of one sub-buffer (records)
+    uint32_t logP;           // partitions = 1 << logP
+    uint32_t nsub;           // sub-buffers per partition (power of two): spreads the cursor atomics over nsub x more L2 lines
+    uint32_t cstride;        // cursor stride in u32 (32 = one cursor per 128-byte line)
+    uint32_t npass, pass;    // outer hash-range passes (when the records of everything would not fit): keep (hash & 0xffff) % npass == pass
+    int* overflow;           // set if a sub-buffer overflowed
+};
+
+W2R_HD uint32_t part_of_hash(uint64_t h, uint32_t logP) { return logP ? (uint32_t)(h >> (64 - logP)) : 0u; }
+W2R_HD uint64_t region_slot_of_hash(uint64_t h, uint32_t logP, uint32_t logR) { return (logP ? (h << logP) : h) >> (64 - logR); }
+
+// Emits records one step behind the cursor atomic so that the atomic's latency overlaps the next k-mer's arithmetic.
+struct PartEmit {
+    const PartParams& pp;
+    ulonglong2 rec;
+    uint64_t addr;           // first record index of the sub-buffer of the pending store, ~0 = none
+    uint32_t pos_pending;
+    uint32_t sub;
+    __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), addr(~0ull), pos_pending(0), sub(sub_) {}
+    __device__ __forceinline__ void flush() {
+        if (addr != ~0ull) {
+            if (pos_pending < pp.cap) pp.recs[addr + pos_pending] = rec;
+            else atomicExch(pp.overflow, 1);
+            addr = ~0ull;
+        }
+    }
+    __device__ __forceinline__ void operator()(Kmer k, uint32_t ctx) {
+        const uint64_t h = kmer_hash(k);
+        if (pp.npass > 1 && (uint32_t)(h & 0xffffu) % pp.npass != pp.pass) return;
+        const uint32_t b = part_of_hash(h, pp.logP) * pp.nsub + sub;
+        const uint32_t pos = atomicAdd(pp.cursor + (uint64_t)b * pp.cstride, 1u);
+        flush();                                            // the previous record goes out while this atomic is in flight
+        rec = make_ulonglong2(k.w0, k.w1 | ctx);
+        addr = (uint64_t)b * pp.cap;
+        pos_pending = pos;
+    }
+};
+
+// paths/long/BuildReadQGraph.cc:1062-1080 (the "map" step): one thread per read.
+__global__ void __launch_bounds__(256) k_extract_partition(ReadsView r, const uint16_t* __restrict__ good, PartParams pp) {
+    const uint32_t sub = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (pp.nsub - 1);   // per warp
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t gl = good[i];
+        if (gl > (uint32_t)K) {
+            PartEmit emit(pp, sub);
+            extract_read_kmers(r.bases + r.base_off[i], gl, emit);
+            emit.flush();
+        }
+    }
+}
+
+struct RegionParams {
+    CountSlot* region;       // 1 << logR slots, resident in L2
+    uint32_t logR, logP;
+    uint32_t sub_mask, sub_id;   // overflow handling: only records with ((hash >> 3) & sub_mask) == sub_id take part
+    int* overflow;
+};
+constexpr uint32_t REGION_MAX_PROBE = 2048;
+
+// one 256-bit load of a whole slot (LDG.E.ENL2.256 on sm_100a), L2-coherent
+__device__ __forceinline__ void ld_slot(const CountSlot* q, uint64_t& w0, uint64_t& w1, uint64_t& meta) {
+    uint64_t pad;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w0), "=l"(w1), "=l"(meta), "=l"(pad) : "l"(q));
+}
+
+__device__ __forceinline__ void region_insert(const RegionParams& rp, uint64_t mask, ulonglong2 rec, uint64_t h) {
+    const uint64_t kw0 = rec.x, kw1 = rec.y & ~0xffull;
+    const uint32_t ctx = (uint32_t)rec.y & 0xffu;
+    uint64_t s = region_slot_of_hash(h, rp.logP, rp.logR);
+    for (uint32_t probe = 0; probe < REGION_MAX_PROBE; ++probe) {
+        CountSlot* q = rp.region + s;
+        uint64_t w0, w1, meta;
+        ld_slot(q, w0, w1, meta);
+        bool hit = false;
+        uint32_t have = (uint32_t)(meta >> 32);
+        if (w0 == kw0 && w1 == kw1) hit = true;
+        else if (w0 == EMPTY_W0) {
+            U128 old = cas128(q, ~0ull, ~0ull, kw0, kw1);
+            hit = (old.lo == ~0ull && old.hi == ~0ull) || (old.lo == kw0 && old.hi == kw1);
+            have = 0;
+        }
+        if (hit) {
+            atomicAdd(&q->count, 1u);
+            if ((have & ctx) != ctx) atomicOr(&q->ctx, ctx);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+    atomicExch(rp.overflow, 1);
+}
+
+// The "reduce" step (BuildReadQGraph.cc:1081-1082 sort+collapse as a hash count).  blockIdx.y selects the sub-buffer of the group.
+// Two records per thread per iteration: their slot loads are independent, which doubles the L2 requests in flight.
+__global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
+                                                      uint32_t b_first, RegionParams rp) {
+    const uint32_t b = b_first + blockIdx.y;
+    uint64_t n = sizes[(uint64_t)b * cstride];
+    if (n > cap) n = cap;
+    const ulonglong2* base = recs + (uint64_t)b * cap;
+    const uint64_t mask = (1ull << rp.logR) - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+        const bool two = i + stride < n;
+        const ulonglong2 ra = __ldcs(base + i);
+        ulonglong2 rb = make_ulonglong2(0, 0);
+        if (two) rb = __ldcs(base + i + stride);
+        const uint64_t ha = kmer_hash(Kmer{ra.x, ra.y & ~0xffull});
+        const uint64_t hb = kmer_hash(Kmer{rb.x, rb.y & ~0xffull});
+        const bool da = !rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id;
+        const bool db = two && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
+        // first probe of both records issued together
+        CountSlot* qa = rp.region + region_slot_of_hash(ha, rp.logP, rp.logR);
+        CountSlot* qb = rp.region + region_slot_of_hash(hb, rp.logP, rp.logR);
+        uint64_t a0 = 0, a1 = 0, am = 0, b0 = 0, b1 = 0, bm = 0;
+        if (da) ld_slot(qa, a0, a1, am);
+        if (db) ld_slot(qb, b0, b1, bm);
+        if (da) {
+            const uint32_t ctx = (uint32_t)ra.y & 0xffu;
+            if (a0 == ra.x && a1 == (ra.y & ~0xffull)) { atomicAdd(&qa->count, 1u); if ((((uint32_t)(am >> 32)) & ctx) != ctx) atomicOr(&qa->ctx, ctx); }
+            else region_insert(rp, mask, ra, ha);
+        }
+        if (db) {
+            const uint32_t ctx = (uint32_t)rb.y & 0xffu;
+            if (b0 == rb.x && b1 == (rb.y & ~0xffull)) { atomicAdd(&qb->count, 1u); if ((((uint32_t)(bm >> 32)) & ctx) != ctx) atomicOr(&qb->ctx, ctx); }
+            else region_insert(rp, mask, rb, hb);
+        }
+    }
+}
+
+struct ScanParams {
+    CountSlot* region;
+    uint64_t R;
+    uint32_t min_freq;
+    unsigned long long* hist;        // [104]: bins 1..100, [101] = solid count
+    ulonglong2* solid_out;           // solid records {w0, w1 | ctx}
+    unsigned long long* solid_cursor;
+    uint64_t solid_cap;
+    DumpRec* dump_out;               // test hook (dump level 2) or nullptr
+    unsigned long long* dump_cursor;
+    const int* overflow;             // if set: the group failed, only reset the region
+    int* solid_overflow;
+};
+// hist[min(100,min(255,count))]++ (BuildReadQGraph.cc:1094-1097), keep count >= minFreq (:1098), reset the region.
+__global__ void __launch_bounds__(256) k_scan_region(ScanParams sp) {
+    __shared__ unsigned int sh[104];
+    for (int j = threadIdx.x; j < 104; j += blockDim.x) sh[j] = 0;
+    __syncthreads();
+    const bool failed = *sp.overflow != 0;
+    uint4* raw = reinterpret_cast<uint4*>(sp.region);
+    const uint4 key_empty = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), zero = make_uint4(0, 0, 0, 0);
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < sp.R; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        bool occ = false, solid = false;
+        uint32_t c = 0, ctx = 0;
+        ulonglong2 k = make_ulonglong2(0, 0);
+        if (i < sp.R) {
+            k = __ldcg(reinterpret_cast<const ulonglong2*>(sp.region + i));
+            if (k.x != EMPTY_W0) {
+                occ = true;
+                uint2 m = __ldcg(reinterpret_cast<const uint2*>(&sp.region[i].count));
+                c = m.x > 255u ? 255u : m.x; ctx = m.y & 0xffu;
+                raw[2 * i] = key_empty; raw[2 * i + 1] = zero;
+            }
+        }
+        if (failed) continue;
+        uint32_t bin = occ ? (c > 100u ? 100u : c) : 103u;
+        unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (occ && (peers & ((1u << lane_id()) - 1u)) == 0) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+        solid = occ && c >= sp.min_freq;
+        uint64_t pos = warp_append(sp.solid_cursor, solid);
+        if (solid) { if (pos < sp.solid_cap) sp.solid_out[pos] = make_ulonglong2(k.x, k.y | ctx); else atomicExch(sp.solid_overflow, 1); }
+        if (sp.dump_out) {
+            uint64_t dp = warp_append(sp.dump_cursor, occ);
+            if (occ) sp.dump_out[dp] = DumpRec{k.x, k.y, c, ctx, NIL, 0};
+        }
+    }
+    __syncthreads();
+    if (!failed) {
+        for (int j = threadIdx.x; j <= 100; j += blockDim.x) if (sh[j]) atomicAdd(&sp.hist[j], (unsigned long long)sh[j]);
+    }
+}
+
+}  // namespace w2r

@@ -1,8 +1,7 @@
 // kernels.cuh — the sm_100a kernels of the step-2 path (device code only).
 //
-// K1 k_good_len / k_extract_count : PQVec quality floor + canonical 60-mer/context extraction fused with the counting-table
-//                                   insert (one 128-bit CAS claims a 32-byte slot = one DRAM sector)
-// K2 k_count_stats / k_collect_solid / k_insert_solid : histogram, min-frequency filter, dictionary build
+// K1 k_good_len                    : PQVec quality floor (count_part.cuh: k_extract_partition = extraction + hash partition)
+// K2 k_count_region / k_scan_region (count_part.cuh) : L2-resident hash count, histogram, min-frequency filter; k_insert_solid
 // K3 k_adjacency                  : recomputeAdjacencies
 // K4 k_links / k_rank_* / k_cycle_* / k_strand_decide / k_collect_heads / k_assign_edges / k_emit_edges : unipaths
 // K5 k_edge_ends / k_vertex_* / k_hbv_edges / k_adj_* : HBV vertices + incidence
@@ -91,101 +90,9 @@ __global__ void k_good_len(ReadsView r, uint32_t min_qual, uint16_t* __restrict_
     }
 }
 
-constexpr uint32_t COUNT_MAX_PROBE = 1u << 14;
-
-struct CountParams {
-    CountSlot* tab;
-    uint64_t T;
-    uint32_t npass, pass;      // keep k-mers with (hash & 0xffff) % npass == pass
-    uint32_t sample;           // 1: keep only k-mers with ((hash >> 16) & 63) == 0 (distinct-count estimate)
-    int* overflow;
-};
-
-struct CountEmit {
-    const CountParams& cp;
-    __device__ __forceinline__ void operator()(Kmer k, uint32_t ctx) const {
-        const uint64_t h = kmer_hash(k);
-        if (cp.sample) { if (((h >> 16) & 63u) != 0) return; }
-        else if (cp.npass > 1 && (uint32_t)(h & 0xffffu) % cp.npass != cp.pass) return;
-        uint64_t s = mulhi64(h, cp.T);
-        for (uint32_t probe = 0; probe < COUNT_MAX_PROBE; ++probe) {
-            CountSlot* p = cp.tab + s;
-            ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(p));
-            bool hit = false;
-            if (cur.x == k.w0 && cur.y == k.w1) hit = true;
-            else if (cur.x == EMPTY_W0) {
-                U128 old = cas128(p, ~0ull, ~0ull, k.w0, k.w1);
-                hit = (old.lo == ~0ull && old.hi == ~0ull) || (old.lo == k.w0 && old.hi == k.w1);
-            }
-            if (hit) {
-                atomicAdd(&p->count, 1u);
-                uint32_t have = __ldcg(&p->ctx);
-                if ((have & ctx) != ctx) atomicOr(&p->ctx, ctx);
-                return;
-            }
-            if (++s == cp.T) s = 0;
-        }
-        atomicExch(cp.overflow, 1);
-    }
-};
-
-// paths/long/BuildReadQGraph.cc:1062-1080 fused with the sort/collapse of :1081-1082 (as a hash count): one thread per read.
-__global__ void __launch_bounds__(256) k_extract_count(ReadsView r, const uint16_t* __restrict__ good, CountParams cp) {
-    CountEmit emit{cp};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t gl = good[i];
-        if (gl > (uint32_t)K) extract_read_kmers(r.bases + r.base_off[i], gl, emit);
-    }
-}
-
-// ================================================================ K2: histogram, filter, dictionary
-
-// hist[min(100,min(255,count))]++ (BuildReadQGraph.cc:1094-1097); hist[101] = k-mers with count >= min_freq; hist[102] = occupied.
-__global__ void k_count_stats(const CountSlot* __restrict__ tab, uint64_t T, uint32_t min_freq, unsigned long long* __restrict__ hist /*[104]*/) {
-    __shared__ unsigned int sh[104];
-    for (int j = threadIdx.x; j < 104; j += blockDim.x) sh[j] = 0;
-    __syncthreads();
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t i = base + threadIdx.x;
-        bool occ = false;
-        uint32_t c = 0;
-        if (i < T) { ulonglong2 k = __ldcs(reinterpret_cast<const ulonglong2*>(tab + i)); if (k.x != EMPTY_W0) { occ = true; c = tab[i].count; if (c > 255u) c = 255u; } }
-        uint32_t bin = occ ? (c > 100u ? 100u : c) : 103u;
-        unsigned peers = __match_any_sync(__activemask(), bin);
-        if (occ && (peers & ((1u << lane_id()) - 1u)) == 0) atomicAdd(&sh[bin], (unsigned)__popc(peers));
-        bool solid = occ && c >= min_freq;
-        unsigned ms = __ballot_sync(__activemask(), solid);
-        if (lane_id() == 0 && ms) atomicAdd(&sh[101], (unsigned)__popc(ms));
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < 103; j += blockDim.x) if (sh[j]) atomicAdd(&hist[j], (unsigned long long)sh[j]);
-}
-
-// Appends every solid k-mer as a 16-byte record: w0, w1 | ctx (the low byte of w1 is free).
-__global__ void k_collect_solid(const CountSlot* __restrict__ tab, uint64_t T, uint32_t min_freq, ulonglong2* __restrict__ out, unsigned long long* cursor) {
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t i = base + threadIdx.x;
-        bool want = false;
-        ulonglong2 k = make_ulonglong2(0, 0);
-        uint32_t ctx = 0;
-        if (i < T) {
-            k = __ldcs(reinterpret_cast<const ulonglong2*>(tab + i));
-            if (k.x != EMPTY_W0) { uint32_t c = tab[i].count; if (c > 255u) c = 255u; want = c >= min_freq; ctx = tab[i].ctx & 0xffu; }
-        }
-        uint64_t pos = warp_append(cursor, want);
-        if (want) out[pos] = make_ulonglong2(k.x, k.y | ctx);
-    }
-}
-// Test hook (dump level 2): every distinct k-mer with its saturated count and raw context.
+// ================================================================ K2: dictionary (the counting kernels live in count_part.cuh)
+// Test hooks: dump records (level 2 = every distinct k-mer with saturated count and raw context; level 1 = the dictionary).
 struct DumpRec { uint64_t w0, w1; uint32_t count, ctx, edge, off; };
-__global__ void k_collect_all(const CountSlot* __restrict__ tab, uint64_t T, DumpRec* __restrict__ out, unsigned long long* cursor) {
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t i = base + threadIdx.x;
-        bool want = i < T && tab[i].w0 != EMPTY_W0;
-        uint64_t pos = warp_append(cursor, want);
-        if (want) { uint32_t c = tab[i].count; out[pos] = DumpRec{tab[i].w0, tab[i].w1, c > 255u ? 255u : c, tab[i].ctx & 0xffu, NIL, 0}; }
-    }
-}
 __global__ void k_dump_solid(SolidTable st, DumpRec* __restrict__ out, unsigned long long* cursor) {
     const uint64_t T = st.size();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {

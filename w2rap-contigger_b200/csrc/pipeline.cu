@@ -14,6 +14,7 @@
 
 #include "../../include/w2rap_step2.h"
 #include "device_reads.cuh"
+#include "count_part.cuh"
 #include "kernels.cuh"
 #include "prims.cuh"
 
@@ -153,7 +154,18 @@ struct Pipeline {
 
     unsigned grid(uint64_t n, unsigned block, unsigned per_sm = 16) const { return grid_for(c, n, block, per_sm); }
 
-    // ---- createDictOMPRecursive (BuildReadQGraph.cc:1015-1117)
+    // ---- createDictOMPRecursive (BuildReadQGraph.cc:1015-1117): partition (map) + L2-resident hash count (reduce), count_part.cuh
+    void set_l2_window(void* base, size_t bytes) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        attr.accessPolicyWindow.base_ptr = base;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = bytes ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+        if (cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    }
+
     void count_stage() {
         const ReadsView rv = dr.view();
         good.alloc(c, dr.n);
@@ -162,93 +174,164 @@ struct Pipeline {
         SBuf<int> flags(c, 4);
         flags.zero();
         if (dr.n) W2R_LAUNCH(c, k_good_len, grid(dr.n, 128), 128, 0, rv, prm.min_qual, good.p, scal.p, flags.p);
-        unsigned long long n_inst = d2h_scalar(c, scal.p);
+        const unsigned long long n_inst = d2h_scalar(c, scal.p);
         if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
         out->n_kmer_instances = n_inst;
         say(c, "%llu k-mer instances in quality-floored reads", n_inst);
 
-        // estimate the number of distinct k-mers from a 1/64 hash sample so that the table is sized for the data, not for the worst case
-        double d_est = (double)n_inst;
-        EventTimer kt(c.stream);
-        float kernel_ms = 0;
-        if (n_inst > (1ull << 22) && !prm.table_slots) {
-            uint64_t Ts = n_inst / 24 + 4096;
-            SBuf<CountSlot> tab(c, Ts);
-            W2R_LAUNCH(c, k_init_count_table, grid(2 * Ts, 256), 256, 0, tab.p, Ts);
-            CountParams cp{tab.p, Ts, 1, 0, 1, flags.p + 1};
-            kt.start();
-            W2R_LAUNCH(c, k_extract_count, grid(dr.n, 256, 8), 256, 0, rv, good.p, cp); c.count_launches++;
-            kernel_ms += kt.stop();
-            SBuf<unsigned long long> h(c, 104); h.zero();
-            W2R_LAUNCH(c, k_count_stats, grid(Ts, 256), 256, 0, tab.p, Ts, prm.min_freq, h.p);
-            std::vector<unsigned long long> hh(104);
-            W2R_CUDA(cudaMemcpyAsync(hh.data(), h.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
-            W2R_CUDA(cudaStreamSynchronize(c.stream));
-            unsigned long long occ = 0; for (int i = 1; i <= 100; ++i) occ += hh[i];
-            if (!d2h_scalar(c, flags.p + 1)) d_est = std::min((double)n_inst, (double)occ * 64.0 * 1.08 + 65536.0);
-            else W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
-            say(c, "sampled distinct estimate: %.0f", d_est);
-        }
-        uint64_t T_total = (uint64_t)(d_est / 0.6) + 1024;
-        size_t budget = (size_t)(device_budget(c) * 0.70);
-        uint64_t T_max = std::max<uint64_t>(1024, budget / sizeof(CountSlot));
+        // region: the L2-resident counting table.  1 Mi slots x 32 B = 32 MB of the 126 MB L2 (smaller for tiny inputs / the test hook).
+        uint32_t logR = 20;
+        while (logR > 8 && (1ull << (logR - 1)) >= 2 * n_inst + 64) --logR;
+        if (prm.table_slots) { logR = 6; while ((2ull << logR) <= prm.table_slots && logR < 24) ++logR; }
+        const uint64_t R = 1ull << logR;
+        // partitions: few enough records each that even an all-distinct partition fits the region at load 0.6
+        uint32_t logP = 0;
+        while ((double)n_inst / (double)(1ull << logP) > 0.6 * (double)R && logP < 24) ++logP;
+        size_t budget = (size_t)(device_budget(c) * 0.80);
+        const uint64_t solid_cap = n_inst / std::max<uint32_t>(1, prm.min_freq) + 1024;
+        const size_t fixed_bytes = solid_cap * sizeof(ulonglong2) + R * sizeof(CountSlot) + (prm.dump_kmers == 2 ? n_inst * sizeof(DumpRec) : 0);
+        if (fixed_bytes + (64u << 20) > budget) W2R_FAIL(W2RAP_ERR_OOM, "not enough device memory for the solid k-mer staging buffer");
+        SBuf<ulonglong2> solid(c, solid_cap);
+        SBuf<CountSlot> region(c, R);
+        SBuf<DumpRec> dump_dev(c, prm.dump_kmers == 2 ? n_inst : 0);
+        SBuf<unsigned long long> hist(c, 104); hist.zero();
+        W2R_LAUNCH(c, k_init_count_table, grid(2 * R, 256), 256, 0, region.p, R);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(R * sizeof(CountSlot), 64u << 20)) != cudaSuccess) cudaGetLastError();
+        float part_ms = 0, region_ms = 0;
         uint32_t npass = 1;
-        uint64_t T = T_total;
-        if (prm.table_slots) { T = std::max<uint64_t>(prm.table_slots, 64); npass = (uint32_t)std::max<uint64_t>(1, (T_total + T - 1) / T); }
-        else if (T_total > T_max) { npass = (uint32_t)((T_total + T_max - 1) / T_max); T = T_total / npass + 1024; }
-
-        std::vector<unsigned long long> hist(104, 0);
-        std::vector<SBuf<ulonglong2>> staged;
-        std::vector<uint64_t> staged_n;
+        double slack = 1.06;
+        uint64_t n_distinct_seen = 0;
+        uint32_t n_groups = 0;
+        EventTimer kt(c.stream);
         for (int attempt = 0;; ++attempt) {
-            if (attempt > 6) W2R_FAIL(W2RAP_ERR_INTERNAL, "counting table overflowed repeatedly");
-            bool overflow = false;
-            std::fill(hist.begin(), hist.end(), 0ull);
-            staged.clear(); staged_n.clear(); dump_host.clear();
-            SBuf<CountSlot> tab(c, T);
-            for (uint32_t pass = 0; pass < npass && !overflow; ++pass) {
-                W2R_LAUNCH(c, k_init_count_table, grid(2 * T, 256), 256, 0, tab.p, T);
-                if (n_inst) {
-                    CountParams cp{tab.p, T, npass, pass, 0, flags.p + 1};
-                    kt.start();
-                    W2R_LAUNCH(c, k_extract_count, grid(dr.n, 256, 8), 256, 0, rv, good.p, cp); c.count_launches++;
-                    kernel_ms += kt.stop();
+            if (attempt > 8) W2R_FAIL(W2RAP_ERR_INTERNAL, "k-mer partitioning did not converge");
+            const uint64_t P = 1ull << logP;
+            // sub-buffers: the cursor atomics of pass A serialise per L2 line; 8 sub-buffers per partition on separate lines
+            const uint32_t nsub = (n_inst / P >= 65536 && !prm.table_slots) ? 8u : 1u;
+            const uint32_t cstride = 32;
+            const uint64_t NB = P * nsub;
+            const uint64_t per = (uint64_t)((double)n_inst / (double)NB / (double)npass * slack) + 1024;
+            if (NB * per * sizeof(ulonglong2) + fixed_bytes > budget && npass < 4096) { npass *= 2; continue; }
+            const uint64_t cap = per;
+            SBuf<ulonglong2> recs(c, NB * cap);
+            SBuf<uint32_t> cursor(c, NB * cstride);
+            std::vector<uint32_t> sizes(P), raw_sizes(NB * cstride);
+            bool retry = false;
+            W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
+            hist.zero();
+            for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
+                cursor.zero();
+                PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1};
+                kt.start();
+                if (n_inst) { W2R_LAUNCH(c, k_extract_partition, grid(dr.n, 256, 8), 256, 0, rv, good.p, pp); c.count_launches++; }
+                part_ms += kt.stop();
+                if (d2h_scalar(c, flags.p + 1)) {        // a partition buffer overflowed (skewed k-mer multiplicities): more slack
+                    W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
+                    slack *= 1.5; retry = true; break;
                 }
-                if (d2h_scalar(c, flags.p + 1)) { overflow = true; break; }
-                SBuf<unsigned long long> h(c, 104); h.zero();
-                W2R_LAUNCH(c, k_count_stats, grid(T, 256), 256, 0, tab.p, T, prm.min_freq, h.p);
-                std::vector<unsigned long long> hh(104);
-                W2R_CUDA(cudaMemcpyAsync(hh.data(), h.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+                W2R_CUDA(cudaMemcpyAsync(raw_sizes.data(), cursor.p, NB * cstride * 4, cudaMemcpyDeviceToHost, c.stream));
                 W2R_CUDA(cudaStreamSynchronize(c.stream));
-                unsigned long long occ = 0;
-                for (int i = 0; i < 104; ++i) hist[i] += hh[i];
-                for (int i = 1; i <= 100; ++i) occ += hh[i];
-                if ((double)occ > 0.92 * (double)T) { overflow = true; break; }   // too dense to trust the probe bound next time; resize
-                uint64_t ns = hh[101];
-                staged.emplace_back(c, ns);
-                staged_n.push_back(ns);
-                W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 8, c.stream));
-                if (ns) W2R_LAUNCH(c, k_collect_solid, grid(T, 256), 256, 0, tab.p, T, prm.min_freq, staged.back().p, scal.p + 1);
-                if (prm.dump_kmers == 2 && occ) {
-                    SBuf<DumpRec> dd(c, occ);
-                    W2R_CUDA(cudaMemsetAsync(scal.p + 2, 0, 8, c.stream));
-                    W2R_LAUNCH(c, k_collect_all, grid(T, 256), 256, 0, tab.p, T, dd.p, scal.p + 2);
-                    size_t o = dump_host.size(); dump_host.resize(o + occ);
-                    W2R_CUDA(cudaMemcpyAsync(dump_host.data() + o, dd.p, occ * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
+                for (uint64_t q = 0; q < P; ++q) { uint32_t mxs = 0; for (uint32_t u = 0; u < nsub; ++u) mxs = std::max(mxs, raw_sizes[(q * nsub + u) * cstride]); sizes[q] = mxs; }   // largest sub-buffer
+                // ---- reduce: groups of consecutive partitions share the region; the group size comes from the first partition's distinct count
+                kt.start();
+                set_l2_window(region.p, R * sizeof(CountSlot));
+                SBuf<int> gflag(c, P + 1); gflag.zero();
+                auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag) {
+                    ++n_groups;
+                    uint32_t mx = 0;
+                    for (uint32_t q = p0; q < p0 + g; ++q) mx = std::max(mx, sizes[q]);
+                    if (mx) {
+                        RegionParams rp{region.p, logR, logP, sub_mask, sub_id, flag};
+                        const uint32_t gy = g * nsub;
+                        dim3 gr(std::max(1u, std::min<unsigned>((mx + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy, 8u))))), gy);
+                        k_count_region<<<gr, 256, 0, c.stream>>>(recs.p, cursor.p, cstride, cap, p0 * nsub, rp); c.launches++;
+                        W2R_CUDA(cudaGetLastError());
+                    }
+                    ScanParams sp{region.p, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
+                    W2R_LAUNCH(c, k_scan_region, grid(R, 256, 4), 256, 0, sp);
+                };
+                uint32_t g = 1;
+                std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first partition, count)
+                // first partition alone: its distinct count sizes the groups
+                run_group(0, 1, 0, 0, gflag.p + 0);
+                groups.push_back({0u, 1u});
+                if (P > 1) {
+                    std::vector<unsigned long long> hh(104);
+                    W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
                     W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    unsigned long long d0 = 0;
+                    for (int i = 1; i <= 100; ++i) d0 += hh[i];
+                    d0 -= std::min<unsigned long long>(d0, n_distinct_seen);
+                    g = (uint32_t)std::max<double>(1.0, std::min<double>(4096.0, 0.5 * (double)R / ((double)d0 * 1.15 + 1.0)));
+                    g = std::min<uint32_t>(g, 32768u / nsub);
+                    for (uint64_t p0 = 1; p0 < P; p0 += g) {
+                        uint32_t gg = (uint32_t)std::min<uint64_t>(g, P - p0);
+                        run_group((uint32_t)p0, gg, 0, 0, gflag.p + p0);
+                        groups.push_back({(uint32_t)p0, gg});
+                    }
+                }
+                std::vector<int> gf(P + 1);
+                W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                W2R_CUDA(cudaStreamSynchronize(c.stream));
+                for (auto& gr : groups) {
+                    if (!gf[gr.first]) continue;
+                    // the group did not fit together: its partitions one by one, and a partition that still fails in hash sub-ranges
+                    for (uint32_t q = gr.first; q < gr.first + gr.second; ++q) {
+                        unsigned long long snapshot[2];
+                        std::vector<unsigned long long> hist_snapshot(104);
+                        W2R_CUDA(cudaMemcpyAsync(snapshot, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
+                        W2R_CUDA(cudaMemcpyAsync(hist_snapshot.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+                        W2R_CUDA(cudaMemsetAsync(gflag.p + P, 0, sizeof(int), c.stream));
+                        run_group(q, 1, 0, 0, gflag.p + P);
+                        if (!d2h_scalar(c, gflag.p + P)) continue;
+                        for (uint32_t S = 2;; S *= 2) {
+                            if (S > 4096) W2R_FAIL(W2RAP_ERR_INTERNAL, "a k-mer partition does not fit the counting region even in 4096 hash sub-ranges");
+                            bool ok = true;
+                            for (uint32_t sid = 0; sid < S && ok; ++sid) {
+                                W2R_CUDA(cudaMemsetAsync(gflag.p + P, 0, sizeof(int), c.stream));
+                                run_group(q, 1, S - 1, sid, gflag.p + P);
+                                if (d2h_scalar(c, gflag.p + P)) ok = false;
+                            }
+                            if (ok) break;
+                            // roll back what the successful sub-ranges of this split emitted, then split finer
+                            W2R_CUDA(cudaMemcpyAsync(scal.p + 1, snapshot, 16, cudaMemcpyHostToDevice, c.stream));
+                            W2R_CUDA(cudaMemcpyAsync(hist.p, hist_snapshot.data(), 104 * 8, cudaMemcpyHostToDevice, c.stream));
+                            W2R_CUDA(cudaStreamSynchronize(c.stream));
+                        }
+                    }
+                }
+                set_l2_window(nullptr, 0);
+                region_ms += kt.stop();
+                {
+                    std::vector<unsigned long long> hh(104);
+                    W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    n_distinct_seen = 0;
+                    for (int i = 1; i <= 100; ++i) n_distinct_seen += hh[i];
                 }
             }
-            if (!overflow) break;
-            W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
-            if (prm.table_slots || T * 2 > T_max) npass *= 2; else T *= 2;
-            say(c, "counting table too small; retrying with %llu slots x %u passes", (unsigned long long)T, npass);
+            if (retry) { n_distinct_seen = 0; n_groups = 0; continue; }
+            if (d2h_scalar(c, flags.p + 2)) W2R_FAIL(W2RAP_ERR_INTERNAL, "solid staging buffer overflow");
+            break;
         }
-        out->timings.count_kernel_ms = kernel_ms;
-        out->timings.count_passes = npass;
-        uint64_t n_distinct = 0, n_solid = 0;
-        for (int i = 1; i <= 100; ++i) { out->hist[i] = hist[i]; n_distinct += hist[i]; }
-        for (uint64_t v : staged_n) n_solid += v;
+        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+        out->timings.count_kernel_ms = part_ms;
+        out->timings.region_ms = region_ms;
+        out->timings.count_passes = n_groups;
+        std::vector<unsigned long long> hh(104);
+        W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+        unsigned long long cursors[2];
+        W2R_CUDA(cudaMemcpyAsync(cursors, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        uint64_t n_distinct = 0;
+        for (int i = 1; i <= 100; ++i) { out->hist[i] = hh[i]; n_distinct += hh[i]; }
+        const uint64_t n_solid = cursors[0];
         out->n_distinct = n_distinct; out->n_solid = n_solid;
+        if (prm.dump_kmers == 2 && cursors[1]) {
+            dump_host.resize(cursors[1]);
+            W2R_CUDA(cudaMemcpyAsync(dump_host.data(), dump_dev.p, cursors[1] * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+        }
         say(c, "%llu kmers counted, filtering...", (unsigned long long)n_distinct);
         say(c, "%llu / %llu kmers with Freq >= %u", (unsigned long long)n_solid, (unsigned long long)n_distinct, prm.min_freq);
 
@@ -256,11 +339,11 @@ struct Pipeline {
         uint32_t lg = 10;
         while ((1ull << lg) < 2 * n_solid) ++lg;
         if (lg > 31) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^30 solid k-mers on one device");
+        region.release(); dump_dev.release();
         solid_slots.alloc(c, 1ull << lg);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, lg};
-        for (size_t i = 0; i < staged.size(); ++i)
-            if (staged_n[i]) W2R_LAUNCH(c, k_insert_solid, grid(staged_n[i], 256), 256, 0, staged[i].p, staged_n[i], st);
+        if (n_solid) W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, solid.p, n_solid, st);
     }
 
     // ---- buildEdges (BuildReadQGraph.cc:314-339)

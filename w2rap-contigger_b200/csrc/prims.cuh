@@ -78,11 +78,10 @@ template <class TIn, class TOut>
 inline void exclusive_scan(Ctx& c, const TIn* in, uint64_t n, TOut* out, TOut* total_dev) {
     if (n == 0) { if (total_dev) W2R_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(TOut), c.stream)); return; }
     uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    DBuf<TOut> sums(tiles);
+    TmpBuf<TOut> sums(c, tiles);
     W2R_LAUNCH(c, (k_scan_tile_sums<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, in, n, sums.p);
     W2R_LAUNCH(c, (k_scan_sums_inplace<TOut>), 1, 1024, 0, sums.p, tiles, total_dev);
     W2R_LAUNCH(c, (k_scan_apply<TIn, TOut>), (unsigned)tiles, SCAN_THREADS, 0, in, n, sums.p, out);
-    W2R_CUDA(cudaStreamSynchronize(c.stream));   // `sums` is freed on return
 }
 
 // ---------------------------------------------------------------- LSD radix sort of a permutation by multi-word keys
@@ -150,7 +149,7 @@ struct SortWord { const uint64_t* word; int lo_bit, hi_bit; };
 inline void radix_sort_perm(Ctx& c, uint32_t* perm, uint32_t* tmp, uint32_t n, const SortWord* words, int nwords) {
     if (n <= 1) return;
     uint32_t nb = (n + RS_TILE - 1) / RS_TILE;
-    DBuf<uint32_t> counts((size_t)256 * nb);
+    TmpBuf<uint32_t> counts(c, (size_t)256 * nb);
     uint32_t* src = perm;
     uint32_t* dst = tmp;
     for (int w = 0; w < nwords; ++w) {
@@ -162,7 +161,6 @@ inline void radix_sort_perm(Ctx& c, uint32_t* perm, uint32_t* tmp, uint32_t n, c
         }
     }
     if (src != perm) W2R_CUDA(cudaMemcpyAsync(perm, src, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
-    W2R_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 }  // namespace w2r

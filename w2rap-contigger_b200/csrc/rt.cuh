@@ -66,6 +66,18 @@ struct DBuf {   // device buffer
     void fill_ff(cudaStream_t s) { if (n) W2R_CUDA(cudaMemsetAsync(p, 0xff, bytes(), s)); }
 };
 
+// Stream-ordered temporary (cudaMallocAsync pool): no driver round trip and no implicit device synchronisation on free.
+template <class T>
+struct TmpBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s;
+    TmpBuf(const Ctx& c, size_t n_) : n(n_), s(c.stream) { if (n) W2R_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), s)); }
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+    ~TmpBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
 template <class T>
 struct HPinned {   // pinned host buffer (results handed to the caller are plain malloc; this is for staging)
     T* p = nullptr;
