@@ -89,7 +89,7 @@ def run_reference_arm(args):
         args.ref_genome_mbp, args.coverage, rs.n, rs.n_bases / 1e6,
         "oracle/_ref/w2rap-contigger --from_step 2 --to_step 2, TIME buildReadQGraph+FixPaths" if kind == "reference" else "oracle/step2_oracle.c")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "bounded sample of the bench workload: " + sample},
             "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -126,9 +126,27 @@ def main():
         raise SystemExit("no B200 visible: this benchmark has no CPU path")
     err = C.create_string_buffer(1024)
     genome = int(args.genome_mbp * 1e6)
-    # weak scaling: every rank builds the graph of its own read shard (replica genomes, different seeds)
-    sp = T.SynthParams(genome, args.read_len, args.coverage, 1000 + rank, 0, 0, 0)
+    # strong scaling: ONE read set (a function of the seed only); rank r holds the reads [r*n/N, (r+1)*n/N) of it
+    total_reads = (genome * args.coverage // args.read_len) & ~1
+    per = (total_reads // world) & ~1
+    first = per * rank
+    mine = per if rank < world - 1 else total_reads - first
+    sp = T.SynthParams(genome, args.read_len, args.coverage, 1000, 0, 0, mine, first)
     h = C.c_void_p()
+    comm = C.c_void_p()
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            if lib.w2rap_step2_comm_unique_id(buf, err, 1024):
+                raise SystemExit("nccl id failed: " + err.value.decode())
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        buf = (C.c_uint8 * 128)(*uid.cpu().tolist())
+        if lib.w2rap_step2_comm_init(buf, world, rank, local, C.byref(comm), err, 1024):
+            raise SystemExit("comm init failed: " + err.value.decode())
     if lib.w2rap_step2_synth(C.byref(sp), local, C.byref(h), err, 1024):
         raise SystemExit("synth failed: " + err.value.decode())
     p = T.default_params(apply_fixpaths=1, device=local)
@@ -144,7 +162,8 @@ def main():
 
     def step_resident():
         g = T.Graph()
-        if lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 1024):
+        rc = lib.w2rap_step2_run_sharded_resident(h, C.byref(p), comm, C.byref(g), err, 1024) if world > 1 else lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 1024)
+        if rc:
             raise SystemExit("run failed: " + err.value.decode())
         t = {n: getattr(g.timings, n) for n, _ in T.Timings._fields_}
         info = (int(g.n_kmer_instances), int(g.n_distinct), int(g.n_solid), int(g.n_edges), int(g.n_edge_bases), int(g.n_pathed), int(g.n_path_edges))
@@ -153,7 +172,8 @@ def main():
 
     def step_e2e():
         g = T.Graph()
-        if lib.w2rap_step2_run(C.byref(hr), C.byref(p), C.byref(g), err, 1024):
+        rc = lib.w2rap_step2_run_sharded(C.byref(hr), C.byref(p), comm, C.byref(g), err, 1024) if world > 1 else lib.w2rap_step2_run(C.byref(hr), C.byref(p), C.byref(g), err, 1024)
+        if rc:
             raise SystemExit("run failed: " + err.value.decode())
         t = {n: getattr(g.timings, n) for n, _ in T.Timings._fields_}
         d2h = 8 * (int(g.n_edges) + 1) + 4 * int(g.n_edges) * 7 + int(g.n_edge_bases) // 4 + 4 * int(g.n_paths) + 8 * (int(g.n_paths) + 1) + 4 * int(g.n_path_edges)
@@ -189,14 +209,21 @@ def main():
     e2e_ms = (time.time() - t0) / args.steps * 1e3
     stop.set()
     th.join(timeout=2)
+    total_bases = n_bases
     if dist is not None:
         import torch
         v = torch.tensor([dev_ms, e2e_ms, full_ms], device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms, full_ms = [float(x) for x in v.tolist()]
+        nb = torch.tensor([n_bases], device="cuda", dtype=torch.int64)
+        dist.all_reduce(nb)
+        total_bases = int(nb.item())
     if rank != 0:
+        if world > 1:
+            lib.w2rap_step2_comm_destroy(comm)
         return
     I, D, S, E, EB, pathed, npe = info
+    I = I // world                      # this rank's share of the k-mer instances (the counters are whole-job)
     h2d = int(hr.base_off and 0) + n_reads * ((args.read_len + 3) // 4) + 0
     qbytes = int(T._arr(hr.qual_off, n_reads + 1, "<u8")[-1])
     b_in = n_reads * ((args.read_len + 3) // 4) + qbytes + 12 * n_reads
@@ -222,14 +249,14 @@ def main():
         except Exception as e:   # the baseline is reported, never required
             cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)[:200]}
     line = {
-        "metric": METRIC, "value": world * n_bases / (dev_ms * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "%.0f Mbp synthetic genome + repeat families, 2x%d bp PE at %dx per GPU (%d reads, %.2f Gbases per GPU), min_qual 7, min_freq 4; whole step 2 incl. read pathing + FixPaths" % (
+        "metric": METRIC, "value": total_bases / (dev_ms * 1e-3) / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "%.0f Mbp synthetic genome + repeat families, 2x%d bp PE at %dx (rank 0 shard: %d reads, %.2f Gbases; whole job = n_gpus shards), min_qual 7, min_freq 4; whole step 2 incl. read pathing + FixPaths" % (
                        args.genome_mbp, args.read_len, args.coverage, n_reads, n_bases / 1e9),
                    "cache": "inputs (%.1f GB) and counting table larger than the 126 MB L2" % (b_in / 1e9),
                    "kmer_instances": I, "distinct": D, "solid": S, "edges": E, "reads_pathed": pathed,
-                   "parallelism": "one process per GPU; read shards are independent graphs in this round (see DESIGN.md §Multi-GPU)"},
-        "e2e": {"value": world * n_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms},
+                   "parallelism": "one process per GPU; reads sharded by index, k-mer records routed to owner GPUs by hash partition (NCCL all-to-all), solid records all-gathered, graph built on every rank, reads pathed by shard"},
+        "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms},
         "gpu_launches": int(tt[-1]["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_count / max(1, count_launches), "launches_per_step": count_launches,

@@ -104,6 +104,7 @@ typedef struct w2rap_timings {
     float h2d_ms, count_ms, solid_ms, adjacency_ms, unipath_ms, hbv_ms, path_ms, d2h_ms, total_ms;
     float count_kernel_ms;        /* the extract+partition kernel (k_extract_partition) launches only */
     float region_ms;              /* the L2-resident count: all k_count_region + k_scan_region launches */
+    float exchange_ms;            /* multi-GPU only: NCCL all-to-all of k-mer records + all-gather of the solid records */
     uint32_t count_launches;      /* launches of k_extract_partition */
     uint32_t kernel_launches;     /* all kernels launched by this call */
     uint32_t count_passes;        /* partition groups reduced through the counting region */
@@ -182,6 +183,22 @@ int w2rap_step2_run_resident(w2rap_device_reads* handle, const w2rap_params* p, 
                              char* err, size_t errlen);
 void w2rap_step2_release(w2rap_device_reads* handle);
 
+/*
+ * Multi-GPU (one process or thread per GPU, NCCL over NVLink/NVSwitch).  Reads are sharded by index by the
+ * caller; every k-mer record is routed to the rank that owns its hash partition with one all-to-all (the reference's
+ * MapReduceEngine "swizzle", MapReduceEngine.h:337-358); owners count; the solid records are all-gathered so that every rank
+ * builds the same graph; each rank paths its own shard.  On return every rank holds the WHOLE graph (identical on all
+ * ranks: edges, vertices, xlat, histogram, counters of the whole job) and the paths of ITS shard (n_paths = shard reads).
+ * world must be a power of two.  Rank 0 creates the id and hands the 128 bytes to the others (any transport).
+ */
+typedef struct w2rap_comm w2rap_comm;
+int w2rap_step2_comm_unique_id(uint8_t* id128, char* err, size_t errlen);
+int w2rap_step2_comm_init(const uint8_t* id128, int world, int rank, int device, w2rap_comm** comm, char* err, size_t errlen);
+void w2rap_step2_comm_destroy(w2rap_comm* comm);
+int w2rap_step2_run_sharded(const w2rap_reads* shard, const w2rap_params* p, w2rap_comm* comm, w2rap_graph* out, char* err, size_t errlen);
+int w2rap_step2_run_sharded_resident(w2rap_device_reads* shard, const w2rap_params* p, w2rap_comm* comm, w2rap_graph* out,
+                                     char* err, size_t errlen);
+
 /* Frees everything w2rap_step2_run* put into `out` and zeroes it. */
 void w2rap_step2_free(w2rap_graph* out);
 
@@ -209,7 +226,8 @@ typedef struct w2rap_synth_params {
     uint64_t seed;
     uint32_t het_per_10k;    /* SNP rate of the second haplotype per 10,000 bases (0 = haploid) */
     uint32_t reserved;
-    uint64_t n_reads;        /* 0 = derive from coverage; otherwise exact */
+    uint64_t n_reads;        /* 0 = derive from coverage; otherwise exact (the number of reads THIS call generates) */
+    uint64_t first_read;     /* index of the first read to generate: a shard of the global read set (pairs stay together if even) */
 } w2rap_synth_params;
 int w2rap_step2_synth(const w2rap_synth_params* sp, int device, w2rap_device_reads** handle,
                       char* err, size_t errlen);

@@ -14,6 +14,8 @@
 
 #include "../../include/w2rap_step2.h"
 #include "../../w2rap-contigger_b200/csrc/extract.cuh"
+#define W2R_COUNT_PART_HOST_ONLY
+#include "../../w2rap-contigger_b200/csrc/shard.cuh"
 #include "../../w2rap-contigger_b200/csrc/kmer.cuh"
 #include "../../w2rap-contigger_b200/csrc/path.cuh"
 #include "../../w2rap-contigger_b200/csrc/pqvec.cuh"
@@ -58,6 +60,43 @@ int hc_count(const w2rap_reads* in, uint32_t min_qual, w2rap_kmer_rec** out, uin
 }
 
 void hc_free(void* p) { free(p); }
+
+// ---- pieces of the sharded (multi-GPU) protocol, for the world_size-2 gloo test: the "map" side (k_extract_partition) and the
+// "reduce" side (k_count_region + k_scan_region) as separate calls, with the product's own partition/owner functions.
+// recs: n x {w0, w1|ctx}; owner[i] = rank that owns record i's hash partition.
+int hc_extract_records(const w2rap_reads* in, uint32_t min_qual, uint32_t logP, uint32_t world, uint64_t** recs_out, uint32_t** owner_out, uint64_t* n_out) {
+    std::vector<Rec> recs;
+    Collect emit{&recs};
+    for (uint64_t r = 0; r < in->n_reads; ++r) {
+        uint32_t nq = 0;
+        uint32_t gl = pq_good_length(in->quals + in->qual_off[r], min_qual, &nq);
+        if (nq != in->len[r]) return 100;
+        if (gl > in->len[r]) gl = in->len[r];
+        extract_read_kmers(in->bases + in->base_off[r], gl, emit);
+    }
+    std::vector<uint64_t> flat(2 * recs.size());
+    std::vector<uint32_t> owner(recs.size());
+    for (size_t i = 0; i < recs.size(); ++i) {
+        flat[2 * i] = recs[i].w0; flat[2 * i + 1] = recs[i].w1 | recs[i].ctx;
+        owner[i] = owner_of_partition(part_of_hash(kmer_hash(Kmer{recs[i].w0, recs[i].w1}), logP), logP, world);
+    }
+    *n_out = recs.size(); *recs_out = dup(flat); *owner_out = dup(owner);
+    return 0;
+}
+int hc_count_records(const uint64_t* recs, uint64_t n, w2rap_kmer_rec** out, uint64_t* n_out) {
+    std::vector<Rec> v(n);
+    for (uint64_t i = 0; i < n; ++i) v[i] = Rec{recs[2 * i], recs[2 * i + 1] & ~0xffull, (uint32_t)(recs[2 * i + 1] & 0xff)};
+    std::sort(v.begin(), v.end(), [](const Rec& a, const Rec& b) { return a.w0 < b.w0 || (a.w0 == b.w0 && a.w1 < b.w1); });
+    std::vector<w2rap_kmer_rec> d;
+    for (size_t i = 0; i < v.size();) {
+        size_t j = i; uint32_t c = 0, ctx = 0;
+        while (j < v.size() && v[j].w0 == v[i].w0 && v[j].w1 == v[i].w1) { ctx |= v[j].ctx; ++c; ++j; }
+        d.push_back(w2rap_kmer_rec{v[i].w0, v[i].w1, c > 255 ? 255 : c, ctx, 0xffffffffu, 0});
+        i = j;
+    }
+    *n_out = d.size(); *out = dup(d);
+    return 0;
+}
 
 // Everything after counting, serially, through the same device functions the kernels call.
 // `all` = distinct k-mers with counts and raw contexts (dump level 2).

@@ -36,7 +36,7 @@ class Params(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "count_ms", "solid_ms", "adjacency_ms", "unipath_ms", "hbv_ms",
-                                         "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms")] + \
+                                         "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms", "exchange_ms")] + \
                [(n, C.c_uint32) for n in ("count_launches", "kernel_launches", "count_passes", "reserved")]
 
 
@@ -65,7 +65,7 @@ class Graph(C.Structure):
 
 class SynthParams(C.Structure):
     _fields_ = [("genome_len", C.c_uint64), ("read_len", C.c_uint32), ("coverage", C.c_uint32), ("seed", C.c_uint64),
-                ("het_per_10k", C.c_uint32), ("reserved", C.c_uint32), ("n_reads", C.c_uint64)]
+                ("het_per_10k", C.c_uint32), ("reserved", C.c_uint32), ("n_reads", C.c_uint64), ("first_read", C.c_uint64)]
 
 
 def default_params(min_qual=7, min_freq=4, want_paths=1, apply_fixpaths=0, dump_kmers=0, workdir=None,
@@ -176,6 +176,12 @@ def product_lib():
         for n in ("w2rap_write_fastb", "w2rap_write_qualp"):
             getattr(lib, n).argtypes = [C.c_char_p, C.POINTER(Reads)] + E
         lib.w2rap_read_fastb_qualp.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Reads)] + E
+        lib.w2rap_step2_comm_unique_id.argtypes = [C.c_void_p] + E
+        lib.w2rap_step2_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + E
+        lib.w2rap_step2_comm_destroy.argtypes = [C.c_void_p]
+        lib.w2rap_step2_comm_destroy.restype = None
+        lib.w2rap_step2_run_sharded.argtypes = [C.POINTER(Reads), C.POINTER(Params), C.c_void_p, C.POINTER(Graph)] + E
+        lib.w2rap_step2_run_sharded_resident.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(Graph)] + E
         _product = lib
     return _product
 
@@ -184,7 +190,9 @@ ABI_SYMBOLS = ["w2rap_step2_abi_version", "w2rap_step2_build_info", "w2rap_step2
                "w2rap_step2_upload", "w2rap_step2_run_resident", "w2rap_step2_release", "w2rap_step2_free",
                "w2rap_step2_run_files", "w2rap_write_hbv", "w2rap_write_paths", "w2rap_write_freqs",
                "w2rap_step2_synth", "w2rap_step2_download_reads", "w2rap_step2_free_host_reads",
-               "w2rap_write_fastb", "w2rap_write_qualp", "w2rap_read_fastb_qualp"]
+               "w2rap_write_fastb", "w2rap_write_qualp", "w2rap_read_fastb_qualp",
+               "w2rap_step2_comm_unique_id", "w2rap_step2_comm_init", "w2rap_step2_comm_destroy", "w2rap_step2_run_sharded",
+               "w2rap_step2_run_sharded_resident"]
 
 
 # ---------------------------------------------------------------- flattened read sets

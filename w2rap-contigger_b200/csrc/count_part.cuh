@@ -14,6 +14,7 @@
 // This is the MapReduceEngine shape (MapReduceEngine.h:288-358: map -> hash-partition -> reduce), on one device.
 #pragma once
 #include "kernels.cuh"
+#include "shard.cuh"
 
 namespace w2r {
 
@@ -28,8 +29,6 @@ struct PartParams {
     int* overflow;           // set if a sub-buffer overflowed
 };
 
-W2R_HD uint32_t part_of_hash(uint64_t h, uint32_t logP) { return logP ? (uint32_t)(h >> (64 - logP)) : 0u; }
-W2R_HD uint64_t region_slot_of_hash(uint64_t h, uint32_t logP, uint32_t logR) { return (logP ? (h << logP) : h) >> (64 - logR); }
 
 // Emits records one step behind the cursor atomic so that the atomic's latency overlaps the next k-mer's arithmetic.
 struct PartEmit {
@@ -113,12 +112,14 @@ __device__ __forceinline__ void region_insert(const RegionParams& rp, uint64_t m
 
 // The "reduce" step (BuildReadQGraph.cc:1081-1082 sort+collapse as a hash count).  blockIdx.y selects the sub-buffer of the group.
 // Two records per thread per iteration: their slot loads are independent, which doubles the L2 requests in flight.
+// recs/sizes hold one slab per source rank ([n_src][owned sub-buffers]); blockIdx.y = src * gy + sub-buffer within the group.
 __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
-                                                      uint32_t b_first, RegionParams rp) {
-    const uint32_t b = b_first + blockIdx.y;
-    uint64_t n = sizes[(uint64_t)b * cstride];
+                                                      uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, RegionParams rp) {
+    const uint32_t src = blockIdx.y / gy;
+    const uint32_t b = b_first + (blockIdx.y - src * gy);
+    uint64_t n = sizes[(uint64_t)src * slab_cur + (uint64_t)b * cstride];
     if (n > cap) n = cap;
-    const ulonglong2* base = recs + (uint64_t)b * cap;
+    const ulonglong2* base = recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
     const uint64_t mask = (1ull << rp.logR) - 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {

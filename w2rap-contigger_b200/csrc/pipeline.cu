@@ -16,6 +16,7 @@
 #include "device_reads.cuh"
 #include "count_part.cuh"
 #include "kernels.cuh"
+#include "nccl_dl.h"
 #include "prims.cuh"
 
 namespace w2r {
@@ -149,6 +150,8 @@ struct Pipeline {
     SBuf<uint32_t> hcanon;
     SBuf<uint8_t> from_n, to_n;
     uint64_t edge_bytes = 0;
+    int world = 1, rank = 0;            // sharded run: one process per GPU, reads sharded by index, k-mers routed to owners
+    ncclComm_t comm = nullptr;
 
     Pipeline(const DeviceReads& dr_, const w2rap_params& p_, w2rap_graph* out_, GraphOwner* ow) : dr(dr_), prm(p_), out(out_), owner(ow) {}
 
@@ -166,6 +169,33 @@ struct Pipeline {
         if (cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
     }
 
+    // ---- multi-GPU plumbing (NCCL over NVLink/NVSwitch); world == 1 needs none of it
+    void nccl_check(ncclResult_t r, const char* what) {
+        if (r != ncclSuccess) W2R_FAIL(W2RAP_ERR_CUDA, "NCCL %s failed: %s", what, NcclApi::get().GetErrorString ? NcclApi::get().GetErrorString(r) : "?");
+    }
+    // element-wise all-reduce of a small host vector of u64 (through a device staging buffer)
+    void allreduce_u64(std::vector<unsigned long long>& v, ncclRedOp_t op) {
+        if (world == 1) return;
+        SBuf<unsigned long long> d(c, v.size());
+        W2R_CUDA(cudaMemcpyAsync(d.p, v.data(), v.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        nccl_check(NcclApi::get().AllReduce(d.p, d.p, v.size(), ncclUint64, op, comm, c.stream), "all-reduce");
+        W2R_CUDA(cudaMemcpyAsync(v.data(), d.p, v.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    // all-to-all of equal slabs: slab d of `send` goes to rank d, slab s of `recv` comes from rank s (MapReduceEngine's "swizzle",
+    // MapReduceEngine.h:337-358, as grouped ncclSend/ncclRecv over NVLink)
+    void alltoall_slabs(const void* send, void* recv, size_t slab_bytes) {
+        NcclApi& n = NcclApi::get();
+        nccl_check(n.GroupStart(), "group start");
+        for (int peer = 0; peer < world; ++peer) {
+            if (peer == rank) continue;
+            nccl_check(n.Send((const char*)send + (size_t)peer * slab_bytes, slab_bytes, ncclUint8, peer, comm, c.stream), "send");
+            nccl_check(n.Recv((char*)recv + (size_t)peer * slab_bytes, slab_bytes, ncclUint8, peer, comm, c.stream), "recv");
+        }
+        nccl_check(n.GroupEnd(), "group end");
+        W2R_CUDA(cudaMemcpyAsync((char*)recv + (size_t)rank * slab_bytes, (const char*)send + (size_t)rank * slab_bytes, slab_bytes, cudaMemcpyDeviceToDevice, c.stream));
+    }
+
     void count_stage() {
         const ReadsView rv = dr.view();
         good.alloc(c, dr.n);
@@ -174,8 +204,13 @@ struct Pipeline {
         SBuf<int> flags(c, 4);
         flags.zero();
         if (dr.n) W2R_LAUNCH(c, k_good_len, grid(dr.n, 128), 128, 0, rv, prm.min_qual, good.p, scal.p, flags.p);
-        const unsigned long long n_inst = d2h_scalar(c, scal.p);
-        if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
+        const unsigned long long n_inst_local = d2h_scalar(c, scal.p);
+        std::vector<unsigned long long> agg = {n_inst_local, (unsigned long long)d2h_scalar(c, flags.p)};
+        allreduce_u64(agg, ncclSum);
+        std::vector<unsigned long long> mx = {n_inst_local};
+        allreduce_u64(mx, ncclMax);
+        if (agg[1]) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
+        const unsigned long long n_inst = agg[0], n_inst_max = mx[0];      // whole job / largest shard
         out->n_kmer_instances = n_inst;
         say(c, "%llu k-mer instances in quality-floored reads", n_inst);
 
@@ -184,20 +219,23 @@ struct Pipeline {
         while (logR > 8 && (1ull << (logR - 1)) >= 2 * n_inst + 64) --logR;
         if (prm.table_slots) { logR = 6; while ((2ull << logR) <= prm.table_slots && logR < 24) ++logR; }
         const uint64_t R = 1ull << logR;
-        // partitions: few enough records each that even an all-distinct partition fits the region at load 0.6
+        // partitions: few enough records each that even an all-distinct partition fits the region at load 0.6;
+        // at least one per rank: rank r owns the contiguous range [r*P/world, (r+1)*P/world)
         uint32_t logP = 0;
-        while ((double)n_inst / (double)(1ull << logP) > 0.6 * (double)R && logP < 24) ++logP;
+        while (((double)n_inst / (double)(1ull << logP) > 0.6 * (double)R || (1ull << logP) < (uint64_t)world) && logP < 24) ++logP;
         size_t budget = (size_t)(device_budget(c) * 0.80);
-        const uint64_t solid_cap = n_inst / std::max<uint32_t>(1, prm.min_freq) + 1024;
-        const size_t fixed_bytes = solid_cap * sizeof(ulonglong2) + R * sizeof(CountSlot) + (prm.dump_kmers == 2 ? n_inst * sizeof(DumpRec) : 0);
+        if (prm.dump_kmers == 2 && world > 1) W2R_FAIL(W2RAP_ERR_BAD_ARG, "dump level 2 is a single-GPU test hook");
+        const size_t fixed_bytes = R * sizeof(CountSlot) + (prm.dump_kmers == 2 ? n_inst * sizeof(DumpRec) : 0) +
+                                   (size_t)((double)n_inst / world / std::max<uint32_t>(1, prm.min_freq) * 1.3) * sizeof(ulonglong2);
         if (fixed_bytes + (64u << 20) > budget) W2R_FAIL(W2RAP_ERR_OOM, "not enough device memory for the solid k-mer staging buffer");
-        SBuf<ulonglong2> solid(c, solid_cap);
+        SBuf<ulonglong2> solid;                       // solid records of the partitions this rank owns
+        uint64_t solid_cap = 0;
         SBuf<CountSlot> region(c, R);
         SBuf<DumpRec> dump_dev(c, prm.dump_kmers == 2 ? n_inst : 0);
         SBuf<unsigned long long> hist(c, 104); hist.zero();
         W2R_LAUNCH(c, k_init_count_table, grid(2 * R, 256), 256, 0, region.p, R);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(R * sizeof(CountSlot), 64u << 20)) != cudaSuccess) cudaGetLastError();
-        float part_ms = 0, region_ms = 0;
+        float part_ms = 0, region_ms = 0, xchg_ms = 0;
         uint32_t npass = 1;
         double slack = 1.06;
         uint64_t n_distinct_seen = 0;
@@ -205,57 +243,87 @@ struct Pipeline {
         EventTimer kt(c.stream);
         for (int attempt = 0;; ++attempt) {
             if (attempt > 8) W2R_FAIL(W2RAP_ERR_INTERNAL, "k-mer partitioning did not converge");
-            const uint64_t P = 1ull << logP;
-            // sub-buffers: the cursor atomics of pass A serialise per L2 line; 8 sub-buffers per partition on separate lines
-            const uint32_t nsub = (n_inst / P >= 65536 && !prm.table_slots) ? 8u : 1u;
+            const uint64_t P = 1ull << logP, Pown = P / world;
+            // sub-buffers: 8 per partition, cursors on separate L2 lines
+            const uint32_t nsub = (n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
             const uint32_t cstride = 32;
-            const uint64_t NB = P * nsub;
-            const uint64_t per = (uint64_t)((double)n_inst / (double)NB / (double)npass * slack) + 1024;
-            if (NB * per * sizeof(ulonglong2) + fixed_bytes > budget && npass < 4096) { npass *= 2; continue; }
-            const uint64_t cap = per;
-            SBuf<ulonglong2> recs(c, NB * cap);
-            SBuf<uint32_t> cursor(c, NB * cstride);
-            std::vector<uint32_t> sizes(P), raw_sizes(NB * cstride);
+            const uint64_t NB = P * nsub, NBown = Pown * nsub;
+            const uint64_t cap = (uint64_t)((double)n_inst_max / (double)NB / (double)npass * slack) + 1024;
+            const size_t rec_bytes = NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);      // + the receive slabs
+            // Scattered appends over a record buffer of tens of GB run into TLB misses (measured: the same kernel is 2x faster per
+            // record on a 41 GB buffer than on an 82 GB one), so the buffer is also capped and the k-mer space split into more
+            // hash-range passes instead; extraction is repeated per pass, which is cheap next to the appends.
+            static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
+            if ((rec_bytes + fixed_bytes > budget || (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9) && npass < 4096) { npass *= 2; continue; }
+            SBuf<ulonglong2> recs(c, NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            SBuf<uint32_t> cursor(c, NB * cstride), xcur_buf(c, world > 1 ? NB * cstride : 0);
+            const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;          // [world][NBown][cap]: what this rank reduces
+            const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [world][NBown][cstride]
+            const uint64_t slab_recs = NBown * cap, slab_cur = NBown * cstride;
+            std::vector<uint32_t> sizes(Pown), raw_sizes((size_t)world * slab_cur);
             bool retry = false;
             W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
             hist.zero();
+            uint64_t solid_used_before = 0;
             for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
                 cursor.zero();
                 PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1};
                 kt.start();
-                if (n_inst) { W2R_LAUNCH(c, k_extract_partition, grid(dr.n, 256, 8), 256, 0, rv, good.p, pp); c.count_launches++; }
+                if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(dr.n, 256, 8), 256, 0, rv, good.p, pp); c.count_launches++; }
                 part_ms += kt.stop();
-                if (d2h_scalar(c, flags.p + 1)) {        // a partition buffer overflowed (skewed k-mer multiplicities): more slack
+                std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, flags.p + 1)};
+                allreduce_u64(of, ncclSum);
+                if (of[0]) {        // a sub-buffer overflowed somewhere (skewed k-mer multiplicities): more slack, on every rank
                     W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
                     slack *= 1.5; retry = true; break;
                 }
-                W2R_CUDA(cudaMemcpyAsync(raw_sizes.data(), cursor.p, NB * cstride * 4, cudaMemcpyDeviceToHost, c.stream));
+                if (world > 1) {    // route every record to the rank that owns its partition
+                    kt.start();
+                    alltoall_slabs(recs.p, xrecs_buf.p, slab_recs * sizeof(ulonglong2));
+                    alltoall_slabs(cursor.p, xcur_buf.p, slab_cur * sizeof(uint32_t));
+                    xchg_ms += kt.stop();
+                }
+                W2R_CUDA(cudaMemcpyAsync(raw_sizes.data(), xcur, raw_sizes.size() * 4, cudaMemcpyDeviceToHost, c.stream));
                 W2R_CUDA(cudaStreamSynchronize(c.stream));
-                for (uint64_t q = 0; q < P; ++q) { uint32_t mxs = 0; for (uint32_t u = 0; u < nsub; ++u) mxs = std::max(mxs, raw_sizes[(q * nsub + u) * cstride]); sizes[q] = mxs; }   // largest sub-buffer
-                // ---- reduce: groups of consecutive partitions share the region; the group size comes from the first partition's distinct count
+                uint64_t owned_records = 0;
+                for (uint64_t q = 0; q < Pown; ++q) {
+                    uint32_t mxs = 0;
+                    for (int sidx = 0; sidx < world; ++sidx)
+                        for (uint32_t u = 0; u < nsub; ++u) { uint32_t v = raw_sizes[sidx * slab_cur + (q * nsub + u) * cstride]; mxs = std::max(mxs, v); owned_records += v; }
+                    sizes[q] = mxs;      // largest sub-buffer of the partition (sizes the grid)
+                }
+                {   // staging for this pass's solid records (each needs >= min_freq instances)
+                    uint64_t need = solid_used_before + owned_records / std::max<uint32_t>(1, prm.min_freq) + 1024;
+                    if (need > solid_cap) {
+                        SBuf<ulonglong2> bigger(c, need + need / 4);
+                        if (solid_used_before) W2R_CUDA(cudaMemcpyAsync(bigger.p, solid.p, solid_used_before * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, c.stream));
+                        solid = std::move(bigger);
+                        solid_cap = solid.n;
+                    }
+                }
+                // ---- reduce: groups of consecutive owned partitions share the region; the group size comes from the first partition's distinct count
                 kt.start();
                 set_l2_window(region.p, R * sizeof(CountSlot));
-                SBuf<int> gflag(c, P + 1); gflag.zero();
+                SBuf<int> gflag(c, Pown + 1); gflag.zero();
                 auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag) {
                     ++n_groups;
-                    uint32_t mx = 0;
-                    for (uint32_t q = p0; q < p0 + g; ++q) mx = std::max(mx, sizes[q]);
-                    if (mx) {
+                    uint32_t mxg = 0;
+                    for (uint32_t q = p0; q < p0 + g; ++q) mxg = std::max(mxg, sizes[q]);
+                    if (mxg) {
                         RegionParams rp{region.p, logR, logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
-                        dim3 gr(std::max(1u, std::min<unsigned>((mx + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy, 8u))))), gy);
-                        k_count_region<<<gr, 256, 0, c.stream>>>(recs.p, cursor.p, cstride, cap, p0 * nsub, rp); c.launches++;
+                        dim3 gr(std::max(1u, std::min<unsigned>((mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * world, 8u))))), gy * world);
+                        k_count_region<<<gr, 256, 0, c.stream>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
                     ScanParams sp{region.p, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
                     W2R_LAUNCH(c, k_scan_region, grid(R, 256, 4), 256, 0, sp);
                 };
                 uint32_t g = 1;
-                std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first partition, count)
-                // first partition alone: its distinct count sizes the groups
-                run_group(0, 1, 0, 0, gflag.p + 0);
+                std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first owned partition, count)
+                run_group(0, 1, 0, 0, gflag.p + 0);                  // first partition alone: its distinct count sizes the groups
                 groups.push_back({0u, 1u});
-                if (P > 1) {
+                if (Pown > 1) {
                     std::vector<unsigned long long> hh(104);
                     W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
                     W2R_CUDA(cudaStreamSynchronize(c.stream));
@@ -263,15 +331,15 @@ struct Pipeline {
                     for (int i = 1; i <= 100; ++i) d0 += hh[i];
                     d0 -= std::min<unsigned long long>(d0, n_distinct_seen);
                     g = (uint32_t)std::max<double>(1.0, std::min<double>(4096.0, 0.5 * (double)R / ((double)d0 * 1.15 + 1.0)));
-                    g = std::min<uint32_t>(g, 32768u / nsub);
-                    for (uint64_t p0 = 1; p0 < P; p0 += g) {
-                        uint32_t gg = (uint32_t)std::min<uint64_t>(g, P - p0);
+                    g = std::max<uint32_t>(1u, std::min<uint32_t>(g, 32768u / (nsub * world)));
+                    for (uint64_t p0 = 1; p0 < Pown; p0 += g) {
+                        uint32_t gg = (uint32_t)std::min<uint64_t>(g, Pown - p0);
                         run_group((uint32_t)p0, gg, 0, 0, gflag.p + p0);
                         groups.push_back({(uint32_t)p0, gg});
                     }
                 }
-                std::vector<int> gf(P + 1);
-                W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                std::vector<int> gf(Pown + 1);
+                W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (Pown + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
                 W2R_CUDA(cudaStreamSynchronize(c.stream));
                 for (auto& gr : groups) {
                     if (!gf[gr.first]) continue;
@@ -281,16 +349,16 @@ struct Pipeline {
                         std::vector<unsigned long long> hist_snapshot(104);
                         W2R_CUDA(cudaMemcpyAsync(snapshot, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
                         W2R_CUDA(cudaMemcpyAsync(hist_snapshot.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
-                        W2R_CUDA(cudaMemsetAsync(gflag.p + P, 0, sizeof(int), c.stream));
-                        run_group(q, 1, 0, 0, gflag.p + P);
-                        if (!d2h_scalar(c, gflag.p + P)) continue;
+                        W2R_CUDA(cudaMemsetAsync(gflag.p + Pown, 0, sizeof(int), c.stream));
+                        run_group(q, 1, 0, 0, gflag.p + Pown);
+                        if (!d2h_scalar(c, gflag.p + Pown)) continue;
                         for (uint32_t S = 2;; S *= 2) {
                             if (S > 4096) W2R_FAIL(W2RAP_ERR_INTERNAL, "a k-mer partition does not fit the counting region even in 4096 hash sub-ranges");
                             bool ok = true;
                             for (uint32_t sid = 0; sid < S && ok; ++sid) {
-                                W2R_CUDA(cudaMemsetAsync(gflag.p + P, 0, sizeof(int), c.stream));
-                                run_group(q, 1, S - 1, sid, gflag.p + P);
-                                if (d2h_scalar(c, gflag.p + P)) ok = false;
+                                W2R_CUDA(cudaMemsetAsync(gflag.p + Pown, 0, sizeof(int), c.stream));
+                                run_group(q, 1, S - 1, sid, gflag.p + Pown);
+                                if (d2h_scalar(c, gflag.p + Pown)) ok = false;
                             }
                             if (ok) break;
                             // roll back what the successful sub-ranges of this split emitted, then split finer
@@ -308,6 +376,7 @@ struct Pipeline {
                     W2R_CUDA(cudaStreamSynchronize(c.stream));
                     n_distinct_seen = 0;
                     for (int i = 1; i <= 100; ++i) n_distinct_seen += hh[i];
+                    solid_used_before = d2h_scalar(c, scal.p + 1);
                 }
             }
             if (retry) { n_distinct_seen = 0; n_groups = 0; continue; }
@@ -317,21 +386,45 @@ struct Pipeline {
         if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
         out->timings.count_kernel_ms = part_ms;
         out->timings.region_ms = region_ms;
+        out->timings.exchange_ms = xchg_ms;
         out->timings.count_passes = n_groups;
         std::vector<unsigned long long> hh(104);
         W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
         unsigned long long cursors[2];
         W2R_CUDA(cudaMemcpyAsync(cursors, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
+        allreduce_u64(hh, ncclSum);                          // histogram of the whole job
         uint64_t n_distinct = 0;
         for (int i = 1; i <= 100; ++i) { out->hist[i] = hh[i]; n_distinct += hh[i]; }
-        const uint64_t n_solid = cursors[0];
-        out->n_distinct = n_distinct; out->n_solid = n_solid;
+        const uint64_t n_solid_local = cursors[0];
         if (prm.dump_kmers == 2 && cursors[1]) {
             dump_host.resize(cursors[1]);
             W2R_CUDA(cudaMemcpyAsync(dump_host.data(), dump_dev.p, cursors[1] * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
             W2R_CUDA(cudaStreamSynchronize(c.stream));
         }
+        region.release(); dump_dev.release();
+        // every rank needs the whole dictionary for adjacency, unipaths and pathing: all-gather the solid records
+        std::vector<unsigned long long> per_rank(world, 0ull);
+        per_rank[rank] = n_solid_local;
+        allreduce_u64(per_rank, ncclSum);
+        uint64_t n_solid = 0;
+        for (auto v : per_rank) n_solid += v;
+        SBuf<ulonglong2> solid_all;
+        const ulonglong2* solid_src = solid.p;
+        if (world > 1) {
+            kt.start();
+            solid_all.alloc(c, n_solid);
+            uint64_t off = 0;
+            for (int sidx = 0; sidx < world; ++sidx) {
+                if (per_rank[sidx]) nccl_check(NcclApi::get().Broadcast(sidx == rank ? (const void*)solid.p : (const void*)(solid_all.p + off), solid_all.p + off,
+                                                                         per_rank[sidx] * sizeof(ulonglong2), ncclUint8, sidx, comm, c.stream), "broadcast");
+                off += per_rank[sidx];
+            }
+            out->timings.exchange_ms += kt.stop();
+            solid_src = solid_all.p;
+            solid.release();
+        }
+        out->n_distinct = n_distinct; out->n_solid = n_solid;
         say(c, "%llu kmers counted, filtering...", (unsigned long long)n_distinct);
         say(c, "%llu / %llu kmers with Freq >= %u", (unsigned long long)n_solid, (unsigned long long)n_distinct, prm.min_freq);
 
@@ -339,11 +432,11 @@ struct Pipeline {
         uint32_t lg = 10;
         while ((1ull << lg) < 2 * n_solid) ++lg;
         if (lg > 31) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^30 solid k-mers on one device");
-        region.release(); dump_dev.release();
         solid_slots.alloc(c, 1ull << lg);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, lg};
-        if (n_solid) W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, solid.p, n_solid, st);
+        if (n_solid) W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, solid_src, n_solid, st);
+        W2R_CUDA(cudaStreamSynchronize(c.stream));   // solid / solid_all are released when this function returns
     }
 
     // ---- buildEdges (BuildReadQGraph.cc:314-339)
@@ -663,12 +756,18 @@ static void check_params(const w2rap_params* p) {
     if (p->min_freq == 0 || p->min_freq > 255) W2R_FAIL(W2RAP_ERR_BAD_ARG, "min_freq must be in 1..255 (counts saturate at 255)");
 }
 
-static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* out, float h2d_ms) {
+}  // namespace w2r
+
+struct w2rap_comm { int world, rank, device; w2r::ncclComm_t comm; };
+
+namespace w2r {
+static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* out, float h2d_ms, const w2rap_comm* cm = nullptr) {
     GraphOwner* owner = new GraphOwner();
     memset(out, 0, sizeof(*out));
     out->_owner = owner;
     try {
         Pipeline pl(dr, *p, out, owner);
+        if (cm) { pl.world = cm->world; pl.rank = cm->rank; pl.comm = cm->comm; }
         check_device(dr.device, pl.c);
         pl.run();
         out->timings.h2d_ms = h2d_ms;
@@ -757,6 +856,74 @@ int w2rap_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* o
     } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
     d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
+    W2R_API_END
+}
+
+int w2rap_step2_comm_unique_id(uint8_t* id128, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!id128) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null id buffer");
+    NcclApi& n = NcclApi::get();
+    if (n.error) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "%s", n.error);
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != ncclSuccess) W2R_FAIL(W2RAP_ERR_CUDA, "ncclGetUniqueId failed");
+    memcpy(id128, id.internal, 128);
+    W2R_API_END
+}
+
+int w2rap_step2_comm_init(const uint8_t* id128, int world, int rank, int device, w2rap_comm** comm, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!id128 || !comm || world < 1 || rank < 0 || rank >= world) W2R_FAIL(W2RAP_ERR_BAD_ARG, "bad communicator arguments");
+    if (world & (world - 1)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "world size must be a power of two (partition ranges are split evenly)");
+    NcclApi& n = NcclApi::get();
+    if (n.error) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "%s", n.error);
+    Ctx c; check_device(device, c);
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    ncclComm_t nc = nullptr;
+    ncclResult_t r = n.CommInitRank(&nc, world, id, rank);
+    if (r != ncclSuccess) W2R_FAIL(W2RAP_ERR_CUDA, "ncclCommInitRank failed: %s", n.GetErrorString(r));
+    *comm = new w2rap_comm{world, rank, c.device, nc};
+    W2R_API_END
+}
+
+void w2rap_step2_comm_destroy(w2rap_comm* comm) {
+    if (!comm) return;
+    cudaSetDevice(comm->device);
+    if (comm->comm) NcclApi::get().CommDestroy(comm->comm);
+    delete comm;
+}
+
+int w2rap_step2_run_sharded_resident(w2rap_device_reads* handle, const w2rap_params* p, w2rap_comm* comm, w2rap_graph* out, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!handle || !out || !comm) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null argument");
+    check_params(p);
+    if (handle->d.device != comm->device) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read shard lives on device %d, communicator on %d", handle->d.device, comm->device);
+    run_on_device(handle->d, p, out, 0.f, comm);
+    if (comm->rank == 0 && p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
+    W2R_API_END
+}
+
+int w2rap_step2_run_sharded(const w2rap_reads* shard, const w2rap_params* p, w2rap_comm* comm, w2rap_graph* out, char* err, size_t errlen) {
+    W2R_API_BEGIN
+    if (!out || !comm) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null argument");
+    check_params(p);
+    validate_reads(shard);
+    Ctx c; check_device(comm->device, c);
+    DeviceReads d;
+    d.pooled = true;
+    cudaStream_t us = nullptr;
+    W2R_CUDA(cudaStreamCreateWithFlags(&us, cudaStreamNonBlocking));
+    d.pool_stream = us;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float h2d = 0;
+    try {
+        cudaEventRecord(e0, us);
+        upload(shard, c.device, &d, us);
+        cudaEventRecord(e1, us); cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
+        run_on_device(d, p, out, h2d, comm);
+    } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (comm->rank == 0 && p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
     W2R_API_END
 }
 

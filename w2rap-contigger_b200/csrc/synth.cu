@@ -79,14 +79,15 @@ __device__ uint32_t pq_encode_greedy(const uint8_t* q, uint32_t n, uint8_t* out)
     return o + 1;
 }
 
-struct SynArgs { const uint8_t* hap0; const uint8_t* hap1; uint64_t G; uint32_t L; uint64_t seed; uint64_t n_reads; };
+struct SynArgs { const uint8_t* hap0; const uint8_t* hap1; uint64_t G; uint32_t L; uint64_t seed; uint64_t n_reads; uint64_t first_read; };
 
 template <bool WRITE>
 __global__ void __launch_bounds__(128) k_syn_reads(SynArgs a, uint32_t* __restrict__ qsize, const uint64_t* __restrict__ qual_off, uint8_t* __restrict__ bases,
                                                    uint8_t* __restrict__ quals) {
     uint8_t q[256], b[256];
     const uint32_t L = a.L, nbb = (L + 3) / 4;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t lr = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lr < a.n_reads; lr += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = lr + a.first_read;      // global read index: the read set is a function of (seed, index) only
         uint64_t pair = r >> 1;
         uint64_t h = splitmix(a.seed ^ (pair * 0x9e3779b97f4a7c15ull));
         const uint8_t* hap = (a.hap1 && (h & 1)) ? a.hap1 : a.hap0;
@@ -110,10 +111,10 @@ __global__ void __launch_bounds__(128) k_syn_reads(SynArgs a, uint32_t* __restri
             if ((uint32_t)(x >> 32) < c_perr[qv]) base = (base + 1 + (uint32_t)((x >> 12) % 3u)) & 3u;
             q[i] = (uint8_t)qv; b[i] = (uint8_t)base;
         }
-        if (!WRITE) qsize[r] = pq_encode_greedy(q, L, nullptr);
+        if (!WRITE) qsize[lr] = pq_encode_greedy(q, L, nullptr);
         else {
-            pq_encode_greedy(q, L, quals + qual_off[r]);
-            uint8_t* pb = bases + r * nbb;
+            pq_encode_greedy(q, L, quals + qual_off[lr]);
+            uint8_t* pb = bases + lr * nbb;
             for (uint32_t j = 0; j < nbb; ++j) {
                 uint32_t v = 0;
                 for (uint32_t k = 0; k < 4 && 4 * j + k < L; ++k) v |= (uint32_t)b[4 * j + k] << (2 * k);
@@ -196,7 +197,7 @@ int w2rap_step2_synth(const w2rap_synth_params* sp, int device, w2rap_device_rea
             W2R_CUDA(cudaMalloc((void**)&d.qual_off, (nr + 1) * 8));
             W2R_CUDA(cudaMalloc((void**)&d.len, (nr + 1) * 4));
             W2R_LAUNCH(c, k_syn_regular, grid_for(c, nr + 1, 256), 256, 0, nr, L, d.base_off, d.len);
-            SynArgs a{hap0.p, sp->het_per_10k ? hap1.p : nullptr, G, L, sp->seed, nr};
+            SynArgs a{hap0.p, sp->het_per_10k ? hap1.p : nullptr, G, L, sp->seed, nr, sp->first_read};
             DBuf<uint32_t> qsize(nr);
             DBuf<unsigned long long> tot(1);
             W2R_LAUNCH(c, (k_syn_reads<false>), grid_for(c, nr, 128), 128, 0, a, qsize.p, (const uint64_t*)nullptr, (uint8_t*)nullptr, (uint8_t*)nullptr);
