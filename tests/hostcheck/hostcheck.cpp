@@ -230,7 +230,11 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     }
     if (!want_paths) return 0;
     // ---- k_path_reads (+ overflow retry), k_path_lens, scan, k_path_gather
-    GraphView g{st, edge_bases.data(), edge_off.data(), edge_len.data(), fwd.data(), rev.data(), hcanon.data(), hleft.data(), hright.data(), from_e.data(), to_e.data(), from_n.data(), to_n.data()};
+    // k_bloom_build: the negative-lookup filter of the pathing kernel
+    std::vector<uint32_t> bloom_words(std::max<uint64_t>(1024, n_solid / 2), 0u);
+    KmerBloom bloom{bloom_words.data(), bloom_words.size()};
+    for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) { uint64_t h = kmer_hash(Kmer{slots[i].w0, slots[i].w1}); bloom_words[bloom_word(bloom, h)] |= bloom_mask(h); }
+    GraphView g{st, bloom, edge_bases.data(), edge_off.data(), edge_len.data(), fwd.data(), rev.data(), hcanon.data(), hleft.data(), hright.data(), from_e.data(), to_e.data(), from_n.data(), to_n.data()};
     const uint64_t n = in->n_reads;
     uint32_t maxlen = 0;
     for (uint64_t r = 0; r < n; ++r) maxlen = std::max(maxlen, in->len[r]);

@@ -201,17 +201,16 @@ class ReadSet:
     """Host-side flattened read store (numpy owners + the ctypes view passed through the C ABI)."""
 
     def __init__(self, bases, base_off, lens, quals, qual_off):
-        self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        # 32 bytes of slack behind both byte stores: the device functions (also run on the host by tests/hostcheck) read packed
+        # bases with aligned 8-byte loads that may touch a few bytes past the last base.  The C ABI itself needs no padding.
+        self._bases_store = np.concatenate([np.ascontiguousarray(bases, dtype=np.uint8), np.zeros(32, np.uint8)])
+        self._quals_store = np.concatenate([np.ascontiguousarray(quals, dtype=np.uint8), np.zeros(32, np.uint8)])
+        self.bases = self._bases_store[:len(self._bases_store) - 32]
         self.base_off = np.ascontiguousarray(base_off, dtype=np.uint64)
         self.len = np.ascontiguousarray(lens, dtype=np.uint32)
-        self.quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        self.quals = self._quals_store[:len(self._quals_store) - 32]
         self.qual_off = np.ascontiguousarray(qual_off, dtype=np.uint64)
         self.n = len(self.len)
-        # keep at least one byte so pointers are never null
-        if self.bases.size == 0:
-            self.bases = np.zeros(1, np.uint8)
-        if self.quals.size == 0:
-            self.quals = np.zeros(1, np.uint8)
         if self.len.size == 0:
             self.len = np.zeros(1, np.uint32)[:0]
 

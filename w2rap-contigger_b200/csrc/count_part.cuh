@@ -27,33 +27,62 @@ struct PartParams {
     uint32_t cstride;        // cursor stride in u32 (32 = one cursor per 128-byte line)
     uint32_t npass, pass;    // outer hash-range passes (when the records of everything would not fit): keep (hash & 0xffff) % npass == pass
     int* overflow;           // set if a sub-buffer overflowed
+    // chunked mode (single GPU): partition buffers grow in chunks of 1 << logC records taken from one pool in arrival order, so
+    // at any moment all appends land in a window of about P chunks (256 MB) instead of all over an 80 GB buffer: the scattered
+    // appends stop missing the TLB.  chunk_of[p * maxk + k] = pool chunk holding records [k << logC, (k+1) << logC) of partition p.
+    uint32_t chunked, logC, maxk;
+    uint32_t* chunk_of;      // NIL = not allocated yet
+    uint32_t* pool_next;     // bump allocator
+    uint32_t pool_chunks;
 };
 
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// Emits records one step behind the cursor atomic so that the atomic's latency overlaps the next k-mer's arithmetic.
+
+// Appends records in PAIRS: the two cursor atomics are independent, so both are in flight together and the thread waits
+// for one round trip per two k-mers (the kernel is bound by the latency of the returning atomic x threads in flight).
 struct PartEmit {
     const PartParams& pp;
-    ulonglong2 rec;
-    uint64_t addr;           // first record index of the sub-buffer of the pending store, ~0 = none
-    uint32_t pos_pending;
+    ulonglong2 rec;          // the stashed first record of a pair
+    uint32_t bucket;
+    bool pending;
     uint32_t sub;
-    __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), addr(~0ull), pos_pending(0), sub(sub_) {}
-    __device__ __forceinline__ void flush() {
-        if (addr != ~0ull) {
-            if (pos_pending < pp.cap) pp.recs[addr + pos_pending] = rec;
+    __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), bucket(0), pending(false), sub(sub_) {}
+    __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r) {
+        if (!pp.chunked) {
+            if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
             else atomicExch(pp.overflow, 1);
-            addr = ~0ull;
+            return;
         }
+        const uint32_t k = pos >> pp.logC, off = pos & ((1u << pp.logC) - 1u);
+        if (k >= pp.maxk) { atomicExch(pp.overflow, 1); return; }
+        uint32_t* tab = pp.chunk_of + (uint64_t)b * pp.maxk;
+        if (off == (1u << (pp.logC - 1)) && k + 1 < pp.maxk) {        // half way through a chunk: allocate the next one ahead of need
+            const uint32_t g = atomicAdd(pp.pool_next, 1u);
+            if (g < pp.pool_chunks) st_volatile_u32(tab + k + 1, g); else atomicExch(pp.overflow, 1);
+        }
+        uint32_t g = ld_volatile_u32(tab + k);
+        while (g == NIL) {                                             // published half a chunk ago in practice
+            if (ld_volatile_u32(reinterpret_cast<const uint32_t*>(pp.overflow))) return;
+            g = ld_volatile_u32(tab + k);
+        }
+        pp.recs[((uint64_t)g << pp.logC) + off] = r;
+    }
+    __device__ __forceinline__ void flush() {
+        if (pending) { put(bucket, atomicAdd(pp.cursor + (uint64_t)bucket * pp.cstride, 1u), rec); pending = false; }
     }
     __device__ __forceinline__ void operator()(Kmer k, uint32_t ctx) {
         const uint64_t h = kmer_hash(k);
         if (pp.npass > 1 && (uint32_t)(h & 0xffffu) % pp.npass != pp.pass) return;
         const uint32_t b = part_of_hash(h, pp.logP) * pp.nsub + sub;
-        const uint32_t pos = atomicAdd(pp.cursor + (uint64_t)b * pp.cstride, 1u);
-        flush();                                            // the previous record goes out while this atomic is in flight
-        rec = make_ulonglong2(k.w0, k.w1 | ctx);
-        addr = (uint64_t)b * pp.cap;
-        pos_pending = pos;
+        const ulonglong2 r = make_ulonglong2(k.w0, k.w1 | ctx);
+        if (!pending) { rec = r; bucket = b; pending = true; return; }
+        const uint32_t pos0 = atomicAdd(pp.cursor + (uint64_t)bucket * pp.cstride, 1u);
+        const uint32_t pos1 = atomicAdd(pp.cursor + (uint64_t)b * pp.cstride, 1u);
+        put(bucket, pos0, rec);
+        put(b, pos1, r);
+        pending = false;
     }
 };
 
@@ -110,43 +139,62 @@ __device__ __forceinline__ void region_insert(const RegionParams& rp, uint64_t m
     atomicExch(rp.overflow, 1);
 }
 
+// Two records at a time: their slot loads are independent, which doubles the L2 requests in flight per thread.
+__device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64_t mask, ulonglong2 ra, ulonglong2 rb, bool two) {
+    const uint64_t ha = kmer_hash(Kmer{ra.x, ra.y & ~0xffull});
+    const uint64_t hb = kmer_hash(Kmer{rb.x, rb.y & ~0xffull});
+    const bool da = !rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id;
+    const bool db = two && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
+    CountSlot* qa = rp.region + region_slot_of_hash(ha, rp.logP, rp.logR);
+    CountSlot* qb = rp.region + region_slot_of_hash(hb, rp.logP, rp.logR);
+    uint64_t a0 = 0, a1 = 0, am = 0, b0 = 0, b1 = 0, bm = 0;
+    if (da) ld_slot(qa, a0, a1, am);
+    if (db) ld_slot(qb, b0, b1, bm);
+    if (da) {
+        const uint32_t ctx = (uint32_t)ra.y & 0xffu;
+        if (a0 == ra.x && a1 == (ra.y & ~0xffull)) { atomicAdd(&qa->count, 1u); if ((((uint32_t)(am >> 32)) & ctx) != ctx) atomicOr(&qa->ctx, ctx); }
+        else region_insert(rp, mask, ra, ha);
+    }
+    if (db) {
+        const uint32_t ctx = (uint32_t)rb.y & 0xffu;
+        if (b0 == rb.x && b1 == (rb.y & ~0xffull)) { atomicAdd(&qb->count, 1u); if ((((uint32_t)(bm >> 32)) & ctx) != ctx) atomicOr(&qb->ctx, ctx); }
+        else region_insert(rp, mask, rb, hb);
+    }
+}
+
 // The "reduce" step (BuildReadQGraph.cc:1081-1082 sort+collapse as a hash count).  blockIdx.y selects the sub-buffer of the group.
-// Two records per thread per iteration: their slot loads are independent, which doubles the L2 requests in flight.
 // recs/sizes hold one slab per source rank ([n_src][owned sub-buffers]); blockIdx.y = src * gy + sub-buffer within the group.
+// Chunked buffers (cv.chunk_of != nullptr): a block takes whole chunks, so the chunk table is read once per 2048 records.
+struct ChunkView { const uint32_t* chunk_of; uint32_t logC, maxk; };   // chunk_of == nullptr: static sub-buffers
 __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
-                                                      uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, RegionParams rp) {
+                                                      uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, ChunkView cv, RegionParams rp) {
     const uint32_t src = blockIdx.y / gy;
     const uint32_t b = b_first + (blockIdx.y - src * gy);
     uint64_t n = sizes[(uint64_t)src * slab_cur + (uint64_t)b * cstride];
     if (n > cap) n = cap;
-    const ulonglong2* base = recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
     const uint64_t mask = (1ull << rp.logR) - 1;
+    if (cv.chunk_of) {
+        const uint32_t* tab = cv.chunk_of + (uint64_t)b * cv.maxk;
+        const uint64_t C = 1ull << cv.logC, nchunks = (n + C - 1) >> cv.logC;
+        for (uint64_t k = blockIdx.x; k < nchunks; k += gridDim.x) {
+            const ulonglong2* cb = recs + ((uint64_t)__ldg(tab + k) << cv.logC);
+            const uint32_t cnt = (uint32_t)(n - (k << cv.logC) < C ? n - (k << cv.logC) : C);
+            for (uint32_t i = threadIdx.x; i < cnt; i += 2 * blockDim.x) {
+                const bool two = i + blockDim.x < cnt;
+                const ulonglong2 ra = __ldcs(cb + i);
+                const ulonglong2 rb = two ? __ldcs(cb + i + blockDim.x) : make_ulonglong2(0, 0);
+                region_count_pair(rp, mask, ra, rb, two);
+            }
+        }
+        return;
+    }
+    const ulonglong2* base = recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
         const bool two = i + stride < n;
         const ulonglong2 ra = __ldcs(base + i);
-        ulonglong2 rb = make_ulonglong2(0, 0);
-        if (two) rb = __ldcs(base + i + stride);
-        const uint64_t ha = kmer_hash(Kmer{ra.x, ra.y & ~0xffull});
-        const uint64_t hb = kmer_hash(Kmer{rb.x, rb.y & ~0xffull});
-        const bool da = !rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id;
-        const bool db = two && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
-        // first probe of both records issued together
-        CountSlot* qa = rp.region + region_slot_of_hash(ha, rp.logP, rp.logR);
-        CountSlot* qb = rp.region + region_slot_of_hash(hb, rp.logP, rp.logR);
-        uint64_t a0 = 0, a1 = 0, am = 0, b0 = 0, b1 = 0, bm = 0;
-        if (da) ld_slot(qa, a0, a1, am);
-        if (db) ld_slot(qb, b0, b1, bm);
-        if (da) {
-            const uint32_t ctx = (uint32_t)ra.y & 0xffu;
-            if (a0 == ra.x && a1 == (ra.y & ~0xffull)) { atomicAdd(&qa->count, 1u); if ((((uint32_t)(am >> 32)) & ctx) != ctx) atomicOr(&qa->ctx, ctx); }
-            else region_insert(rp, mask, ra, ha);
-        }
-        if (db) {
-            const uint32_t ctx = (uint32_t)rb.y & 0xffu;
-            if (b0 == rb.x && b1 == (rb.y & ~0xffull)) { atomicAdd(&qb->count, 1u); if ((((uint32_t)(bm >> 32)) & ctx) != ctx) atomicOr(&qb->ctx, ctx); }
-            else region_insert(rp, mask, rb, hb);
-        }
+        const ulonglong2 rb = two ? __ldcs(base + i + stride) : make_ulonglong2(0, 0);
+        region_count_pair(rp, mask, ra, rb, two);
     }
 }
 

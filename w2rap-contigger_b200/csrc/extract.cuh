@@ -5,27 +5,6 @@
 
 namespace w2r {
 
-// Sequential base reader over a 2-bit packed read (LSB-first in byte); one byte load per four bases.
-struct BaseReader {
-    const uint8_t* p;
-    uint32_t cur, pos;
-    W2R_HD explicit BaseReader(const uint8_t* bases, uint32_t start = 0) : p(bases + (start >> 2)), cur(0), pos(start) { cur = (uint32_t)(*p++) >> ((start & 3) * 2); }
-    W2R_HD uint32_t next() {
-        uint32_t b = cur & 3u;
-        cur >>= 2;
-        if ((++pos & 3u) == 0) cur = *p++;   // may read one byte past the last base: callers guarantee a padded store
-        return b;
-    }
-};
-
-// Builds the k-mer starting at base `pos` of a packed read.
-W2R_HD Kmer kmer_at(const uint8_t* bases, uint32_t pos) {
-    uint64_t w0 = 0, w1 = 0;
-    for (int i = 0; i < 32; ++i) w0 = (w0 << 2) | packed_base(bases, pos + i);
-    for (int i = 32; i < K; ++i) w1 = (w1 << 2) | packed_base(bases, pos + i);
-    return Kmer{w0, w1 << 8};
-}
-
 // Calls emit(canonical k-mer, context byte) for every k-mer of the quality-floored read prefix [0, good_len).
 //   - only reads with good_len > K contribute (BuildReadQGraph.cc:1064)
 //   - first k-mer: successor bit only; last: predecessor bit only (:1066-1078)
@@ -37,11 +16,18 @@ W2R_HD void extract_read_kmers(const uint8_t* bases, uint32_t good_len, Emit& em
     Kmer r = kmer_rc(f);
     const uint32_t last = good_len - K;       // index of the last k-mer
     uint32_t prev_first = 0;
+    uint64_t buf = 0;                         // the next bases of the read, 32 at a time (one pair of 8-byte loads per 32 k-mers)
     for (uint32_t j = 0;; ++j) {
         uint32_t nxt = 0, c = 0;
-        if (j < last) { nxt = packed_base(bases, j + K); c |= 1u << nxt; }
+        if ((j & 31u) == 0) buf = bases32_at(bases, (uint64_t)j + K);
+        if (j < last) { nxt = (uint32_t)buf & 3u; c |= 1u << nxt; }
+        buf >>= 2;
         if (j > 0) c |= 16u << prev_first;
-        if (kmer_less(r, f)) emit(r, ctx_rc(c)); else emit(f, c);
+        {   // select first, emit once: the two orientations must not become two divergent copies of the emit body
+            const bool rev = kmer_less(r, f);
+            const Kmer canon{rev ? r.w0 : f.w0, rev ? r.w1 : f.w1};
+            emit(canon, rev ? ctx_rc(c) : c);
+        }
         if (j == last) break;
         prev_first = kmer_first(f);
         f = kmer_succ(f, nxt);

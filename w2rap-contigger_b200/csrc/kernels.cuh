@@ -120,6 +120,16 @@ __global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, 
     }
 }
 
+__global__ void k_bloom_build(SolidTable st, KmerBloom b) {
+    const uint64_t T = st.size();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) {
+        const SolidSlot* s = st.slots + i;
+        if (s->w0 == EMPTY_W0) continue;
+        const uint64_t h = kmer_hash(Kmer{s->w0, s->w1});
+        atomicOr(b.words + bloom_word(b, h), bloom_mask(h));
+    }
+}
+
 // ================================================================ K3: adjacency pruning (kmers/ReadPather.h:307-346)
 __global__ void k_adjacency(SolidTable st) {
     const uint64_t T = st.size();

@@ -90,6 +90,13 @@ W2R_HD uint64_t kmer_hash(Kmer k) {
     a ^= a >> 31;
     return a;
 }
+W2R_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
 W2R_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
     return __umul64hi(a, b);
@@ -100,6 +107,21 @@ W2R_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 
 // ---------------------------------------------------------------- packed reads / edges (feudal/FieldVec.h:765-769)
 W2R_HD uint32_t packed_base(const uint8_t* p, uint64_t i) { return (p[i >> 2] >> ((i & 3) * 2)) & 3u; }
+
+// 32 consecutive bases starting at base index i of a packed sequence (any byte alignment), LSB-first: base i in bits 1:0.
+// Two aligned 8-byte loads + a funnel shift instead of up to 32 byte loads; may touch up to 15 bytes past the last base
+// needed, so every packed store (reads, edges) carries >= 16 bytes of padding.
+W2R_HD uint64_t bases32_at(const uint8_t* p, uint64_t i) {
+    const uintptr_t addr = (uintptr_t)p + (uintptr_t)(i >> 2);
+    const uint64_t* q = (const uint64_t*)(addr & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(addr & 7u) * 8u + (uint32_t)(i & 3u) * 2u;   // 0..62
+    const uint64_t lo = q[0], hi = q[1];
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+}
+// The k-mer starting at base `pos` of a packed sequence.
+W2R_HD Kmer kmer_at(const uint8_t* bases, uint64_t pos) {
+    return Kmer{rev2(bases32_at(bases, pos)), rev2(bases32_at(bases, pos + 32)) & ~0xffull};
+}
 
 // ---------------------------------------------------------------- tables
 // Counting table slot: one 32-byte sector.  {w0,w1} is claimed with a single 128-bit CAS.
@@ -130,6 +152,43 @@ W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) {
         h = (h + 1) & mask;
     }
 }
+// Blocked Bloom filter over the dictionary keys (two bits in one 32-bit word per key).  Read pathing looks up every k-mer of
+// a read's error-laden tail, almost all of them absent; the filter is small enough to stay in L2, so a negative lookup costs
+// one L2 hit instead of a random DRAM sector (+ a TLB miss) in the multi-GB table.  No false negatives.
+struct KmerBloom {
+    uint32_t* words;        // nullptr = no filter
+    uint64_t nwords;
+};
+W2R_HD uint64_t bloom_word(const KmerBloom& b, uint64_t h) { return mulhi64((h << 32) | (h >> 32), b.nwords); }
+W2R_HD uint32_t bloom_mask(uint64_t h) { return (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)); }
+W2R_HD bool bloom_may_contain(const KmerBloom& b, uint64_t h) {
+    if (!b.words) return true;
+    const uint32_t m = bloom_mask(h);
+#if defined(__CUDA_ARCH__)
+    return (__ldg(b.words + bloom_word(b, h)) & m) == m;
+#else
+    return (b.words[bloom_word(b, h)] & m) == m;
+#endif
+}
+// Canonical lookup through the filter.
+W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer k) {
+    const uint64_t hh = kmer_hash(k);
+    if (!bloom_may_contain(b, hh)) return -1;
+    uint64_t mask = t.size() - 1, h = hh >> (64 - t.log2n);
+    for (;;) {
+        const SolidSlot* s = t.slots + h;
+#if defined(__CUDA_ARCH__)
+        ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(s));
+        uint64_t a = kk.x, bb = kk.y;
+#else
+        uint64_t a = s->w0, bb = s->w1;
+#endif
+        if (a == k.w0 && bb == k.w1) return (int64_t)h;
+        if (a == EMPTY_W0) return -1;
+        h = (h + 1) & mask;
+    }
+}
+
 // kmers/ReadPather.h:196-199 findEntry: canonicalise then look up.  *rev = query was in REV form (rc < query).
 W2R_HD int64_t solid_find_any(const SolidTable& t, Kmer k, bool* rev) {
     Kmer r = kmer_rc(k);

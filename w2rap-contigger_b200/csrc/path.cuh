@@ -13,6 +13,7 @@ namespace w2r {
 
 struct GraphView {
     SolidTable solid;
+    KmerBloom bloom;               // negative-lookup filter over the dictionary (may be empty)
     const uint8_t* edge_bases;     // canonical edges, bvec packing, byte aligned per edge
     const uint64_t* edge_off;      // byte offsets
     const uint32_t* edge_len;      // bases
@@ -136,14 +137,19 @@ W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32
     while (itr < nk) {                                      // :500-550 BRQ_Pather::path
         Kmer f = kmer_at(bases, itr);
         Kmer r = kmer_rc(f);
-        int64_t slot = solid_find(g.solid, kmer_less(r, f) ? r : f);
+        int64_t slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
         if (slot < 0) {
             uint32_t gl = 1;
             ++itr;
-            while (itr < nk) {
-                uint32_t nb = packed_base(bases, itr + K - 1);
+            // (fetching the home slots of several gap positions at once was tried: slower — the kernel is bound by TLB/DRAM
+            //  throughput of random 64-byte fetches, not by latency, and the extra registers cost occupancy)
+            uint64_t nxt = 0;
+            for (uint32_t t = 0; itr < nk; ++t) {
+                if ((t & 31u) == 0) nxt = bases32_at(bases, (uint64_t)itr + K - 1);
+                const uint32_t nb = (uint32_t)nxt & 3u;
+                nxt >>= 2;
                 f = kmer_succ(f, nb); r = kmer_pred(r, 3u - nb);
-                slot = solid_find(g.solid, kmer_less(r, f) ? r : f);
+                slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
                 if (slot >= 0) break;
                 ++gl; ++itr;
             }
@@ -164,14 +170,31 @@ W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32
         h.rc = !(ek == f);
         h.elen = elen - K + 1;
         uint32_t len = 1;
+        // matchLen (:341-350), 32 bases per step: XOR of two packed words, first differing 2-bit group by count-trailing-zeros
         if (!h.rc) {
             uint64_t rp = (uint64_t)itr + K, e2 = (uint64_t)o + K;
-            while (rp < rlen && e2 < elen && packed_base(bases, rp) == packed_base(ep, e2)) { ++len; ++rp; ++e2; }
+            while (rp < rlen && e2 < elen) {
+                uint64_t n = rlen - rp < elen - e2 ? rlen - rp : elen - e2;
+                if (n > 32) n = 32;
+                uint64_t x = bases32_at(bases, rp) ^ bases32_at(ep, e2);
+                if (n < 32) x &= (1ull << (2 * n)) - 1;
+                if (x) { len += (uint32_t)(ctz64(x) >> 1); break; }
+                len += (uint32_t)n; rp += n; e2 += n;
+            }
             h.off = o;
         } else {
             uint64_t ro = (uint64_t)elen - o;               // position in rc(edge) just past the k-mer
             uint64_t rp = (uint64_t)itr + K, e2 = ro;
-            while (rp < rlen && e2 < elen && packed_base(bases, rp) == 3u - packed_base(ep, (uint64_t)elen - 1 - e2)) { ++len; ++rp; ++e2; }
+            while (rp < rlen && e2 < elen) {
+                uint64_t n = rlen - rp < elen - e2 ? rlen - rp : elen - e2;
+                if (n > 32) n = 32;
+                // rc(edge)[e2 .. e2+n) = reverse complement of edge[elen-e2-n .. elen-e2)
+                uint64_t c = rev2(~bases32_at(ep, (uint64_t)elen - e2 - n)) >> (2 * (32 - n));
+                uint64_t x = bases32_at(bases, rp) ^ c;
+                if (n < 32) x &= (1ull << (2 * n)) - 1;
+                if (x) { len += (uint32_t)(ctz64(x) >> 1); break; }
+                len += (uint32_t)n; rp += n; e2 += n;
+            }
             h.off = (uint32_t)(ro - K);
         }
         h.len = len;

@@ -245,17 +245,27 @@ struct Pipeline {
             if (attempt > 8) W2R_FAIL(W2RAP_ERR_INTERNAL, "k-mer partitioning did not converge");
             const uint64_t P = 1ull << logP, Pown = P / world;
             // sub-buffers: 8 per partition, cursors on separate L2 lines
-            const uint32_t nsub = (n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
+            // single GPU: chunked partition buffers (one pass, TLB-friendly); several GPUs: static sub-buffers = contiguous slabs to exchange
+            const bool chunked = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS");
+            const uint32_t nsub = (!chunked && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
             const uint32_t cstride = 32;
             const uint64_t NB = P * nsub, NBown = Pown * nsub;
-            const uint64_t cap = (uint64_t)((double)n_inst_max / (double)NB / (double)npass * slack) + 1024;
-            const size_t rec_bytes = NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);      // + the receive slabs
+            const uint32_t logC = 11;                                    // 2048 records = 32 KB per chunk
+            const uint64_t per_part = (uint64_t)((double)n_inst_max / (double)NB / (double)npass);
+            const uint32_t maxk = (uint32_t)((per_part * slack * 1.5) / (1u << logC)) + 4;
+            const uint64_t pool_chunks = chunked ? (uint64_t)((double)n_inst_max / npass * 1.01) / (1u << logC) + 2 * P + 1024 : 0;
+            const uint64_t cap = chunked ? (uint64_t)maxk << logC : (uint64_t)((double)per_part * slack) + 1024;
+            const size_t rec_bytes = chunked ? (pool_chunks << logC) * sizeof(ulonglong2) : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
             // Scattered appends over a record buffer of tens of GB run into TLB misses (measured: the same kernel is 2x faster per
             // record on a 41 GB buffer than on an 82 GB one), so the buffer is also capped and the k-mer space split into more
             // hash-range passes instead; extraction is repeated per pass, which is cheap next to the appends.
             static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
-            if ((rec_bytes + fixed_bytes > budget || (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9) && npass < 4096) { npass *= 2; continue; }
-            SBuf<ulonglong2> recs(c, NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            if ((rec_bytes + fixed_bytes > budget || (!chunked && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) && npass < 4096) { npass *= 2; continue; }
+            if (pool_chunks >= 0xfffffff0ull) { npass *= 2; continue; }
+            SBuf<ulonglong2> recs(c, chunked ? (pool_chunks << logC) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 1);
+            std::vector<uint32_t> first_chunks;
+            if (chunked) { first_chunks.resize(P); for (uint64_t q = 0; q < P; ++q) first_chunks[q] = (uint32_t)q; }
             SBuf<uint32_t> cursor(c, NB * cstride), xcur_buf(c, world > 1 ? NB * cstride : 0);
             const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;          // [world][NBown][cap]: what this rank reduces
             const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [world][NBown][cstride]
@@ -267,7 +277,14 @@ struct Pipeline {
             uint64_t solid_used_before = 0;
             for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
                 cursor.zero();
-                PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1};
+                if (chunked) {      // chunk 0 of partition p is pool chunk p; everything else is allocated on the fly
+                    chunk_of.fill_ff();
+                    W2R_CUDA(cudaMemcpy2DAsync(chunk_of.p, (size_t)maxk * 4, first_chunks.data(), 4, 4, P, cudaMemcpyHostToDevice, c.stream));
+                    const uint32_t p32 = (uint32_t)P;
+                    W2R_CUDA(cudaMemcpyAsync(pool_next.p, &p32, 4, cudaMemcpyHostToDevice, c.stream));
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
+                }
+                PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks};
                 kt.start();
                 if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(dr.n, 256, 8), 256, 0, rv, good.p, pp); c.count_launches++; }
                 part_ms += kt.stop();
@@ -312,8 +329,8 @@ struct Pipeline {
                     if (mxg) {
                         RegionParams rp{region.p, logR, logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
-                        dim3 gr(std::max(1u, std::min<unsigned>((mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * world, 8u))))), gy * world);
-                        k_count_region<<<gr, 256, 0, c.stream>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, rp); c.launches++;
+                        dim3 gr(std::max(1u, std::min<unsigned>(chunked ? ((mxg >> logC) + 1) : (mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * world, 8u))))), gy * world);
+                        k_count_region<<<gr, 256, 0, c.stream>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk}, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
                     ScanParams sp{region.p, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
@@ -530,7 +547,7 @@ struct Pipeline {
         edge_bytes = E ? d2h_scalar(c, tot.p) : 0;
         W2R_CUDA(cudaMemcpyAsync(edge_off.p + E, &edge_bytes, 8, cudaMemcpyHostToDevice, c.stream));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
-        edge_bases.alloc(c, (edge_bytes + 3 + 16) & ~3ull);
+        edge_bases.alloc(c, (edge_bytes + 3 + 32) & ~3ull);
         edge_bases.zero();
         W2R_LAUNCH(c, k_emit_edges, grid(nn, 256), 256, 0, st, R, edge_of_head.p, edge_off.p, edge_bases.p);
         W2R_CUDA(cudaStreamSynchronize(c.stream));
@@ -576,7 +593,20 @@ struct Pipeline {
         d_offset.alloc(c, n); d_path_off.alloc(c, n + 1);
         *n_path_edges = 0; *pathed = 0; *multipathed = 0;
         if (!n) { W2R_CUDA(cudaMemsetAsync(d_path_off.p, 0, 8, c.stream)); return; }
-        GraphView g{st, edge_bases.p, edge_off.p, edge_len.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, from_e.p, to_e.p, from_n.p, to_n.p};
+        // negative-lookup filter, pinned in L2 for the duration of the pathing kernel (kmer.cuh: KmerBloom)
+        SBuf<uint32_t> bloom_words;
+        KmerBloom bloom{nullptr, 0};
+        if (out->n_solid >= 4096 && !getenv("W2RAP_NO_BLOOM")) {
+            uint64_t bytes = std::min<uint64_t>(96ull << 20, std::max<uint64_t>(4096, out->n_solid * 2));
+            if (bytes * 8 >= 3 * out->n_solid) {          // below ~3 bits per key the filter passes most queries: not worth its L2
+                bloom_words.alloc(c, bytes / 4); bloom_words.zero();
+                bloom = KmerBloom{bloom_words.p, bytes / 4};
+                W2R_LAUNCH(c, k_bloom_build, grid(st.size(), 256), 256, 0, st, bloom);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) cudaGetLastError();
+                set_l2_window(bloom_words.p, bytes);
+            }
+        }
+        GraphView g{st, bloom, edge_bases.p, edge_off.p, edge_len.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, from_e.p, to_e.p, from_n.p, to_n.p};
         const ReadsView rv = dr.view();
         const unsigned block = 128;
         const unsigned gr = grid(n, block, 12);
@@ -617,6 +647,7 @@ struct Pipeline {
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         d_path_edges.alloc(c, *n_path_edges);
         W2R_LAUNCH(c, k_path_gather, grid(n, 256), 256, 0, stage.p, cap, meta.p, (const uint32_t*)nullptr, row_off.p, d_path_off.p, n, d_path_edges.p, d_offset.p);
+        if (bloom.words) { set_l2_window(nullptr, 0); if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError(); }
         if (n_ovf) W2R_LAUNCH(c, k_path_gather, grid(n_ovf, 256), 256, 0, stage2.p, cap2, meta2.p, (const uint32_t*)olist.p, row_off2.p, d_path_off.p, n_ovf, d_path_edges.p, d_offset.p);
         W2R_CUDA(cudaStreamSynchronize(c.stream));
     }

@@ -44,14 +44,38 @@ struct PQReader {
 // maximal run of >= K good quals, which a forward scan finds as "the last position at which the current run is >= K".
 // The result is stored in a uint16_t by the reference.  *n_quals receives the number of qualities in the stream.
 W2R_HD uint32_t pq_good_length(const uint8_t* stream, uint32_t min_qual, uint32_t* n_quals) {
-    PQReader r(stream);
+    const uint8_t* p = stream;
     uint32_t run = 0, good = 0, i = 0;
     for (;;) {
-        int q = r.next();
-        if (q < 0) break;
-        ++i;
-        if ((uint32_t)q < min_qual) run = 0;
-        else if (++run >= (uint32_t)K) good = i;
+        const uint32_t nq = *p++;
+        if (!nq) break;
+        const uint32_t hdr = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+        const uint32_t nbits = hdr & 7u, minq = (hdr >> 3) & 63u;
+        if (nbits == 0) {                       // a constant block is one step: the run grows by nq or is reset
+            p += 2;
+            i += nq;
+            if (minq < min_qual) run = 0;
+            else { run += nq; if (run >= (uint32_t)K) good = i; }
+            continue;
+        }
+        if (minq >= min_qual) {                 // every quality of the block is >= minq >= minQual: no need to look at the deltas
+            p += (9u + nq * nbits + 7u) >> 3;
+            i += nq; run += nq;
+            if (run >= (uint32_t)K) good = i;
+            continue;
+        }
+        uint64_t acc = hdr >> 9;
+        uint32_t have = 7;
+        p += 2;
+        const uint32_t mask = (1u << nbits) - 1u;
+        for (uint32_t k = 0; k < nq; ++k) {
+            while (have < nbits) { acc |= (uint64_t)(*p++) << have; have += 8; }
+            const uint32_t q = minq + ((uint32_t)acc & mask);
+            acc >>= nbits; have -= nbits;
+            ++i;
+            if (q < min_qual) run = 0;
+            else if (++run >= (uint32_t)K) good = i;
+        }
     }
     if (n_quals) *n_quals = i;
     return good & 0xffffu;
