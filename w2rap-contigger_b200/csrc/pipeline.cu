@@ -230,11 +230,18 @@ struct Pipeline {
         if (fixed_bytes + (64u << 20) > budget) W2R_FAIL(W2RAP_ERR_OOM, "not enough device memory for the solid k-mer staging buffer");
         SBuf<ulonglong2> solid;                       // solid records of the partitions this rank owns
         uint64_t solid_cap = 0;
-        SBuf<CountSlot> region(c, R);
+        // Two regions on two streams: groups alternate between them, so the scan/reset of one group overlaps the inserts of the next.
+        SBuf<CountSlot> region(c, 2 * R);
         SBuf<DumpRec> dump_dev(c, prm.dump_kmers == 2 ? n_inst : 0);
         SBuf<unsigned long long> hist(c, 104); hist.zero();
-        W2R_LAUNCH(c, k_init_count_table, grid(2 * R, 256), 256, 0, region.p, R);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(R * sizeof(CountSlot), 64u << 20)) != cudaSuccess) cudaGetLastError();
+        W2R_LAUNCH(c, k_init_count_table, grid(4 * R, 256), 256, 0, region.p, 2 * R);
+        cudaStream_t s2 = nullptr;
+        W2R_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        struct StreamGuard { cudaStream_t s; ~StreamGuard() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } } s2_guard{s2};
+        cudaEvent_t ev_fork, ev_join;
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+        struct EventGuard { cudaEvent_t a, b; ~EventGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_guard{ev_fork, ev_join};
+        uint32_t group_parity = 0;
         float part_ms = 0, region_ms = 0, xchg_ms = 0;
         uint32_t npass = 1;
         double slack = 1.06;
@@ -320,21 +327,36 @@ struct Pipeline {
                 }
                 // ---- reduce: groups of consecutive owned partitions share the region; the group size comes from the first partition's distinct count
                 kt.start();
-                set_l2_window(region.p, R * sizeof(CountSlot));
+                // the persisting carve-out is taken from the normal L2, which pass A needs for write combining: hold it only while reducing
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(2 * R * sizeof(CountSlot), 80u << 20)) != cudaSuccess) cudaGetLastError();
+                set_l2_window(region.p, 2 * R * sizeof(CountSlot));
+                {   // the second stream gets the same L2 window and starts after everything queued so far
+                    cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+                    attr.accessPolicyWindow.base_ptr = region.p; attr.accessPolicyWindow.num_bytes = 2 * R * sizeof(CountSlot);
+                    attr.accessPolicyWindow.hitRatio = 1.0f; attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    if (cudaStreamSetAttribute(s2, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+                }
                 SBuf<int> gflag(c, Pown + 1); gflag.zero();
+                auto fork = [&] { W2R_CUDA(cudaEventRecord(ev_fork, c.stream)); W2R_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0)); };
+                auto join = [&] { W2R_CUDA(cudaEventRecord(ev_join, s2)); W2R_CUDA(cudaStreamWaitEvent(c.stream, ev_join, 0)); };
+                fork();
                 auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag) {
                     ++n_groups;
                     uint32_t mxg = 0;
                     for (uint32_t q = p0; q < p0 + g; ++q) mxg = std::max(mxg, sizes[q]);
+                    cudaStream_t gs = (group_parity & 1u) ? s2 : c.stream;
+                    CountSlot* greg = region.p + ((group_parity & 1u) ? R : 0);
+                    ++group_parity;
                     if (mxg) {
-                        RegionParams rp{region.p, logR, logP, sub_mask, sub_id, flag};
+                        RegionParams rp{greg, logR, logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
                         dim3 gr(std::max(1u, std::min<unsigned>(chunked ? ((mxg >> logC) + 1) : (mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * world, 8u))))), gy * world);
-                        k_count_region<<<gr, 256, 0, c.stream>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk}, rp); c.launches++;
+                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk}, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
-                    ScanParams sp{region.p, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
-                    W2R_LAUNCH(c, k_scan_region, grid(R, 256, 4), 256, 0, sp);
+                    ScanParams sp{greg, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
+                    k_scan_region<<<grid(R, 256, 4), 256, 0, gs>>>(sp); c.launches++;
+                    W2R_CUDA(cudaGetLastError());
                 };
                 uint32_t g = 1;
                 std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first owned partition, count)
@@ -355,6 +377,7 @@ struct Pipeline {
                         groups.push_back({(uint32_t)p0, gg});
                     }
                 }
+                join();
                 std::vector<int> gf(Pown + 1);
                 W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (Pown + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
                 W2R_CUDA(cudaStreamSynchronize(c.stream));
@@ -367,14 +390,14 @@ struct Pipeline {
                         W2R_CUDA(cudaMemcpyAsync(snapshot, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
                         W2R_CUDA(cudaMemcpyAsync(hist_snapshot.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
                         W2R_CUDA(cudaMemsetAsync(gflag.p + Pown, 0, sizeof(int), c.stream));
-                        run_group(q, 1, 0, 0, gflag.p + Pown);
+                        fork(); run_group(q, 1, 0, 0, gflag.p + Pown); join();
                         if (!d2h_scalar(c, gflag.p + Pown)) continue;
                         for (uint32_t S = 2;; S *= 2) {
                             if (S > 4096) W2R_FAIL(W2RAP_ERR_INTERNAL, "a k-mer partition does not fit the counting region even in 4096 hash sub-ranges");
                             bool ok = true;
                             for (uint32_t sid = 0; sid < S && ok; ++sid) {
                                 W2R_CUDA(cudaMemsetAsync(gflag.p + Pown, 0, sizeof(int), c.stream));
-                                run_group(q, 1, S - 1, sid, gflag.p + Pown);
+                                fork(); run_group(q, 1, S - 1, sid, gflag.p + Pown); join();
                                 if (d2h_scalar(c, gflag.p + Pown)) ok = false;
                             }
                             if (ok) break;
@@ -387,6 +410,8 @@ struct Pipeline {
                 }
                 set_l2_window(nullptr, 0);
                 region_ms += kt.stop();
+                if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
                 {
                     std::vector<unsigned long long> hh(104);
                     W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
@@ -647,7 +672,12 @@ struct Pipeline {
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         d_path_edges.alloc(c, *n_path_edges);
         W2R_LAUNCH(c, k_path_gather, grid(n, 256), 256, 0, stage.p, cap, meta.p, (const uint32_t*)nullptr, row_off.p, d_path_off.p, n, d_path_edges.p, d_offset.p);
-        if (bloom.words) { set_l2_window(nullptr, 0); if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError(); }
+        if (bloom.words) {
+            set_l2_window(nullptr, 0);
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
+        }
         if (n_ovf) W2R_LAUNCH(c, k_path_gather, grid(n_ovf, 256), 256, 0, stage2.p, cap2, meta2.p, (const uint32_t*)olist.p, row_off2.p, d_path_off.p, n_ovf, d_path_edges.p, d_offset.p);
         W2R_CUDA(cudaStreamSynchronize(c.stream));
     }
