@@ -203,8 +203,10 @@ def main():
     barrier()
     t0 = time.time()
     e2e_d2h = 0
+    e2e_t = []
     for _ in range(args.steps):
-        _, e2e_d2h = step_e2e()
+        tt_e, e2e_d2h = step_e2e()
+        e2e_t.append(tt_e)
     barrier()
     e2e_ms = (time.time() - t0) / args.steps * 1e3
     stop.set()
@@ -256,7 +258,8 @@ def main():
                    "cache": "inputs (%.1f GB) and counting table larger than the 126 MB L2" % (b_in / 1e9),
                    "kmer_instances": I, "distinct": D, "solid": S, "edges": E, "reads_pathed": pathed,
                    "parallelism": "one process per GPU; reads sharded by index, k-mer records routed to owner GPUs by hash partition (NCCL all-to-all), solid records all-gathered, graph built on every rank, reads pathed by shard"},
-        "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms},
+        "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms,
+                "inside": {k: sum(t[k] for t in e2e_t) / len(e2e_t) for k in ("h2d_ms", "total_ms", "count_ms", "count_kernel_ms", "region_ms", "path_ms", "d2h_ms", "host_pre_ms", "host_post_ms", "wall_ms")}},
         "gpu_launches": int(tt[-1]["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_count / max(1, count_launches), "launches_per_step": count_launches,

@@ -105,6 +105,9 @@ typedef struct w2rap_timings {
     float count_kernel_ms;        /* the extract+partition kernel (k_extract_partition) launches only */
     float region_ms;              /* the L2-resident count: all k_count_region + k_scan_region launches */
     float exchange_ms;            /* multi-GPU only: NCCL all-to-all of k-mer records + all-gather of the solid records */
+    float host_pre_ms;            /* host wall time from entry to the first pipeline launch (validation, allocation, copy enqueue) */
+    float host_post_ms;           /* host wall time after the pipeline finished (buffer release, stream teardown) */
+    float wall_ms;                /* host wall time of the whole call */
     uint32_t count_launches;      /* launches of k_extract_partition */
     uint32_t kernel_launches;     /* all kernels launched by this call */
     uint32_t count_passes;        /* partition groups reduced through the counting region */

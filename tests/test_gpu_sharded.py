@@ -46,7 +46,7 @@ def run_sharded(T, rs, world, **kw):
     return results, bounds
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_equals_oracle(T, world):
     rs = T.rich_set(seed=12, genome=80000, cov=50, families=5, palindromes=3, plasmid=1500)
     want = T.run_oracle(rs, T.default_params(dump_kmers=1, apply_fixpaths=1))

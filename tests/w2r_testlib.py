@@ -36,7 +36,7 @@ class Params(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "count_ms", "solid_ms", "adjacency_ms", "unipath_ms", "hbv_ms",
-                                         "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms", "exchange_ms")] + \
+                                         "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms", "exchange_ms", "host_pre_ms", "host_post_ms", "wall_ms")] + \
                [(n, C.c_uint32) for n in ("count_launches", "kernel_launches", "count_passes", "reserved")]
 
 

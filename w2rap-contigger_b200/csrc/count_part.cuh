@@ -86,10 +86,19 @@ struct PartEmit {
     }
 };
 
+// chunk 0 of partition p is pool chunk p; everything else is allocated on the fly.  (A kernel, not a memcpy: while the read
+// stores are still being uploaded the H2D copy engine is busy, and a small copy would queue behind gigabytes of reads.)
+__global__ void k_init_chunks(uint32_t* chunk_of, uint32_t maxk, uint32_t P, uint32_t* pool_next) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)P * maxk; i += (uint64_t)gridDim.x * blockDim.x)
+        chunk_of[i] = (i % maxk == 0) ? (uint32_t)(i / maxk) : NIL;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *pool_next = P;
+}
+
 // paths/long/BuildReadQGraph.cc:1062-1080 (the "map" step): one thread per read.
-__global__ void __launch_bounds__(256) k_extract_partition(ReadsView r, const uint16_t* __restrict__ good, PartParams pp) {
+__global__ void __launch_bounds__(256) k_extract_partition(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, PartParams pp) {
     const uint32_t sub = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (pp.nsub - 1);   // per warp
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t end = first + count;
+    for (uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t gl = good[i];
         if (gl > (uint32_t)K) {
             PartEmit emit(pp, sub);

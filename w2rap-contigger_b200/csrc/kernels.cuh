@@ -72,11 +72,13 @@ __global__ void k_init_count_table(CountSlot* tab, uint64_t T) {
 }
 
 // paths/long/BuildReadQGraph.cc:962-987: one thread decodes one read's PQVec stream and finds its good length.
-__global__ void k_good_len(ReadsView r, uint32_t min_qual, uint16_t* __restrict__ good, unsigned long long* __restrict__ n_inst, int* __restrict__ bad) {
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < r.n; base += (uint64_t)gridDim.x * blockDim.x) {
+__global__ void k_good_len(ReadsView r, uint64_t first, uint64_t count, uint32_t min_qual, uint16_t* __restrict__ good, unsigned long long* __restrict__ n_inst,
+                           int* __restrict__ bad) {
+    const uint64_t end = first + count;
+    for (uint64_t base = first + (uint64_t)blockIdx.x * blockDim.x; base < end; base += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t i = base + threadIdx.x;
         unsigned long long mine = 0;
-        if (i < r.n) {
+        if (i < end) {
             uint32_t nq = 0;
             uint32_t gl = pq_good_length(r.quals + r.qual_off[i], min_qual, &nq);
             if (nq != r.len[i]) atomicExch(bad, 1);              // a valid store has one quality per base

@@ -9,8 +9,10 @@
 // No CPU fallback: without a usable sm_100 device every compute entry point fails with W2RAP_ERR_NO_DEVICE.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <mutex>
+#include <thread>
 
 #include "../../include/w2rap_step2.h"
 #include "device_reads.cuh"
@@ -20,6 +22,8 @@
 #include "prims.cuh"
 
 namespace w2r {
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Output arrays live in pinned host memory.  cudaMallocHost is slow (it maps and locks pages), so blocks are kept in a
 // process-wide pool and reused by later calls: steady-state steps pay no allocation.
@@ -67,12 +71,21 @@ static void check_device(int device, Ctx& c) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); W2R_FAIL(W2RAP_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path"); }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     if (device >= n) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d does not exist (%d visible)", device, n);
-    cudaDeviceProp pr;
-    W2R_CUDA(cudaGetDeviceProperties(&pr, device));
-    if (pr.major < 10) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not sm_100; this library only carries sm_100a code", device, pr.name, pr.major, pr.minor);
+    // cudaGetDeviceProperties is slow (it queries everything); three attributes, cached per device, are all that is needed
+    static int cached_major[16], cached_sms[16];
+    static bool cached[16];
+    const int slot = device & 15;
+    if (!cached[slot]) {
+        int major = 0, minor = 0, sms = 0;
+        W2R_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        W2R_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+        W2R_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        if (major < 10) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d (sm_%d%d) is not sm_100; this library only carries sm_100a code", device, major, minor);
+        cached_major[slot] = major; cached_sms[slot] = sms; cached[slot] = true;
+    }
     W2R_CUDA(cudaSetDevice(device));
     c.device = device;
-    c.sm_count = pr.multiProcessorCount;
+    c.sm_count = cached_sms[slot];
     static std::once_flag pool_once[16];
     std::call_once(pool_once[device & 15], [&] {
         cudaMemPool_t pool;
@@ -203,16 +216,20 @@ struct Pipeline {
         scal.zero();
         SBuf<int> flags(c, 4);
         flags.zero();
-        if (dr.n) W2R_LAUNCH(c, k_good_len, grid(dr.n, 128), 128, 0, rv, prm.min_qual, good.p, scal.p, flags.p);
-        const unsigned long long n_inst_local = d2h_scalar(c, scal.p);
-        std::vector<unsigned long long> agg = {n_inst_local, (unsigned long long)d2h_scalar(c, flags.p)};
+        // Everything is sized from an upper bound of the instance count that needs no qualities (sum of len-59), so that the
+        // quality floor + extraction of the first read batch can start while later batches are still crossing PCIe.
+        const unsigned long long n_inst_local = dr.n_inst_upper;
+        std::vector<unsigned long long> agg = {n_inst_local};
         allreduce_u64(agg, ncclSum);
         std::vector<unsigned long long> mx = {n_inst_local};
         allreduce_u64(mx, ncclMax);
-        if (agg[1]) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
-        const unsigned long long n_inst = agg[0], n_inst_max = mx[0];      // whole job / largest shard
-        out->n_kmer_instances = n_inst;
-        say(c, "%llu k-mer instances in quality-floored reads", n_inst);
+        const unsigned long long n_inst = agg[0], n_inst_max = mx[0];      // whole job / largest shard (upper bounds)
+        // read batches: [first, first+count) with an event to wait for (nullptr = already resident)
+        struct Batch { uint64_t first, count; cudaEvent_t ready; };
+        std::vector<Batch> batches;
+        if (!dr.batch_ready.empty()) for (size_t b = 0; b < dr.batch_ready.size(); ++b) batches.push_back(Batch{dr.batch_first[b], dr.batch_first[b + 1] - dr.batch_first[b], dr.batch_ready[b]});
+        else batches.push_back(Batch{0, dr.n, nullptr});
+        bool good_done = false;
 
         // region: the L2-resident counting table.  1 Mi slots x 32 B = 32 MB of the 126 MB L2 (smaller for tiny inputs / the test hook).
         uint32_t logR = 20;
@@ -222,7 +239,9 @@ struct Pipeline {
         // partitions: few enough records each that even an all-distinct partition fits the region at load 0.6;
         // at least one per rank: rank r owns the contiguous range [r*P/world, (r+1)*P/world)
         uint32_t logP = 0;
-        while (((double)n_inst / (double)(1ull << logP) > 0.6 * (double)R || (1ull << logP) < (uint64_t)world) && logP < 24) ++logP;
+        // (n_inst is an upper bound, and real read sets are far from all-distinct: 0.9 R records per partition; a partition that
+        //  does not fit is handled by the hash sub-range fallback)
+        while (((double)n_inst / (double)(1ull << logP) > 0.9 * (double)R || (1ull << logP) < (uint64_t)world) && logP < 24) ++logP;
         size_t budget = (size_t)(device_budget(c) * 0.80);
         if (prm.dump_kmers == 2 && world > 1) W2R_FAIL(W2RAP_ERR_BAD_ARG, "dump level 2 is a single-GPU test hook");
         const size_t fixed_bytes = R * sizeof(CountSlot) + (prm.dump_kmers == 2 ? n_inst * sizeof(DumpRec) : 0) +
@@ -257,7 +276,9 @@ struct Pipeline {
             const uint32_t nsub = (!chunked && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
             const uint32_t cstride = 32;
             const uint64_t NB = P * nsub, NBown = Pown * nsub;
-            const uint32_t logC = 11;                                    // 2048 records = 32 KB per chunk
+            // chunk size: keep the append window (P open chunks) within ~128 MB, i.e. inside the TLB reach; 256..2048 records per chunk
+            uint32_t logC = 11;
+            while (logC > 8 && (P << logC) * sizeof(ulonglong2) > (128ull << 20)) --logC;
             const uint64_t per_part = (uint64_t)((double)n_inst_max / (double)NB / (double)npass);
             const uint32_t maxk = (uint32_t)((per_part * slack * 1.5) / (1u << logC)) + 4;
             const uint64_t pool_chunks = chunked ? (uint64_t)((double)n_inst_max / npass * 1.01) / (1u << logC) + 2 * P + 1024 : 0;
@@ -271,8 +292,6 @@ struct Pipeline {
             if (pool_chunks >= 0xfffffff0ull) { npass *= 2; continue; }
             SBuf<ulonglong2> recs(c, chunked ? (pool_chunks << logC) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
             SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 1);
-            std::vector<uint32_t> first_chunks;
-            if (chunked) { first_chunks.resize(P); for (uint64_t q = 0; q < P; ++q) first_chunks[q] = (uint32_t)q; }
             SBuf<uint32_t> cursor(c, NB * cstride), xcur_buf(c, world > 1 ? NB * cstride : 0);
             const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;          // [world][NBown][cap]: what this rank reduces
             const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [world][NBown][cstride]
@@ -284,17 +303,18 @@ struct Pipeline {
             uint64_t solid_used_before = 0;
             for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
                 cursor.zero();
-                if (chunked) {      // chunk 0 of partition p is pool chunk p; everything else is allocated on the fly
-                    chunk_of.fill_ff();
-                    W2R_CUDA(cudaMemcpy2DAsync(chunk_of.p, (size_t)maxk * 4, first_chunks.data(), 4, 4, P, cudaMemcpyHostToDevice, c.stream));
-                    const uint32_t p32 = (uint32_t)P;
-                    W2R_CUDA(cudaMemcpyAsync(pool_next.p, &p32, 4, cudaMemcpyHostToDevice, c.stream));
-                    W2R_CUDA(cudaStreamSynchronize(c.stream));
-                }
+                if (chunked) W2R_LAUNCH(c, k_init_chunks, grid(P * maxk, 256), 256, 0, chunk_of.p, maxk, (uint32_t)P, pool_next.p);
                 PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks};
                 kt.start();
-                if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(dr.n, 256, 8), 256, 0, rv, good.p, pp); c.count_launches++; }
+                for (const Batch& bt : batches) {
+                    if (!bt.count) continue;
+                    if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
+                    if (!good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
+                    if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(bt.count, 256, 8), 256, 0, rv, bt.first, bt.count, good.p, pp); c.count_launches++; }
+                }
+                good_done = true;
                 part_ms += kt.stop();
+                if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
                 std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, flags.p + 1)};
                 allreduce_u64(of, ncclSum);
                 if (of[0]) {        // a sub-buffer overflowed somewhere (skewed k-mer multiplicities): more slack, on every rank
@@ -426,6 +446,12 @@ struct Pipeline {
             break;
         }
         if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+        {   // the exact instance count of the whole job (the bound above only sized buffers)
+            std::vector<unsigned long long> exact = {(unsigned long long)d2h_scalar(c, scal.p)};
+            allreduce_u64(exact, ncclSum);
+            out->n_kmer_instances = exact[0];
+            say(c, "%llu k-mer instances in quality-floored reads", exact[0]);
+        }
         out->timings.count_kernel_ms = part_ms;
         out->timings.region_ms = region_ms;
         out->timings.exchange_ms = xchg_ms;
@@ -770,44 +796,111 @@ static void validate_reads(const w2rap_reads* in) {
     if (in->n_reads >= (1ull << 32)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "more than 2^32-1 reads on one device");
 }
 
-static void dev_alloc(DeviceReads* d, void** p, size_t bytes, cudaStream_t s) {
+// Device buffers for the read stores of the host-buffer entry points.  They are kept between calls (grow-only, one set per
+// device): taking them from the stream-ordered pool instead fragments it, and the 80+ GB record pool of the counting stage then
+// has to be re-created by the driver on every call (measured: +120 ms per step).
+struct UploadArena {
+    std::mutex mu;
+    bool in_use = false;
+    void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[5] = {0, 0, 0, 0, 0};
+    static UploadArena& get(int device) { static UploadArena* a = new UploadArena[16]; return a[device & 15]; }
+};
+void arena_release(int device) { UploadArena& a = UploadArena::get(device); std::lock_guard<std::mutex> g(a.mu); a.in_use = false; }
+static void dev_alloc(DeviceReads* d, void** p, size_t bytes, cudaStream_t s, int which) {
+    if (d->arena) {
+        UploadArena& a = UploadArena::get(d->device);
+        if (a.cap[which] < bytes) {
+            if (a.buf[which]) cudaFree(a.buf[which]);
+            a.buf[which] = nullptr; a.cap[which] = 0;
+            size_t want = bytes + bytes / 16;
+            W2R_CUDA(cudaMalloc(&a.buf[which], want));
+            a.cap[which] = want;
+        }
+        *p = a.buf[which];
+        return;
+    }
     if (d->pooled) W2R_CUDA(cudaMallocAsync(p, bytes, s)); else W2R_CUDA(cudaMalloc(p, bytes));
 }
-static void upload(const w2rap_reads* in, int device, DeviceReads* d, cudaStream_t s) {
+// Validates the flattened store and starts its transfer.  With `batched`, the copy is issued as up to 8 read batches with an
+// event each and NOT waited for: the pipeline consumes batch b while batch b+1 is in flight.  Host buffers must stay valid until
+// the stream has drained (the entry points synchronise before returning).
+static void upload(const w2rap_reads* in, int device, DeviceReads* d, cudaStream_t s, bool batched) {
     d->device = device;
     d->n = in->n_reads;
     const uint64_t n = d->n;
     d->bases_bytes = n ? in->base_off[n] : 0;
     d->quals_bytes = n ? in->qual_off[n] : 0;
-    uint64_t nb = 0; uint32_t mx = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        uint32_t L = in->len[i];
-        nb += L; if (L > mx) mx = L;
-        if (in->base_off[i + 1] < in->base_off[i] || in->base_off[i + 1] - in->base_off[i] < (uint64_t)(L + 3) / 4) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: base offsets do not hold its %u bases", (unsigned long long)i, L);
-        if (in->qual_off[i + 1] <= in->qual_off[i]) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: empty quality stream (at least the terminator byte is required)", (unsigned long long)i);
+    const double t0 = now_ms();
+    {   // one pass over the offsets/lengths, on a few host threads
+        const unsigned nt = n > (1u << 20) ? 8u : 1u;
+        std::vector<uint64_t> t_nb(nt, 0), t_inst(nt, 0), t_bad(nt, ~0ull);
+        std::vector<uint32_t> t_mx(nt, 0), t_kind(nt, 0);
+        auto work = [&](unsigned t) {
+            uint64_t lo = n * t / nt, hi = n * (t + 1) / nt, nb = 0, inst = 0; uint32_t mx = 0;
+            for (uint64_t i = lo; i < hi; ++i) {
+                uint32_t L = in->len[i];
+                nb += L; if (L > mx) mx = L;
+                if (L > 59) inst += L - 59;
+                if (in->base_off[i + 1] < in->base_off[i] || in->base_off[i + 1] - in->base_off[i] < (uint64_t)(L + 3) / 4) { t_bad[t] = i; t_kind[t] = 1; break; }
+                if (in->qual_off[i + 1] <= in->qual_off[i]) { t_bad[t] = i; t_kind[t] = 2; break; }
+            }
+            t_nb[t] = nb; t_inst[t] = inst; t_mx[t] = mx;
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        uint64_t nb = 0, inst = 0; uint32_t mx = 0;
+        for (unsigned t = 0; t < nt; ++t) {
+            if (t_kind[t] == 1) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: base offsets do not hold its bases", (unsigned long long)t_bad[t]);
+            if (t_kind[t] == 2) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: empty quality stream (at least the terminator byte is required)", (unsigned long long)t_bad[t]);
+            nb += t_nb[t]; inst += t_inst[t]; mx = std::max(mx, t_mx[t]);
+        }
+        if (mx > 65535u) W2R_FAIL(W2RAP_ERR_BAD_ARG, "reads longer than 65535 bases are not supported (the reference stores good lengths in uint16_t)");
+        d->n_bases = nb; d->max_len = mx; d->n_inst_upper = inst;
     }
-    if (mx > 65535u) W2R_FAIL(W2RAP_ERR_BAD_ARG, "reads longer than 65535 bases are not supported (the reference stores good lengths in uint16_t)");
-    d->n_bases = nb; d->max_len = mx;
-    // +32 bytes of padding: the extraction loop may look one byte past a read, and the last stream must end inside the buffer
-    dev_alloc(d, (void**)&d->bases, d->bases_bytes + 32, s);
-    dev_alloc(d, (void**)&d->quals, d->quals_bytes + 32, s);
-    dev_alloc(d, (void**)&d->base_off, (n + 1) * 8, s);
-    dev_alloc(d, (void**)&d->qual_off, (n + 1) * 8, s);
-    dev_alloc(d, (void**)&d->len, (n + 1) * 4, s);
+    const double t1 = now_ms();
+    // +32 bytes of padding: packed bases are read with aligned 8-byte loads that may touch a few bytes past a read
+    if (d->pooled) {        // host-buffer entry point: try to take the per-device arena
+        UploadArena& a = UploadArena::get(device);
+        std::lock_guard<std::mutex> g(a.mu);
+        if (!a.in_use) { a.in_use = true; d->arena = true; }
+    }
+    dev_alloc(d, (void**)&d->bases, d->bases_bytes + 32, s, 0);
+    dev_alloc(d, (void**)&d->quals, d->quals_bytes + 32, s, 1);
+    dev_alloc(d, (void**)&d->base_off, (n + 1) * 8, s, 2);
+    dev_alloc(d, (void**)&d->qual_off, (n + 1) * 8, s, 3);
+    dev_alloc(d, (void**)&d->len, (n + 1) * 4, s, 4);
     W2R_CUDA(cudaMemsetAsync(d->bases + d->bases_bytes, 0, 32, s));
     W2R_CUDA(cudaMemsetAsync(d->quals + d->quals_bytes, 0, 32, s));
+    const double t2 = now_ms();
     if (n) {
-        W2R_CUDA(cudaMemcpyAsync(d->bases, in->bases, d->bases_bytes, cudaMemcpyHostToDevice, s));
-        W2R_CUDA(cudaMemcpyAsync(d->quals, in->quals, d->quals_bytes, cudaMemcpyHostToDevice, s));
-        W2R_CUDA(cudaMemcpyAsync(d->base_off, in->base_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-        W2R_CUDA(cudaMemcpyAsync(d->qual_off, in->qual_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-        W2R_CUDA(cudaMemcpyAsync(d->len, in->len, n * 4, cudaMemcpyHostToDevice, s));
+        const unsigned nbatch = (batched && n >= (1u << 20)) ? 8u : 1u;
+        for (unsigned b = 0; b < nbatch; ++b) {
+            const uint64_t r0 = n * b / nbatch, r1 = n * (b + 1) / nbatch;
+            const uint64_t b0 = in->base_off[r0], b1 = in->base_off[r1], q0 = in->qual_off[r0], q1 = in->qual_off[r1];
+            W2R_CUDA(cudaMemcpyAsync(d->len + r0, in->len + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, s));
+            W2R_CUDA(cudaMemcpyAsync(d->base_off + r0, in->base_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
+            W2R_CUDA(cudaMemcpyAsync(d->qual_off + r0, in->qual_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
+            W2R_CUDA(cudaMemcpyAsync(d->bases + b0, in->bases + b0, b1 - b0, cudaMemcpyHostToDevice, s));
+            W2R_CUDA(cudaMemcpyAsync(d->quals + q0, in->quals + q0, q1 - q0, cudaMemcpyHostToDevice, s));
+            if (batched) {
+                cudaEvent_t e;
+                W2R_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                W2R_CUDA(cudaEventRecord(e, s));
+                d->batch_ready.push_back(e);
+                d->batch_first.push_back(r0);
+            }
+        }
+        if (batched) d->batch_first.push_back(n);
     } else {
         uint64_t z = 0;
         W2R_CUDA(cudaMemcpyAsync(d->base_off, &z, 8, cudaMemcpyHostToDevice, s));
         W2R_CUDA(cudaMemcpyAsync(d->qual_off, &z, 8, cudaMemcpyHostToDevice, s));
     }
-    W2R_CUDA(cudaStreamSynchronize(s));
+    if (!batched) W2R_CUDA(cudaStreamSynchronize(s));
+    if (getenv("W2RAP_TRACE")) fprintf(stderr, "[w2rap] upload: validate %.1f ms, alloc %.1f ms, enqueue %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
 }
 
 static void check_params(const w2rap_params* p) {
@@ -822,7 +915,7 @@ static void check_params(const w2rap_params* p) {
 struct w2rap_comm { int world, rank, device; w2r::ncclComm_t comm; };
 
 namespace w2r {
-static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* out, float h2d_ms, const w2rap_comm* cm = nullptr) {
+static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* out, float h2d_ms, const w2rap_comm* cm = nullptr, double t_entry = 0) {
     GraphOwner* owner = new GraphOwner();
     memset(out, 0, sizeof(*out));
     out->_owner = owner;
@@ -830,9 +923,12 @@ static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* o
         Pipeline pl(dr, *p, out, owner);
         if (cm) { pl.world = cm->world; pl.rank = cm->rank; pl.comm = cm->comm; }
         check_device(dr.device, pl.c);
+        const double t_run = now_ms();
         pl.run();
         out->timings.h2d_ms = h2d_ms;
         out->timings.total_ms += h2d_ms;
+        out->timings.host_pre_ms = t_entry ? (float)(t_run - t_entry) : 0.f;
+        out->timings.wall_ms = (float)(now_ms() - (t_entry ? t_entry : t_run));
     } catch (...) {
         delete owner;
         memset(out, 0, sizeof(*out));
@@ -875,7 +971,7 @@ int w2rap_step2_upload(const w2rap_reads* in, int device, w2rap_device_reads** h
     validate_reads(in);
     Ctx c; check_device(device, c);
     w2rap_device_reads* h = new w2rap_device_reads();
-    try { upload(in, c.device, &h->d, 0); } catch (...) { h->d.release(); delete h; throw; }
+    try { upload(in, c.device, &h->d, 0, false); } catch (...) { h->d.release(); delete h; throw; }
     *handle = h;
     W2R_API_END
 }
@@ -898,6 +994,7 @@ int w2rap_step2_run_resident(w2rap_device_reads* handle, const w2rap_params* p, 
 
 int w2rap_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* out, char* err, size_t errlen) {
     W2R_API_BEGIN
+    const double t_entry = now_ms();
     if (!out) W2R_FAIL(W2RAP_ERR_BAD_ARG, "null output");
     check_params(p);
     validate_reads(in);
@@ -911,11 +1008,16 @@ int w2rap_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* o
     float h2d = 0;
     try {
         cudaEventRecord(e0, us);
-        upload(in, c.device, &d, us);
-        cudaEventRecord(e1, us); cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
-        run_on_device(d, p, out, h2d);
+        upload(in, c.device, &d, us, true);
+        cudaEventRecord(e1, us);
+        run_on_device(d, p, out, 0.f, nullptr, t_entry);          // consumes the batches as they land
+        cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
+        out->timings.h2d_ms = h2d;              // overlapped with the quality floor + extraction, already inside total_ms
     } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    const double t_post = now_ms();
     d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    out->timings.host_post_ms = (float)(now_ms() - t_post);
+    out->timings.wall_ms = (float)(now_ms() - t_entry);
     if (p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
     W2R_API_END
 }
@@ -979,9 +1081,11 @@ int w2rap_step2_run_sharded(const w2rap_reads* shard, const w2rap_params* p, w2r
     float h2d = 0;
     try {
         cudaEventRecord(e0, us);
-        upload(shard, c.device, &d, us);
-        cudaEventRecord(e1, us); cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
-        run_on_device(d, p, out, h2d, comm);
+        upload(shard, c.device, &d, us, true);
+        cudaEventRecord(e1, us);
+        run_on_device(d, p, out, 0.f, comm);
+        cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
+        out->timings.h2d_ms = h2d;
     } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
     d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (comm->rank == 0 && p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
