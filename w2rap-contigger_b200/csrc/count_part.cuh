@@ -32,9 +32,14 @@ struct PartParams {
     // appends stop missing the TLB.  chunk_of[p * maxk + k] = pool chunk holding records [k << logC, (k+1) << logC) of partition p.
     uint32_t chunked, logC, maxk;
     uint32_t* chunk_of;      // NIL = not allocated yet
-    uint32_t* pool_next;     // bump allocator
-    uint32_t pool_chunks;
+    uint32_t* pool_next;     // bump allocators, one per sub-pool, each on its own 128-byte line (stride 32 u32)
+    uint32_t pool_chunks;    // chunks per sub-pool
+    uint32_t npool_log;      // 1 << npool_log sub-pools; partition p allocates from sub-pool p & (npool-1)
+    unsigned long long* ring;// optional [P][2]: (k << 32 | chunk) of the two newest chunks of every partition — small enough to
+                             // stay in L2 when the full table is not (fine partitions: 2^18 x ~1000 entries)
 };
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -49,7 +54,14 @@ struct PartEmit {
     bool pending;
     uint32_t sub;
     __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), bucket(0), pending(false), sub(sub_) {}
-    __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r) {
+    // Both ring entries of a partition in one 16-byte load, issued BEFORE the cursor atomic returns (they are validated by
+    // their chunk-number tag afterwards), so that appending costs one L2 round trip, not two.
+    __device__ __forceinline__ ulonglong2 ring_peek(uint32_t b) const {
+        ulonglong2 e = make_ulonglong2(~0ull, ~0ull);
+        if (pp.ring) asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(e.x), "=l"(e.y) : "l"(pp.ring + 2ull * b) : "memory");
+        return e;
+    }
+    __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r, ulonglong2 peek = make_ulonglong2(~0ull, ~0ull)) {
         if (!pp.chunked) {
             if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
             else atomicExch(pp.overflow, 1);
@@ -59,10 +71,21 @@ struct PartEmit {
         if (k >= pp.maxk) { atomicExch(pp.overflow, 1); return; }
         uint32_t* tab = pp.chunk_of + (uint64_t)b * pp.maxk;
         if (off == (1u << (pp.logC - 1)) && k + 1 < pp.maxk) {        // half way through a chunk: allocate the next one ahead of need
-            const uint32_t g = atomicAdd(pp.pool_next, 1u);
-            if (g < pp.pool_chunks) st_volatile_u32(tab + k + 1, g); else atomicExch(pp.overflow, 1);
+            const uint32_t sp = b & ((1u << pp.npool_log) - 1u);
+            const uint32_t a = atomicAdd(pp.pool_next + sp * 32u, 1u);
+            if (a < pp.pool_chunks) {
+                const uint32_t cid = sp * pp.pool_chunks + a;
+                st_volatile_u32(tab + k + 1, cid);
+                if (pp.ring) st_volatile_u64(pp.ring + 2ull * b + ((k + 1) & 1u), ((unsigned long long)(k + 1) << 32) | cid);
+            } else atomicExch(pp.overflow, 1);
         }
-        uint32_t g = ld_volatile_u32(tab + k);
+        uint32_t g = NIL;
+        if (pp.ring) {
+            unsigned long long e = (k & 1u) ? peek.y : peek.x;
+            if ((uint32_t)(e >> 32) != k) e = ld_volatile_u64(pp.ring + 2ull * b + (k & 1u));       // the peek was too early: look again
+            if ((uint32_t)(e >> 32) == k) g = (uint32_t)e;
+        }
+        if (g == NIL) g = ld_volatile_u32(tab + k);
         while (g == NIL) {                                             // published half a chunk ago in practice
             if (ld_volatile_u32(reinterpret_cast<const uint32_t*>(pp.overflow))) return;
             g = ld_volatile_u32(tab + k);
@@ -78,20 +101,28 @@ struct PartEmit {
         const uint32_t b = part_of_hash(h, pp.logP) * pp.nsub + sub;
         const ulonglong2 r = make_ulonglong2(k.w0, k.w1 | ctx);
         if (!pending) { rec = r; bucket = b; pending = true; return; }
+        const ulonglong2 pk0 = ring_peek(bucket), pk1 = ring_peek(b);
         const uint32_t pos0 = atomicAdd(pp.cursor + (uint64_t)bucket * pp.cstride, 1u);
         const uint32_t pos1 = atomicAdd(pp.cursor + (uint64_t)b * pp.cstride, 1u);
-        put(bucket, pos0, rec);
-        put(b, pos1, r);
+        put(bucket, pos0, rec, pk0);
+        put(b, pos1, r, pk1);
         pending = false;
     }
 };
 
 // chunk 0 of partition p is pool chunk p; everything else is allocated on the fly.  (A kernel, not a memcpy: while the read
 // stores are still being uploaded the H2D copy engine is busy, and a small copy would queue behind gigabytes of reads.)
-__global__ void k_init_chunks(uint32_t* chunk_of, uint32_t maxk, uint32_t P, uint32_t* pool_next) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)P * maxk; i += (uint64_t)gridDim.x * blockDim.x)
-        chunk_of[i] = (i % maxk == 0) ? (uint32_t)(i / maxk) : NIL;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *pool_next = P;
+// Chunk 0 of partition p is entry p >> npool_log of sub-pool p & (npool-1).
+__global__ void k_init_chunks(uint32_t* chunk_of, uint32_t maxk, uint32_t P, uint32_t* pool_next, uint32_t pool_chunks, uint32_t npool_log, unsigned long long* ring) {
+    const uint32_t npool = 1u << npool_log;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)P * maxk; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)(i / maxk);
+        const bool first = i % maxk == 0;
+        const uint32_t cid0 = (p & (npool - 1u)) * pool_chunks + (p >> npool_log);
+        chunk_of[i] = first ? cid0 : NIL;
+        if (first && ring) { ring[2ull * p] = cid0; ring[2ull * p + 1] = ~0ull; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < npool) pool_next[threadIdx.x * 32u] = P >> npool_log;
 }
 
 // paths/long/BuildReadQGraph.cc:1062-1080 (the "map" step): one thread per read.
@@ -205,6 +236,98 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
         const ulonglong2 rb = two ? __ldcs(base + i + stride) : make_ulonglong2(0, 0);
         region_count_pair(rp, mask, ra, rb, two);
     }
+}
+
+// ---------------------------------------------------------------- reduce in SHARED memory (fine partitions, single GPU)
+// With ~2^18 partitions a partition holds ~20 k records and a few thousand distinct k-mers: one CTA counts it in a shared-memory
+// table, so the per-record atomics are shared-memory atomics instead of L2 atomics (the L2-resident region count is limited by
+// L2 atomic throughput, about one record per 30 ps chip-wide).  One warp streams one 32-record chunk (512 contiguous bytes).
+// Partitions whose distinct k-mers do not fit are listed in `failed` and go through the region path afterwards.
+constexpr uint32_t SMEM_SLOTS = 8192;                          // 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
+constexpr uint32_t SMEM_MAX_PROBE = 512;
+struct SmemCountParams {
+    const ulonglong2* recs;
+    const uint32_t* cursor;         // records per partition
+    const uint32_t* chunk_of;       // [P][maxk]
+    uint32_t logC, maxk, P, logP;
+    uint32_t min_freq;
+    unsigned long long* hist;       // [104]
+    ulonglong2* solid_out; unsigned long long* solid_cursor; uint64_t solid_cap; int* solid_overflow;
+    DumpRec* dump_out; unsigned long long* dump_cursor;
+    uint32_t* failed; unsigned long long* failed_cursor;       // partitions that need the region path
+};
+__global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* w0s = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* w1s = w0s + SMEM_SLOTS;
+    uint32_t* ccs = reinterpret_cast<uint32_t*>(w1s + SMEM_SLOTS);          // count (low 24 bits) | ctx << 24
+    __shared__ unsigned int sh_hist[104];
+    __shared__ int sh_fail;
+    for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
+    const uint32_t C = 1u << sp.logC;
+    for (uint32_t p = blockIdx.x; p < sp.P; p += gridDim.x) {
+        for (uint32_t j = threadIdx.x; j < SMEM_SLOTS; j += blockDim.x) { w0s[j] = ~0ull; w1s[j] = ~0ull; ccs[j] = 0; }
+        if (threadIdx.x == 0) sh_fail = 0;
+        __syncthreads();
+        const uint32_t n = sp.cursor[p];
+        const uint32_t* tab = sp.chunk_of + (uint64_t)p * sp.maxk;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t cid = __ldg(tab + (i >> sp.logC));
+            const ulonglong2 rec = __ldcs(sp.recs + (((uint64_t)cid) << sp.logC) + (i & (C - 1u)));
+            const unsigned long long kw0 = rec.x, kw1 = rec.y & ~0xffull;
+            const uint32_t ctx = (uint32_t)rec.y & 0xffu;
+            const uint64_t h = kmer_hash(Kmer{kw0, kw1});
+            uint32_t s = (uint32_t)((sp.logP ? (h << sp.logP) : h) >> (64 - 13));            // 13 bits below the partition bits
+            bool done = false;
+            for (uint32_t probe = 0; probe < SMEM_MAX_PROBE && !done; ++probe) {
+                unsigned long long k0 = *(volatile unsigned long long*)(w0s + s);
+                bool mine = false;
+                if (k0 == ~0ull) {
+                    const unsigned long long old = atomicCAS(w0s + s, ~0ull, kw0);
+                    if (old == ~0ull) { *(volatile unsigned long long*)(w1s + s) = kw1; __threadfence_block(); mine = true; }
+                    else k0 = old;
+                }
+                if (!mine && k0 == kw0) {                     // same first 32 bases: the owner publishes the second word right after its CAS
+                    unsigned long long w = *(volatile unsigned long long*)(w1s + s);
+                    while (w == ~0ull) w = *(volatile unsigned long long*)(w1s + s);
+                    mine = (w == kw1);
+                }
+                if (mine) {
+                    const uint32_t old = atomicAdd(ccs + s, 1u);
+                    if ((((old >> 24) & ctx) != ctx)) atomicOr(ccs + s, ctx << 24);
+                    done = true;
+                } else s = (s + 1u) & (SMEM_SLOTS - 1u);
+            }
+            if (!done) sh_fail = 1;
+        }
+        __syncthreads();
+        const bool failed = sh_fail != 0;
+        if (failed) {
+            if (threadIdx.x == 0) sp.failed[atomicAdd(sp.failed_cursor, 1ull)] = p;
+        } else {
+            for (uint32_t base = 0; base < SMEM_SLOTS; base += blockDim.x) {
+                const uint32_t j = base + threadIdx.x;
+                const unsigned long long k0 = w0s[j];
+                const bool occ = k0 != ~0ull;
+                const uint32_t cc = ccs[j];
+                uint32_t c = cc & 0xffffffu; if (c > 255u) c = 255u;
+                const uint32_t ctx = cc >> 24;
+                const uint32_t bin = occ ? (c > 100u ? 100u : c) : 103u;
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (occ && (peers & ((1u << lane_id()) - 1u)) == 0) atomicAdd(&sh_hist[bin], (unsigned)__popc(peers));
+                const bool solid = occ && c >= sp.min_freq;
+                const uint64_t pos = warp_append(sp.solid_cursor, solid);
+                if (solid) { if (pos < sp.solid_cap) sp.solid_out[pos] = make_ulonglong2(k0, w1s[j] | ctx); else atomicExch(sp.solid_overflow, 1); }
+                if (sp.dump_out) {
+                    const uint64_t dp = warp_append(sp.dump_cursor, occ);
+                    if (occ) sp.dump_out[dp] = DumpRec{k0, w1s[j], c, ctx, NIL, 0};
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j <= 100; j += blockDim.x) if (sh_hist[j]) atomicAdd(&sp.hist[j], (unsigned long long)sh_hist[j]);
 }
 
 struct ScanParams {

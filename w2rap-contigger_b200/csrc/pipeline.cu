@@ -238,7 +238,12 @@ struct Pipeline {
         const uint64_t R = 1ull << logR;
         // partitions: few enough records each that even an all-distinct partition fits the region at load 0.6;
         // at least one per rank: rank r owns the contiguous range [r*P/world, (r+1)*P/world)
+        // single GPU: FINE partitions (~24 k records each) that one CTA counts in shared memory (count_part.cuh: k_count_smem)
+        const bool fine = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS") && !getenv("W2RAP_COARSE");
         uint32_t logP = 0;
+        static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : 24000.0;
+        if (fine) { while ((double)n_inst / (double)(1ull << logP) > fine_recs && logP < 22) ++logP; }
+        else
         // (n_inst is an upper bound, and real read sets are far from all-distinct: 0.9 R records per partition; a partition that
         //  does not fit is handled by the hash sub-range fallback)
         while (((double)n_inst / (double)(1ull << logP) > 0.9 * (double)R || (1ull << logP) < (uint64_t)world) && logP < 24) ++logP;
@@ -274,24 +279,28 @@ struct Pipeline {
             // single GPU: chunked partition buffers (one pass, TLB-friendly); several GPUs: static sub-buffers = contiguous slabs to exchange
             const bool chunked = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS");
             const uint32_t nsub = (!chunked && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
-            const uint32_t cstride = 32;
+            const uint32_t cstride = fine ? 1 : 32;
             const uint64_t NB = P * nsub, NBown = Pown * nsub;
-            // chunk size: keep the append window (P open chunks) within ~128 MB, i.e. inside the TLB reach; 256..2048 records per chunk
+            // chunk size: keep the append window (P open chunks) within ~128 MB, i.e. inside the TLB reach
             uint32_t logC = 11;
-            while (logC > 8 && (P << logC) * sizeof(ulonglong2) > (128ull << 20)) --logC;
+            static const double window_mb = getenv("W2RAP_WINDOW_MB") ? atof(getenv("W2RAP_WINDOW_MB")) : 128.0;
+            while (logC > (fine ? 4u : 8u) && (double)((P << logC) * sizeof(ulonglong2)) > window_mb * 1048576.0) --logC;
             const uint64_t per_part = (uint64_t)((double)n_inst_max / (double)NB / (double)npass);
             const uint32_t maxk = (uint32_t)((per_part * slack * 1.5) / (1u << logC)) + 4;
-            const uint64_t pool_chunks = chunked ? (uint64_t)((double)n_inst_max / npass * 1.01) / (1u << logC) + 2 * P + 1024 : 0;
+            const uint32_t npool_log = fine ? std::min<uint32_t>(6, logP) : 0;       // bump allocators: one address would serialise 10^8 chunk allocations
+            const uint64_t chunks_total = chunked ? (uint64_t)((double)n_inst_max / npass * 1.01) / (1u << logC) + 2 * P + 1024 : 0;
+            const uint64_t pool_chunks = chunked ? (uint64_t)((double)(chunks_total >> npool_log) * (npool_log ? 1.05 : 1.0)) + 1024 : 0;   // per sub-pool
             const uint64_t cap = chunked ? (uint64_t)maxk << logC : (uint64_t)((double)per_part * slack) + 1024;
-            const size_t rec_bytes = chunked ? (pool_chunks << logC) * sizeof(ulonglong2) : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
+            const size_t rec_bytes = chunked ? ((pool_chunks << npool_log) << logC) * sizeof(ulonglong2) : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
             // Scattered appends over a record buffer of tens of GB run into TLB misses (measured: the same kernel is 2x faster per
             // record on a 41 GB buffer than on an 82 GB one), so the buffer is also capped and the k-mer space split into more
             // hash-range passes instead; extraction is repeated per pass, which is cheap next to the appends.
             static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
             if ((rec_bytes + fixed_bytes > budget || (!chunked && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) && npass < 4096) { npass *= 2; continue; }
-            if (pool_chunks >= 0xfffffff0ull) { npass *= 2; continue; }
-            SBuf<ulonglong2> recs(c, chunked ? (pool_chunks << logC) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
-            SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 1);
+            if ((pool_chunks << npool_log) >= 0xfffffff0ull) { npass *= 2; continue; }
+            SBuf<ulonglong2> recs(c, chunked ? ((pool_chunks << npool_log) << logC) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 32ull << npool_log);
+            SBuf<unsigned long long> ring(c, fine ? 2 * P : 0);
             SBuf<uint32_t> cursor(c, NB * cstride), xcur_buf(c, world > 1 ? NB * cstride : 0);
             const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;          // [world][NBown][cap]: what this rank reduces
             const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [world][NBown][cstride]
@@ -303,8 +312,8 @@ struct Pipeline {
             uint64_t solid_used_before = 0;
             for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
                 cursor.zero();
-                if (chunked) W2R_LAUNCH(c, k_init_chunks, grid(P * maxk, 256), 256, 0, chunk_of.p, maxk, (uint32_t)P, pool_next.p);
-                PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks};
+                if (chunked) W2R_LAUNCH(c, k_init_chunks, grid(P * maxk, 256), 256, 0, chunk_of.p, maxk, (uint32_t)P, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr);
+                PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr};
                 kt.start();
                 for (const Batch& bt : batches) {
                     if (!bt.count) continue;
@@ -380,6 +389,24 @@ struct Pipeline {
                 };
                 uint32_t g = 1;
                 std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first owned partition, count)
+                std::vector<int> gf(Pown + 1, 0);
+                if (fine) {
+                    // every partition is counted by one CTA in shared memory; the few that do not fit are redone through the region below
+                    SBuf<uint32_t> failed(c, P);
+                    W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 8, c.stream));
+                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, logC, maxk, (uint32_t)P, logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
+                                       prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4};
+                    const size_t smem_bytes = (size_t)SMEM_SLOTS * 20;
+                    static bool attr_set = false;
+                    if (!attr_set) { W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_set = true; }
+                    k_count_smem<<<(unsigned)std::min<uint64_t>(P, (uint64_t)c.sm_count), 1024, smem_bytes, c.stream>>>(sc); c.launches++; ++n_groups;
+                    W2R_CUDA(cudaGetLastError());
+                    const uint64_t nfail = d2h_scalar(c, scal.p + 4);
+                    std::vector<uint32_t> fl(nfail);
+                    if (nfail) { W2R_CUDA(cudaMemcpyAsync(fl.data(), failed.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream)); W2R_CUDA(cudaStreamSynchronize(c.stream)); }
+                    for (uint32_t q : fl) { groups.push_back({q, 1u}); gf[q] = 1; }
+                    if (nfail) say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)P);
+                } else {
                 run_group(0, 1, 0, 0, gflag.p + 0);                  // first partition alone: its distinct count sizes the groups
                 groups.push_back({0u, 1u});
                 if (Pown > 1) {
@@ -398,9 +425,9 @@ struct Pipeline {
                     }
                 }
                 join();
-                std::vector<int> gf(Pown + 1);
                 W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (Pown + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
                 W2R_CUDA(cudaStreamSynchronize(c.stream));
+                }
                 for (auto& gr : groups) {
                     if (!gf[gr.first]) continue;
                     // the group did not fit together: its partitions one by one, and a partition that still fails in hash sub-ranges
