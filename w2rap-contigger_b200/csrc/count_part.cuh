@@ -54,14 +54,7 @@ struct PartEmit {
     bool pending;
     uint32_t sub;
     __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), bucket(0), pending(false), sub(sub_) {}
-    // Both ring entries of a partition in one 16-byte load, issued BEFORE the cursor atomic returns (they are validated by
-    // their chunk-number tag afterwards), so that appending costs one L2 round trip, not two.
-    __device__ __forceinline__ ulonglong2 ring_peek(uint32_t b) const {
-        ulonglong2 e = make_ulonglong2(~0ull, ~0ull);
-        if (pp.ring) asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(e.x), "=l"(e.y) : "l"(pp.ring + 2ull * b) : "memory");
-        return e;
-    }
-    __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r, ulonglong2 peek = make_ulonglong2(~0ull, ~0ull)) {
+    __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r) {
         if (!pp.chunked) {
             if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
             else atomicExch(pp.overflow, 1);
@@ -81,8 +74,7 @@ struct PartEmit {
         }
         uint32_t g = NIL;
         if (pp.ring) {
-            unsigned long long e = (k & 1u) ? peek.y : peek.x;
-            if ((uint32_t)(e >> 32) != k) e = ld_volatile_u64(pp.ring + 2ull * b + (k & 1u));       // the peek was too early: look again
+            const unsigned long long e = ld_volatile_u64(pp.ring + 2ull * b + (k & 1u));
             if ((uint32_t)(e >> 32) == k) g = (uint32_t)e;
         }
         if (g == NIL) g = ld_volatile_u32(tab + k);
@@ -101,11 +93,10 @@ struct PartEmit {
         const uint32_t b = part_of_hash(h, pp.logP) * pp.nsub + sub;
         const ulonglong2 r = make_ulonglong2(k.w0, k.w1 | ctx);
         if (!pending) { rec = r; bucket = b; pending = true; return; }
-        const ulonglong2 pk0 = ring_peek(bucket), pk1 = ring_peek(b);
         const uint32_t pos0 = atomicAdd(pp.cursor + (uint64_t)bucket * pp.cstride, 1u);
         const uint32_t pos1 = atomicAdd(pp.cursor + (uint64_t)b * pp.cstride, 1u);
-        put(bucket, pos0, rec, pk0);
-        put(b, pos1, r, pk1);
+        put(bucket, pos0, rec);
+        put(b, pos1, r);
         pending = false;
     }
 };
@@ -126,7 +117,7 @@ __global__ void k_init_chunks(uint32_t* chunk_of, uint32_t maxk, uint32_t P, uin
 }
 
 // paths/long/BuildReadQGraph.cc:1062-1080 (the "map" step): one thread per read.
-__global__ void __launch_bounds__(256) k_extract_partition(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, PartParams pp) {
+__global__ void __launch_bounds__(256, 6) k_extract_partition(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, PartParams pp) {
     const uint32_t sub = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (pp.nsub - 1);   // per warp
     const uint64_t end = first + count;
     for (uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -183,8 +174,9 @@ __device__ __forceinline__ void region_insert(const RegionParams& rp, uint64_t m
 __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64_t mask, ulonglong2 ra, ulonglong2 rb, bool two) {
     const uint64_t ha = kmer_hash(Kmer{ra.x, ra.y & ~0xffull});
     const uint64_t hb = kmer_hash(Kmer{rb.x, rb.y & ~0xffull});
-    const bool da = !rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id;
-    const bool db = two && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
+    // (records with w0 == ~0 are sentinels of count2.cuh's CTA-private runs: skipped)
+    const bool da = ra.x != ~0ull && (!rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id);
+    const bool db = two && rb.x != ~0ull && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
     CountSlot* qa = rp.region + region_slot_of_hash(ha, rp.logP, rp.logR);
     CountSlot* qb = rp.region + region_slot_of_hash(hb, rp.logP, rp.logR);
     uint64_t a0 = 0, a1 = 0, am = 0, b0 = 0, b1 = 0, bm = 0;

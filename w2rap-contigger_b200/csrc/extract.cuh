@@ -5,34 +5,45 @@
 
 namespace w2r {
 
-// Calls emit(canonical k-mer, context byte) for every k-mer of the quality-floored read prefix [0, good_len).
+// Resumable form of the extraction loop: open() a read, then next() yields one (canonical k-mer, context) at a time.
 //   - only reads with good_len > K contribute (BuildReadQGraph.cc:1064)
 //   - first k-mer: successor bit only; last: predecessor bit only (:1066-1078)
 //   - REV k-mers are stored reverse-complemented with the context bit-reversed (:1069,1074,1078); palindromes as seen.
-template <class Emit>
-W2R_HD void extract_read_kmers(const uint8_t* bases, uint32_t good_len, Emit& emit) {
-    if (good_len <= (uint32_t)K) return;
-    Kmer f = kmer_at(bases, 0);
-    Kmer r = kmer_rc(f);
-    const uint32_t last = good_len - K;       // index of the last k-mer
-    uint32_t prev_first = 0;
-    uint64_t buf = 0;                         // the next bases of the read, 32 at a time (one pair of 8-byte loads per 32 k-mers)
-    for (uint32_t j = 0;; ++j) {
+struct KmerCursor {
+    const uint8_t* bases;
+    Kmer f, r;
+    uint64_t buf;             // the next bases of the read, 32 at a time (one pair of 8-byte loads per 32 k-mers)
+    uint32_t j, last, prev_first;
+    bool live;
+    W2R_HD KmerCursor() : bases(nullptr), f{0, 0}, r{0, 0}, buf(0), j(0), last(0), prev_first(0), live(false) {}
+    W2R_HD void open(const uint8_t* b, uint32_t good_len) {
+        live = good_len > (uint32_t)K;
+        if (!live) return;
+        bases = b; f = kmer_at(b, 0); r = kmer_rc(f); last = good_len - K; j = 0; prev_first = 0; buf = 0;
+    }
+    W2R_HD bool next(Kmer* canon, uint32_t* ctx) {
+        if (!live) return false;
         uint32_t nxt = 0, c = 0;
         if ((j & 31u) == 0) buf = bases32_at(bases, (uint64_t)j + K);
         if (j < last) { nxt = (uint32_t)buf & 3u; c |= 1u << nxt; }
         buf >>= 2;
         if (j > 0) c |= 16u << prev_first;
-        {   // select first, emit once: the two orientations must not become two divergent copies of the emit body
-            const bool rev = kmer_less(r, f);
-            const Kmer canon{rev ? r.w0 : f.w0, rev ? r.w1 : f.w1};
-            emit(canon, rev ? ctx_rc(c) : c);
-        }
-        if (j == last) break;
-        prev_first = kmer_first(f);
-        f = kmer_succ(f, nxt);
-        r = kmer_pred(r, 3u - nxt);
+        const bool rev = kmer_less(r, f);       // select first, emit once: no divergent copies of the consumer
+        *canon = Kmer{rev ? r.w0 : f.w0, rev ? r.w1 : f.w1};
+        *ctx = rev ? ctx_rc(c) : c;
+        if (j == last) live = false;
+        else { prev_first = kmer_first(f); f = kmer_succ(f, nxt); r = kmer_pred(r, 3u - nxt); ++j; }
+        return true;
     }
+};
+
+// Calls emit(canonical k-mer, context byte) for every k-mer of the quality-floored read prefix [0, good_len).
+template <class Emit>
+W2R_HD void extract_read_kmers(const uint8_t* bases, uint32_t good_len, Emit& emit) {
+    KmerCursor cur;
+    cur.open(bases, good_len);
+    Kmer k; uint32_t ctx;
+    while (cur.next(&k, &ctx)) emit(k, ctx);
 }
 
 }  // namespace w2r
