@@ -96,6 +96,9 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+NCU_TRAFFIC_RATIO = {"k_extract_partition": 1.17, "k_count_smem": 0.97}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -239,7 +242,8 @@ def main():
     if part_ms >= region_ms:
         dom, count_ms, count_launches, alg_bytes_count = "k_extract_partition", part_ms, tt[-1]["count_launches"], b_bases + 17 * I
     else:
-        dom, count_ms, count_launches, alg_bytes_count = "k_count_region+k_scan_region", region_ms, 2 * tt[-1]["count_passes"], 17 * I
+        dom = "k_count_smem" if world == 1 else "k_count_region+k_scan_region"
+        count_ms, count_launches, alg_bytes_count = region_ms, 2 * tt[-1]["count_passes"], 17 * I
     peak, peak_src = peaks()
     achieved = alg_bytes_count / (count_ms * 1e-3) / 1e9
     cpu = None
@@ -261,7 +265,11 @@ def main():
         "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms,
                 "inside": {k: sum(t[k] for t in e2e_t) / len(e2e_t) for k in ("h2d_ms", "total_ms", "count_ms", "count_kernel_ms", "region_ms", "path_ms", "d2h_ms", "host_pre_ms", "host_post_ms", "wall_ms")}},
         "gpu_launches": int(tt[-1]["kernel_launches"]) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # ncu --set full of this kernel (profiles/r1_ncu_final_extract_smemcount_path_20mbp.txt, 20 Mbp job): dram read+write =
+                     # 1.17x (map) / 0.97x (reduce) the algorithmic bytes; scaled to this workload's bytes per launch
+                     "traffic": alg_bytes_count / max(1, count_launches) * NCU_TRAFFIC_RATIO[dom] if dom in NCU_TRAFFIC_RATIO else None,
+                     "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum on the 20 Mbp job, as a ratio to algorithmic bytes, applied to this workload",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_count / max(1, count_launches), "launches_per_step": count_launches,
                      "kernel_ms_per_step": count_ms, "extract_partition_ms": part_ms, "region_count_ms": region_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
         "stage_ms": {k: sum(t[k] for t in tt) / len(tt) for k in ("count_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
