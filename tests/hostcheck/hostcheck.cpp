@@ -83,6 +83,29 @@ int hc_extract_records(const w2rap_reads* in, uint32_t min_qual, uint32_t logP, 
     *n_out = recs.size(); *recs_out = dup(flat); *owner_out = dup(owner);
     return 0;
 }
+// Strand symmetry of the minimiser partition key (extract.cuh): the k-mer at position j of a read and the k-mer at position
+// len-K-j of its reverse complement are the same canonical k-mer and must get the same key.  Returns the number of mismatches.
+uint64_t hc_minimizer_symmetry(const w2rap_reads* in, uint64_t* n_checked) {
+    uint64_t bad = 0, n = 0;
+    for (uint64_t r = 0; r < in->n_reads; ++r) {
+        const uint32_t len = in->len[r];
+        if (len < (uint32_t)K) continue;
+        const uint8_t* fw = in->bases + in->base_off[r];
+        std::vector<uint8_t> rc((len + 3) / 4 + 32, 0);
+        for (uint32_t i = 0; i < len; ++i) { uint32_t b = 3u - packed_base(fw, len - 1 - i); rc[i >> 2] |= (uint8_t)(b << ((i & 3) * 2)); }
+        for (uint32_t j = 0; j + K <= len; ++j) {
+            const uint32_t a = kmer_minimizer_hash(fw, j), b = kmer_minimizer_hash(rc.data(), len - K - j);
+            if (a != b || mini_mix(a) != mini_mix(b)) ++bad;
+            Kmer f, rcq;                                            // the one-pass (k-mer, reverse complement) pair of the map kernel
+            kmer_pair_at(fw, j, &f, &rcq);
+            const Kmer f0 = kmer_at(fw, j), r0 = kmer_rc(f0);
+            if (!(f == f0) || !(rcq == r0)) ++bad;
+            ++n;
+        }
+    }
+    *n_checked = n;
+    return bad;
+}
 int hc_count_records(const uint64_t* recs, uint64_t n, w2rap_kmer_rec** out, uint64_t* n_out) {
     std::vector<Rec> v(n);
     for (uint64_t i = 0; i < n; ++i) v[i] = Rec{recs[2 * i], recs[2 * i + 1] & ~0xffull, (uint32_t)(recs[2 * i + 1] & 0xff)};

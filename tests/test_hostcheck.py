@@ -84,3 +84,14 @@ def test_device_functions_golden_circ(T, hc):
 def test_device_functions_low_coverage_fragmented(T, hc):
     """min_freq high relative to coverage: a shattered graph with many tips, gaps and short edges."""
     check_against_oracle(T, hc, T.rich_set(seed=7, genome=30000, cov=12, families=4, palindromes=2, plasmid=800), min_freq=3)
+
+
+def test_minimizer_partition_key_is_strand_symmetric(T, hc):
+    """Every instance of a canonical k-mer must reach the same partition, whichever strand the read shows."""
+    rs = T.rich_set(seed=11, genome=6000, cov=6, families=2, palindromes=2, plasmid=500)
+    reads = rs.c()
+    hc.hc_minimizer_symmetry.argtypes = [C.POINTER(T.Reads), C.POINTER(C.c_uint64)]
+    hc.hc_minimizer_symmetry.restype = C.c_uint64
+    n = C.c_uint64(0)
+    assert hc.hc_minimizer_symmetry(C.byref(reads), C.byref(n)) == 0
+    assert n.value > 1000

@@ -26,6 +26,9 @@ def main():
         for w in WANT:
             if w in idx:
                 print("  %-82s %18s %s" % (w, r[idx[w]], units[idx[w]]))
+        stalls = sorted(((float(r[i].replace(",", "") or 0), h) for h, i in idx.items() if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and h not in WANT), reverse=True)
+        for v, h in stalls[:6]:
+            print("  %-82s %18.3f" % (h, v))
 
 
 if __name__ == "__main__":

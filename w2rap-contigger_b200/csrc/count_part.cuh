@@ -45,6 +45,43 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { uint32_
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 
+// Record `pos` of (sub-)buffer b, in two steps so that a warp can run step 1 on all its lanes before any lane waits in step 2.
+// Step 1: the writer of the record half way through a chunk allocates the next chunk of that partition ahead of need.
+__device__ __forceinline__ void chunk_alloc_ahead(const PartParams& pp, uint32_t b, uint32_t pos) {
+    if (!pp.chunked) return;
+    const uint32_t k = pos >> pp.logC, off = pos & ((1u << pp.logC) - 1u);
+    if (off != (1u << (pp.logC - 1)) || k + 1 >= pp.maxk) return;
+    const uint32_t sp = b & ((1u << pp.npool_log) - 1u);
+    const uint32_t a = atomicAdd(pp.pool_next + sp * 32u, 1u);
+    if (a < pp.pool_chunks) {
+        const uint32_t cid = sp * pp.pool_chunks + a;
+        st_volatile_u32(pp.chunk_of + (uint64_t)b * pp.maxk + k + 1, cid);
+        if (pp.ring) st_volatile_u64(pp.ring + 2ull * b + ((k + 1) & 1u), ((unsigned long long)(k + 1) << 32) | cid);
+    } else atomicExch(pp.overflow, 1);
+}
+// Step 2: find the chunk (ring of the two newest chunks first, then the table) and store.
+__device__ __forceinline__ void chunk_store(const PartParams& pp, uint32_t b, uint32_t pos, ulonglong2 r) {
+    if (!pp.chunked) {
+        if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
+        else atomicExch(pp.overflow, 1);
+        return;
+    }
+    const uint32_t k = pos >> pp.logC, off = pos & ((1u << pp.logC) - 1u);
+    if (k >= pp.maxk) { atomicExch(pp.overflow, 1); return; }
+    const uint32_t* tab = pp.chunk_of + (uint64_t)b * pp.maxk;
+    uint32_t g = NIL;
+    if (pp.ring) {
+        const unsigned long long e = ld_volatile_u64(pp.ring + 2ull * b + (k & 1u));
+        if ((uint32_t)(e >> 32) == k) g = (uint32_t)e;
+    }
+    if (g == NIL) g = ld_volatile_u32(tab + k);
+    while (g == NIL) {                                             // published half a chunk ago in practice
+        if (ld_volatile_u32(reinterpret_cast<const uint32_t*>(pp.overflow))) return;
+        g = ld_volatile_u32(tab + k);
+    }
+    pp.recs[((uint64_t)g << pp.logC) + off] = r;
+}
+
 // Appends records in PAIRS: the two cursor atomics are independent, so both are in flight together and the thread waits
 // for one round trip per two k-mers (the kernel is bound by the latency of the returning atomic x threads in flight).
 struct PartEmit {
@@ -55,34 +92,8 @@ struct PartEmit {
     uint32_t sub;
     __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), bucket(0), pending(false), sub(sub_) {}
     __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r) {
-        if (!pp.chunked) {
-            if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
-            else atomicExch(pp.overflow, 1);
-            return;
-        }
-        const uint32_t k = pos >> pp.logC, off = pos & ((1u << pp.logC) - 1u);
-        if (k >= pp.maxk) { atomicExch(pp.overflow, 1); return; }
-        uint32_t* tab = pp.chunk_of + (uint64_t)b * pp.maxk;
-        if (off == (1u << (pp.logC - 1)) && k + 1 < pp.maxk) {        // half way through a chunk: allocate the next one ahead of need
-            const uint32_t sp = b & ((1u << pp.npool_log) - 1u);
-            const uint32_t a = atomicAdd(pp.pool_next + sp * 32u, 1u);
-            if (a < pp.pool_chunks) {
-                const uint32_t cid = sp * pp.pool_chunks + a;
-                st_volatile_u32(tab + k + 1, cid);
-                if (pp.ring) st_volatile_u64(pp.ring + 2ull * b + ((k + 1) & 1u), ((unsigned long long)(k + 1) << 32) | cid);
-            } else atomicExch(pp.overflow, 1);
-        }
-        uint32_t g = NIL;
-        if (pp.ring) {
-            const unsigned long long e = ld_volatile_u64(pp.ring + 2ull * b + (k & 1u));
-            if ((uint32_t)(e >> 32) == k) g = (uint32_t)e;
-        }
-        if (g == NIL) g = ld_volatile_u32(tab + k);
-        while (g == NIL) {                                             // published half a chunk ago in practice
-            if (ld_volatile_u32(reinterpret_cast<const uint32_t*>(pp.overflow))) return;
-            g = ld_volatile_u32(tab + k);
-        }
-        pp.recs[((uint64_t)g << pp.logC) + off] = r;
+        chunk_alloc_ahead(pp, b, pos);
+        chunk_store(pp, b, pos, r);
     }
     __device__ __forceinline__ void flush() {
         if (pending) { put(bucket, atomicAdd(pp.cursor + (uint64_t)bucket * pp.cstride, 1u), rec); pending = false; }
@@ -126,6 +137,109 @@ __global__ void __launch_bounds__(256, 6) k_extract_partition(ReadsView r, uint6
             PartEmit emit(pp, sub);
             extract_read_kmers(r.bases + r.base_off[i], gl, emit);
             emit.flush();
+        }
+    }
+}
+
+// The "map" step, single GPU: one WARP per read, partitions keyed by minimiser (extract.cuh).  Lane l of step t handles k-mer
+// 32t + l: k-mer, context and window minimum are all computed independently per position (no rolling state), lanes whose
+// neighbours fall into the same partition form a segment, the segment head reserves the whole segment with one cursor atomic
+// and the lanes store their records side by side.  Window minima: the hashes of all m-mers of a tile live in registers (8 per
+// lane), five doubling steps of shuffles give the min over 32 consecutive hashes, the 46-wide window is two overlapping 32-wide ones.
+// Two launches: COUNT_ONLY sizes every partition exactly (count[p] += segment lengths; no k-mers are formed), an exclusive
+// scan turns the counts into partition bases, and the second launch stores.  Exact sizes mean no capacity guess can overflow,
+// whatever the multiplicity skew of the read set (a repeat with 10^4 copies just makes its partitions long).
+constexpr uint32_t MINI_TILE = 192;                       // k-mers per tile (a 250-base read is one tile)
+constexpr uint32_t MINI_NU = 8;                           // hashes per lane: positions 32u + lane, u < 8, cover the 192 + 45 m-mers of a tile
+struct MiniParams {
+    uint32_t logP, npass, pass;
+    uint32_t* count;                 // COUNT_ONLY: records per partition
+    const uint64_t* base;            // store: first record of every partition
+    uint32_t* cursor;                // store: records appended so far
+    ulonglong2* recs;
+};
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, MiniParams mp) {
+    __shared__ uint32_t wbuf[8][MINI_TILE];
+    uint32_t* wb = wbuf[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned upto = (2u << lane) - 1u;                  // lanes 0..lane
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5, end = first + count;
+    for (uint64_t i = first + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < end; i += nwarps) {
+        const uint32_t gl = good[i];
+        if (gl <= (uint32_t)K) continue;
+        const uint8_t* bases = r.bases + r.base_off[i];
+        const uint32_t nk = gl - K + 1, last = gl - K;
+        for (uint32_t j0 = 0; j0 < nk; j0 += MINI_TILE) {
+            const uint32_t n_k = nk - j0 < MINI_TILE ? nk - j0 : MINI_TILE, n_h = n_k + MINI_W - 1;
+            // window minima in registers: h[u] = hash of the m-mer at tile position 32u + lane; a doubling step with shift s takes
+            // position p + s from lane (lane + s) & 31 of the same or the next register
+            uint32_t h[MINI_NU + 1];
+#pragma unroll
+            for (uint32_t u = 0; u < MINI_NU; ++u) { const uint32_t t = 32u * u + lane; h[u] = t < n_h ? mmer_hash_at(bases, (uint64_t)j0 + t) : 0xffffffffu; }
+            h[MINI_NU] = 0xffffffffu;
+#pragma unroll
+            for (uint32_t s = 1; s <= 16; s <<= 1) {                      // after these: h = min over 32 consecutive positions
+                const uint32_t src = (lane + s) & 31u;
+                const bool wrap = lane + s >= 32u;
+                uint32_t x = __shfl_sync(0xffffffffu, h[0], src);
+#pragma unroll
+                for (uint32_t u = 0; u < MINI_NU; ++u) {
+                    const uint32_t y = u + 1 < MINI_NU ? __shfl_sync(0xffffffffu, h[u + 1], src) : 0xffffffffu;
+                    const uint32_t o = wrap ? y : x;
+                    h[u] = h[u] < o ? h[u] : o;
+                    x = y;
+                }
+            }
+            {                                                             // 46-wide window = two 32-wide ones, 14 apart
+                const uint32_t src = (lane + (MINI_W - 32)) & 31u;
+                const bool wrap = lane + (MINI_W - 32) >= 32u;
+                uint32_t x = __shfl_sync(0xffffffffu, h[0], src);
+                __syncwarp();
+#pragma unroll
+                for (uint32_t u = 0; u < MINI_TILE / 32; ++u) {
+                    const uint32_t y = __shfl_sync(0xffffffffu, h[u + 1], src);
+                    const uint32_t o = wrap ? y : x;
+                    wb[32u * u + lane] = h[u] < o ? h[u] : o;
+                    x = y;
+                }
+                __syncwarp();
+            }
+            for (uint32_t t0 = 0; t0 < n_k; t0 += 32) {
+                const uint32_t jj = t0 + lane, j = j0 + jj;
+                bool active = jj < n_k;
+                uint32_t b = 0;
+                if (active) {
+                    const uint32_t mh = mini_mix(wb[jj]);
+                    if (mp.npass > 1 && (mh & 0xffffu) % mp.npass != mp.pass) active = false;
+                    b = mini_part(mh, mp.logP);
+                }
+                const unsigned amask = __ballot_sync(0xffffffffu, active);
+                const uint32_t pb = __shfl_up_sync(0xffffffffu, b, 1);
+                const bool head = active && (lane == 0 || !((amask >> (lane - 1)) & 1u) || pb != b);
+                const unsigned heads = __ballot_sync(0xffffffffu, head);
+                unsigned long long pos0 = 0;
+                if (head) {
+                    const unsigned stop = (heads | ~amask) & ~upto;       // next segment head or first idle lane above this one
+                    const uint32_t seglen = (stop ? (uint32_t)__ffs((int)stop) - 1u : 32u) - lane;
+                    if (COUNT_ONLY) atomicAdd(mp.count + b, seglen);
+                    else pos0 = mp.base[b] + atomicAdd(mp.cursor + b, seglen);
+                }
+                if (COUNT_ONLY) continue;
+                ulonglong2 rec = make_ulonglong2(0, 0);
+                if (active) {                                             // (independent of the atomic: overlaps its round trip)
+                    Kmer f, rc;
+                    kmer_pair_at(bases, j, &f, &rc);
+                    uint32_t c = 0;
+                    if (j < last) c |= 1u << packed_base(bases, (uint64_t)j + K);
+                    if (j > 0) c |= 16u << packed_base(bases, (uint64_t)j - 1);
+                    const bool rev = kmer_less(rc, f);
+                    rec = make_ulonglong2(rev ? rc.w0 : f.w0, (rev ? rc.w1 : f.w1) | (rev ? ctx_rc(c) : c));
+                }
+                const uint32_t hl = active ? 31u - (uint32_t)__clz((int)(heads & upto)) : lane;
+                const unsigned long long pos = __shfl_sync(0xffffffffu, pos0, hl) + (lane - hl);
+                if (active) mp.recs[pos] = rec;
+            }
         }
     }
 }
@@ -197,7 +311,8 @@ __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64
 // The "reduce" step (BuildReadQGraph.cc:1081-1082 sort+collapse as a hash count).  blockIdx.y selects the sub-buffer of the group.
 // recs/sizes hold one slab per source rank ([n_src][owned sub-buffers]); blockIdx.y = src * gy + sub-buffer within the group.
 // Chunked buffers (cv.chunk_of != nullptr): a block takes whole chunks, so the chunk table is read once per 2048 records.
-struct ChunkView { const uint32_t* chunk_of; uint32_t logC, maxk; };   // chunk_of == nullptr: static sub-buffers
+struct ChunkView { const uint32_t* chunk_of; uint32_t logC, maxk; const uint64_t* part_base; };   // chunk_of == nullptr: static sub-buffers,
+                                                                                                  // at recs + part_base[b] if part_base is set
 __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
                                                       uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, ChunkView cv, RegionParams rp) {
     const uint32_t src = blockIdx.y / gy;
@@ -220,7 +335,7 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
         }
         return;
     }
-    const ulonglong2* base = recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
+    const ulonglong2* base = cv.part_base ? recs + cv.part_base[b] : recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
         const bool two = i + stride < n;
@@ -241,6 +356,7 @@ struct SmemCountParams {
     const ulonglong2* recs;
     const uint32_t* cursor;         // records per partition
     const uint32_t* chunk_of;       // [P][maxk]
+    const uint64_t* part_base;      // if set: partition p is the contiguous run recs[part_base[p] .. + cursor[p])
     uint32_t logC, maxk, P, logP;
     uint32_t min_freq;
     unsigned long long* hist;       // [104]
@@ -263,9 +379,9 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
         __syncthreads();
         const uint32_t n = sp.cursor[p];
         const uint32_t* tab = sp.chunk_of + (uint64_t)p * sp.maxk;
+        const ulonglong2* run = sp.part_base ? sp.recs + sp.part_base[p] : nullptr;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t cid = __ldg(tab + (i >> sp.logC));
-            const ulonglong2 rec = __ldcs(sp.recs + (((uint64_t)cid) << sp.logC) + (i & (C - 1u)));
+            const ulonglong2 rec = run ? __ldcs(run + i) : __ldcs(sp.recs + (((uint64_t)__ldg(tab + (i >> sp.logC))) << sp.logC) + (i & (C - 1u)));
             const unsigned long long kw0 = rec.x, kw1 = rec.y & ~0xffull;
             const uint32_t ctx = (uint32_t)rec.y & 0xffu;
             const uint64_t h = kmer_hash(Kmer{kw0, kw1});

@@ -46,4 +46,35 @@ W2R_HD void extract_read_kmers(const uint8_t* bases, uint32_t good_len, Emit& em
     while (cur.next(&k, &ctx)) emit(k, ctx);
 }
 
+// ---------------------------------------------------------------- minimisers (partition key of the single-GPU count)
+// The partition of a k-mer is derived from its MINIMISER: the canonical 15-mer with the smallest hash among the 46 inside the
+// k-mer.  It is strand-symmetric (a k-mer and its reverse complement contain the same canonical m-mers), so every instance of a
+// canonical k-mer lands in the same partition, and consecutive k-mers of a read share it for ~24 positions on average: a read
+// appends RUNS of records to a partition (one cursor atomic per run, contiguous stores) instead of scattering single records.
+// The counts do not depend on the partition function; this is purely a data-movement choice (the reference's own bucketing,
+// MapReduceEngine.h:288-358, hashes whole k-mers).
+constexpr int MINI_M = 15;
+constexpr int MINI_W = K - MINI_M + 1;     // m-mers per k-mer
+// hash of the canonical m-mer starting at base `pos` (a bijection of its 30-bit value, so equal hash <=> equal canonical m-mer)
+W2R_HD uint32_t mmer_hash_at(const uint8_t* bases, uint64_t pos) {
+    const uint32_t v = bases16_at(bases, pos) & ((1u << (2 * MINI_M)) - 1u);                 // base pos in bits 1:0
+    const uint32_t rc = rev2_32(~v) >> (32 - 2 * MINI_M);                                    // reverse complement, same encoding
+    uint32_t c = v < rc ? v : rc;
+    c ^= c >> 16; c *= 0x85ebca6bu; c ^= c >> 13; c *= 0xc2b2ae35u; c ^= c >> 16;
+    return c;
+}
+// window minima are biased towards 0: re-mix before taking partition bits (top) and pass bits (low 16)
+W2R_HD uint32_t mini_mix(uint32_t wmin) {
+    uint32_t x = wmin * 0x9e3779b1u;
+    x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 13;
+    return x;
+}
+W2R_HD uint32_t mini_part(uint32_t mixed, uint32_t logP) { return logP ? mixed >> (32u - logP) : 0u; }
+// reference form for tests: the minimiser hash of the k-mer starting at base j
+W2R_HD uint32_t kmer_minimizer_hash(const uint8_t* bases, uint64_t j) {
+    uint32_t m = 0xffffffffu;
+    for (int t = 0; t < MINI_W; ++t) { const uint32_t h = mmer_hash_at(bases, j + t); if (h < m) m = h; }
+    return m;
+}
+
 }  // namespace w2r

@@ -123,6 +123,44 @@ W2R_HD Kmer kmer_at(const uint8_t* bases, uint64_t pos) {
     return Kmer{rev2(bases32_at(bases, pos)), rev2(bases32_at(bases, pos + 32)) & ~0xffull};
 }
 
+// The k-mer starting at base `pos` AND its reverse complement, from three aligned 8-byte loads.  In the packed store a base sits
+// LSB-first, in the Kmer layout MSB-first: the reverse complement of the k-mer is therefore just the complement of the packed
+// bits moved up by 8 (no bit reversal); only the forward k-mer needs rev2.
+W2R_HD void kmer_pair_at(const uint8_t* bases, uint64_t pos, Kmer* f, Kmer* rc) {
+    const uintptr_t addr = (uintptr_t)bases + (uintptr_t)(pos >> 2);
+    const uint64_t* q = (const uint64_t*)(addr & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(addr & 7u) * 8u + (uint32_t)(pos & 3u) * 2u;   // 0..62
+    const uint64_t a = q[0], b = q[1], c = q[2];
+    const uint64_t lo = sh ? (a >> sh) | (b << (64u - sh)) : a;                    // bases pos .. pos+31
+    const uint64_t hi = sh ? (b >> sh) | (c << (64u - sh)) : b;                    // bases pos+32 .. pos+63
+    *f = Kmer{rev2(lo), rev2(hi) & ~0xffull};
+    *rc = Kmer{(~hi << 8) | (~lo >> 56), ~lo << 8};
+}
+// 16 consecutive bases starting at base i, LSB-first (two aligned 4-byte loads + a funnel shift; may touch 7 bytes past the end)
+W2R_HD uint32_t bases16_at(const uint8_t* p, uint64_t i) {
+    const uintptr_t addr = (uintptr_t)p + (uintptr_t)(i >> 2);
+    const uint32_t* q = (const uint32_t*)(addr & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(addr & 3u) * 8u + (uint32_t)(i & 3u) * 2u;     // 0..30
+    const uint32_t lo = q[0], hi = q[1];
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+// reverse the order of the 16 two-bit groups of a 32-bit word
+W2R_HD uint32_t rev2_32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    x = __brev(x);
+    return ((x & 0xaaaaaaaau) >> 1) | ((x & 0x55555555u) << 1);
+#else
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+
 // ---------------------------------------------------------------- tables
 // Counting table slot: one 32-byte sector.  {w0,w1} is claimed with a single 128-bit CAS.
 struct __attribute__((aligned(32))) CountSlot { uint64_t w0, w1; uint32_t count, ctx; uint64_t pad; };

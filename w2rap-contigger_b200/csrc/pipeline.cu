@@ -240,6 +240,9 @@ struct Pipeline {
         // at least one per rank: rank r owns the contiguous range [r*P/world, (r+1)*P/world)
         // single GPU: FINE partitions (~24 k records each) that one CTA counts in shared memory (count_part.cuh: k_count_smem)
         const bool fine = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS") && !getenv("W2RAP_COARSE");
+        // ... keyed by minimiser, so that a read appends runs of records (count_part.cuh: k_minimizer_map); the k-mer hash bits
+        // are then all free for the slot inside the table (rlogP = 0)
+        const bool mini = fine && !getenv("W2RAP_NO_MINIMIZER");
         uint32_t logP = 0;
         static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : 24000.0;
         if (fine) { while ((double)n_inst / (double)(1ull << logP) > fine_recs && logP < 22) ++logP; }
@@ -277,7 +280,7 @@ struct Pipeline {
             const uint64_t P = 1ull << logP, Pown = P / world;
             // sub-buffers: 8 per partition, cursors on separate L2 lines
             // single GPU: chunked partition buffers (one pass, TLB-friendly); several GPUs: static sub-buffers = contiguous slabs to exchange
-            const bool chunked = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS");
+            const bool chunked = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS") && !mini;
             const uint32_t nsub = (!chunked && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
             const uint32_t cstride = fine ? 1 : 32;
             const uint64_t NB = P * nsub, NBown = Pown * nsub;
@@ -290,15 +293,20 @@ struct Pipeline {
             const uint32_t npool_log = fine ? std::min<uint32_t>(6, logP) : 0;       // bump allocators: one address would serialise 10^8 chunk allocations
             const uint64_t chunks_total = chunked ? (uint64_t)((double)n_inst_max / npass * 1.01) / (1u << logC) + 2 * P + 1024 : 0;
             const uint64_t pool_chunks = chunked ? (uint64_t)((double)(chunks_total >> npool_log) * (npool_log ? 1.05 : 1.0)) + 1024 : 0;   // per sub-pool
-            const uint64_t cap = chunked ? (uint64_t)maxk << logC : (uint64_t)((double)per_part * slack) + 1024;
-            const size_t rec_bytes = chunked ? ((pool_chunks << npool_log) << logC) * sizeof(ulonglong2) : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
+            const uint64_t cap = chunked ? (uint64_t)maxk << logC : mini ? (1ull << 40) : (uint64_t)((double)per_part * slack) + 1024;
+            // (minimiser mode: exact sizes come from the counting launch; passes are split by minimiser hash, so allow for uneven passes)
+            const size_t rec_bytes = chunked ? ((pool_chunks << npool_log) << logC) * sizeof(ulonglong2)
+                                   : mini    ? (size_t)((double)n_inst_max / npass * (npass > 1 ? slack * 1.2 : 1.0)) * sizeof(ulonglong2)
+                                             : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
             // Scattered appends over a record buffer of tens of GB run into TLB misses (measured: the same kernel is 2x faster per
             // record on a 41 GB buffer than on an 82 GB one), so the buffer is also capped and the k-mer space split into more
             // hash-range passes instead; extraction is repeated per pass, which is cheap next to the appends.
             static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
-            if ((rec_bytes + fixed_bytes > budget || (!chunked && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) && npass < 4096) { npass *= 2; continue; }
+            if ((rec_bytes + fixed_bytes > budget || (!chunked && !mini && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) && npass < 4096) { npass *= 2; continue; }
             if ((pool_chunks << npool_log) >= 0xfffffff0ull) { npass *= 2; continue; }
-            SBuf<ulonglong2> recs(c, chunked ? ((pool_chunks << npool_log) << logC) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            SBuf<ulonglong2> recs(c, chunked ? ((pool_chunks << npool_log) << logC) : mini ? rec_bytes / sizeof(ulonglong2) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            SBuf<uint32_t> part_count(c, mini ? P : 0);
+            SBuf<uint64_t> part_base(c, mini ? P + 1 : 0);
             SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 32ull << npool_log);
             SBuf<unsigned long long> ring(c, fine ? 2 * P : 0);
             SBuf<uint32_t> cursor(c, NB * cstride), xcur_buf(c, world > 1 ? NB * cstride : 0);
@@ -314,6 +322,25 @@ struct Pipeline {
                 cursor.zero();
                 if (chunked) W2R_LAUNCH(c, k_init_chunks, grid(P * maxk, 256), 256, 0, chunk_of.p, maxk, (uint32_t)P, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr);
                 PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr};
+                if (mini) {
+                    // launch 1 sizes the partitions exactly (runs per read batch, under the upload), the scan lays them out, launch 2 stores
+                    static const unsigned map_ctas = getenv("W2RAP_MAP_CTAS") ? (unsigned)atoi(getenv("W2RAP_MAP_CTAS")) : 6u;
+                    part_count.zero();
+                    MiniParams mp{logP, npass, pass, part_count.p, part_base.p, cursor.p, recs.p};
+                    for (const Batch& bt : batches) {
+                        if (!bt.count) continue;
+                        if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
+                        if (!good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
+                        if (n_inst_local) W2R_LAUNCH(c, k_minimizer_map<true>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp);
+                    }
+                    good_done = true;
+                    exclusive_scan<uint32_t, uint64_t>(c, part_count.p, P, part_base.p, part_base.p + P);
+                    const uint64_t total = d2h_scalar(c, part_base.p + P);
+                    if (total > recs.n) { slack *= 1.5; retry = true; break; }      // only with several uneven passes
+                    kt.start();
+                    if (total) { W2R_LAUNCH(c, k_minimizer_map<false>, grid(dr.n * 32, 256, map_ctas), 256, 0, rv, (uint64_t)0, (uint64_t)dr.n, good.p, mp); c.count_launches++; }
+                    part_ms += kt.stop();
+                } else {
                 kt.start();
                 for (const Batch& bt : batches) {
                     if (!bt.count) continue;
@@ -323,6 +350,7 @@ struct Pipeline {
                 }
                 good_done = true;
                 part_ms += kt.stop();
+                }
                 if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
                 std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, flags.p + 1)};
                 allreduce_u64(of, ncclSum);
@@ -377,10 +405,10 @@ struct Pipeline {
                     CountSlot* greg = region.p + ((group_parity & 1u) ? R : 0);
                     ++group_parity;
                     if (mxg) {
-                        RegionParams rp{greg, logR, logP, sub_mask, sub_id, flag};
+                        RegionParams rp{greg, logR, mini ? 0u : logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
                         dim3 gr(std::max(1u, std::min<unsigned>(chunked ? ((mxg >> logC) + 1) : (mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * world, 8u))))), gy * world);
-                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk}, rp); c.launches++;
+                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk, mini ? part_base.p : nullptr}, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
                     ScanParams sp{greg, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
@@ -394,7 +422,7 @@ struct Pipeline {
                     // every partition is counted by one CTA in shared memory; the few that do not fit are redone through the region below
                     SBuf<uint32_t> failed(c, P);
                     W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 8, c.stream));
-                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, logC, maxk, (uint32_t)P, logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
+                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, mini ? part_base.p : nullptr, logC, maxk, (uint32_t)P, mini ? 0u : logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
                                        prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4};
                     const size_t smem_bytes = (size_t)SMEM_SLOTS * 20;
                     static bool attr_set = false;
