@@ -154,9 +154,12 @@ constexpr uint32_t MINI_NU = 8;                           // hashes per lane: po
 struct MiniParams {
     uint32_t logP, npass, pass;
     uint32_t* count;                 // COUNT_ONLY: records per partition
-    const uint64_t* base;            // store: first record of every partition
+    const uint64_t* base;            // store: first record of every partition, relative to *batch_off
     uint32_t* cursor;                // store: records appended so far
     ulonglong2* recs;
+    const unsigned long long* batch_off;   // store: where this read batch's records start (device scalar: no host round trip)
+    uint64_t recs_cap;               // records the buffer holds (it is sized from an upper bound; checked all the same)
+    int* overflow;
 };
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, MiniParams mp) {
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t 
     const uint32_t lane = threadIdx.x & 31u;
     const unsigned upto = (2u << lane) - 1u;                  // lanes 0..lane
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5, end = first + count;
+    const unsigned long long boff = COUNT_ONLY ? 0ull : *mp.batch_off;
     for (uint64_t i = first + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < end; i += nwarps) {
         const uint32_t gl = good[i];
         if (gl <= (uint32_t)K) continue;
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t 
                     const unsigned stop = (heads | ~amask) & ~upto;       // next segment head or first idle lane above this one
                     const uint32_t seglen = (stop ? (uint32_t)__ffs((int)stop) - 1u : 32u) - lane;
                     if (COUNT_ONLY) atomicAdd(mp.count + b, seglen);
-                    else pos0 = mp.base[b] + atomicAdd(mp.cursor + b, seglen);
+                    else pos0 = boff + mp.base[b] + atomicAdd(mp.cursor + b, seglen);
                 }
                 if (COUNT_ONLY) continue;
                 ulonglong2 rec = make_ulonglong2(0, 0);
@@ -238,11 +242,14 @@ __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t 
                 }
                 const uint32_t hl = active ? 31u - (uint32_t)__clz((int)(heads & upto)) : lane;
                 const unsigned long long pos = __shfl_sync(0xffffffffu, pos0, hl) + (lane - hl);
-                if (active) mp.recs[pos] = rec;
+                if (active) { if (pos < mp.recs_cap) mp.recs[pos] = rec; else atomicExch(mp.overflow, 1); }
             }
         }
     }
 }
+
+// batch_off[1] = batch_off[0] + total[0]: chains the record areas of consecutive read batches on the device
+__global__ void k_next_batch_off(unsigned long long* batch_off, const uint64_t* total) { batch_off[1] = batch_off[0] + *total; }
 
 struct RegionParams {
     CountSlot* region;       // 1 << logR slots, resident in L2
@@ -311,8 +318,9 @@ __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64
 // The "reduce" step (BuildReadQGraph.cc:1081-1082 sort+collapse as a hash count).  blockIdx.y selects the sub-buffer of the group.
 // recs/sizes hold one slab per source rank ([n_src][owned sub-buffers]); blockIdx.y = src * gy + sub-buffer within the group.
 // Chunked buffers (cv.chunk_of != nullptr): a block takes whole chunks, so the chunk table is read once per 2048 records.
-struct ChunkView { const uint32_t* chunk_of; uint32_t logC, maxk; const uint64_t* part_base; };   // chunk_of == nullptr: static sub-buffers,
-                                                                                                  // at recs + part_base[b] if part_base is set
+// chunk_of == nullptr: static sub-buffers; with part_base set, slab `src` is a read batch and partition b of it is the run
+// recs[batch_off[src] + part_base[src * P + b] ...)
+struct ChunkView { const uint32_t* chunk_of; uint32_t logC, maxk; const uint64_t* part_base; const unsigned long long* batch_off; uint64_t P; };
 __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
                                                       uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, ChunkView cv, RegionParams rp) {
     const uint32_t src = blockIdx.y / gy;
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
         }
         return;
     }
-    const ulonglong2* base = cv.part_base ? recs + cv.part_base[b] : recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
+    const ulonglong2* base = cv.part_base ? recs + cv.batch_off[src] + cv.part_base[(uint64_t)src * cv.P + b] : recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
         const bool two = i + stride < n;
@@ -352,11 +360,14 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
 // Partitions whose distinct k-mers do not fit are listed in `failed` and go through the region path afterwards.
 constexpr uint32_t SMEM_SLOTS = 8192;                          // 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
 constexpr uint32_t SMEM_MAX_PROBE = 512;
+constexpr uint32_t SMEM_MAX_BATCH = 16;                        // read batches whose runs make up one partition
 struct SmemCountParams {
     const ulonglong2* recs;
     const uint32_t* cursor;         // records per partition
     const uint32_t* chunk_of;       // [P][maxk]
-    const uint64_t* part_base;      // if set: partition p is the contiguous run recs[part_base[p] .. + cursor[p])
+    const uint64_t* part_base;      // if set: partition p is, per read batch bi < nbatch, the contiguous run
+    const unsigned long long* batch_off;   //   recs[batch_off[bi] + part_base[bi * P + p] .. + cursor[bi * P + p])
+    uint32_t nbatch;
     uint32_t logC, maxk, P, logP;
     uint32_t min_freq;
     unsigned long long* hist;       // [104]
@@ -371,17 +382,34 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     uint32_t* ccs = reinterpret_cast<uint32_t*>(w1s + SMEM_SLOTS);          // count (low 24 bits) | ctx << 24
     __shared__ unsigned int sh_hist[104];
     __shared__ int sh_fail;
+    __shared__ unsigned long long sh_run[SMEM_MAX_BATCH];
+    __shared__ uint32_t sh_pre[SMEM_MAX_BATCH + 1];
     for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
     const uint32_t C = 1u << sp.logC;
     for (uint32_t p = blockIdx.x; p < sp.P; p += gridDim.x) {
         for (uint32_t j = threadIdx.x; j < SMEM_SLOTS; j += blockDim.x) { w0s[j] = ~0ull; w1s[j] = ~0ull; ccs[j] = 0; }
-        if (threadIdx.x == 0) sh_fail = 0;
+        if (threadIdx.x == 0) {
+            sh_fail = 0;
+            if (sp.part_base) {
+                uint32_t acc = 0;
+                for (uint32_t bi = 0; bi < sp.nbatch; ++bi) {
+                    sh_run[bi] = sp.batch_off[bi] + sp.part_base[(uint64_t)bi * sp.P + p];
+                    sh_pre[bi] = acc;
+                    acc += sp.cursor[(uint64_t)bi * sp.P + p];
+                }
+                for (uint32_t bi = sp.nbatch; bi <= SMEM_MAX_BATCH; ++bi) sh_pre[bi] = acc;
+            }
+        }
         __syncthreads();
-        const uint32_t n = sp.cursor[p];
+        const uint32_t n = sp.part_base ? sh_pre[SMEM_MAX_BATCH] : sp.cursor[p];
         const uint32_t* tab = sp.chunk_of + (uint64_t)p * sp.maxk;
-        const ulonglong2* run = sp.part_base ? sp.recs + sp.part_base[p] : nullptr;
+        uint32_t bi = 0;                                          // i only grows: the run index is carried along
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const ulonglong2 rec = run ? __ldcs(run + i) : __ldcs(sp.recs + (((uint64_t)__ldg(tab + (i >> sp.logC))) << sp.logC) + (i & (C - 1u)));
+            ulonglong2 rec;
+            if (sp.part_base) {
+                while (i >= sh_pre[bi + 1]) ++bi;
+                rec = __ldcs(sp.recs + sh_run[bi] + (i - sh_pre[bi]));
+            } else rec = __ldcs(sp.recs + (((uint64_t)__ldg(tab + (i >> sp.logC))) << sp.logC) + (i & (C - 1u)));
             const unsigned long long kw0 = rec.x, kw1 = rec.y & ~0xffull;
             const uint32_t ctx = (uint32_t)rec.y & 0xffu;
             const uint64_t h = kmer_hash(Kmer{kw0, kw1});

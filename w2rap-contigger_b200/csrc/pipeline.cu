@@ -304,16 +304,23 @@ struct Pipeline {
             static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
             if ((rec_bytes + fixed_bytes > budget || (!chunked && !mini && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) && npass < 4096) { npass *= 2; continue; }
             if ((pool_chunks << npool_log) >= 0xfffffff0ull) { npass *= 2; continue; }
+            const double t_alloc0 = now_ms();
             SBuf<ulonglong2> recs(c, chunked ? ((pool_chunks << npool_log) << logC) : mini ? rec_bytes / sizeof(ulonglong2) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
-            SBuf<uint32_t> part_count(c, mini ? P : 0);
-            SBuf<uint64_t> part_base(c, mini ? P + 1 : 0);
+            if (getenv("W2RAP_TRACE")) fprintf(stderr, "[w2rap] count: record buffer %.2f GB allocated in %.1f ms (host)\n", recs.bytes() / 1e9, now_ms() - t_alloc0);
+            // minimiser mode: every read batch gets its own exactly sized record area, so that a batch is mapped as soon as it has
+            // arrived; a partition is then one run per batch (the batches play the part the source ranks play in the sharded layout)
+            const uint32_t nslab = mini ? (uint32_t)batches.size() : (uint32_t)world;
+            if (mini && nslab > SMEM_MAX_BATCH) W2R_FAIL(W2RAP_ERR_INTERNAL, "more read batches than the reduce kernel handles");
+            SBuf<uint32_t> part_count(c, mini ? nslab * P : 0);
+            SBuf<uint64_t> part_base(c, mini ? nslab * P : 0), batch_total(c, mini ? nslab : 0);
+            SBuf<unsigned long long> batch_off(c, mini ? nslab + 1 : 0);
             SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 32ull << npool_log);
             SBuf<unsigned long long> ring(c, fine ? 2 * P : 0);
-            SBuf<uint32_t> cursor(c, NB * cstride), xcur_buf(c, world > 1 ? NB * cstride : 0);
+            SBuf<uint32_t> cursor(c, NB * cstride * (mini ? nslab : 1)), xcur_buf(c, world > 1 ? NB * cstride : 0);
             const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;          // [world][NBown][cap]: what this rank reduces
             const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [world][NBown][cstride]
             const uint64_t slab_recs = NBown * cap, slab_cur = NBown * cstride;
-            std::vector<uint32_t> sizes(Pown), raw_sizes((size_t)world * slab_cur);
+            std::vector<uint32_t> sizes(Pown), raw_sizes((size_t)nslab * slab_cur);
             bool retry = false;
             W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
             hist.zero();
@@ -324,22 +331,27 @@ struct Pipeline {
                 PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr};
                 if (mini) {
                     // launch 1 sizes the partitions exactly (runs per read batch, under the upload), the scan lays them out, launch 2 stores
-                    static const unsigned map_ctas = getenv("W2RAP_MAP_CTAS") ? (unsigned)atoi(getenv("W2RAP_MAP_CTAS")) : 6u;
+                    static const unsigned map_ctas = getenv("W2RAP_MAP_CTAS") ? (unsigned)atoi(getenv("W2RAP_MAP_CTAS")) : 8u;
                     part_count.zero();
-                    MiniParams mp{logP, npass, pass, part_count.p, part_base.p, cursor.p, recs.p};
-                    for (const Batch& bt : batches) {
-                        if (!bt.count) continue;
+                    W2R_CUDA(cudaMemsetAsync(batch_off.p, 0, sizeof(unsigned long long), c.stream));
+                    std::vector<cudaEvent_t> ev(2 * nslab, nullptr);                 // the store launches are timed without stalling the queue
+                    struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); } } evg{ev};
+                    for (uint32_t bi = 0; bi < nslab; ++bi) {
+                        const Batch& bt = batches[bi];
+                        MiniParams mp{logP, npass, pass, part_count.p + bi * P, part_base.p + bi * P, cursor.p + bi * P, recs.p, batch_off.p + bi, recs.n, flags.p + 1};
                         if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
-                        if (!good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
-                        if (n_inst_local) W2R_LAUNCH(c, k_minimizer_map<true>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp);
+                        if (bt.count && !good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
+                        if (bt.count && n_inst_local) W2R_LAUNCH(c, k_minimizer_map<true>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp);
+                        exclusive_scan<uint32_t, uint64_t>(c, part_count.p + bi * P, P, part_base.p + bi * P, batch_total.p + bi);
+                        W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, batch_off.p + bi, batch_total.p + bi);
+                        W2R_CUDA(cudaEventCreate(&ev[2 * bi])); W2R_CUDA(cudaEventCreate(&ev[2 * bi + 1]));
+                        W2R_CUDA(cudaEventRecord(ev[2 * bi], c.stream));
+                        if (bt.count && n_inst_local) { W2R_LAUNCH(c, k_minimizer_map<false>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp); c.count_launches++; }
+                        W2R_CUDA(cudaEventRecord(ev[2 * bi + 1], c.stream));
                     }
                     good_done = true;
-                    exclusive_scan<uint32_t, uint64_t>(c, part_count.p, P, part_base.p, part_base.p + P);
-                    const uint64_t total = d2h_scalar(c, part_base.p + P);
-                    if (total > recs.n) { slack *= 1.5; retry = true; break; }      // only with several uneven passes
-                    kt.start();
-                    if (total) { W2R_LAUNCH(c, k_minimizer_map<false>, grid(dr.n * 32, 256, map_ctas), 256, 0, rv, (uint64_t)0, (uint64_t)dr.n, good.p, mp); c.count_launches++; }
-                    part_ms += kt.stop();
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    for (uint32_t bi = 0; bi < nslab; ++bi) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * bi], ev[2 * bi + 1]); part_ms += ms; }
                 } else {
                 kt.start();
                 for (const Batch& bt : batches) {
@@ -369,7 +381,7 @@ struct Pipeline {
                 uint64_t owned_records = 0;
                 for (uint64_t q = 0; q < Pown; ++q) {
                     uint32_t mxs = 0;
-                    for (int sidx = 0; sidx < world; ++sidx)
+                    for (uint32_t sidx = 0; sidx < nslab; ++sidx)
                         for (uint32_t u = 0; u < nsub; ++u) { uint32_t v = raw_sizes[sidx * slab_cur + (q * nsub + u) * cstride]; mxs = std::max(mxs, v); owned_records += v; }
                     sizes[q] = mxs;      // largest sub-buffer of the partition (sizes the grid)
                 }
@@ -407,8 +419,8 @@ struct Pipeline {
                     if (mxg) {
                         RegionParams rp{greg, logR, mini ? 0u : logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
-                        dim3 gr(std::max(1u, std::min<unsigned>(chunked ? ((mxg >> logC) + 1) : (mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * world, 8u))))), gy * world);
-                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk, mini ? part_base.p : nullptr}, rp); c.launches++;
+                        dim3 gr(std::max(1u, std::min<unsigned>(chunked ? ((mxg >> logC) + 1) : (mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * nslab, 8u))))), gy * nslab);
+                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk, mini ? part_base.p : nullptr, batch_off.p, P}, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
                     ScanParams sp{greg, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
@@ -422,7 +434,7 @@ struct Pipeline {
                     // every partition is counted by one CTA in shared memory; the few that do not fit are redone through the region below
                     SBuf<uint32_t> failed(c, P);
                     W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 8, c.stream));
-                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, mini ? part_base.p : nullptr, logC, maxk, (uint32_t)P, mini ? 0u : logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
+                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, mini ? part_base.p : nullptr, batch_off.p, nslab, logC, maxk, (uint32_t)P, mini ? 0u : logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
                                        prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4};
                     const size_t smem_bytes = (size_t)SMEM_SLOTS * 20;
                     static bool attr_set = false;
