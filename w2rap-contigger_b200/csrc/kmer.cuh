@@ -208,10 +208,8 @@ W2R_HD bool bloom_may_contain(const KmerBloom& b, uint64_t h) {
     return (b.words[bloom_word(b, h)] & m) == m;
 #endif
 }
-// Canonical lookup through the filter.
-W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer k) {
-    const uint64_t hh = kmer_hash(k);
-    if (!bloom_may_contain(b, hh)) return -1;
+// Canonical lookup with the k-mer's hash already known.
+W2R_HD int64_t solid_find_hashed(const SolidTable& t, Kmer k, uint64_t hh) {
     uint64_t mask = t.size() - 1, h = hh >> (64 - t.log2n);
     for (;;) {
         const SolidSlot* s = t.slots + h;
@@ -225,6 +223,12 @@ W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer
         if (a == EMPTY_W0) return -1;
         h = (h + 1) & mask;
     }
+}
+// Canonical lookup through the filter.
+W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer k) {
+    const uint64_t hh = kmer_hash(k);
+    if (!bloom_may_contain(b, hh)) return -1;
+    return solid_find_hashed(t, k, hh);
 }
 
 // kmers/ReadPather.h:196-199 findEntry: canonicalise then look up.  *rev = query was in REV form (rc < query).

@@ -108,66 +108,53 @@ W2R_HD int32_t choose_extension(const GraphView& g, int32_t v, bool leftward, ui
 
 struct PathResult { int32_t offset; uint32_t start, len; bool overflow; };
 
-// Paths one read.  `row` is this read's staging row of `cap` ints; `qscratch` holds >= rlen bytes for lazily decoded quals.
-W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32_t rlen, const uint8_t* qstream, uint8_t* qscratch,
-                                int32_t* row, uint32_t cap, uint32_t left_cap, bool apply_fixpaths) {
-    const uint32_t PATH_LEFT_CAP = left_cap;
-    PathResult res{0, left_cap, 0, false};
-    if (rlen < (uint32_t)K) return res;                     // :503-506 a single gap part: empty path
-    const uint32_t nk = rlen - K + 1;
-    const uint32_t right_cap = cap - PATH_LEFT_CAP;
-
+// Pathing of one read as a resumable walker.  scan() runs the seed loop of BRQ_Pather::path (:500-550) until the read is
+// exhausted (returns false) or a k-mer misses the dictionary (returns true).  The caller then finds the first position
+// p in (itr, nk) whose k-mer IS in the dictionary — serially (path_one_read below, the host check) or with the whole warp
+// (k_path_reads: 32 positions per step) — and hands it back with gap_found(p, slot) (p = nk, slot = -1 if there is none).
+// finish() applies the tail rules, the quality-aware extensions and FixPaths.
+struct PathWalker {
+    const GraphView* g;
+    const uint8_t* bases;
+    int32_t* row;
+    uint32_t rlen, nk, left_cap, right_cap;
     PathPart pend[2];
-    int npend = 0;
-    bool last_kept_valid = false; uint32_t lk_edge = 0, lk_rc = 0;
-    uint32_t n_ids = 0, sum_kmers = 0, seeds = 0, nparts = 0;
-    bool first_is_gap = false, have_first_hit = false;
-    uint32_t gap0_len = 0, first_hit_off = 0;
-    bool last_is_gap = false, last2_is_gap = false;
-    bool pending_gap = false; uint32_t gap_len = 0, gap_index = 0;
+    int npend;
+    bool last_kept_valid; uint32_t lk_edge, lk_rc;
+    uint32_t n_ids, sum_kmers, seeds, nparts;
+    bool first_is_gap, have_first_hit;
+    uint32_t gap0_len, first_hit_off;
+    bool last_is_gap, last2_is_gap;
+    bool pending_gap; uint32_t gap_len, gap_index;
+    uint32_t itr;
+    bool overflow, scan_done;
 
-    auto commit = [&](const PathPart& h) {                  // :804-815 pathPartsToReadPath, one kept seed
+    W2R_HD void init(const GraphView& g_, const uint8_t* bases_, uint32_t rlen_, int32_t* row_, uint32_t cap, uint32_t left_cap_) {
+        g = &g_; bases = bases_; row = row_; rlen = rlen_; left_cap = left_cap_; right_cap = cap - left_cap_;
+        nk = rlen >= (uint32_t)K ? rlen - K + 1 : 0;           // :503-506 a read shorter than K is a single gap part: empty path
+        npend = 0; last_kept_valid = false; lk_edge = lk_rc = 0;
+        n_ids = sum_kmers = seeds = nparts = 0;
+        first_is_gap = have_first_hit = false; gap0_len = first_hit_off = 0;
+        last_is_gap = last2_is_gap = false; pending_gap = false; gap_len = gap_index = 0;
+        itr = 0; overflow = false; scan_done = false;
+    }
+    W2R_HD void commit(const PathPart& h) {                     // :804-815 pathPartsToReadPath, one kept seed
         if (last_kept_valid && lk_edge == h.edge && lk_rc == h.rc) return;
-        if (n_ids < right_cap) row[PATH_LEFT_CAP + n_ids] = h.rc ? g.rev_xlat[h.edge] : g.fwd_xlat[h.edge]; else res.overflow = true;
+        if (n_ids < right_cap) row[left_cap + n_ids] = h.rc ? g->rev_xlat[h.edge] : g->fwd_xlat[h.edge]; else overflow = true;
         ++n_ids; sum_kmers += h.elen;
         last_kept_valid = true; lk_edge = h.edge; lk_rc = h.rc;
-    };
-
-    uint32_t itr = 0;
-    while (itr < nk) {                                      // :500-550 BRQ_Pather::path
-        Kmer f = kmer_at(bases, itr);
-        Kmer r = kmer_rc(f);
-        int64_t slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
-        if (slot < 0) {
-            uint32_t gl = 1;
-            ++itr;
-            // (fetching the home slots of several gap positions at once was tried: slower — the kernel is bound by TLB/DRAM
-            //  throughput of random 64-byte fetches, not by latency, and the extra registers cost occupancy)
-            uint64_t nxt = 0;
-            for (uint32_t t = 0; itr < nk; ++t) {
-                if ((t & 31u) == 0) nxt = bases32_at(bases, (uint64_t)itr + K - 1);
-                const uint32_t nb = (uint32_t)nxt & 3u;
-                nxt >>= 2;
-                f = kmer_succ(f, nb); r = kmer_pred(r, 3u - nb);
-                slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
-                if (slot >= 0) break;
-                ++gl; ++itr;
-            }
-            if (nparts == 0) { first_is_gap = true; gap0_len = gl; }
-            gap_len = gl; gap_index = nparts; ++nparts;
-            last2_is_gap = last_is_gap; last_is_gap = true;
-            pending_gap = true;
-            if (slot < 0) break;
-        }
-        const SolidSlot& ss = g.solid.slots[slot];
+    }
+    // the k-mer at itr is dictionary entry `slot`: extend the match along its edge; false = the path ends here (captured-gap rule)
+    W2R_HD bool seed(int64_t slot) {
+        const SolidSlot& ss = g->solid.slots[slot];
         PathPart h;
         h.edge = ss.edge;
-        const uint32_t elen = g.edge_len[h.edge];
+        const uint32_t elen = g->edge_len[h.edge];
         uint32_t o = ss.off;
-        const uint8_t* ep = g.edge_bases + g.edge_off[h.edge];
+        const uint8_t* ep = g->edge_bases + g->edge_off[h.edge];
         // dna/CanonicalForm.h:85-92 isRC: the read k-mer is the reverse complement of the edge k-mer at that offset
         Kmer ek = kmer_at(ep, o);
-        h.rc = !(ek == f);
+        h.rc = !(ek == kmer_at(bases, itr));
         h.elen = elen - K + 1;
         uint32_t len = 1;
         // matchLen (:341-350), 32 bases per step: XOR of two packed words, first differing 2-bit group by count-trailing-zeros
@@ -206,11 +193,11 @@ W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32
             if (!part_same_edge(pv, h)) gd += pv.elen;
             int32_t diff = (int32_t)(gap_len - gd);
             uint32_t ad = (uint32_t)(diff < 0 ? -diff : diff);
-            if (!(ad <= 3u) || !part_joinable(g, pv, h)) {
+            if (!(ad <= 3u) || !part_joinable(*g, pv, h)) {
                 if (seeds > 1) { last2_is_gap = pv.after_gap; --npend; }   // drop the seed before the gap and everything after it
                 else { last2_is_gap = false; }                             // the gap absorbs everything after it
                 last_is_gap = true;
-                break;
+                return false;
             }
         }
         pending_gap = false;
@@ -220,52 +207,103 @@ W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32
         if (!have_first_hit) { have_first_hit = true; first_hit_off = h.off; }
         ++nparts; last2_is_gap = last_is_gap; last_is_gap = false;
         itr += len;
+        return true;
     }
-    // :904-918 a trailing seed that only reached <= 5 k-mers into an edge from its very start is dropped
-    if (last_is_gap) {
-        if (nparts > 1 && !last2_is_gap && npend > 0) { const PathPart& l2 = pend[npend - 1]; if (l2.off == 0 && l2.len <= 5) --npend; }
-    } else if (npend > 0) {
-        const PathPart& l = pend[npend - 1];
-        if (l.off == 0 && l.len <= 5) --npend;
+    W2R_HD bool scan() {
+        while (!scan_done && itr < nk) {
+            Kmer f = kmer_at(bases, itr);
+            Kmer r = kmer_rc(f);
+            const int64_t slot = solid_find_filtered(g->solid, g->bloom, kmer_less(r, f) ? r : f);
+            if (slot < 0) return true;
+            if (!seed(slot)) scan_done = true;
+        }
+        return false;
     }
-    for (int i = 0; i < npend; ++i) commit(pend[i]);
-    if (n_ids == 0 || res.overflow) return res;
-    int32_t offset = first_is_gap ? (int32_t)first_hit_off - (int32_t)gap0_len : (int32_t)first_hit_off;   // :816-826
+    W2R_HD void gap_found(uint32_t p, int64_t slot) {
+        const uint32_t gl = p - itr;
+        itr = p;
+        if (nparts == 0) { first_is_gap = true; gap0_len = gl; }
+        gap_len = gl; gap_index = nparts; ++nparts;
+        last2_is_gap = last_is_gap; last_is_gap = true;
+        pending_gap = true;
+        if (slot < 0 || !seed(slot)) scan_done = true;
+    }
+    W2R_HD PathResult finish(const uint8_t* qstream, uint8_t* qscratch, bool apply_fixpaths) {
+        PathResult res{0, left_cap, 0, false};
+        // :904-918 a trailing seed that only reached <= 5 k-mers into an edge from its very start is dropped
+        if (last_is_gap) {
+            if (nparts > 1 && !last2_is_gap && npend > 0) { const PathPart& l2 = pend[npend - 1]; if (l2.off == 0 && l2.len <= 5) --npend; }
+        } else if (npend > 0) {
+            const PathPart& l = pend[npend - 1];
+            if (l.off == 0 && l.len <= 5) --npend;
+        }
+        for (int i = 0; i < npend; ++i) commit(pend[i]);
+        res.overflow = overflow;
+        if (n_ids == 0 || res.overflow) return res;
+        int32_t offset = first_is_gap ? (int32_t)first_hit_off - (int32_t)gap0_len : (int32_t)first_hit_off;   // :816-826
 
-    // :922-923 quality-aware extension (ExtendReadPath.cc:115-348); all left extensions first, then right
-    bool have_quals = false;
-    uint32_t nl = 0;
-    int32_t front = row[PATH_LEFT_CAP], back = row[PATH_LEFT_CAP + n_ids - 1];
-    while (offset < 0 && (uint32_t)(-offset) >= 10u) {
-        if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
-        int32_t e = choose_extension(g, g.hleft[front], true, (uint32_t)(-offset), bases, qscratch, rlen);
-        if (e < 0) break;
-        uint32_t ek = hbv_edge_len(g, e) - K + 1;
-        offset += (int32_t)ek; sum_kmers += ek;
-        if (nl < PATH_LEFT_CAP) row[PATH_LEFT_CAP - 1 - nl] = e; else res.overflow = true;
-        ++nl; front = e;
+        // :922-923 quality-aware extension (ExtendReadPath.cc:115-348); all left extensions first, then right
+        bool have_quals = false;
+        uint32_t nl = 0;
+        int32_t front = row[left_cap], back = row[left_cap + n_ids - 1];
+        while (offset < 0 && (uint32_t)(-offset) >= 10u) {
+            if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
+            int32_t e = choose_extension(*g, g->hleft[front], true, (uint32_t)(-offset), bases, qscratch, rlen);
+            if (e < 0) break;
+            uint32_t ek = hbv_edge_len(*g, e) - K + 1;
+            offset += (int32_t)ek; sum_kmers += ek;
+            if (nl < left_cap) row[left_cap - 1 - nl] = e; else res.overflow = true;
+            ++nl; front = e;
+        }
+        for (;;) {
+            int32_t lastg = (int32_t)rlen + offset - (int32_t)sum_kmers - (K - 1);
+            if (lastg < 10) break;
+            if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
+            // the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
+            int32_t e = choose_extension(*g, g->hleft[back], false, (uint32_t)lastg, bases, qscratch, rlen);
+            if (e < 0) break;
+            sum_kmers += hbv_edge_len(*g, e) - K + 1;
+            if (n_ids < right_cap) row[left_cap + n_ids] = e; else res.overflow = true;
+            ++n_ids; back = e;
+        }
+        if (res.overflow) return res;
+        res.offset = offset;
+        res.start = left_cap - nl;
+        res.len = nl + n_ids;
+        if (apply_fixpaths) {                                    // large/GapToyTools.cc:322-335
+            const int32_t* p = row + res.start;
+            for (uint32_t i = 0; i + 1 < res.len; ++i)
+                if (g->hright[p[i]] != g->hleft[p[i + 1]]) { res.len = i + 1; break; }
+        }
+        return res;
     }
-    for (;;) {
-        int32_t lastg = (int32_t)rlen + offset - (int32_t)sum_kmers - (K - 1);
-        if (lastg < 10) break;
-        if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
-        // the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
-        int32_t e = choose_extension(g, g.hleft[back], false, (uint32_t)lastg, bases, qscratch, rlen);
-        if (e < 0) break;
-        sum_kmers += hbv_edge_len(g, e) - K + 1;
-        if (n_ids < right_cap) row[PATH_LEFT_CAP + n_ids] = e; else res.overflow = true;
-        ++n_ids; back = e;
+};
+
+// Paths one read, serially (the host check; the device kernel drives the walker itself and resolves gaps with the whole warp).
+// `row` is this read's staging row of `cap` ints; `qscratch` holds >= rlen bytes for lazily decoded quals.
+W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32_t rlen, const uint8_t* qstream, uint8_t* qscratch,
+                                int32_t* row, uint32_t cap, uint32_t left_cap, bool apply_fixpaths) {
+    PathWalker w;
+    w.init(g, bases, rlen, row, cap, left_cap);
+    while (w.scan()) {
+        uint32_t p = w.itr + 1;
+        int64_t slot = -1;
+        if (p < w.nk) {
+            Kmer f = kmer_at(bases, p), r = kmer_rc(f);
+            uint64_t nxt = 0;
+            for (uint32_t t = 0;; ++t) {
+                slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
+                if (slot >= 0 || p + 1 >= w.nk) { if (slot < 0) ++p; break; }
+                if ((t & 31u) == 0) nxt = bases32_at(bases, (uint64_t)p + K);
+                const uint32_t nb = (uint32_t)nxt & 3u;
+                nxt >>= 2;
+                f = kmer_succ(f, nb); r = kmer_pred(r, 3u - nb);
+                ++p;
+            }
+        }
+        w.gap_found(p, slot);
     }
-    if (res.overflow) return res;
-    res.offset = offset;
-    res.start = PATH_LEFT_CAP - nl;
-    res.len = nl + n_ids;
-    if (apply_fixpaths) {                                    // large/GapToyTools.cc:322-335
-        const int32_t* p = row + res.start;
-        for (uint32_t i = 0; i + 1 < res.len; ++i)
-            if (g.hright[p[i]] != g.hleft[p[i + 1]]) { res.len = i + 1; break; }
-    }
-    return res;
+    return w.finish(qstream, qscratch, apply_fixpaths);
 }
 
 }  // namespace w2r

@@ -711,12 +711,14 @@ struct Pipeline {
         d_offset.alloc(c, n); d_path_off.alloc(c, n + 1);
         *n_path_edges = 0; *pathed = 0; *multipathed = 0;
         if (!n) { W2R_CUDA(cudaMemsetAsync(d_path_off.p, 0, 8, c.stream)); return; }
-        // negative-lookup filter, pinned in L2 for the duration of the pathing kernel (kmer.cuh: KmerBloom)
+        // negative-lookup filter (kmer.cuh: KmerBloom), with an L2 persistence window for the duration of the pathing kernel.  Its
+        // false-positive rate matters more than full L2 residency: every false positive is a random DRAM fetch in the dictionary.
         SBuf<uint32_t> bloom_words;
         KmerBloom bloom{nullptr, 0};
         if (out->n_solid >= 4096 && !getenv("W2RAP_NO_BLOOM")) {
-            uint64_t bytes = std::min<uint64_t>(96ull << 20, std::max<uint64_t>(4096, out->n_solid * 2));
-            if (bytes * 8 >= 3 * out->n_solid) {          // below ~3 bits per key the filter passes most queries: not worth its L2
+            static const uint64_t bloom_mb = getenv("W2RAP_BLOOM_MB") ? (uint64_t)atoi(getenv("W2RAP_BLOOM_MB")) : 192;   // measured (config 2): 40 MB 111 ms, 96 MB 100 ms, 192 MB 97.5 ms
+            uint64_t bytes = std::min<uint64_t>(bloom_mb << 20, std::max<uint64_t>(4096, out->n_solid * 2));
+            if (bytes * 8 >= 2 * out->n_solid) {          // below ~2 bits per key the filter passes most queries: not worth its L2
                 bloom_words.alloc(c, bytes / 4); bloom_words.zero();
                 bloom = KmerBloom{bloom_words.p, bytes / 4};
                 W2R_LAUNCH(c, k_bloom_build, grid(st.size(), 256), 256, 0, st, bloom);
