@@ -46,6 +46,14 @@ def test_varlen_reads_fixpaths(T):
     T.assert_graph_equal(want, got)
 
 
+def test_long_reads_span_several_map_tiles(T):
+    """600-base reads: the map kernel handles a read in tiles of 192 k-mers, the path kernel screens gaps 32 positions at a time."""
+    rs = T.rich_set(seed=9, genome=50000, cov=40, read_len=600, families=3, palindromes=2, plasmid=2000, vary_len=True)
+    want, got = both(T, rs, dump_kmers=2, apply_fixpaths=1)
+    T.assert_graph_equal(want, got)
+    assert int(rs.len.max()) > 500 and got["n_pathed"] > 0
+
+
 @pytest.mark.parametrize("case", ["circ", "rich"])
 def test_golden_reference_outputs(T, case):
     """Straight against the files the UNMODIFIED reference wrote (tests/golden): modulo its racy edge numbering."""

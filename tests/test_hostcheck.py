@@ -73,6 +73,11 @@ def test_device_functions_rich_varlen_fixpaths(T, hc):
     check_against_oracle(T, hc, T.rich_set(seed=5, genome=40000, cov=50, families=5, palindromes=4, plasmid=1500, vary_len=True), apply_fixpaths=1)
 
 
+def test_device_functions_long_reads(T, hc):
+    """600-base reads of varying length (several gaps per read: the resumable path walker is resumed many times)."""
+    check_against_oracle(T, hc, T.rich_set(seed=9, genome=50000, cov=40, read_len=600, families=3, palindromes=2, plasmid=2000, vary_len=True), apply_fixpaths=1)
+
+
 def test_device_functions_golden_circ(T, hc):
     """Circles of both length parities, palindromes; tiny staging rows force the overflow path."""
     rs = T.read_fastb_qualp(os.path.join(HERE, "golden", "circ"))

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
 // table, so the per-record atomics are shared-memory atomics instead of L2 atomics (the L2-resident region count is limited by
 // L2 atomic throughput, about one record per 30 ps chip-wide).  One warp streams one 32-record chunk (512 contiguous bytes).
 // Partitions whose distinct k-mers do not fit are listed in `failed` and go through the region path afterwards.
-constexpr uint32_t SMEM_SLOTS = 8192;                          // 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
+constexpr uint32_t SMEM_LOG_SLOTS_MAX = 13;                    // 8192 slots: 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
 constexpr uint32_t SMEM_MAX_PROBE = 512;
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // read batches whose runs make up one partition
 struct SmemCountParams {
@@ -373,10 +373,13 @@ struct SmemCountParams {
     unsigned long long* hist;       // [104]
     ulonglong2* solid_out; unsigned long long* solid_cursor; uint64_t solid_cap; int* solid_overflow;
     DumpRec* dump_out; unsigned long long* dump_cursor;
-    uint32_t* failed; unsigned long long* failed_cursor;       // partitions that need the region path
+    uint32_t* failed; unsigned long long* failed_cursor;       // partitions that did not fit this table size
+    uint32_t log_slots;                                        // table size of this launch: 12 (two CTAs of 512 threads per SM) or 13
+    const uint32_t* plist; uint32_t nlist;                     // if set: only these partitions (the ones a smaller table could not hold)
 };
 __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t SMEM_SLOTS = 1u << sp.log_slots;
     unsigned long long* w0s = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* w1s = w0s + SMEM_SLOTS;
     uint32_t* ccs = reinterpret_cast<uint32_t*>(w1s + SMEM_SLOTS);          // count (low 24 bits) | ctx << 24
@@ -386,7 +389,9 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     __shared__ uint32_t sh_pre[SMEM_MAX_BATCH + 1];
     for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
     const uint32_t C = 1u << sp.logC;
-    for (uint32_t p = blockIdx.x; p < sp.P; p += gridDim.x) {
+    const uint32_t n_todo = sp.plist ? sp.nlist : sp.P;
+    for (uint32_t pi = blockIdx.x; pi < n_todo; pi += gridDim.x) {
+        const uint32_t p = sp.plist ? sp.plist[pi] : pi;
         for (uint32_t j = threadIdx.x; j < SMEM_SLOTS; j += blockDim.x) { w0s[j] = ~0ull; w1s[j] = ~0ull; ccs[j] = 0; }
         if (threadIdx.x == 0) {
             sh_fail = 0;
@@ -403,17 +408,11 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
         __syncthreads();
         const uint32_t n = sp.part_base ? sh_pre[SMEM_MAX_BATCH] : sp.cursor[p];
         const uint32_t* tab = sp.chunk_of + (uint64_t)p * sp.maxk;
-        uint32_t bi = 0;                                          // i only grows: the run index is carried along
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            ulonglong2 rec;
-            if (sp.part_base) {
-                while (i >= sh_pre[bi + 1]) ++bi;
-                rec = __ldcs(sp.recs + sh_run[bi] + (i - sh_pre[bi]));
-            } else rec = __ldcs(sp.recs + (((uint64_t)__ldg(tab + (i >> sp.logC))) << sp.logC) + (i & (C - 1u)));
+        auto insert = [&](const ulonglong2 rec) {
             const unsigned long long kw0 = rec.x, kw1 = rec.y & ~0xffull;
             const uint32_t ctx = (uint32_t)rec.y & 0xffu;
             const uint64_t h = kmer_hash(Kmer{kw0, kw1});
-            uint32_t s = (uint32_t)((sp.logP ? (h << sp.logP) : h) >> (64 - 13));            // 13 bits below the partition bits
+            uint32_t s = (uint32_t)((sp.logP ? (h << sp.logP) : h) >> (64 - sp.log_slots));   // the bits below the partition bits
             bool done = false;
             for (uint32_t probe = 0; probe < SMEM_MAX_PROBE && !done; ++probe) {
                 unsigned long long k0 = *(volatile unsigned long long*)(w0s + s);
@@ -435,6 +434,26 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
                 } else s = (s + 1u) & (SMEM_SLOTS - 1u);
             }
             if (!done) sh_fail = 1;
+        };
+        // four records per thread are in flight before the first is inserted: with one, the stream of records is latency-bound
+        // (bytes in flight per SM = 1024 threads x 16 B against ~1 us of DRAM latency)
+        constexpr int UNROLL = 4;
+        uint32_t bi = 0;                                          // i only grows: the run index is carried along
+        for (uint32_t i0 = threadIdx.x; i0 < n; i0 += UNROLL * blockDim.x) {
+            ulonglong2 rr[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+                if (i < n) {
+                    if (sp.part_base) {
+                        while (i >= sh_pre[bi + 1]) ++bi;
+                        rr[u] = __ldcs(sp.recs + sh_run[bi] + (i - sh_pre[bi]));
+                    } else rr[u] = __ldcs(sp.recs + (((uint64_t)__ldg(tab + (i >> sp.logC))) << sp.logC) + (i & (C - 1u)));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                if (i0 + (uint32_t)u * blockDim.x < n) insert(rr[u]);
         }
         __syncthreads();
         const bool failed = sh_fail != 0;

@@ -244,7 +244,10 @@ struct Pipeline {
         // are then all free for the slot inside the table (rlogP = 0)
         const bool mini = fine && !getenv("W2RAP_NO_MINIMIZER");
         uint32_t logP = 0;
-        static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : 24000.0;
+        // first table size tried by k_count_smem: 4096 slots (two 512-thread CTAs per SM, so that the table reset / output scan of one
+        // overlaps the inserts of the other) for partitions of ~12 k records, or 8192 slots and ~24 k records
+        static const uint32_t smem_log = getenv("W2RAP_SMEM_LOG") ? (uint32_t)atoi(getenv("W2RAP_SMEM_LOG")) : 13u;   // measured (config 2): 13 -> 73 ms, 12 -> 79 ms
+        static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : (smem_log <= 12 ? 12000.0 : 24000.0);
         if (fine) { while ((double)n_inst / (double)(1ull << logP) > fine_recs && logP < 22) ++logP; }
         else
         // (n_inst is an upper bound, and real read sets are far from all-distinct: 0.9 R records per partition; a partition that
@@ -432,18 +435,28 @@ struct Pipeline {
                 std::vector<int> gf(Pown + 1, 0);
                 if (fine) {
                     // every partition is counted by one CTA in shared memory; the few that do not fit are redone through the region below
-                    SBuf<uint32_t> failed(c, P);
-                    W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 8, c.stream));
-                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, mini ? part_base.p : nullptr, batch_off.p, nslab, logC, maxk, (uint32_t)P, mini ? 0u : logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
-                                       prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4};
-                    const size_t smem_bytes = (size_t)SMEM_SLOTS * 20;
+                    SBuf<uint32_t> failed(c, P), failed2(c, P);
+                    W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 16, c.stream));
                     static bool attr_set = false;
-                    if (!attr_set) { W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); attr_set = true; }
-                    k_count_smem<<<(unsigned)std::min<uint64_t>(P, (uint64_t)c.sm_count), 1024, smem_bytes, c.stream>>>(sc); c.launches++; ++n_groups;
+                    if (!attr_set) { W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((20u << SMEM_LOG_SLOTS_MAX)))); attr_set = true; }
+                    const uint32_t log1 = std::min(std::max(smem_log, 10u), SMEM_LOG_SLOTS_MAX);
+                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, mini ? part_base.p : nullptr, batch_off.p, nslab, logC, maxk, (uint32_t)P, mini ? 0u : logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
+                                       prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4, log1, nullptr, 0};
+                    const bool two_per_sm = log1 <= 12;
+                    k_count_smem<<<(unsigned)std::min<uint64_t>(P, (uint64_t)c.sm_count * (two_per_sm ? 2 : 1)), two_per_sm ? 512 : 1024, (size_t)20u << log1, c.stream>>>(sc); c.launches++; ++n_groups;
                     W2R_CUDA(cudaGetLastError());
-                    const uint64_t nfail = d2h_scalar(c, scal.p + 4);
+                    uint64_t nfail1 = log1 < SMEM_LOG_SLOTS_MAX ? d2h_scalar(c, scal.p + 4) : 0;
+                    if (nfail1) {       // second tier: the partitions that did not fit, with the largest table
+                        SmemCountParams sc2 = sc;
+                        sc2.failed = failed2.p; sc2.failed_cursor = scal.p + 5; sc2.log_slots = SMEM_LOG_SLOTS_MAX; sc2.plist = failed.p; sc2.nlist = (uint32_t)nfail1;
+                        k_count_smem<<<(unsigned)std::min<uint64_t>(nfail1, (uint64_t)c.sm_count), 1024, (size_t)20u << SMEM_LOG_SLOTS_MAX, c.stream>>>(sc2); c.launches++; ++n_groups;
+                        W2R_CUDA(cudaGetLastError());
+                    }
+                    const SBuf<uint32_t>& failed_final = nfail1 ? failed2 : failed;
+                    const unsigned long long* failed_final_cursor = nfail1 ? scal.p + 5 : scal.p + 4;
+                    const uint64_t nfail = d2h_scalar(c, failed_final_cursor);
                     std::vector<uint32_t> fl(nfail);
-                    if (nfail) { W2R_CUDA(cudaMemcpyAsync(fl.data(), failed.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream)); W2R_CUDA(cudaStreamSynchronize(c.stream)); }
+                    if (nfail) { W2R_CUDA(cudaMemcpyAsync(fl.data(), failed_final.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream)); W2R_CUDA(cudaStreamSynchronize(c.stream)); }
                     for (uint32_t q : fl) { groups.push_back({q, 1u}); gf[q] = 1; }
                     if (nfail) say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)P);
                 } else {
