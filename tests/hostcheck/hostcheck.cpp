@@ -61,26 +61,27 @@ int hc_count(const w2rap_reads* in, uint32_t min_qual, w2rap_kmer_rec** out, uin
 
 void hc_free(void* p) { free(p); }
 
-// ---- pieces of the sharded (multi-GPU) protocol, for the world_size-2 gloo test: the "map" side (k_extract_partition) and the
-// "reduce" side (k_count_region + k_scan_region) as separate calls, with the product's own partition/owner functions.
-// recs: n x {w0, w1|ctx}; owner[i] = rank that owns record i's hash partition.
+// ---- pieces of the sharded (multi-GPU) protocol, for the world_size-2 gloo test: the "map" side (k_minimizer_map) and the
+// "reduce" side (k_count_smem) as separate calls, with the product's own partition/owner functions.
+// recs: n x {w0, w1|ctx}; owner[i] = rank that owns record i's partition (keyed by the k-mer's minimiser, extract.cuh).
 int hc_extract_records(const w2rap_reads* in, uint32_t min_qual, uint32_t logP, uint32_t world, uint64_t** recs_out, uint32_t** owner_out, uint64_t* n_out) {
-    std::vector<Rec> recs;
-    Collect emit{&recs};
+    std::vector<uint64_t> flat;
+    std::vector<uint32_t> owner;
     for (uint64_t r = 0; r < in->n_reads; ++r) {
         uint32_t nq = 0;
         uint32_t gl = pq_good_length(in->quals + in->qual_off[r], min_qual, &nq);
         if (nq != in->len[r]) return 100;
         if (gl > in->len[r]) gl = in->len[r];
-        extract_read_kmers(in->bases + in->base_off[r], gl, emit);
+        const uint8_t* bases = in->bases + in->base_off[r];
+        KmerCursor cur;
+        cur.open(bases, gl);
+        Kmer k; uint32_t ctx;
+        for (uint64_t j = 0; cur.next(&k, &ctx); ++j) {
+            flat.push_back(k.w0); flat.push_back(k.w1 | ctx);
+            owner.push_back(owner_of_partition(mini_part(mini_mix(kmer_minimizer_hash(bases, j)), logP), logP, world));
+        }
     }
-    std::vector<uint64_t> flat(2 * recs.size());
-    std::vector<uint32_t> owner(recs.size());
-    for (size_t i = 0; i < recs.size(); ++i) {
-        flat[2 * i] = recs[i].w0; flat[2 * i + 1] = recs[i].w1 | recs[i].ctx;
-        owner[i] = owner_of_partition(part_of_hash(kmer_hash(Kmer{recs[i].w0, recs[i].w1}), logP), logP, world);
-    }
-    *n_out = recs.size(); *recs_out = dup(flat); *owner_out = dup(owner);
+    *n_out = owner.size(); *recs_out = dup(flat); *owner_out = dup(owner);
     return 0;
 }
 // Strand symmetry of the minimiser partition key (extract.cuh): the k-mer at position j of a read and the k-mer at position

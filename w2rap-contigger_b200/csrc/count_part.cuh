@@ -1,23 +1,24 @@
-// count_part.cuh — k-mer counting as partition + L2-resident hash count.
+// count_part.cuh — k-mer counting as map (partition) + reduce (count per partition).
 //
-// A global hash table ≫ L2 costs one random DRAM sector read and one write-back per k-mer INSTANCE (measured: 13 G inserts/s
-// on B200, 0.84 TB/s of 32-byte sector traffic).  Instead:
-//   pass A  k_extract_partition : every instance becomes a 16-byte record {w0, w1 | ctx} appended to the buffer of partition
-//                                 hash >> (64-logP).  Appends are one atomicAdd on the partition cursor + one 16-byte store;
-//                                 consecutive records of a partition fill whole sectors in L2 before they are evicted, so DRAM
-//                                 sees a streaming write of 16 B per instance.
-//   pass B  k_count_region      : the records of a group of partitions are streamed back (16 B per instance) and inserted into
-//                                 a 32 MB table REGION that stays resident in the 126 MB L2; all probing, the 128-bit CAS and
-//                                 the count/context REDs hit L2.
-//           k_scan_region       : histogram, min-frequency filter (solid records out), and the region is reset for the next group.
+// A global hash table >> L2 costs one random DRAM sector read and one write-back per k-mer INSTANCE (measured: 13 G inserts/s
+// on B200, 0.84 TB/s of 32-byte sector traffic).  Instead, the MapReduceEngine shape (MapReduceEngine.h:288-358) on the device:
+//   map     k_minimizer_map     : every instance becomes a 16-byte record {w0, w1 | ctx} in the record area of its partition.
+//                                 Partitions are keyed by MINIMISER, so a read appends runs of ~24 records; a counting launch
+//                                 sizes every partition exactly, a scan lays them out, a second launch stores (no capacity guess).
+//   reduce  k_count_smem        : one CTA counts one partition (~20 k records, a few thousand distinct k-mers) in a shared-memory
+//                                 hash table, then emits histogram + solid records.
+//           k_count_region /    : fallback for partitions that do not fit shared memory, and the legacy path behind the
+//           k_scan_region         table_slots test hook: inserts into a 32 MB table region that stays resident in L2
+//                                 (128-bit CAS, count/context REDs), then scan + reset.
+//   legacy map k_extract_partition : one thread per read, partition = top bits of the k-mer hash, static sub-buffers.
 // DRAM traffic: 16 B written + 16 B read per instance — the 34 B/instance of the SURVEY §8d model — and nothing else.
-// This is the MapReduceEngine shape (MapReduceEngine.h:288-358: map -> hash-partition -> reduce), on one device.
 #pragma once
 #include "kernels.cuh"
 #include "shard.cuh"
 
 namespace w2r {
 
+// ---------------------------------------------------------------- legacy map: hash partitions in static sub-buffers
 struct PartParams {
     ulonglong2* recs;        // [P * nsub][cap]
     uint32_t* cursor;        // [P * nsub] * cstride: records appended per sub-buffer, one cursor per L2 line
@@ -27,60 +28,7 @@ struct PartParams {
     uint32_t cstride;        // cursor stride in u32 (32 = one cursor per 128-byte line)
     uint32_t npass, pass;    // outer hash-range passes (when the records of everything would not fit): keep (hash & 0xffff) % npass == pass
     int* overflow;           // set if a sub-buffer overflowed
-    // chunked mode (single GPU): partition buffers grow in chunks of 1 << logC records taken from one pool in arrival order, so
-    // at any moment all appends land in a window of about P chunks (256 MB) instead of all over an 80 GB buffer: the scattered
-    // appends stop missing the TLB.  chunk_of[p * maxk + k] = pool chunk holding records [k << logC, (k+1) << logC) of partition p.
-    uint32_t chunked, logC, maxk;
-    uint32_t* chunk_of;      // NIL = not allocated yet
-    uint32_t* pool_next;     // bump allocators, one per sub-pool, each on its own 128-byte line (stride 32 u32)
-    uint32_t pool_chunks;    // chunks per sub-pool
-    uint32_t npool_log;      // 1 << npool_log sub-pools; partition p allocates from sub-pool p & (npool-1)
-    unsigned long long* ring;// optional [P][2]: (k << 32 | chunk) of the two newest chunks of every partition — small enough to
-                             // stay in L2 when the full table is not (fine partitions: 2^18 x ~1000 entries)
 };
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
-
-// Record `pos` of (sub-)buffer b, in two steps so that a warp can run step 1 on all its lanes before any lane waits in step 2.
-// Step 1: the writer of the record half way through a chunk allocates the next chunk of that partition ahead of need.
-__device__ __forceinline__ void chunk_alloc_ahead(const PartParams& pp, uint32_t b, uint32_t pos) {
-    if (!pp.chunked) return;
-    const uint32_t k = pos >> pp.logC, off = pos & ((1u << pp.logC) - 1u);
-    if (off != (1u << (pp.logC - 1)) || k + 1 >= pp.maxk) return;
-    const uint32_t sp = b & ((1u << pp.npool_log) - 1u);
-    const uint32_t a = atomicAdd(pp.pool_next + sp * 32u, 1u);
-    if (a < pp.pool_chunks) {
-        const uint32_t cid = sp * pp.pool_chunks + a;
-        st_volatile_u32(pp.chunk_of + (uint64_t)b * pp.maxk + k + 1, cid);
-        if (pp.ring) st_volatile_u64(pp.ring + 2ull * b + ((k + 1) & 1u), ((unsigned long long)(k + 1) << 32) | cid);
-    } else atomicExch(pp.overflow, 1);
-}
-// Step 2: find the chunk (ring of the two newest chunks first, then the table) and store.
-__device__ __forceinline__ void chunk_store(const PartParams& pp, uint32_t b, uint32_t pos, ulonglong2 r) {
-    if (!pp.chunked) {
-        if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
-        else atomicExch(pp.overflow, 1);
-        return;
-    }
-    const uint32_t k = pos >> pp.logC, off = pos & ((1u << pp.logC) - 1u);
-    if (k >= pp.maxk) { atomicExch(pp.overflow, 1); return; }
-    const uint32_t* tab = pp.chunk_of + (uint64_t)b * pp.maxk;
-    uint32_t g = NIL;
-    if (pp.ring) {
-        const unsigned long long e = ld_volatile_u64(pp.ring + 2ull * b + (k & 1u));
-        if ((uint32_t)(e >> 32) == k) g = (uint32_t)e;
-    }
-    if (g == NIL) g = ld_volatile_u32(tab + k);
-    while (g == NIL) {                                             // published half a chunk ago in practice
-        if (ld_volatile_u32(reinterpret_cast<const uint32_t*>(pp.overflow))) return;
-        g = ld_volatile_u32(tab + k);
-    }
-    pp.recs[((uint64_t)g << pp.logC) + off] = r;
-}
 
 // Appends records in PAIRS: the two cursor atomics are independent, so both are in flight together and the thread waits
 // for one round trip per two k-mers (the kernel is bound by the latency of the returning atomic x threads in flight).
@@ -92,8 +40,8 @@ struct PartEmit {
     uint32_t sub;
     __device__ __forceinline__ PartEmit(const PartParams& p, uint32_t sub_) : pp(p), rec(make_ulonglong2(0, 0)), bucket(0), pending(false), sub(sub_) {}
     __device__ __forceinline__ void put(uint32_t b, uint32_t pos, ulonglong2 r) {
-        chunk_alloc_ahead(pp, b, pos);
-        chunk_store(pp, b, pos, r);
+        if (pos < pp.cap) pp.recs[(uint64_t)b * pp.cap + pos] = r;
+        else atomicExch(pp.overflow, 1);
     }
     __device__ __forceinline__ void flush() {
         if (pending) { put(bucket, atomicAdd(pp.cursor + (uint64_t)bucket * pp.cstride, 1u), rec); pending = false; }
@@ -112,21 +60,6 @@ struct PartEmit {
     }
 };
 
-// chunk 0 of partition p is pool chunk p; everything else is allocated on the fly.  (A kernel, not a memcpy: while the read
-// stores are still being uploaded the H2D copy engine is busy, and a small copy would queue behind gigabytes of reads.)
-// Chunk 0 of partition p is entry p >> npool_log of sub-pool p & (npool-1).
-__global__ void k_init_chunks(uint32_t* chunk_of, uint32_t maxk, uint32_t P, uint32_t* pool_next, uint32_t pool_chunks, uint32_t npool_log, unsigned long long* ring) {
-    const uint32_t npool = 1u << npool_log;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)P * maxk; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t p = (uint32_t)(i / maxk);
-        const bool first = i % maxk == 0;
-        const uint32_t cid0 = (p & (npool - 1u)) * pool_chunks + (p >> npool_log);
-        chunk_of[i] = first ? cid0 : NIL;
-        if (first && ring) { ring[2ull * p] = cid0; ring[2ull * p + 1] = ~0ull; }
-    }
-    if (blockIdx.x == 0 && threadIdx.x < npool) pool_next[threadIdx.x * 32u] = P >> npool_log;
-}
-
 // paths/long/BuildReadQGraph.cc:1062-1080 (the "map" step): one thread per read.
 __global__ void __launch_bounds__(256, 6) k_extract_partition(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, PartParams pp) {
     const uint32_t sub = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (pp.nsub - 1);   // per warp
@@ -141,7 +74,8 @@ __global__ void __launch_bounds__(256, 6) k_extract_partition(ReadsView r, uint6
     }
 }
 
-// The "map" step, single GPU: one WARP per read, partitions keyed by minimiser (extract.cuh).  Lane l of step t handles k-mer
+// ---------------------------------------------------------------- map keyed by minimiser
+// The "map" step: one WARP per read, partitions keyed by minimiser (extract.cuh).  Lane l of step t handles k-mer
 // 32t + l: k-mer, context and window minimum are all computed independently per position (no rolling state), lanes whose
 // neighbours fall into the same partition form a segment, the segment head reserves the whole segment with one cursor atomic
 // and the lanes store their records side by side.  Window minima: the hashes of all m-mers of a tile live in registers (8 per
@@ -295,9 +229,8 @@ __device__ __forceinline__ void region_insert(const RegionParams& rp, uint64_t m
 __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64_t mask, ulonglong2 ra, ulonglong2 rb, bool two) {
     const uint64_t ha = kmer_hash(Kmer{ra.x, ra.y & ~0xffull});
     const uint64_t hb = kmer_hash(Kmer{rb.x, rb.y & ~0xffull});
-    // (records with w0 == ~0 are sentinels of count2.cuh's CTA-private runs: skipped)
-    const bool da = ra.x != ~0ull && (!rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id);
-    const bool db = two && rb.x != ~0ull && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
+    const bool da = (!rp.sub_mask || (((uint32_t)(ha >> 3)) & rp.sub_mask) == rp.sub_id);
+    const bool db = two && (!rp.sub_mask || (((uint32_t)(hb >> 3)) & rp.sub_mask) == rp.sub_id);
     CountSlot* qa = rp.region + region_slot_of_hash(ha, rp.logP, rp.logR);
     CountSlot* qb = rp.region + region_slot_of_hash(hb, rp.logP, rp.logR);
     uint64_t a0 = 0, a1 = 0, am = 0, b0 = 0, b1 = 0, bm = 0;
@@ -316,34 +249,19 @@ __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64
 }
 
 // The "reduce" step (BuildReadQGraph.cc:1081-1082 sort+collapse as a hash count).  blockIdx.y selects the sub-buffer of the group.
-// recs/sizes hold one slab per source rank ([n_src][owned sub-buffers]); blockIdx.y = src * gy + sub-buffer within the group.
-// Chunked buffers (cv.chunk_of != nullptr): a block takes whole chunks, so the chunk table is read once per 2048 records.
-// chunk_of == nullptr: static sub-buffers; with part_base set, slab `src` is a read batch and partition b of it is the run
-// recs[batch_off[src] + part_base[src * P + b] ...)
-struct ChunkView { const uint32_t* chunk_of; uint32_t logC, maxk; const uint64_t* part_base; const unsigned long long* batch_off; uint64_t P; };
+// recs/sizes hold one slab per source ([n_src][owned sub-buffers]); blockIdx.y = src * gy + sub-buffer within the group.
+// Legacy layout (rv.part_base == nullptr): static sub-buffers of `cap` records, slab src at recs + src * slab_recs.
+// Minimiser layout: slab src (a read batch, or a source rank) starts at rv.slab_off[src]; partition b of it is the run
+// recs[slab_off[src] + part_base[src * P + b] ...) of sizes[src * slab_cur + b] records.
+struct RunView { const uint64_t* part_base; const unsigned long long* slab_off; uint64_t P; };
 __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
-                                                      uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, ChunkView cv, RegionParams rp) {
+                                                      uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, RunView rv, RegionParams rp) {
     const uint32_t src = blockIdx.y / gy;
     const uint32_t b = b_first + (blockIdx.y - src * gy);
     uint64_t n = sizes[(uint64_t)src * slab_cur + (uint64_t)b * cstride];
     if (n > cap) n = cap;
     const uint64_t mask = (1ull << rp.logR) - 1;
-    if (cv.chunk_of) {
-        const uint32_t* tab = cv.chunk_of + (uint64_t)b * cv.maxk;
-        const uint64_t C = 1ull << cv.logC, nchunks = (n + C - 1) >> cv.logC;
-        for (uint64_t k = blockIdx.x; k < nchunks; k += gridDim.x) {
-            const ulonglong2* cb = recs + ((uint64_t)__ldg(tab + k) << cv.logC);
-            const uint32_t cnt = (uint32_t)(n - (k << cv.logC) < C ? n - (k << cv.logC) : C);
-            for (uint32_t i = threadIdx.x; i < cnt; i += 2 * blockDim.x) {
-                const bool two = i + blockDim.x < cnt;
-                const ulonglong2 ra = __ldcs(cb + i);
-                const ulonglong2 rb = two ? __ldcs(cb + i + blockDim.x) : make_ulonglong2(0, 0);
-                region_count_pair(rp, mask, ra, rb, two);
-            }
-        }
-        return;
-    }
-    const ulonglong2* base = cv.part_base ? recs + cv.batch_off[src] + cv.part_base[(uint64_t)src * cv.P + b] : recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
+    const ulonglong2* base = rv.part_base ? recs + rv.slab_off[src] + rv.part_base[(uint64_t)src * rv.P + b] : recs + (uint64_t)src * slab_recs + (uint64_t)b * cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
         const bool two = i + stride < n;
@@ -356,19 +274,19 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
 // ---------------------------------------------------------------- reduce in SHARED memory (fine partitions, single GPU)
 // With ~2^18 partitions a partition holds ~20 k records and a few thousand distinct k-mers: one CTA counts it in a shared-memory
 // table, so the per-record atomics are shared-memory atomics instead of L2 atomics (the L2-resident region count is limited by
-// L2 atomic throughput, about one record per 30 ps chip-wide).  One warp streams one 32-record chunk (512 contiguous bytes).
-// Partitions whose distinct k-mers do not fit are listed in `failed` and go through the region path afterwards.
+// L2 atomic throughput, about one record per 30 ps chip-wide).  A partition is one contiguous run of records per slab (read
+// batch on one GPU, source rank when sharded).  Partitions whose distinct k-mers do not fit are listed in `failed`: they are
+// retried with a larger table and, failing that, go through the region path.
 constexpr uint32_t SMEM_LOG_SLOTS_MAX = 13;                    // 8192 slots: 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
 constexpr uint32_t SMEM_MAX_PROBE = 512;
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // read batches whose runs make up one partition
 struct SmemCountParams {
     const ulonglong2* recs;
-    const uint32_t* cursor;         // records per partition
-    const uint32_t* chunk_of;       // [P][maxk]
-    const uint64_t* part_base;      // if set: partition p is, per read batch bi < nbatch, the contiguous run
+    const uint32_t* cursor;         // [nbatch][P] records of partition p in slab bi
+    const uint64_t* part_base;      // partition p is, per slab bi < nbatch, the contiguous run
     const unsigned long long* batch_off;   //   recs[batch_off[bi] + part_base[bi * P + p] .. + cursor[bi * P + p])
     uint32_t nbatch;
-    uint32_t logC, maxk, P, logP;
+    uint32_t P, logP;
     uint32_t min_freq;
     unsigned long long* hist;       // [104]
     ulonglong2* solid_out; unsigned long long* solid_cursor; uint64_t solid_cap; int* solid_overflow;
@@ -388,26 +306,22 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     __shared__ unsigned long long sh_run[SMEM_MAX_BATCH];
     __shared__ uint32_t sh_pre[SMEM_MAX_BATCH + 1];
     for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
-    const uint32_t C = 1u << sp.logC;
     const uint32_t n_todo = sp.plist ? sp.nlist : sp.P;
     for (uint32_t pi = blockIdx.x; pi < n_todo; pi += gridDim.x) {
         const uint32_t p = sp.plist ? sp.plist[pi] : pi;
         for (uint32_t j = threadIdx.x; j < SMEM_SLOTS; j += blockDim.x) { w0s[j] = ~0ull; w1s[j] = ~0ull; ccs[j] = 0; }
         if (threadIdx.x == 0) {
             sh_fail = 0;
-            if (sp.part_base) {
-                uint32_t acc = 0;
-                for (uint32_t bi = 0; bi < sp.nbatch; ++bi) {
-                    sh_run[bi] = sp.batch_off[bi] + sp.part_base[(uint64_t)bi * sp.P + p];
-                    sh_pre[bi] = acc;
-                    acc += sp.cursor[(uint64_t)bi * sp.P + p];
-                }
-                for (uint32_t bi = sp.nbatch; bi <= SMEM_MAX_BATCH; ++bi) sh_pre[bi] = acc;
+            uint32_t acc = 0;
+            for (uint32_t bi = 0; bi < sp.nbatch; ++bi) {
+                sh_run[bi] = sp.batch_off[bi] + sp.part_base[(uint64_t)bi * sp.P + p];
+                sh_pre[bi] = acc;
+                acc += sp.cursor[(uint64_t)bi * sp.P + p];
             }
+            for (uint32_t bi = sp.nbatch; bi <= SMEM_MAX_BATCH; ++bi) sh_pre[bi] = acc;
         }
         __syncthreads();
-        const uint32_t n = sp.part_base ? sh_pre[SMEM_MAX_BATCH] : sp.cursor[p];
-        const uint32_t* tab = sp.chunk_of + (uint64_t)p * sp.maxk;
+        const uint32_t n = sh_pre[SMEM_MAX_BATCH];
         auto insert = [&](const ulonglong2 rec) {
             const unsigned long long kw0 = rec.x, kw1 = rec.y & ~0xffull;
             const uint32_t ctx = (uint32_t)rec.y & 0xffu;
@@ -445,10 +359,8 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t i = i0 + (uint32_t)u * blockDim.x;
                 if (i < n) {
-                    if (sp.part_base) {
-                        while (i >= sh_pre[bi + 1]) ++bi;
-                        rr[u] = __ldcs(sp.recs + sh_run[bi] + (i - sh_pre[bi]));
-                    } else rr[u] = __ldcs(sp.recs + (((uint64_t)__ldg(tab + (i >> sp.logC))) << sp.logC) + (i & (C - 1u)));
+                    while (i >= sh_pre[bi + 1]) ++bi;
+                    rr[u] = __ldcs(sp.recs + sh_run[bi] + (i - sh_pre[bi]));
                 }
             }
 #pragma unroll

@@ -209,15 +209,31 @@ struct Pipeline {
         W2R_CUDA(cudaMemcpyAsync((char*)recv + (size_t)rank * slab_bytes, (const char*)send + (size_t)rank * slab_bytes, slab_bytes, cudaMemcpyDeviceToDevice, c.stream));
     }
 
+    // byte-granular all-to-all with per-peer sizes (the minimiser layout: every rank sends each peer exactly the runs of the
+    // partitions that peer owns)
+    void alltoall_v(const void* send, const std::vector<size_t>& soff, const std::vector<size_t>& scnt, void* recv, const std::vector<size_t>& roff,
+                    const std::vector<size_t>& rcnt) {
+        NcclApi& n = NcclApi::get();
+        nccl_check(n.GroupStart(), "group start");
+        for (int peer = 0; peer < world; ++peer) {
+            if (peer == rank) continue;
+            if (scnt[peer]) nccl_check(n.Send((const char*)send + soff[peer], scnt[peer], ncclUint8, peer, comm, c.stream), "send");
+            if (rcnt[peer]) nccl_check(n.Recv((char*)recv + roff[peer], rcnt[peer], ncclUint8, peer, comm, c.stream), "recv");
+        }
+        nccl_check(n.GroupEnd(), "group end");
+        if (scnt[rank]) W2R_CUDA(cudaMemcpyAsync((char*)recv + roff[rank], (const char*)send + soff[rank], scnt[rank], cudaMemcpyDeviceToDevice, c.stream));
+    }
+
+    // ---- createDictOMPRecursive (BuildReadQGraph.cc:1000-1108): quality floor, k-mer counting, min-frequency filter, dictionary
     void count_stage() {
         const ReadsView rv = dr.view();
         good.alloc(c, dr.n);
-        SBuf<unsigned long long> scal(c, 8);
+        SBuf<unsigned long long> scal(c, 8);       // [0] k-mer instances, [1] solid cursor, [2] dump cursor, [4], [5] failed-partition cursors
         scal.zero();
-        SBuf<int> flags(c, 4);
+        SBuf<int> flags(c, 4);                     // [0] malformed quality vector, [1] record buffer overflow, [2] solid staging overflow
         flags.zero();
         // Everything is sized from an upper bound of the instance count that needs no qualities (sum of len-59), so that the
-        // quality floor + extraction of the first read batch can start while later batches are still crossing PCIe.
+        // quality floor + map of the first read batch can start while later batches are still crossing PCIe.
         const unsigned long long n_inst_local = dr.n_inst_upper;
         std::vector<unsigned long long> agg = {n_inst_local};
         allreduce_u64(agg, ncclSum);
@@ -236,19 +252,18 @@ struct Pipeline {
         while (logR > 8 && (1ull << (logR - 1)) >= 2 * n_inst + 64) --logR;
         if (prm.table_slots) { logR = 6; while ((2ull << logR) <= prm.table_slots && logR < 24) ++logR; }
         const uint64_t R = 1ull << logR;
-        // partitions: few enough records each that even an all-distinct partition fits the region at load 0.6;
-        // at least one per rank: rank r owns the contiguous range [r*P/world, (r+1)*P/world)
-        // single GPU: FINE partitions (~24 k records each) that one CTA counts in shared memory (count_part.cuh: k_count_smem)
-        const bool fine = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS") && !getenv("W2RAP_COARSE");
-        // ... keyed by minimiser, so that a read appends runs of records (count_part.cuh: k_minimizer_map); the k-mer hash bits
-        // are then all free for the slot inside the table (rlogP = 0)
-        const bool mini = fine && !getenv("W2RAP_NO_MINIMIZER");
-        uint32_t logP = 0;
-        // first table size tried by k_count_smem: 4096 slots (two 512-thread CTAs per SM, so that the table reset / output scan of one
-        // overlaps the inserts of the other) for partitions of ~12 k records, or 8192 slots and ~24 k records
-        static const uint32_t smem_log = getenv("W2RAP_SMEM_LOG") ? (uint32_t)atoi(getenv("W2RAP_SMEM_LOG")) : 13u;   // measured (config 2): 13 -> 73 ms, 12 -> 79 ms
+        // Default: FINE partitions keyed by minimiser (count_part.cuh: k_minimizer_map), each small enough for one CTA to count in
+        // shared memory (k_count_smem); the k-mer hash bits are then all free for the slot inside the table.  Rank r owns the
+        // contiguous partition range [r*P/world, (r+1)*P/world).
+        // Legacy (the table_slots test hook, W2RAP_STATIC_PARTITIONS): hash partitions in static sub-buffers, counted through the
+        // L2 region; few enough records each that even an all-distinct partition fits the region.
+        const bool mini = !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS");
+        // table size of the first k_count_smem launch: 8192 slots and partitions of ~24 k records (measured, config 2: 73 ms; 4096
+        // slots with two 512-thread CTAs per SM and ~12 k records: 79 ms)
+        static const uint32_t smem_log = getenv("W2RAP_SMEM_LOG") ? (uint32_t)atoi(getenv("W2RAP_SMEM_LOG")) : 13u;
         static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : (smem_log <= 12 ? 12000.0 : 24000.0);
-        if (fine) { while ((double)n_inst / (double)(1ull << logP) > fine_recs && logP < 22) ++logP; }
+        uint32_t logP = 0;
+        if (mini) { while (((double)n_inst / (double)(1ull << logP) > fine_recs || (1ull << logP) < (uint64_t)world) && logP < 22) ++logP; }
         else
         // (n_inst is an upper bound, and real read sets are far from all-distinct: 0.9 R records per partition; a partition that
         //  does not fit is handled by the hash sub-range fallback)
@@ -281,48 +296,45 @@ struct Pipeline {
         for (int attempt = 0;; ++attempt) {
             if (attempt > 8) W2R_FAIL(W2RAP_ERR_INTERNAL, "k-mer partitioning did not converge");
             const uint64_t P = 1ull << logP, Pown = P / world;
-            // sub-buffers: 8 per partition, cursors on separate L2 lines
-            // single GPU: chunked partition buffers (one pass, TLB-friendly); several GPUs: static sub-buffers = contiguous slabs to exchange
-            const bool chunked = world == 1 && !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS") && !mini;
-            const uint32_t nsub = (!chunked && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
-            const uint32_t cstride = fine ? 1 : 32;
+            // legacy layout: 8 sub-buffers per partition with cursors on separate L2 lines; minimiser layout: one cursor per partition
+            const uint32_t nsub = (!mini && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
+            const uint32_t cstride = mini ? 1 : 32;
             const uint64_t NB = P * nsub, NBown = Pown * nsub;
-            // chunk size: keep the append window (P open chunks) within ~128 MB, i.e. inside the TLB reach
-            uint32_t logC = 11;
-            static const double window_mb = getenv("W2RAP_WINDOW_MB") ? atof(getenv("W2RAP_WINDOW_MB")) : 128.0;
-            while (logC > (fine ? 4u : 8u) && (double)((P << logC) * sizeof(ulonglong2)) > window_mb * 1048576.0) --logC;
             const uint64_t per_part = (uint64_t)((double)n_inst_max / (double)NB / (double)npass);
-            const uint32_t maxk = (uint32_t)((per_part * slack * 1.5) / (1u << logC)) + 4;
-            const uint32_t npool_log = fine ? std::min<uint32_t>(6, logP) : 0;       // bump allocators: one address would serialise 10^8 chunk allocations
-            const uint64_t chunks_total = chunked ? (uint64_t)((double)n_inst_max / npass * 1.01) / (1u << logC) + 2 * P + 1024 : 0;
-            const uint64_t pool_chunks = chunked ? (uint64_t)((double)(chunks_total >> npool_log) * (npool_log ? 1.05 : 1.0)) + 1024 : 0;   // per sub-pool
-            const uint64_t cap = chunked ? (uint64_t)maxk << logC : mini ? (1ull << 40) : (uint64_t)((double)per_part * slack) + 1024;
-            // (minimiser mode: exact sizes come from the counting launch; passes are split by minimiser hash, so allow for uneven passes)
-            const size_t rec_bytes = chunked ? ((pool_chunks << npool_log) << logC) * sizeof(ulonglong2)
-                                   : mini    ? (size_t)((double)n_inst_max / npass * (npass > 1 ? slack * 1.2 : 1.0)) * sizeof(ulonglong2)
-                                             : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
-            // Scattered appends over a record buffer of tens of GB run into TLB misses (measured: the same kernel is 2x faster per
-            // record on a 41 GB buffer than on an 82 GB one), so the buffer is also capped and the k-mer space split into more
-            // hash-range passes instead; extraction is repeated per pass, which is cheap next to the appends.
+            const uint64_t cap = mini ? (1ull << 40) : (uint64_t)((double)per_part * slack) + 1024;
+            // minimiser layout: the local record area is sized from the upper bound (exact sizes come from the counting launch, but
+            // only on the device); with several passes the k-mer space is split by minimiser hash, so allow for uneven passes.
+            // Sharded: plus the records this rank owns (allocated exactly once the counts have been exchanged).
+            const size_t local_recs = mini ? (size_t)((double)n_inst_local / npass * (npass > 1 ? slack * 1.2 : 1.0)) + 64 : NB * cap;
+            const size_t rec_bytes = mini ? (local_recs + (world > 1 ? (size_t)((double)n_inst / world / npass * 1.25) : 0)) * sizeof(ulonglong2)
+                                          : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
+            // Legacy layout: scattered single-record appends over tens of GB run into TLB misses (measured: 2x slower per record on
+            // an 82 GB buffer than on a 41 GB one), so that buffer is capped and the k-mer space split into hash-range passes.
             static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
-            if ((rec_bytes + fixed_bytes > budget || (!chunked && !mini && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) && npass < 4096) { npass *= 2; continue; }
-            if ((pool_chunks << npool_log) >= 0xfffffff0ull) { npass *= 2; continue; }
+            std::vector<unsigned long long> too_big = {(rec_bytes + fixed_bytes > budget || (!mini && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) ? 1ull : 0ull};
+            allreduce_u64(too_big, ncclMax);                     // every rank must run the same number of passes
+            if (too_big[0] && npass < 4096) { npass *= 2; continue; }
             const double t_alloc0 = now_ms();
-            SBuf<ulonglong2> recs(c, chunked ? ((pool_chunks << npool_log) << logC) : mini ? rec_bytes / sizeof(ulonglong2) : NB * cap), xrecs_buf(c, world > 1 ? NB * cap : 0);
+            SBuf<ulonglong2> recs(c, local_recs), xrecs_buf(c, (!mini && world > 1) ? NB * cap : 0);
             if (getenv("W2RAP_TRACE")) fprintf(stderr, "[w2rap] count: record buffer %.2f GB allocated in %.1f ms (host)\n", recs.bytes() / 1e9, now_ms() - t_alloc0);
-            // minimiser mode: every read batch gets its own exactly sized record area, so that a batch is mapped as soon as it has
-            // arrived; a partition is then one run per batch (the batches play the part the source ranks play in the sharded layout)
-            const uint32_t nslab = mini ? (uint32_t)batches.size() : (uint32_t)world;
-            if (mini && nslab > SMEM_MAX_BATCH) W2R_FAIL(W2RAP_ERR_INTERNAL, "more read batches than the reduce kernel handles");
-            SBuf<uint32_t> part_count(c, mini ? nslab * P : 0);
-            SBuf<uint64_t> part_base(c, mini ? nslab * P : 0), batch_total(c, mini ? nslab : 0);
-            SBuf<unsigned long long> batch_off(c, mini ? nslab + 1 : 0);
-            SBuf<uint32_t> chunk_of(c, chunked ? P * maxk : 0), pool_next(c, 32ull << npool_log);
-            SBuf<unsigned long long> ring(c, fine ? 2 * P : 0);
-            SBuf<uint32_t> cursor(c, NB * cstride * (mini ? nslab : 1)), xcur_buf(c, world > 1 ? NB * cstride : 0);
-            const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;          // [world][NBown][cap]: what this rank reduces
-            const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [world][NBown][cstride]
+            // Minimiser layout, one GPU: every read batch gets its own exactly sized record area, so that a batch is mapped as soon
+            // as it has arrived; a partition is then one run per batch.  Sharded: one local area, laid out by partition = by owner,
+            // and after the exchange a partition is one run per source rank.  Either way the reduce sees `nslab` runs per partition.
+            const uint32_t nmap = mini ? (world > 1 ? 1u : (uint32_t)batches.size()) : 0u;
+            const uint32_t nslab = mini ? (world > 1 ? (uint32_t)world : nmap) : (uint32_t)world;
+            if (mini && nslab > SMEM_MAX_BATCH) W2R_FAIL(W2RAP_ERR_INTERNAL, "more record slabs per partition than the reduce kernel handles");
+            SBuf<uint32_t> part_count(c, nmap * P);
+            SBuf<uint64_t> part_base(c, nmap * P), batch_total(c, nmap);
+            SBuf<unsigned long long> batch_off(c, mini ? nmap + 1 : 0);
+            SBuf<uint32_t> cursor(c, mini ? nmap * P : NB * cstride), xcur_buf(c, world > 1 ? (mini ? world * Pown : NB * cstride) : 0);
+            SBuf<uint64_t> xbase(c, (mini && world > 1) ? world * Pown : 0), xtot(c, (mini && world > 1) ? world : 0);
+            SBuf<unsigned long long> xoff(c, (mini && world > 1) ? world + 1 : 0);
             const uint64_t slab_recs = NBown * cap, slab_cur = NBown * cstride;
+            // what this rank reduces: records, per-slab partition sizes, and (minimiser layout) where the runs start
+            const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;
+            const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [nslab][NBown][cstride]
+            RunView runs{nullptr, nullptr, Pown};
+            if (mini) runs = world > 1 ? RunView{xbase.p, xoff.p, Pown} : RunView{part_base.p, batch_off.p, Pown};
             std::vector<uint32_t> sizes(Pown), raw_sizes((size_t)nslab * slab_cur);
             bool retry = false;
             W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
@@ -330,17 +342,24 @@ struct Pipeline {
             uint64_t solid_used_before = 0;
             for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
                 cursor.zero();
-                if (chunked) W2R_LAUNCH(c, k_init_chunks, grid(P * maxk, 256), 256, 0, chunk_of.p, maxk, (uint32_t)P, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr);
-                PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1, chunked ? 1u : 0u, logC, maxk, chunk_of.p, pool_next.p, (uint32_t)pool_chunks, npool_log, fine ? ring.p : nullptr};
                 if (mini) {
-                    // launch 1 sizes the partitions exactly (runs per read batch, under the upload), the scan lays them out, launch 2 stores
+                    // launch 1 sizes the partitions exactly (per read batch, under the upload), the scan lays them out, launch 2 stores
                     static const unsigned map_ctas = getenv("W2RAP_MAP_CTAS") ? (unsigned)atoi(getenv("W2RAP_MAP_CTAS")) : 8u;
                     part_count.zero();
                     W2R_CUDA(cudaMemsetAsync(batch_off.p, 0, sizeof(unsigned long long), c.stream));
-                    std::vector<cudaEvent_t> ev(2 * nslab, nullptr);                 // the store launches are timed without stalling the queue
+                    std::vector<Batch> mb = batches;
+                    if (world > 1) {        // sharded: one map batch (the layout must be by owner rank), after the whole shard has arrived
+                        for (const Batch& bt : batches) {
+                            if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
+                            if (bt.count && !good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
+                        }
+                        good_done = true;
+                        mb.assign(1, Batch{0, dr.n, nullptr});
+                    }
+                    std::vector<cudaEvent_t> ev(2 * nmap, nullptr);                 // the store launches are timed without stalling the queue
                     struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); } } evg{ev};
-                    for (uint32_t bi = 0; bi < nslab; ++bi) {
-                        const Batch& bt = batches[bi];
+                    for (uint32_t bi = 0; bi < nmap; ++bi) {
+                        const Batch& bt = mb[bi];
                         MiniParams mp{logP, npass, pass, part_count.p + bi * P, part_base.p + bi * P, cursor.p + bi * P, recs.p, batch_off.p + bi, recs.n, flags.p + 1};
                         if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
                         if (bt.count && !good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
@@ -354,29 +373,54 @@ struct Pipeline {
                     }
                     good_done = true;
                     W2R_CUDA(cudaStreamSynchronize(c.stream));
-                    for (uint32_t bi = 0; bi < nslab; ++bi) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * bi], ev[2 * bi + 1]); part_ms += ms; }
+                    for (uint32_t bi = 0; bi < nmap; ++bi) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * bi], ev[2 * bi + 1]); part_ms += ms; }
                 } else {
-                kt.start();
-                for (const Batch& bt : batches) {
-                    if (!bt.count) continue;
-                    if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
-                    if (!good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
-                    if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(bt.count, 256, 8), 256, 0, rv, bt.first, bt.count, good.p, pp); c.count_launches++; }
-                }
-                good_done = true;
-                part_ms += kt.stop();
+                    PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1};
+                    kt.start();
+                    for (const Batch& bt : batches) {
+                        if (!bt.count) continue;
+                        if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
+                        if (!good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
+                        if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(bt.count, 256, 8), 256, 0, rv, bt.first, bt.count, good.p, pp); c.count_launches++; }
+                    }
+                    good_done = true;
+                    part_ms += kt.stop();
                 }
                 if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
                 std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, flags.p + 1)};
                 allreduce_u64(of, ncclSum);
-                if (of[0]) {        // a sub-buffer overflowed somewhere (skewed k-mer multiplicities): more slack, on every rank
+                if (of[0]) {        // a record buffer overflowed somewhere (legacy: skewed k-mer multiplicities; minimiser: an uneven pass): more slack, on every rank
                     W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
                     slack *= 1.5; retry = true; break;
                 }
-                if (world > 1) {    // route every record to the rank that owns its partition
+                if (world > 1 && !mini) {    // route every record to the rank that owns its partition: fixed-size slabs
                     kt.start();
                     alltoall_slabs(recs.p, xrecs_buf.p, slab_recs * sizeof(ulonglong2));
                     alltoall_slabs(cursor.p, xcur_buf.p, slab_cur * sizeof(uint32_t));
+                    xchg_ms += kt.stop();
+                }
+                if (world > 1 && mini) {     // ... exactly sized runs: counts first, then the records
+                    kt.start();
+                    alltoall_slabs(part_count.p, xcur_buf.p, Pown * sizeof(uint32_t));          // xcur[s][q] = records of my partition q held by rank s
+                    W2R_CUDA(cudaMemsetAsync(xoff.p, 0, sizeof(unsigned long long), c.stream));
+                    for (int sidx = 0; sidx < world; ++sidx) {
+                        exclusive_scan<uint32_t, uint64_t>(c, xcur_buf.p + (uint64_t)sidx * Pown, Pown, xbase.p + (uint64_t)sidx * Pown, xtot.p + sidx);
+                        W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, xoff.p + sidx, xtot.p + sidx);
+                    }
+                    std::vector<uint64_t> sbeg(world + 1, 0), rtot(world, 0);
+                    for (int d = 0; d < world; ++d) W2R_CUDA(cudaMemcpyAsync(&sbeg[d], part_base.p + (uint64_t)d * Pown, 8, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaMemcpyAsync(&sbeg[world], batch_total.p, 8, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaMemcpyAsync(rtot.data(), xtot.p, world * 8, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    std::vector<size_t> soff(world), scnt(world), roff(world), rcnt(world);
+                    size_t racc = 0;
+                    for (int d = 0; d < world; ++d) {
+                        soff[d] = sbeg[d] * sizeof(ulonglong2); scnt[d] = (sbeg[d + 1] - sbeg[d]) * sizeof(ulonglong2);
+                        roff[d] = racc * sizeof(ulonglong2); rcnt[d] = rtot[d] * sizeof(ulonglong2); racc += rtot[d];
+                    }
+                    xrecs_buf.alloc(c, racc + 1);
+                    xrecs = xrecs_buf.p;
+                    alltoall_v(recs.p, soff, scnt, xrecs_buf.p, roff, rcnt);
                     xchg_ms += kt.stop();
                 }
                 W2R_CUDA(cudaMemcpyAsync(raw_sizes.data(), xcur, raw_sizes.size() * 4, cudaMemcpyDeviceToHost, c.stream));
@@ -386,7 +430,7 @@ struct Pipeline {
                     uint32_t mxs = 0;
                     for (uint32_t sidx = 0; sidx < nslab; ++sidx)
                         for (uint32_t u = 0; u < nsub; ++u) { uint32_t v = raw_sizes[sidx * slab_cur + (q * nsub + u) * cstride]; mxs = std::max(mxs, v); owned_records += v; }
-                    sizes[q] = mxs;      // largest sub-buffer of the partition (sizes the grid)
+                    sizes[q] = mxs;      // largest run / sub-buffer of the partition (sizes the grid)
                 }
                 {   // staging for this pass's solid records (each needs >= min_freq instances)
                     uint64_t need = solid_used_before + owned_records / std::max<uint32_t>(1, prm.min_freq) + 1024;
@@ -397,9 +441,9 @@ struct Pipeline {
                         solid_cap = solid.n;
                     }
                 }
-                // ---- reduce: groups of consecutive owned partitions share the region; the group size comes from the first partition's distinct count
+                // ---- reduce
                 kt.start();
-                // the persisting carve-out is taken from the normal L2, which pass A needs for write combining: hold it only while reducing
+                // the persisting carve-out is taken from the normal L2, which the map needs for write combining: hold it only while reducing
                 if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(2 * R * sizeof(CountSlot), 80u << 20)) != cudaSuccess) cudaGetLastError();
                 set_l2_window(region.p, 2 * R * sizeof(CountSlot));
                 {   // the second stream gets the same L2 window and starts after everything queued so far
@@ -412,6 +456,7 @@ struct Pipeline {
                 auto fork = [&] { W2R_CUDA(cudaEventRecord(ev_fork, c.stream)); W2R_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0)); };
                 auto join = [&] { W2R_CUDA(cudaEventRecord(ev_join, s2)); W2R_CUDA(cudaStreamWaitEvent(c.stream, ev_join, 0)); };
                 fork();
+                // a group of consecutive owned partitions goes through one counting region
                 auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag) {
                     ++n_groups;
                     uint32_t mxg = 0;
@@ -422,64 +467,64 @@ struct Pipeline {
                     if (mxg) {
                         RegionParams rp{greg, logR, mini ? 0u : logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
-                        dim3 gr(std::max(1u, std::min<unsigned>(chunked ? ((mxg >> logC) + 1) : (mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * nslab, 8u))))), gy * nslab);
-                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, ChunkView{chunked ? chunk_of.p : nullptr, logC, maxk, mini ? part_base.p : nullptr, batch_off.p, P}, rp); c.launches++;
+                        dim3 gr(std::max(1u, std::min<unsigned>((mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * nslab, 8u))))), gy * nslab);
+                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, runs, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
                     ScanParams sp{greg, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
                     k_scan_region<<<grid(R, 256, 4), 256, 0, gs>>>(sp); c.launches++;
                     W2R_CUDA(cudaGetLastError());
                 };
-                uint32_t g = 1;
                 std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first owned partition, count)
                 std::vector<int> gf(Pown + 1, 0);
-                if (fine) {
-                    // every partition is counted by one CTA in shared memory; the few that do not fit are redone through the region below
-                    SBuf<uint32_t> failed(c, P), failed2(c, P);
+                if (mini) {
+                    // every partition is counted by one CTA in shared memory; the few that do not fit are retried with the largest
+                    // table, and what still fails is redone through the region below
+                    SBuf<uint32_t> failed(c, Pown), failed2(c, Pown);
                     W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 16, c.stream));
                     static bool attr_set = false;
                     if (!attr_set) { W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((20u << SMEM_LOG_SLOTS_MAX)))); attr_set = true; }
                     const uint32_t log1 = std::min(std::max(smem_log, 10u), SMEM_LOG_SLOTS_MAX);
-                    SmemCountParams sc{recs.p, cursor.p, chunk_of.p, mini ? part_base.p : nullptr, batch_off.p, nslab, logC, maxk, (uint32_t)P, mini ? 0u : logP, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
+                    SmemCountParams sc{xrecs, xcur, runs.part_base, runs.slab_off, nslab, (uint32_t)Pown, 0u, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
                                        prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4, log1, nullptr, 0};
                     const bool two_per_sm = log1 <= 12;
-                    k_count_smem<<<(unsigned)std::min<uint64_t>(P, (uint64_t)c.sm_count * (two_per_sm ? 2 : 1)), two_per_sm ? 512 : 1024, (size_t)20u << log1, c.stream>>>(sc); c.launches++; ++n_groups;
+                    k_count_smem<<<(unsigned)std::min<uint64_t>(Pown, (uint64_t)c.sm_count * (two_per_sm ? 2 : 1)), two_per_sm ? 512 : 1024, (size_t)20u << log1, c.stream>>>(sc); c.launches++; ++n_groups;
                     W2R_CUDA(cudaGetLastError());
-                    uint64_t nfail1 = log1 < SMEM_LOG_SLOTS_MAX ? d2h_scalar(c, scal.p + 4) : 0;
-                    if (nfail1) {       // second tier: the partitions that did not fit, with the largest table
+                    const uint64_t nfail1 = log1 < SMEM_LOG_SLOTS_MAX ? d2h_scalar(c, scal.p + 4) : 0;
+                    if (nfail1) {
                         SmemCountParams sc2 = sc;
                         sc2.failed = failed2.p; sc2.failed_cursor = scal.p + 5; sc2.log_slots = SMEM_LOG_SLOTS_MAX; sc2.plist = failed.p; sc2.nlist = (uint32_t)nfail1;
                         k_count_smem<<<(unsigned)std::min<uint64_t>(nfail1, (uint64_t)c.sm_count), 1024, (size_t)20u << SMEM_LOG_SLOTS_MAX, c.stream>>>(sc2); c.launches++; ++n_groups;
                         W2R_CUDA(cudaGetLastError());
                     }
                     const SBuf<uint32_t>& failed_final = nfail1 ? failed2 : failed;
-                    const unsigned long long* failed_final_cursor = nfail1 ? scal.p + 5 : scal.p + 4;
-                    const uint64_t nfail = d2h_scalar(c, failed_final_cursor);
+                    const uint64_t nfail = d2h_scalar(c, nfail1 ? scal.p + 5 : scal.p + 4);
                     std::vector<uint32_t> fl(nfail);
                     if (nfail) { W2R_CUDA(cudaMemcpyAsync(fl.data(), failed_final.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream)); W2R_CUDA(cudaStreamSynchronize(c.stream)); }
                     for (uint32_t q : fl) { groups.push_back({q, 1u}); gf[q] = 1; }
-                    if (nfail) say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)P);
+                    if (nfail) say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)Pown);
                 } else {
-                run_group(0, 1, 0, 0, gflag.p + 0);                  // first partition alone: its distinct count sizes the groups
-                groups.push_back({0u, 1u});
-                if (Pown > 1) {
-                    std::vector<unsigned long long> hh(104);
-                    W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
-                    W2R_CUDA(cudaStreamSynchronize(c.stream));
-                    unsigned long long d0 = 0;
-                    for (int i = 1; i <= 100; ++i) d0 += hh[i];
-                    d0 -= std::min<unsigned long long>(d0, n_distinct_seen);
-                    g = (uint32_t)std::max<double>(1.0, std::min<double>(4096.0, 0.5 * (double)R / ((double)d0 * 1.15 + 1.0)));
-                    g = std::max<uint32_t>(1u, std::min<uint32_t>(g, 32768u / (nsub * world)));
-                    for (uint64_t p0 = 1; p0 < Pown; p0 += g) {
-                        uint32_t gg = (uint32_t)std::min<uint64_t>(g, Pown - p0);
-                        run_group((uint32_t)p0, gg, 0, 0, gflag.p + p0);
-                        groups.push_back({(uint32_t)p0, gg});
+                    // groups of consecutive owned partitions share the region; the group size comes from the first partition's distinct count
+                    run_group(0, 1, 0, 0, gflag.p + 0);
+                    groups.push_back({0u, 1u});
+                    if (Pown > 1) {
+                        std::vector<unsigned long long> hh(104);
+                        W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+                        W2R_CUDA(cudaStreamSynchronize(c.stream));
+                        unsigned long long d0 = 0;
+                        for (int i = 1; i <= 100; ++i) d0 += hh[i];
+                        d0 -= std::min<unsigned long long>(d0, n_distinct_seen);
+                        uint32_t g = (uint32_t)std::max<double>(1.0, std::min<double>(4096.0, 0.5 * (double)R / ((double)d0 * 1.15 + 1.0)));
+                        g = std::max<uint32_t>(1u, std::min<uint32_t>(g, 32768u / (nsub * world)));
+                        for (uint64_t p0 = 1; p0 < Pown; p0 += g) {
+                            uint32_t gg = (uint32_t)std::min<uint64_t>(g, Pown - p0);
+                            run_group((uint32_t)p0, gg, 0, 0, gflag.p + p0);
+                            groups.push_back({(uint32_t)p0, gg});
+                        }
                     }
-                }
-                join();
-                W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (Pown + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-                W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    join();
+                    W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (Pown + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
                 }
                 for (auto& gr : groups) {
                     if (!gf[gr.first]) continue;
@@ -520,6 +565,7 @@ struct Pipeline {
                     for (int i = 1; i <= 100; ++i) n_distinct_seen += hh[i];
                     solid_used_before = d2h_scalar(c, scal.p + 1);
                 }
+                if (mini && world > 1) { xrecs_buf.release(); xrecs = nullptr; }
             }
             if (retry) { n_distinct_seen = 0; n_groups = 0; continue; }
             if (d2h_scalar(c, flags.p + 2)) W2R_FAIL(W2RAP_ERR_INTERNAL, "solid staging buffer overflow");
