@@ -96,7 +96,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-NCU_TRAFFIC_RATIO = {"k_extract_partition": 1.17, "k_count_smem": 0.97}
+NCU_TRAFFIC_RATIO = {"k_minimizer_map<store>": 0.95, "k_count_smem": 0.97}
 
 
 def main():
@@ -226,6 +226,7 @@ def main():
     if rank != 0:
         if world > 1:
             lib.w2rap_step2_comm_destroy(comm)
+            dist.destroy_process_group()
         return
     I, D, S, E, EB, pathed, npe = info
     I = I // world                      # this rank's share of the k-mer instances (the counters are whole-job)
@@ -234,16 +235,15 @@ def main():
     b_in = n_reads * ((args.read_len + 3) // 4) + qbytes + 12 * n_reads
     b_path = 6 * n_reads + 4 * npe
     alg_bytes_total = 2 * b_in + 34 * I + 48 * S + EB // 2 + b_path
-    # dominant kernel: k_extract_partition (map: reads the packed bases, writes one record per instance) or the region count
+    # dominant kernel: k_minimizer_map, store launch (map: reads the packed bases, writes one record per instance) or k_count_smem
     # (reduce: reads every record back).  SURVEY 8(d) charges 34 B per instance for "written once and read once": 17 B each.
     part_ms = sum(t["count_kernel_ms"] for t in tt) / len(tt)
     region_ms = sum(t["region_ms"] for t in tt) / len(tt)
     b_bases = n_reads * ((args.read_len + 3) // 4) + 14 * n_reads
     if part_ms >= region_ms:
-        dom, count_ms, count_launches, alg_bytes_count = "k_extract_partition", part_ms, tt[-1]["count_launches"], b_bases + 17 * I
+        dom, count_ms, count_launches, alg_bytes_count = "k_minimizer_map<store>", part_ms, tt[-1]["count_launches"], b_bases + 17 * I
     else:
-        dom = "k_count_smem" if world == 1 else "k_count_region+k_scan_region"
-        count_ms, count_launches, alg_bytes_count = region_ms, 2 * tt[-1]["count_passes"], 17 * I
+        dom, count_ms, count_launches, alg_bytes_count = "k_count_smem", region_ms, 1, 17 * I      # (+ a handful of fallback launches for oversized partitions)
     peak, peak_src = peaks()
     achieved = alg_bytes_count / (count_ms * 1e-3) / 1e9
     cpu = None
@@ -261,24 +261,28 @@ def main():
                        args.genome_mbp, args.read_len, args.coverage, n_reads, n_bases / 1e9),
                    "cache": "inputs (%.1f GB) and counting table larger than the 126 MB L2" % (b_in / 1e9),
                    "kmer_instances": I, "distinct": D, "solid": S, "edges": E, "reads_pathed": pathed,
-                   "parallelism": "one process per GPU; reads sharded by index, k-mer records routed to owner GPUs by hash partition (NCCL all-to-all), solid records all-gathered, graph built on every rank, reads pathed by shard"},
+                   "parallelism": "one process per GPU; reads sharded by index, k-mer records routed to owner GPUs by minimiser partition (NCCL all-to-all of exactly sized runs), solid records all-gathered, graph built on every rank, reads pathed by shard"},
         "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in - 0, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms,
                 "inside": {k: sum(t[k] for t in e2e_t) / len(e2e_t) for k in ("h2d_ms", "total_ms", "count_ms", "count_kernel_ms", "region_ms", "path_ms", "d2h_ms", "host_pre_ms", "host_post_ms", "wall_ms")}},
         "gpu_launches": int(tt[-1]["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # ncu --set full of this kernel (profiles/r1_ncu_final_extract_smemcount_path_20mbp.txt, 20 Mbp job): dram read+write =
-                     # 1.17x (map) / 0.97x (reduce) the algorithmic bytes; scaled to this workload's bytes per launch
+                     # ncu --set full of this kernel (profiles/r1_ncu_minimizer_map_count_smem_20mbp.txt, 20 Mbp job): dram read+write =
+                     # 0.95x (map) / 0.97x (reduce) the algorithmic bytes; scaled to this workload's bytes per launch
                      "traffic": alg_bytes_count / max(1, count_launches) * NCU_TRAFFIC_RATIO[dom] if dom in NCU_TRAFFIC_RATIO else None,
                      "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum on the 20 Mbp job, as a ratio to algorithmic bytes, applied to this workload",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_count / max(1, count_launches), "launches_per_step": count_launches,
-                     "kernel_ms_per_step": count_ms, "extract_partition_ms": part_ms, "region_count_ms": region_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
-        "stage_ms": {k: sum(t[k] for t in tt) / len(tt) for k in ("count_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
+                     "kernel_ms_per_step": count_ms, "map_store_ms": part_ms, "reduce_ms": region_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
+        "stage_ms": {k: sum(t[k] for t in tt) / len(tt) for k in ("count_ms", "exchange_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
         "clocks": summarize_clocks(samples),
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     lib.w2rap_step2_free_host_reads(C.byref(hr))
     lib.w2rap_step2_release(h)
+    if world > 1:
+        lib.w2rap_step2_comm_destroy(comm)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
