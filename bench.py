@@ -108,7 +108,7 @@ def main():
     ap.add_argument("--genome-mbp", type=float, default=135.0, help="Arabidopsis-sized (BASELINE.json configs[1])")
     ap.add_argument("--coverage", type=int, default=60)
     ap.add_argument("--read-len", type=int, default=250)
-    ap.add_argument("--ref-genome-mbp", type=float, default=1.0, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--ref-genome-mbp", type=float, default=2.0, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -482,8 +482,8 @@ struct Pipeline {
                     // table, and what still fails is redone through the region below
                     SBuf<uint32_t> failed(c, Pown), failed2(c, Pown);
                     W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 16, c.stream));
-                    static bool attr_set = false;
-                    if (!attr_set) { W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((20u << SMEM_LOG_SLOTS_MAX)))); attr_set = true; }
+                    // (a per-device attribute: set on every call — ranks driven from threads of one process each have their own device)
+                    W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((20u << SMEM_LOG_SLOTS_MAX))));
                     const uint32_t log1 = std::min(std::max(smem_log, 10u), SMEM_LOG_SLOTS_MAX);
                     SmemCountParams sc{xrecs, xcur, runs.part_base, runs.slab_off, nslab, (uint32_t)Pown, 0u, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
                                        prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4, log1, nullptr, 0};
