@@ -3,6 +3,7 @@ single-GPU / oracle result, and the paths of its own read shard.  Ranks are driv
 one rank per thread); `bench.py` drives the same entry points with one process per GPU under torchrun."""
 import ctypes as C
 import threading
+import time
 
 import numpy as np
 import pytest
@@ -39,9 +40,11 @@ def run_sharded(T, rs, world, **kw):
             lib.w2rap_step2_free(C.byref(g))
         lib.w2rap_step2_comm_destroy(comm)
 
-    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    th = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(world)]      # daemon: a hung rank must not block exit
     [t.start() for t in th]
-    [t.join(600) for t in th]
+    deadline = time.time() + 240
+    [t.join(max(0.0, deadline - time.time())) for t in th]
+    assert not any(t.is_alive() for t in th), "sharded run did not finish within 240 s (ranks alive: %s; errors so far: %s)" % ([t.is_alive() for t in th], errors)
     assert all(e is None for e in errors), errors
     return results, bounds
 
