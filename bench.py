@@ -24,17 +24,34 @@ METRIC = "step-2 K=60 graph build Gbases/s"
 
 
 def clocks_sampler(stop, out):
+    """SM clock + throttle reasons during the timed region.  In-process NVML (a few microseconds per sample); spawning nvidia-smi
+    five times a second re-initialises NVML every time, which takes driver locks and perturbs the very calls being timed."""
+    idx = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not stop.is_set():
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = int(reasons_fn(h))
+            act = lambda bit: "Active" if r & bit else "Not Active"
+            out.append([str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)])      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+            stop.wait(0.05)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
         try:
-            r = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", os.environ.get("LOCAL_RANK", "0")],
-                               capture_output=True, text=True, timeout=5)
+            r = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(idx)], capture_output=True, text=True, timeout=5)
             f = [x.strip() for x in r.stdout.strip().split(",")]
             if len(f) >= 6:
                 out.append(f)
         except Exception:
             pass
-        stop.wait(0.2)
+        stop.wait(1.0)
 
 
 def summarize_clocks(samples):
@@ -274,6 +291,8 @@ def main():
                      "kernel_ms_per_step": count_ms, "map_store_ms": part_ms, "reduce_ms": region_ms, "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9},
         "stage_ms": {k: sum(t[k] for t in tt) / len(tt) for k in ("count_ms", "exchange_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
         "clocks": summarize_clocks(samples),
+        "per_step": {"resident_ms": [round(t["total_ms"] - t["d2h_ms"], 2) for t in tt], "resident_count_ms": [round(t["count_ms"], 2) for t in tt],
+                     "e2e_wall_ms": [round(t["wall_ms"], 2) for t in e2e_t]},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

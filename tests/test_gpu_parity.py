@@ -6,6 +6,8 @@ edge sequences, vertex ids, hbv ids and every read path.
 """
 import ctypes as C
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -52,6 +54,19 @@ def test_long_reads_span_several_map_tiles(T):
     want, got = both(T, rs, dump_kmers=2, apply_fixpaths=1)
     T.assert_graph_equal(want, got)
     assert int(rs.len.max()) > 500 and got["n_pathed"] > 0
+
+
+@pytest.mark.parametrize("fine_recs,smem_log", [("300000", "13"), ("4000000", "13"), ("24000", "10")])
+def test_partitions_that_do_not_fit_shared_memory(fine_recs, smem_log):
+    """Oversized partitions: every partition fails the shared-memory count and goes through the L2 region in bulk groups
+    (300 k records each), one partition larger than the region itself is split into hash sub-ranges (4 M), and a small first
+    table (1024 slots) hands most partitions to the second, larger one."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, W2RAP_FINE_RECS=fine_recs, W2RAP_SMEM_LOG=smem_log, PYTHONPATH=here)
+    r = subprocess.run([sys.executable, os.path.join(here, "env_case_runner.py"), "100000", "60", "21"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    passes = int(r.stdout.split("passes=")[1].split()[0])
+    assert passes >= 2, "the fallback path did not run"
 
 
 @pytest.mark.parametrize("case", ["circ", "rich"])

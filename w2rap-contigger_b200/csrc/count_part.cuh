@@ -192,6 +192,7 @@ struct RegionParams {
     int* overflow;
 };
 constexpr uint32_t REGION_MAX_PROBE = 2048;
+constexpr uint32_t COUNT_STOP_REGION = 1u << 24;               // the u32 counter of a region slot stops here (it cannot wrap)
 
 // one 256-bit load of a whole slot (LDG.E.ENL2.256 on sm_100a), L2-coherent
 __device__ __forceinline__ void ld_slot(const CountSlot* q, uint64_t& w0, uint64_t& w1, uint64_t& meta) {
@@ -216,7 +217,7 @@ __device__ __forceinline__ void region_insert(const RegionParams& rp, uint64_t m
             have = 0;
         }
         if (hit) {
-            atomicAdd(&q->count, 1u);
+            if ((uint32_t)meta < COUNT_STOP_REGION || w0 == EMPTY_W0) atomicAdd(&q->count, 1u);
             if ((have & ctx) != ctx) atomicOr(&q->ctx, ctx);
             return;
         }
@@ -238,12 +239,12 @@ __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64
     if (db) ld_slot(qb, b0, b1, bm);
     if (da) {
         const uint32_t ctx = (uint32_t)ra.y & 0xffu;
-        if (a0 == ra.x && a1 == (ra.y & ~0xffull)) { atomicAdd(&qa->count, 1u); if ((((uint32_t)(am >> 32)) & ctx) != ctx) atomicOr(&qa->ctx, ctx); }
+        if (a0 == ra.x && a1 == (ra.y & ~0xffull)) { if ((uint32_t)am < COUNT_STOP_REGION) atomicAdd(&qa->count, 1u); if ((((uint32_t)(am >> 32)) & ctx) != ctx) atomicOr(&qa->ctx, ctx); }
         else region_insert(rp, mask, ra, ha);
     }
     if (db) {
         const uint32_t ctx = (uint32_t)rb.y & 0xffu;
-        if (b0 == rb.x && b1 == (rb.y & ~0xffull)) { atomicAdd(&qb->count, 1u); if ((((uint32_t)(bm >> 32)) & ctx) != ctx) atomicOr(&qb->ctx, ctx); }
+        if (b0 == rb.x && b1 == (rb.y & ~0xffull)) { if ((uint32_t)bm < COUNT_STOP_REGION) atomicAdd(&qb->count, 1u); if ((((uint32_t)(bm >> 32)) & ctx) != ctx) atomicOr(&qb->ctx, ctx); }
         else region_insert(rp, mask, rb, hb);
     }
 }
@@ -253,11 +254,13 @@ __device__ __forceinline__ void region_count_pair(const RegionParams& rp, uint64
 // Legacy layout (rv.part_base == nullptr): static sub-buffers of `cap` records, slab src at recs + src * slab_recs.
 // Minimiser layout: slab src (a read batch, or a source rank) starts at rv.slab_off[src]; partition b of it is the run
 // recs[slab_off[src] + part_base[src * P + b] ...) of sizes[src * slab_cur + b] records.
-struct RunView { const uint64_t* part_base; const unsigned long long* slab_off; uint64_t P; };
+// plist (optional): the group is partitions plist[b_first .. b_first + gy) instead of the consecutive range starting at b_first.
+struct RunView { const uint64_t* part_base; const unsigned long long* slab_off; uint64_t P; const uint32_t* plist; };
 __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restrict__ recs, const uint32_t* __restrict__ sizes, uint32_t cstride, uint64_t cap,
                                                       uint32_t b_first, uint32_t gy, uint64_t slab_recs, uint64_t slab_cur, RunView rv, RegionParams rp) {
     const uint32_t src = blockIdx.y / gy;
-    const uint32_t b = b_first + (blockIdx.y - src * gy);
+    const uint32_t bi = b_first + (blockIdx.y - src * gy);
+    const uint32_t b = rv.plist ? rv.plist[bi] : bi;
     uint64_t n = sizes[(uint64_t)src * slab_cur + (uint64_t)b * cstride];
     if (n > cap) n = cap;
     const uint64_t mask = (1ull << rp.logR) - 1;
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(256) k_count_region(const ulonglong2* __restri
 // retried with a larger table and, failing that, go through the region path.
 constexpr uint32_t SMEM_LOG_SLOTS_MAX = 13;                    // 8192 slots: 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
 constexpr uint32_t SMEM_MAX_PROBE = 512;
+constexpr uint32_t COUNT_STOP = 1u << 16;                      // counters stop here (>= 255 is all anyone asks); + one add per racing thread
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // read batches whose runs make up one partition
 struct SmemCountParams {
     const ulonglong2* recs;
@@ -342,7 +346,10 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
                     mine = (w == kw1);
                 }
                 if (mine) {
-                    const uint32_t old = atomicAdd(ccs + s, 1u);
+                    // counts saturate at 255 downstream; the 24-bit field must not run into the context bits however many
+                    // instances a k-mer has (a poly-G artefact can have 10^8): stop adding well before that
+                    const uint32_t cur = *(volatile uint32_t*)(ccs + s);
+                    const uint32_t old = (cur & 0xffffffu) < COUNT_STOP ? atomicAdd(ccs + s, 1u) : cur;
                     if ((((old >> 24) & ctx) != ctx)) atomicOr(ccs + s, ctx << 24);
                     done = true;
                 } else s = (s + 1u) & (SMEM_SLOTS - 1u);

@@ -333,9 +333,10 @@ struct Pipeline {
             // what this rank reduces: records, per-slab partition sizes, and (minimiser layout) where the runs start
             const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;
             const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [nslab][NBown][cstride]
-            RunView runs{nullptr, nullptr, Pown};
-            if (mini) runs = world > 1 ? RunView{xbase.p, xoff.p, Pown} : RunView{part_base.p, batch_off.p, Pown};
+            RunView runs{nullptr, nullptr, Pown, nullptr};
+            if (mini) runs = world > 1 ? RunView{xbase.p, xoff.p, Pown, nullptr} : RunView{part_base.p, batch_off.p, Pown, nullptr};
             std::vector<uint32_t> sizes(Pown), raw_sizes((size_t)nslab * slab_cur);
+            std::vector<uint64_t> totals(Pown);
             bool retry = false;
             W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
             hist.zero();
@@ -428,9 +429,12 @@ struct Pipeline {
                 uint64_t owned_records = 0;
                 for (uint64_t q = 0; q < Pown; ++q) {
                     uint32_t mxs = 0;
+                    uint64_t tq = 0;
                     for (uint32_t sidx = 0; sidx < nslab; ++sidx)
-                        for (uint32_t u = 0; u < nsub; ++u) { uint32_t v = raw_sizes[sidx * slab_cur + (q * nsub + u) * cstride]; mxs = std::max(mxs, v); owned_records += v; }
+                        for (uint32_t u = 0; u < nsub; ++u) { uint32_t v = raw_sizes[sidx * slab_cur + (q * nsub + u) * cstride]; mxs = std::max(mxs, v); tq += v; }
                     sizes[q] = mxs;      // largest run / sub-buffer of the partition (sizes the grid)
+                    totals[q] = tq;
+                    owned_records += tq;
                 }
                 {   // staging for this pass's solid records (each needs >= min_freq instances)
                     uint64_t need = solid_used_before + owned_records / std::max<uint32_t>(1, prm.min_freq) + 1024;
@@ -456,11 +460,12 @@ struct Pipeline {
                 auto fork = [&] { W2R_CUDA(cudaEventRecord(ev_fork, c.stream)); W2R_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0)); };
                 auto join = [&] { W2R_CUDA(cudaEventRecord(ev_join, s2)); W2R_CUDA(cudaStreamWaitEvent(c.stream, ev_join, 0)); };
                 fork();
-                // a group of consecutive owned partitions goes through one counting region
-                auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag) {
+                // a group of owned partitions goes through one counting region: the consecutive range [p0, p0+g), or entries
+                // [p0, p0+g) of a partition list (hlist on the host, dlist on the device)
+                auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag, const uint32_t* dlist = nullptr, const uint32_t* hlist = nullptr) {
                     ++n_groups;
                     uint32_t mxg = 0;
-                    for (uint32_t q = p0; q < p0 + g; ++q) mxg = std::max(mxg, sizes[q]);
+                    for (uint32_t q = p0; q < p0 + g; ++q) mxg = std::max(mxg, sizes[hlist ? hlist[q] : q]);
                     cudaStream_t gs = (group_parity & 1u) ? s2 : c.stream;
                     CountSlot* greg = region.p + ((group_parity & 1u) ? R : 0);
                     ++group_parity;
@@ -468,7 +473,9 @@ struct Pipeline {
                         RegionParams rp{greg, logR, mini ? 0u : logP, sub_mask, sub_id, flag};
                         const uint32_t gy = g * nsub;
                         dim3 gr(std::max(1u, std::min<unsigned>((mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * nslab, 8u))))), gy * nslab);
-                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, runs, rp); c.launches++;
+                        RunView rv2 = runs;
+                        rv2.plist = dlist;
+                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, rv2, rp); c.launches++;
                         W2R_CUDA(cudaGetLastError());
                     }
                     ScanParams sp{greg, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
@@ -501,8 +508,28 @@ struct Pipeline {
                     const uint64_t nfail = d2h_scalar(c, nfail1 ? scal.p + 5 : scal.p + 4);
                     std::vector<uint32_t> fl(nfail);
                     if (nfail) { W2R_CUDA(cudaMemcpyAsync(fl.data(), failed_final.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream)); W2R_CUDA(cudaStreamSynchronize(c.stream)); }
-                    for (uint32_t q : fl) { groups.push_back({q, 1u}); gf[q] = 1; }
-                    if (nfail) say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)Pown);
+                    if (nfail) {
+                        say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)Pown);
+                        // in bulk: as many listed partitions per region pass as fit it even if every record were distinct (load <= 0.6),
+                        // alternating regions/streams, no host round trip per group; a group that overflows all the same is redone
+                        // partition by partition below
+                        std::vector<std::pair<uint32_t, uint32_t>> lgroups;        // (offset into fl, count)
+                        const uint32_t gmax = std::max(1u, 4000u / nslab);          // gridDim.y = g * nslab <= 65535
+                        for (size_t i0 = 0; i0 < fl.size();) {
+                            uint64_t acc = 0; size_t j = i0;
+                            while (j < fl.size() && j - i0 < gmax && (j == i0 || (double)(acc + totals[fl[j]]) <= 0.6 * (double)R)) { acc += totals[fl[j]]; ++j; }
+                            lgroups.push_back({(uint32_t)i0, (uint32_t)(j - i0)});
+                            i0 = j;
+                        }
+                        fork();
+                        for (size_t gi = 0; gi < lgroups.size(); ++gi) run_group(lgroups[gi].first, lgroups[gi].second, 0, 0, gflag.p + gi, failed_final.p, fl.data());
+                        join();
+                        std::vector<int> lgf(lgroups.size());
+                        W2R_CUDA(cudaMemcpyAsync(lgf.data(), gflag.p, lgroups.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                        W2R_CUDA(cudaStreamSynchronize(c.stream));
+                        for (size_t gi = 0; gi < lgroups.size(); ++gi)
+                            if (lgf[gi]) for (uint32_t k = lgroups[gi].first; k < lgroups[gi].first + lgroups[gi].second; ++k) { groups.push_back({fl[k], 1u}); gf[fl[k]] = 1; }
+                    }
                 } else {
                     // groups of consecutive owned partitions share the region; the group size comes from the first partition's distinct count
                     run_group(0, 1, 0, 0, gflag.p + 0);
