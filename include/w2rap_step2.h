@@ -102,13 +102,13 @@ typedef struct w2rap_kmer_rec {
 /* Stage timings, device milliseconds from CUDA events on the stream the kernels run on. */
 typedef struct w2rap_timings {
     float h2d_ms, count_ms, solid_ms, adjacency_ms, unipath_ms, hbv_ms, path_ms, d2h_ms, total_ms;
-    float count_kernel_ms;        /* the extract+partition kernel (k_extract_partition) launches only */
-    float region_ms;              /* the L2-resident count: all k_count_region + k_scan_region launches */
+    float count_kernel_ms;        /* the map kernel's store launches only (k_minimizer_map<store>; legacy path: k_extract_partition) */
+    float region_ms;              /* the reduce: k_count_smem + all k_count_region / k_scan_region launches */
     float exchange_ms;            /* multi-GPU only: NCCL all-to-all of k-mer records + all-gather of the solid records */
     float host_pre_ms;            /* host wall time from entry to the first pipeline launch (validation, allocation, copy enqueue) */
     float host_post_ms;           /* host wall time after the pipeline finished (buffer release, stream teardown) */
     float wall_ms;                /* host wall time of the whole call */
-    uint32_t count_launches;      /* launches of k_extract_partition */
+    uint32_t count_launches;      /* store launches of the map kernel */
     uint32_t kernel_launches;     /* all kernels launched by this call */
     uint32_t count_passes;        /* partition groups reduced through the counting region */
     uint32_t reserved;

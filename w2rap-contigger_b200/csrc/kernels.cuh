@@ -1,7 +1,8 @@
 // kernels.cuh — the sm_100a kernels of the step-2 path (device code only).
 //
-// K1 k_good_len                    : PQVec quality floor (count_part.cuh: k_extract_partition = extraction + hash partition)
-// K2 k_count_region / k_scan_region (count_part.cuh) : L2-resident hash count, histogram, min-frequency filter; k_insert_solid
+// K1 k_good_len                    : PQVec quality floor (count_part.cuh: k_minimizer_map = k-mer extraction + partition by minimiser)
+// K2 k_count_smem, k_count_region / k_scan_region (count_part.cuh) : count per partition in shared memory / in an L2-resident
+//    region, histogram, min-frequency filter; k_insert_solid
 // K3 k_adjacency                  : recomputeAdjacencies
 // K4 k_links / k_rank_* / k_cycle_* / k_strand_decide / k_collect_heads / k_assign_edges / k_emit_edges : unipaths
 // K5 k_edge_ends / k_vertex_* / k_hbv_edges / k_adj_* : HBV vertices + incidence

@@ -1,7 +1,8 @@
 // pipeline.cu — host orchestration of the step-2 path on one B200 and the C ABI over it (include/w2rap_step2.h).
 //
 // Mirrors buildReadQGraph (paths/long/BuildReadQGraph.cc:1253-1327) stage by stage:
-//   createDictOMPRecursive  -> count_stage()      (k_good_len, k_extract_partition, k_count_smem / k_count_region + k_scan_region, k_insert_solid)
+//   createDictOMPRecursive  -> count_stage()      (k_good_len, k_minimizer_map x2, [NCCL exchange], k_count_smem, k_count_region + k_scan_region as
+//                                                  fallback / legacy path, k_insert_solid)
 //   recomputeAdjacencies    -> k_adjacency
 //   buildEdges              -> unipath_stage()    (k_links, pointer-jumping list ranking, circles, edge emission)
 //   buildHBVFromEdges       -> hbv_stage()        (end keys, radix sort, vertex ids, incidence)
