@@ -6,6 +6,7 @@ committed because /root/reference does not exist on the GPU box.
              files written by the reference's own encoder) + the quals/bases the FASTQ held (expected.npz)
   circ/    : 12 circular replicons (odd/even lengths) + planted palindromes -> reference step 2 (-t 1)
   rich/    : repeats + SNP haplotype + palindromes + plasmid, variable read lengths -> reference step 2 (-t 1)
+  long/    : the same kind of genome with reads of up to 600 bases -> reference step 2 (-t 1)
 Each step-2 case holds the input read stores and the reference's x.small_K.hbv / x.small_K.paths / small_K.freqs.
 """
 import os
@@ -76,6 +77,9 @@ def main():
     reps.append((T.make_genome(rng, 5000, 0, 3), False, 5000.0))
     tot = sum(r[2] for r in reps)
     step2_case("circ", T.flatten_reads(*T.simulate_reads(rng, reps, int(tot * 80 // 500), 250, frag_mean=300, frag_sd=20), pq_mode=1))
+
+    # ---- long: 600-base reads of varying length (several 192-k-mer map tiles per read, many gaps per read)
+    step2_case("long", T.rich_set(seed=9, genome=20000, cov=30, read_len=600, families=3, palindromes=2, plasmid=1500, vary_len=True, pq_mode=1))
 
     # ---- rich
     step2_case("rich", T.rich_set(seed=5, genome=40000, cov=50, families=5, palindromes=4, plasmid=1500, vary_len=True, pq_mode=1))

@@ -69,7 +69,7 @@ def test_partitions_that_do_not_fit_shared_memory(fine_recs, smem_log):
     assert passes >= 2, "the fallback path did not run"
 
 
-@pytest.mark.parametrize("case", ["circ", "rich"])
+@pytest.mark.parametrize("case", ["circ", "rich", "long"])
 def test_golden_reference_outputs(T, case):
     """Straight against the files the UNMODIFIED reference wrote (tests/golden): modulo its racy edge numbering."""
     d = os.path.join(GOLD, case)

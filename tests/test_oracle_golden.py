@@ -1,6 +1,6 @@
 """The CPU oracle (oracle/step2_oracle.c) against outputs of the UNMODIFIED reference binary.
 
-tests/golden/{circ,rich} were produced by tests/golden/make_golden.py running oracle/_ref/w2rap-contigger
+tests/golden/{circ,rich,long} were produced by tests/golden/make_golden.py running oracle/_ref/w2rap-contigger
 (--from_step 2 --to_step 2, -t 1).  Equality is modulo the reference's racy edge numbering: hbv edges are matched by
 sequence; vertex ids, incidence, the k-mer histogram and every read path must then be identical; a path difference is
 tolerated only when it is an extension tie between parallel equal-length edges.
@@ -13,7 +13,7 @@ import pytest
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("case", ["circ", "rich"])
+@pytest.mark.parametrize("case", ["circ", "rich", "long"])
 def test_oracle_matches_reference_files(T, case):
     d = os.path.join(GOLD, case)
     rs = T.read_fastb_qualp(d)
