@@ -386,7 +386,8 @@ struct alignas(8) PathMeta { uint32_t x, y; };   // x = first id in the staging 
 // and the requester gets the 32-bit candidate mask.  Each requester then looks up its own first candidate in the dictionary
 // (all requesters at once), and continues along its read.
 constexpr int PATH_GAP_BATCH = 4;
-__global__ void __launch_bounds__(128) k_path_reads(ReadsView r, GraphView g, const uint32_t* __restrict__ list, uint64_t n_rows, uint8_t* __restrict__ qscratch,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, GraphView g, const uint32_t* __restrict__ list, uint64_t n_rows, uint8_t* __restrict__ qscratch,
                                                     uint32_t qstride, int32_t* __restrict__ stage, uint32_t cap, uint32_t left_cap, int32_t* __restrict__ out_offset,
                                                     PathMeta* __restrict__ out_meta, uint32_t apply_fixpaths) {
     uint8_t* myq = qscratch + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * qstride;
