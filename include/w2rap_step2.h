@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define W2RAP_STEP2_ABI_VERSION 1
+#define W2RAP_STEP2_ABI_VERSION 2
 #define W2RAP_K 60
 
 /* status codes (0 = ok).  The reference aborts (FatalErr / ForceAssert / CRD::exit(1)) where these are
@@ -85,9 +85,11 @@ typedef struct w2rap_params {
     uint32_t dump_kmers;     /* test hook: 0 none, 1 solid k-mers (pruned ctx, edge, offset), 2 all distinct k-mers (count, raw ctx) */
     int32_t device;          /* CUDA device ordinal, -1 = current */
     const char* workdir;     /* if non-null and non-empty: write <workdir>/small_K.freqs (BuildReadQGraph.cc:1108-1112) */
-    uint64_t table_slots;    /* 0 = auto; otherwise force the counting-table size (test hook for multi-pass) */
+    uint64_t table_slots;    /* 0 = auto; otherwise force the size of the counting tables (test hook: tiny tables push partitions
+                                through every fallback of the reduce) */
     uint32_t verbose;        /* 1: reference-style progress lines on stdout */
-    uint32_t reserved;
+    uint32_t force_passes;   /* test hook: 0 = auto; n > 0 = count in exactly n hash-range passes (the replacement of the
+                                reference's disk batches, BuildReadQGraph.cc:1120-1250; normally chosen from free device memory) */
 } w2rap_params;
 
 /* One record of the optional k-mer dump (sorted by k-mer). */
@@ -99,10 +101,17 @@ typedef struct w2rap_kmer_rec {
     uint32_t offset;      /* k-mer offset in that edge (level 1) */
 } w2rap_kmer_rec;
 
+/* indices into w2rap_timings.kernel_ms */
+enum {
+    W2RAP_KT_GOOD_LEN = 0, W2RAP_KT_MAP_COUNT = 1, W2RAP_KT_MAP_STORE = 2, W2RAP_KT_REDUCE = 3, W2RAP_KT_INSERT_SOLID = 4,
+    W2RAP_KT_ADJACENCY = 5, W2RAP_KT_LINKS = 6, W2RAP_KT_SPLITTER_WALK = 7, W2RAP_KT_SPLITTER_FINISH = 8, W2RAP_KT_EMIT_EDGES = 9,
+    W2RAP_KT_BLOOM_BUILD = 10, W2RAP_KT_PATH_READS = 11, W2RAP_KT_COUNT
+};
+
 /* Stage timings, device milliseconds from CUDA events on the stream the kernels run on. */
 typedef struct w2rap_timings {
     float h2d_ms, count_ms, solid_ms, adjacency_ms, unipath_ms, hbv_ms, path_ms, d2h_ms, total_ms;
-    float count_kernel_ms;        /* the map kernel's store launches only (k_minimizer_map<store>; legacy path: k_extract_partition) */
+    float count_kernel_ms;        /* the map: k_minimizer_map counting launch + scan + store launch, all read batches */
     float region_ms;              /* the reduce: k_count_smem + all k_count_region / k_scan_region launches */
     float exchange_ms;            /* multi-GPU only: NCCL all-to-all of k-mer records + all-gather of the solid records */
     float host_pre_ms;            /* host wall time from entry to the first pipeline launch (validation, allocation, copy enqueue) */
@@ -110,8 +119,13 @@ typedef struct w2rap_timings {
     float wall_ms;                /* host wall time of the whole call */
     uint32_t count_launches;      /* store launches of the map kernel */
     uint32_t kernel_launches;     /* all kernels launched by this call */
-    uint32_t count_passes;        /* partition groups reduced through the counting region */
+    uint32_t count_passes;        /* reduce launches: k_count_smem launches + partition groups that went through the counting region */
     uint32_t reserved;
+    float dict_ms;                /* dictionary build (k_insert_solid; sharded: + gather of the records it is built from) */
+    float graph_exchange_ms;      /* multi-GPU only: the exchanges of the sharded graph stage (neighbour queries, chain ends, edges) */
+    uint64_t exchange_bytes;      /* multi-GPU only: bytes this rank sent over NVLink in the whole step */
+    /* CUDA-event time of individual kernels (all launches of the kernel in this call), index = W2RAP_KT_*; 0 where not run */
+    float kernel_ms[16];
 } w2rap_timings;
 
 /*
@@ -146,6 +160,9 @@ typedef struct w2rap_graph {
     int32_t* edge_vertices;     /* 4*n_edges */
     int32_t* fwd_xlat;          /* n_edges */
     int32_t* rev_xlat;          /* n_edges */
+    int32_t* involution;        /* n_hbv_edges: hbv edge id -> id of its reverse complement (itself for a palindrome).  What step 3 asks
+                                   the reference for right after step 2 (hbv.Involution, paths/HyperBasevector.cc:648-660: two sorts of
+                                   all edges); here it is known from the fwd/rc pairing */
 
     uint64_t n_paths;           /* n_reads if want_paths else 0 */
     uint64_t n_path_edges;
@@ -154,6 +171,13 @@ typedef struct w2rap_graph {
     int32_t* path_edges;
     uint64_t n_pathed;          /* paths with >0 edges */
     uint64_t n_multipathed;     /* paths with >2 edges */
+
+    /* Order-sensitive 64-bit digests computed on the device (sum over elements of a mix of index and value), for comparing
+     * whole results across runs and GPU counts without shipping them: digest_graph covers hist, edge lengths, edge bases,
+     * vertex ids and xlat tables; digest_paths covers (read sequence, path offset, path edges) of every read and is summed over
+     * all ranks in a sharded run, so both are independent of the number of GPUs. */
+    uint64_t digest_graph;
+    uint64_t digest_paths;
 
     uint64_t n_dump;
     w2rap_kmer_rec* dump;       /* sorted by (w0,w1); null unless params.dump_kmers */

@@ -339,6 +339,18 @@ typedef struct {
     uint64_t* to_off; int32_t* to_v; int32_t* to_e;        /* To(v)/ToEdgeObj(v) */
 } hbv_t;
 
+/* paths/HyperBasevector.cc:648-660 HyperBasevector::Involution: sort all hbv edges by sequence, sort their reverse complements by
+ * sequence, pair rank with rank: inv[e] = the edge whose reverse complement spells e. */
+typedef struct { const uint8_t* seq; uint64_t len; int rc; int32_t id; } invkey_t;
+static inline uint8_t invkey_base(const invkey_t* k, uint64_t i) { return k->rc ? (uint8_t)(3 - k->seq[k->len - 1 - i]) : k->seq[i]; }
+static int invkey_cmp(const void* pa, const void* pb) {   /* feudal/BaseVec.h operator<: base-wise, then the shorter one first */
+    const invkey_t* a = (const invkey_t*)pa; const invkey_t* b = (const invkey_t*)pb;
+    uint64_t n = a->len < b->len ? a->len : b->len;
+    for (uint64_t i = 0; i < n; ++i) { uint8_t x = invkey_base(a, i), y = invkey_base(b, i); if (x != y) return x < y ? -1 : 1; }
+    if (a->len != b->len) return a->len < b->len ? -1 : 1;
+    return a->id < b->id ? -1 : (a->id > b->id ? 1 : 0);
+}
+
 typedef struct { int32_t a, b, e; } adj_t;
 static int adj_cmp(const void* pa, const void* pb) { /* graph/DigraphTemplate.h:1829-1839: upper_bound insertion => (owner, neighbour, edge id) order */
     const adj_t* x = (const adj_t*)pa; const adj_t* y = (const adj_t*)pb;
@@ -626,6 +638,18 @@ int oracle_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* 
         h.left[f] = out->edge_vertices[4 * e]; h.right[f] = out->edge_vertices[4 * e + 1]; h.elen[f] = (uint32_t)el.e[e].len; h.canon[f] = e; h.is_rc[f] = 0;
         if (r != f) { h.left[r] = out->edge_vertices[4 * e + 2]; h.right[r] = out->edge_vertices[4 * e + 3]; h.elen[r] = (uint32_t)el.e[e].len; h.canon[r] = e; h.is_rc[r] = 1; }
     }
+    {   /* step 3's first question (w2rap-contigger.cc:361-371): the involution of the hbv edges */
+        invkey_t* x1 = (invkey_t*)xmalloc(sizeof(invkey_t) * h.n_e); invkey_t* x2 = (invkey_t*)xmalloc(sizeof(invkey_t) * h.n_e);
+        for (uint64_t i = 0; i < h.n_e; ++i) {
+            const edge_t* ce = &el.e[h.canon[i]];
+            x1[i].seq = x2[i].seq = ce->seq; x1[i].len = x2[i].len = ce->len; x1[i].id = x2[i].id = (int32_t)i;
+            x1[i].rc = h.is_rc[i]; x2[i].rc = !h.is_rc[i];
+        }
+        qsort(x1, h.n_e, sizeof(invkey_t), invkey_cmp); qsort(x2, h.n_e, sizeof(invkey_t), invkey_cmp);
+        out->involution = (int32_t*)xmalloc(sizeof(int32_t) * h.n_e);
+        for (uint64_t i = 0; i < h.n_e; ++i) out->involution[x1[i].id] = x2[i].id;
+        free(x1); free(x2);
+    }
     { adj_t* a = (adj_t*)xmalloc(sizeof(adj_t) * h.n_e);
       h.from_off = (uint64_t*)xcalloc(h.n_v + 1, sizeof(uint64_t)); h.to_off = (uint64_t*)xcalloc(h.n_v + 1, sizeof(uint64_t));
       h.from_v = (int32_t*)xmalloc(sizeof(int32_t) * h.n_e); h.from_e = (int32_t*)xmalloc(sizeof(int32_t) * h.n_e);
@@ -736,7 +760,7 @@ int oracle_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* 
 
 void oracle_step2_free(w2rap_graph* g) {
     if (!g) return;
-    free(g->edge_off); free(g->edge_len); free(g->edge_bases); free(g->edge_vertices); free(g->fwd_xlat); free(g->rev_xlat);
+    free(g->edge_off); free(g->edge_len); free(g->edge_bases); free(g->edge_vertices); free(g->fwd_xlat); free(g->rev_xlat); free(g->involution);
     free(g->path_offset); free(g->path_off); free(g->path_edges); free(g->dump);
     memset(g, 0, sizeof(*g));
 }

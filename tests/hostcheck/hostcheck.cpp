@@ -20,6 +20,7 @@
 #include "../../w2rap-contigger_b200/csrc/path.cuh"
 #include "../../w2rap-contigger_b200/csrc/pqvec.cuh"
 #include "../../w2rap-contigger_b200/csrc/unipath.cuh"
+#include "../../w2rap-contigger_b200/csrc/shardgraph.cuh"
 
 using namespace w2r;
 
@@ -61,9 +62,61 @@ int hc_count(const w2rap_reads* in, uint32_t min_qual, w2rap_kmer_rec** out, uin
 
 void hc_free(void* p) { free(p); }
 
+// ---- the map side as the kernel does it (k_minimizer_map): partition of every k-mer by minimiser, runs of equal partition inside a
+// 32-position step become one super-k-mer record.  Appends records (4 u64 each) and, per record, its partition.
+static int map_read_records(const uint8_t* bases, uint32_t gl, uint32_t logP, uint32_t npass, uint32_t pass, std::vector<uint64_t>* recs, std::vector<uint32_t>* parts) {
+    if (gl <= (uint32_t)K) return 0;
+    const uint32_t nk = gl - K + 1, last = gl - K;
+    std::vector<uint32_t> part(nk);
+    for (uint32_t j = 0; j < nk; ++j) {
+        const uint32_t mh = mini_mix(kmer_minimizer_hash(bases, j));
+        part[j] = (npass > 1 && (mh & 0xffffu) % npass != pass) ? NIL : mini_part(mh, logP);
+    }
+    for (uint32_t j = 0; j < nk;) {
+        if (part[j] == NIL) { ++j; continue; }
+        uint32_t e = j + 1;
+        while (e < nk && part[e] == part[j] && (e % 32u) != 0) ++e;       // steps are 32 k-mers wide, tiles 192: boundaries at multiples of 32
+        const SkmRec r = skm_build(bases, j, e - j, last);
+        for (int w = 0; w < 4; ++w) recs->push_back(r.q[w]);
+        parts->push_back(part[j]);
+        j = e;
+    }
+    return 0;
+}
+// Records -> (canonical k-mer, context) per instance, as the reduce expands them (k_count_smem / k_count_region: skm_kmer_at).
+static void expand_records(const uint64_t* recs, uint64_t nrec, std::vector<Rec>* out) {
+    for (uint64_t i = 0; i < nrec; ++i) {
+        const uint64_t* q = recs + 4 * i;
+        const uint32_t n = skm_n(q[3]);
+        for (uint32_t j = 0; j < n; ++j) { Kmer k; uint32_t ctx; skm_kmer_at(q, j, &k, &ctx); out->push_back(Rec{k.w0, k.w1, ctx}); }
+    }
+}
+// Round trip of the record format: for every read, build + expand must give exactly what extract_read_kmers emits, in order.
+// Returns the number of mismatching instances; *n_rec / *n_inst receive the totals.
+uint64_t hc_skm_roundtrip(const w2rap_reads* in, uint32_t min_qual, uint32_t logP, uint64_t* n_rec, uint64_t* n_inst) {
+    uint64_t bad = 0, nr = 0, ni = 0;
+    for (uint64_t r = 0; r < in->n_reads; ++r) {
+        uint32_t nq = 0;
+        uint32_t gl = pq_good_length(in->quals + in->qual_off[r], min_qual, &nq);
+        if (gl > in->len[r]) gl = in->len[r];
+        const uint8_t* bases = in->bases + in->base_off[r];
+        std::vector<Rec> want, got;
+        Collect emit{&want};
+        extract_read_kmers(bases, gl, emit);
+        std::vector<uint64_t> recs; std::vector<uint32_t> parts;
+        map_read_records(bases, gl, logP, 1, 0, &recs, &parts);
+        expand_records(recs.data(), parts.size(), &got);
+        nr += parts.size(); ni += want.size();
+        if (got.size() != want.size()) { bad += want.size() > got.size() ? want.size() - got.size() : got.size() - want.size(); continue; }
+        for (size_t i = 0; i < want.size(); ++i) if (want[i].w0 != got[i].w0 || want[i].w1 != got[i].w1 || want[i].ctx != got[i].ctx) ++bad;
+    }
+    *n_rec = nr; *n_inst = ni;
+    return bad;
+}
+
 // ---- pieces of the sharded (multi-GPU) protocol, for the world_size-2 gloo test: the "map" side (k_minimizer_map) and the
 // "reduce" side (k_count_smem) as separate calls, with the product's own partition/owner functions.
-// recs: n x {w0, w1|ctx}; owner[i] = rank that owns record i's partition (keyed by the k-mer's minimiser, extract.cuh).
+// recs: n x 4 u64 (SkmRec); owner[i] = rank that owns record i's partition (keyed by minimiser, extract.cuh).
 int hc_extract_records(const w2rap_reads* in, uint32_t min_qual, uint32_t logP, uint32_t world, uint64_t** recs_out, uint32_t** owner_out, uint64_t* n_out) {
     std::vector<uint64_t> flat;
     std::vector<uint32_t> owner;
@@ -72,15 +125,9 @@ int hc_extract_records(const w2rap_reads* in, uint32_t min_qual, uint32_t logP, 
         uint32_t gl = pq_good_length(in->quals + in->qual_off[r], min_qual, &nq);
         if (nq != in->len[r]) return 100;
         if (gl > in->len[r]) gl = in->len[r];
-        const uint8_t* bases = in->bases + in->base_off[r];
-        KmerCursor cur;
-        cur.open(bases, gl);
-        Kmer k; uint32_t ctx;
-        for (uint64_t j = 0; cur.next(&k, &ctx); ++j) {
-            flat.push_back(k.w0); flat.push_back(k.w1 | ctx);
-            owner.push_back(owner_of_partition(mini_part(mini_mix(kmer_minimizer_hash(bases, j)), logP), logP, world));
-        }
+        map_read_records(in->bases + in->base_off[r], gl, logP, 1, 0, &flat, &owner);
     }
+    for (uint32_t& o : owner) o = owner_of_partition(o, logP, world);
     *n_out = owner.size(); *recs_out = dup(flat); *owner_out = dup(owner);
     return 0;
 }
@@ -108,8 +155,8 @@ uint64_t hc_minimizer_symmetry(const w2rap_reads* in, uint64_t* n_checked) {
     return bad;
 }
 int hc_count_records(const uint64_t* recs, uint64_t n, w2rap_kmer_rec** out, uint64_t* n_out) {
-    std::vector<Rec> v(n);
-    for (uint64_t i = 0; i < n; ++i) v[i] = Rec{recs[2 * i], recs[2 * i + 1] & ~0xffull, (uint32_t)(recs[2 * i + 1] & 0xff)};
+    std::vector<Rec> v;
+    expand_records(recs, n, &v);
     std::sort(v.begin(), v.end(), [](const Rec& a, const Rec& b) { return a.w0 < b.w0 || (a.w0 == b.w0 && a.w1 < b.w1); });
     std::vector<w2rap_kmer_rec> d;
     for (size_t i = 0; i < v.size();) {
@@ -122,39 +169,16 @@ int hc_count_records(const uint64_t* recs, uint64_t n, w2rap_kmer_rec** out, uin
     return 0;
 }
 
-// Everything after counting, serially, through the same device functions the kernels call.
-// `all` = distinct k-mers with counts and raw contexts (dump level 2).
-int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const w2rap_reads* in, int want_paths, int apply_fixpaths, uint32_t cap,
-             uint32_t left_cap, w2rap_graph* out) {
-    memset(out, 0, sizeof(*out));
-    // ---- k_insert_solid
-    uint64_t n_solid = 0;
-    for (uint64_t i = 0; i < n_all; ++i) if (all[i].count >= min_freq) ++n_solid;
-    uint32_t lg = 10;
-    while ((1ull << lg) < 2 * n_solid) ++lg;
-    std::vector<SolidSlot> slots(1ull << lg);
-    memset(slots.data(), 0xff, slots.size() * sizeof(SolidSlot));
-    SolidTable st{slots.data(), lg};
-    const uint64_t T = st.size(), mask = T - 1, nn = 2 * T;
-    for (uint64_t i = 0; i < n_all; ++i) {
-        if (all[i].count < min_freq) continue;
-        Kmer k{all[i].w0, all[i].w1};
-        uint64_t h = st.home(k);
-        while (slots[h].w0 != EMPTY_W0) h = (h + 1) & mask;
-        slots[h].w0 = k.w0; slots[h].w1 = k.w1; slots[h].ctx = all[i].ctx; slots[h].edge = NIL; slots[h].off = 0; slots[h].pad = 0;
-    }
-    out->n_solid = n_solid; out->n_distinct = n_all;
-    // ---- k_adjacency
-    for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) slots[i].ctx = pruned_context(st, Kmer{slots[i].w0, slots[i].w1}, slots[i].ctx & 0xff);
-    // ---- k_links, k_rank_*
-    std::vector<uint32_t> next0(nn);
-    int missing = 0;
-    for (uint64_t x = 0; x < nn; ++x) next0[x] = unipath_succ_link(st, (uint32_t)x, &missing);
-    if (missing) return 101;
+}  // extern "C"
+
+namespace {
+// k_splitter_walk, k_rank_step_inplace, k_splitter_finish, k_cycle_*: list ranking of one (local) table.  R receives the final
+// (tail, distance | RESOLVED) of every node; returns the number of nodes that went through the circle path, or -1 on failure.
+int64_t rank_local(const SolidTable& st, std::vector<uint32_t>& next0, const uint8_t* ghead, std::vector<RankState>& R) {
+    const uint64_t nn = next0.size();
     std::vector<RankState> A(nn, RankState{NIL, 0xffffffffu}), B(nn), D(nn);
-    // k_splitter_walk, k_rank_step_inplace, k_splitter_finish
     std::vector<uint32_t> splist;
-    for (uint64_t x = 0; x < nn; ++x) if (node_is_splitter(next0.data(), (uint32_t)x)) { splist.push_back((uint32_t)x); splitter_walk(next0.data(), (uint32_t)x, A.data(), B.data()); }
+    for (uint64_t x = 0; x < nn; ++x) if (node_is_splitter(next0.data(), ghead, (uint32_t)x)) { splist.push_back((uint32_t)x); splitter_walk(next0.data(), (uint32_t)x, A.data(), B.data()); }
     uint64_t prev_un = ~0ull;
     for (int round = 0; round < 48 && !splist.empty(); ++round) {
         uint64_t un = 0;
@@ -165,7 +189,6 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     prev_un = 0;
     for (uint64_t x = 0; x < nn; ++x) { A[x] = splitter_finish_node(next0.data(), A.data(), B.data(), (uint32_t)x); prev_un += !(A[x].y & RANK_RESOLVED); }
     RankState* cur = A.data(); RankState* oth = B.data();
-    out->timings.count_passes = (uint32_t)prev_un;   // reported to the test: nodes that went through the circle path
     if (prev_un) {
         std::vector<uint32_t> list;
         for (uint64_t x = 0; x < nn; ++x) if (!(cur[x].y & RANK_RESOLVED)) list.push_back((uint32_t)x);
@@ -180,7 +203,7 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
         for (uint32_t x : list) cycle_cut_node(x0, next0.data(), x);
         for (uint32_t x : list) x0[x] = rank_init_node(next0.data(), x);
         for (int round = 0; round < 41; ++round) {
-            if (round == 40) return 102;
+            if (round == 40) return -1;
             uint64_t un = 0;
             for (uint32_t x : list) { bool u; x1[x] = rank_step_node(x0, x, &u); un += u; }
             std::swap(x0, x1);
@@ -188,21 +211,24 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
         }
         for (uint32_t x : list) cur[x] = x0[x];
     }
-    const RankState* R = cur;
-    // ---- k_strand_decide, k_collect_heads, sort, k_assign_edges, k_emit_edges
-    std::vector<uint8_t> keep(nn, 0);
-    for (uint64_t x = 0; x < nn; ++x) if (strand_decide_node(st, R, (uint32_t)x, keep.data())) return 103;
-    struct Head { Kmer k; uint32_t node, n; };
-    std::vector<Head> heads;
-    for (uint64_t x = 0; x < nn; ++x) if (head_is_kept(st, R, keep.data(), (uint32_t)x)) heads.push_back(Head{node_kmer(st, (uint32_t)x), (uint32_t)x, (R[x].y & ~RANK_RESOLVED) + 1u});
-    std::sort(heads.begin(), heads.end(), [](const Head& a, const Head& b) { return kmer_less(a.k, b.k); });
-    const uint64_t E = heads.size();
-    std::vector<uint32_t> edge_of_head(nn, NIL), edge_len(E);
-    std::vector<uint64_t> edge_off(E + 1, 0);
-    for (uint64_t i = 0; i < E; ++i) { edge_of_head[heads[i].node] = (uint32_t)i; edge_len[i] = heads[i].n + K - 1; edge_off[i + 1] = edge_off[i] + (edge_len[i] + 3) / 4; }
-    std::vector<uint8_t> edge_bases(edge_off[E] + 32, 0);
-    struct Put { uint8_t* b; void operator()(uint64_t bo, uint64_t pos, uint32_t c) const { b[bo + (pos >> 2)] |= (uint8_t)(c << ((pos & 3) * 2)); } } put{edge_bases.data()};
-    for (uint64_t x = 0; x < nn; ++x) emit_node(st, R, edge_of_head.data(), edge_off.data(), (uint32_t)x, put);
+    R.assign(cur, cur + nn);
+    return (int64_t)prev_un;
+}
+
+struct EdgeSet {
+    uint64_t E = 0;
+    std::vector<uint32_t> edge_len;
+    std::vector<uint64_t> edge_off;
+    std::vector<uint8_t> edge_bases;     // + 32 bytes of padding
+};
+struct PutBase { uint8_t* b; void operator()(uint64_t bo, uint64_t pos, uint32_t c) const { b[bo + (pos >> 2)] |= (uint8_t)(c << ((pos & 3) * 2)); } };
+
+// k_edge_ends .. k_adj_sort, dump level 1, k_path_reads: everything that follows the edges, on the WHOLE dictionary `st`
+// (every solid k-mer with its pruned context, edge and offset).
+int finish_graph(const SolidTable& st, EdgeSet& es, uint64_t n_solid, const w2rap_reads* in, int want_paths, int apply_fixpaths, uint32_t cap, uint32_t left_cap, w2rap_graph* out) {
+    const uint64_t E = es.E, T = st.size();
+    SolidSlot* slots = st.slots;
+    std::vector<uint32_t>& edge_len = es.edge_len; std::vector<uint64_t>& edge_off = es.edge_off; std::vector<uint8_t>& edge_bases = es.edge_bases;
     // ---- k_edge_ends .. k_adj_sort
     std::vector<EndKey> keys(4 * E);
     std::vector<uint8_t> is_pal(E, 0);
@@ -245,6 +271,11 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     out->edge_bases = dup(edge_bases);
     edge_bases.resize(edge_off[E] + 32, 0);
     out->edge_vertices = dup(edge_vertices); out->fwd_xlat = dup(fwd); out->rev_xlat = dup(rev);
+    {   // k_involution
+        std::vector<int32_t> inv(nh);
+        for (uint64_t e = 0; e < E; ++e) { inv[fwd[e]] = rev[e]; inv[rev[e]] = fwd[e]; }
+        out->involution = dup(inv);
+    }
     for (uint64_t e = 0; e < E; ++e) out->n_edge_bases += edge_len[e];
     {   // dump level 1
         std::vector<w2rap_kmer_rec> d;
@@ -290,8 +321,305 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     return 0;
 }
 
+
+}  // namespace
+
+extern "C" {
+
+// Everything after counting, serially, through the same device functions the kernels call.
+// `all` = distinct k-mers with counts and raw contexts (dump level 2).
+int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const w2rap_reads* in, int want_paths, int apply_fixpaths, uint32_t cap,
+             uint32_t left_cap, w2rap_graph* out) {
+    memset(out, 0, sizeof(*out));
+    // ---- k_insert_solid
+    uint64_t n_solid = 0;
+    for (uint64_t i = 0; i < n_all; ++i) if (all[i].count >= min_freq) ++n_solid;
+    uint32_t lg = 10;
+    while ((1ull << lg) < 2 * n_solid) ++lg;
+    std::vector<SolidSlot> slots(1ull << lg);
+    memset(slots.data(), 0xff, slots.size() * sizeof(SolidSlot));
+    SolidTable st{slots.data(), lg};
+    const uint64_t T = st.size(), mask = T - 1, nn = 2 * T;
+    for (uint64_t i = 0; i < n_all; ++i) {
+        if (all[i].count < min_freq) continue;
+        Kmer k{all[i].w0, all[i].w1};
+        uint64_t h = st.home(k);
+        while (slots[h].w0 != EMPTY_W0) h = (h + 1) & mask;
+        slots[h].w0 = k.w0; slots[h].w1 = k.w1; slots[h].ctx = all[i].ctx; slots[h].edge = NIL; slots[h].off = 0; slots[h].pad = 0;
+    }
+    out->n_solid = n_solid; out->n_distinct = n_all;
+    // ---- k_adjacency
+    for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) slots[i].ctx = pruned_context(st, Kmer{slots[i].w0, slots[i].w1}, slots[i].ctx & 0xff);
+    // ---- k_links, k_rank_*
+    std::vector<uint32_t> next0(nn);
+    int missing = 0;
+    for (uint64_t x = 0; x < nn; ++x) next0[x] = unipath_succ_link(st, (uint32_t)x, &missing);
+    if (missing) return 101;
+    std::vector<RankState> Rv;
+    const int64_t ncyc = rank_local(st, next0, nullptr, Rv);
+    if (ncyc < 0) return 102;
+    out->timings.count_passes = (uint32_t)ncyc;   // reported to the test: nodes that went through the circle path
+    const RankState* R = Rv.data();
+    // ---- k_strand_decide, k_collect_heads, sort, k_assign_edges, k_emit_edges
+    std::vector<uint8_t> keep(nn, 0);
+    for (uint64_t x = 0; x < nn; ++x) if (strand_decide_node(st, R, (uint32_t)x, keep.data())) return 103;
+    struct Head { Kmer k; uint32_t node, n; };
+    std::vector<Head> heads;
+    for (uint64_t x = 0; x < nn; ++x) if (head_is_kept(st, R, keep.data(), (uint32_t)x)) heads.push_back(Head{node_kmer(st, (uint32_t)x), (uint32_t)x, (R[x].y & ~RANK_RESOLVED) + 1u});
+    std::sort(heads.begin(), heads.end(), [](const Head& a, const Head& b) { return kmer_less(a.k, b.k); });
+    EdgeSet es;
+    es.E = heads.size();
+    const uint64_t E = es.E;
+    std::vector<uint32_t> edge_of_head(nn, NIL);
+    es.edge_len.resize(E); es.edge_off.assign(E + 1, 0);
+    for (uint64_t i = 0; i < E; ++i) { edge_of_head[heads[i].node] = (uint32_t)i; es.edge_len[i] = heads[i].n + K - 1; es.edge_off[i + 1] = es.edge_off[i] + (es.edge_len[i] + 3) / 4; }
+    es.edge_bases.assign(es.edge_off[E] + 32, 0);
+    PutBase put{es.edge_bases.data()};
+    for (uint64_t x = 0; x < nn; ++x) emit_node(st, R, edge_of_head.data(), es.edge_off.data(), (uint32_t)x, put);
+    return finish_graph(st, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
+}
+
+// ---- the SHARDED graph stage (csrc/shardgraph.cuh) with `world` simulated ranks: every rank owns the solid k-mers of its
+// minimiser partitions; exchanges are plain copies between the per-rank structures, in the order pipeline.cu issues them.
+// Result: the same graph the single-table path builds.  out->timings.reserved receives the number of ghost entries,
+// out->timings.count_passes the number of pieces (local chains).
+int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, uint32_t world, uint32_t logP, const w2rap_reads* in, int want_paths,
+                     int apply_fixpaths, uint32_t cap, uint32_t left_cap, w2rap_graph* out) {
+    memset(out, 0, sizeof(*out));
+    struct Rank {
+        std::vector<w2rap_kmer_rec> owned;
+        std::vector<std::vector<Kmer>> q;            // q[d] = canonical k-mers asked of rank d
+        std::vector<std::vector<uint32_t>> reply;    // reply[d][i] = slot on d or NIL
+        std::vector<SolidSlot> slots;
+        SolidTable st{nullptr, 0};
+        std::vector<uint32_t> next0;
+        std::vector<uint8_t> ghead;
+        std::vector<RankState> R;
+        std::vector<uint32_t> lpiece;                // per node: local piece index of the piece whose tail it is
+        std::vector<PieceRec> pieces;
+        uint32_t piece0 = 0;
+    };
+    std::vector<Rank> rk(world);
+    uint64_t n_solid = 0;
+    for (uint64_t i = 0; i < n_all; ++i) {
+        if (all[i].count < min_freq) continue;
+        ++n_solid;
+        rk[kmer_owner(Kmer{all[i].w0, all[i].w1}, logP, world)].owned.push_back(all[i]);
+    }
+    out->n_solid = n_solid; out->n_distinct = n_all;
+    // ---- k_neighbour_queries (on the solid records), local tables (k_insert_solid)
+    for (uint32_t r = 0; r < world; ++r) {
+        Rank& me = rk[r];
+        me.q.assign(world, {}); me.reply.assign(world, {});
+        struct Emit { std::vector<std::vector<Kmer>>* q; void operator()(uint32_t o, Kmer k) const { (*q)[o].push_back(k); } } emit{&me.q};
+        uint64_t nq = 0;
+        for (const w2rap_kmer_rec& e : me.owned) neighbour_queries(Kmer{e.w0, e.w1}, e.ctx & 0xffu, logP, world, r, emit);
+        for (auto& v : me.q) nq += v.size();
+        uint32_t lg = 6;
+        while ((1ull << lg) < 2 * (me.owned.size() + nq)) ++lg;
+        me.slots.resize(1ull << lg);
+        memset(me.slots.data(), 0xff, me.slots.size() * sizeof(SolidSlot));
+        me.st = SolidTable{me.slots.data(), lg};
+        const uint64_t mask = me.st.size() - 1;
+        for (const w2rap_kmer_rec& e : me.owned) {
+            uint64_t h = me.st.home(Kmer{e.w0, e.w1});
+            while (me.slots[h].w0 != EMPTY_W0) h = (h + 1) & mask;
+            me.slots[h] = SolidSlot{e.w0, e.w1, e.ctx & 0xffu, NIL, 0, 0};
+        }
+    }
+    // ---- all-to-all of the keys, k_answer_queries, all-to-all of the replies, k_insert_ghosts
+    uint64_t n_ghost = 0;
+    for (uint32_t r = 0; r < world; ++r)
+        for (uint32_t d = 0; d < world; ++d) {
+            rk[r].reply[d].resize(rk[r].q[d].size());
+            for (size_t i = 0; i < rk[r].q[d].size(); ++i) { const int64_t s = solid_find(rk[d].st, rk[r].q[d][i]); rk[r].reply[d][i] = s < 0 ? NIL : (uint32_t)s; }
+        }
+    for (uint32_t r = 0; r < world; ++r) {
+        Rank& me = rk[r];
+        const uint64_t mask = me.st.size() - 1;
+        for (uint32_t d = 0; d < world; ++d)
+            for (size_t i = 0; i < me.q[d].size(); ++i) {
+                if (me.reply[d][i] == NIL) continue;
+                const Kmer k = me.q[d][i];
+                uint64_t h = me.st.home(k);
+                while (me.slots[h].w0 != EMPTY_W0 && !(me.slots[h].w0 == k.w0 && me.slots[h].w1 == k.w1)) h = (h + 1) & mask;
+                if (me.slots[h].w0 == EMPTY_W0) { me.slots[h] = SolidSlot{k.w0, k.w1, 0, me.reply[d][i], 0, d + 1u}; ++n_ghost; }
+            }
+    }
+    // ---- k_adjacency on owned entries; then the ghosts' pruned contexts (second query round: slot -> context)
+    for (Rank& me : rk)
+        for (uint64_t i = 0; i < me.st.size(); ++i)
+            if (me.slots[i].w0 != EMPTY_W0 && !slot_is_ghost(me.slots[i])) me.slots[i].ctx = pruned_context(me.st, Kmer{me.slots[i].w0, me.slots[i].w1}, me.slots[i].ctx & 0xff);
+    for (Rank& me : rk)
+        for (uint64_t i = 0; i < me.st.size(); ++i)
+            if (me.slots[i].w0 != EMPTY_W0 && slot_is_ghost(me.slots[i])) me.slots[i].ctx = rk[me.slots[i].pad - 1].slots[me.slots[i].edge].ctx;
+    // ---- k_links (+ ghost-predecessor flags), local list ranking
+    uint64_t ncyc_local = 0;
+    for (Rank& me : rk) {
+        const uint64_t nn = 2 * me.st.size();
+        me.next0.resize(nn); me.ghead.assign(nn, 0);
+        int missing = 0;
+        for (uint64_t x = 0; x < nn; ++x) { bool tg; me.next0[x] = unipath_succ_link(me.st, (uint32_t)x, &missing, &tg); if (tg) me.ghead[x ^ 1u] = 1; }
+        if (missing) return 101;
+    }
+    std::vector<PieceRec> P;
+    std::vector<uint32_t> nxt, flip;
+    std::vector<RankState> S;
+    for (int iteration = 0;; ++iteration) {
+        if (iteration > 1) return 106;
+        for (Rank& me : rk) {
+            const int64_t nc = rank_local(me.st, me.next0, me.ghead.data(), me.R);
+            if (nc < 0) return 102;
+            ncyc_local += (uint64_t)nc;
+        }
+        // ---- k_emit_pieces, all-gather, k_piece_map / k_piece_link, piece ranking
+        P.clear();
+        for (uint32_t r = 0; r < world; ++r) {
+            Rank& me = rk[r];
+            const uint64_t nn = me.next0.size();
+            me.pieces.clear(); me.lpiece.assign(nn, NIL);
+            for (uint64_t x = 0; x < nn; ++x)
+                if (node_is_piece_head(me.next0.data(), me.ghead.data(), (uint32_t)x)) {
+                    const PieceRec p = piece_of_head(me.st, me.next0.data(), me.R.data(), r, (uint32_t)x);
+                    me.lpiece[p.tail] = (uint32_t)me.pieces.size();
+                    me.pieces.push_back(p);
+                }
+            me.piece0 = (uint32_t)P.size();
+            P.insert(P.end(), me.pieces.begin(), me.pieces.end());
+        }
+        const uint64_t np = P.size();
+        uint64_t msz = 64; while (msz < 2 * np) msz <<= 1;
+        std::vector<uint64_t> mkeys(msz, GID_NONE); std::vector<uint32_t> mvals(msz, NIL);
+        GidMap gm{mkeys.data(), mvals.data(), msz - 1};
+        for (uint64_t i = 0; i < np; ++i) { uint64_t h = gid_hash(P[i].head) & gm.mask; while (mkeys[h] != GID_NONE) h = (h + 1) & gm.mask; mkeys[h] = P[i].head; mvals[h] = (uint32_t)i; }
+        nxt.assign(np, NIL); flip.assign(np, NIL);
+        for (uint64_t i = 0; i < np; ++i) {
+            if (P[i].succ != GID_NONE) { nxt[i] = gid_find(gm, P[i].succ); if (nxt[i] == NIL) return 107; }
+            flip[i] = gid_find(gm, gid_make((uint32_t)(P[i].head >> 32), P[i].tail ^ 1u));
+            if (flip[i] == NIL) return 108;
+        }
+        S.resize(np);
+        for (uint64_t i = 0; i < np; ++i) S[i] = piece_rank_init(P.data(), nxt.data(), (uint32_t)i);
+        uint64_t prev = ~0ull, un = 0;
+        for (int round = 0; round < 64; ++round) {
+            un = 0;
+            for (uint64_t i = 0; i < np; ++i) if (!(S[i].y & RANK_RESOLVED)) { S[i] = piece_rank_step(S[i], S[S[i].x]); un += !(S[i].y & RANK_RESOLVED); }
+            if (un == 0 || un == prev) break;
+            prev = un;
+        }
+        if (un == 0) break;
+        // ---- circles that span ranks (BuildReadQGraph.cc:126-180): unresolved pieces.  Label every circle (min piece index by
+        // pointer doubling), gather its nodes, find the minimum canonical k-mer per circle, cut there, and rank again.
+        std::vector<uint32_t> lab(np), jmp(np);
+        for (uint64_t i = 0; i < np; ++i) { lab[i] = (uint32_t)i; jmp[i] = nxt[i]; }
+        for (int round = 0; round < 40; ++round) {
+            bool any = false;
+            std::vector<uint32_t> lab2 = lab, jmp2 = jmp;
+            for (uint64_t i = 0; i < np; ++i) if (!(S[i].y & RANK_RESOLVED)) { const uint32_t j = jmp[i]; if (lab[j] < lab2[i]) { lab2[i] = lab[j]; any = true; } jmp2[i] = jmp[j]; }
+            lab.swap(lab2); jmp.swap(jmp2);
+            if (!any) break;
+        }
+        struct CNode { uint32_t lab; Kmer canon; uint64_t gid; };
+        std::vector<CNode> cn;
+        for (uint32_t r = 0; r < world; ++r) {
+            Rank& me = rk[r];
+            for (uint64_t x = 0; x < me.next0.size(); ++x) {
+                if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL || !(me.R[x].y & RANK_RESOLVED)) continue;
+                const uint32_t pi = me.piece0 + me.lpiece[me.R[x].x];
+                if (S[pi].y & RANK_RESOLVED) continue;
+                const SolidSlot& sl = me.slots[x >> 1];
+                cn.push_back(CNode{lab[pi], Kmer{sl.w0, sl.w1}, gid_make(r, (uint32_t)x)});
+            }
+        }
+        std::sort(cn.begin(), cn.end(), [](const CNode& a, const CNode& b) { return a.lab != b.lab ? a.lab < b.lab : (kmer_less(a.canon, b.canon) || (a.canon == b.canon && a.gid < b.gid)); });
+        // per circle label: the first entry holds the minimum canonical k-mer.  Both strand circles contain that slot: the one through
+        // (kmin,+) starts there, the one through (kmin,-) ends there.
+        std::vector<uint64_t> heads_g, tails_g;            // (kmin,+) becomes a head, (kmin,-) a tail
+        for (size_t i = 0; i < cn.size(); ++i) {
+            if (i > 0 && cn[i].lab == cn[i - 1].lab) continue;
+            for (size_t j = i; j < cn.size() && cn[j].lab == cn[i].lab && cn[j].canon == cn[i].canon; ++j)      // (a circle that is its own reverse complement holds both)
+                if (cn[j].gid & 1ull) tails_g.push_back(cn[j].gid); else heads_g.push_back(cn[j].gid);
+        }
+        std::sort(heads_g.begin(), heads_g.end());
+        for (uint32_t r = 0; r < world; ++r) {
+            Rank& me = rk[r];
+            for (uint64_t g : tails_g) if ((uint32_t)(g >> 32) == r) me.next0[(uint32_t)g] = NIL;          // (kmin,-) ends its strand
+            for (uint64_t x = 0; x < me.next0.size(); ++x) {                                              // the predecessor of (kmin,+) ends its strand
+                const uint32_t nx = me.next0[x];
+                if (nx >= GHOST_TAIL) continue;
+                const SolidSlot& sl = me.slots[nx >> 1];
+                const uint64_t g = slot_is_ghost(sl) ? gid_make(sl.pad - 1u, 2u * sl.edge + (nx & 1u)) : gid_make(r, nx);
+                if (std::binary_search(heads_g.begin(), heads_g.end(), g)) me.next0[x] = NIL;
+            }
+            for (uint64_t g : heads_g) if ((uint32_t)(g >> 32) == r) me.ghead[(uint32_t)g] = 0;
+        }
+    }
+    out->timings.count_passes = (uint32_t)P.size();
+    out->timings.reserved = (uint32_t)n_ghost;
+    // ---- strands: even lengths from the piece records (replicated), odd lengths by the owner of the middle k-mer (all-reduce max)
+    const uint64_t np = P.size();
+    PieceView pv{P.data(), flip.data(), S.data(), np};
+    std::vector<uint8_t> keepp(np, 0), is_head(np, 0);
+    std::vector<uint64_t> chain_n(np, 0);
+    for (uint64_t i = 0; i < np; ++i) {
+        if (nxt[i] != NIL) continue;
+        uint32_t hp; uint64_t n;
+        chain_of_tail_piece(pv, (uint32_t)i, &hp, &n);
+        if (n > 0x1000000ull) return 103;
+        is_head[hp] = 1; chain_n[hp] = n;
+        const uint32_t kf = chain_keep_even(pv, (uint32_t)i, hp, n);
+        if (kf != 2u) keepp[hp] = (uint8_t)kf;
+    }
+    for (Rank& me : rk)
+        for (uint64_t x = 0; x < me.next0.size(); ++x) {
+            if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL) continue;
+            const NodePos pos = node_position(pv, me.R.data(), me.lpiece.data(), me.piece0, (uint32_t)x);
+            const int kf = node_keep_odd(me.st, pos, (uint32_t)x);
+            if (kf >= 0) keepp[pos.head_piece] = (uint8_t)kf;
+        }
+    // ---- edges: kept heads sorted by k-mer (replicated), emission by the owners, all-reduce of the bases
+    struct Head { Kmer k; uint32_t piece; };
+    std::vector<Head> heads;
+    for (uint64_t i = 0; i < np; ++i) if (is_head[i] && keepp[i]) heads.push_back(Head{P[i].head_k, (uint32_t)i});
+    std::sort(heads.begin(), heads.end(), [](const Head& a, const Head& b) { return kmer_less(a.k, b.k); });
+    EdgeSet es;
+    es.E = heads.size();
+    const uint64_t E = es.E;
+    std::vector<uint32_t> edge_of_piece(np, NIL);
+    es.edge_len.resize(E); es.edge_off.assign(E + 1, 0);
+    for (uint64_t i = 0; i < E; ++i) { edge_of_piece[heads[i].piece] = (uint32_t)i; es.edge_len[i] = (uint32_t)chain_n[heads[i].piece] + K - 1; es.edge_off[i + 1] = es.edge_off[i] + (es.edge_len[i] + 3) / 4; }
+    es.edge_bases.assign(es.edge_off[E] + 32, 0);
+    PutBase put{es.edge_bases.data()};
+    for (Rank& me : rk)
+        for (uint64_t x = 0; x < me.next0.size(); ++x) {
+            if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL) continue;
+            const NodePos pos = node_position(pv, me.R.data(), me.lpiece.data(), me.piece0, (uint32_t)x);
+            const uint32_t e = edge_of_piece[pos.head_piece];
+            if (e != NIL) emit_node_sharded(me.st, pos, e, es.edge_off.data(), (uint32_t)x, put);
+        }
+    // ---- all-gather of the owned entries (with pruned context, edge, offset): the whole dictionary for pathing
+    uint32_t lg = 10;
+    while ((1ull << lg) < 2 * n_solid) ++lg;
+    std::vector<SolidSlot> full(1ull << lg);
+    memset(full.data(), 0xff, full.size() * sizeof(SolidSlot));
+    SolidTable fst{full.data(), lg};
+    for (Rank& me : rk)
+        for (uint64_t i = 0; i < me.st.size(); ++i) {
+            const SolidSlot& sl = me.slots[i];
+            if (sl.w0 == EMPTY_W0 || slot_is_ghost(sl)) continue;
+            uint64_t h = fst.home(Kmer{sl.w0, sl.w1});
+            while (full[h].w0 != EMPTY_W0) h = (h + 1) & (fst.size() - 1);
+            full[h] = sl;
+        }
+    const uint32_t keep_passes = out->timings.count_passes, keep_res = out->timings.reserved;
+    const int rc = finish_graph(fst, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
+    out->timings.count_passes = keep_passes;
+    if (!want_paths) out->timings.reserved = keep_res;
+    return rc;
+}
+
 void hc_graph_free(w2rap_graph* g) {
-    free(g->edge_off); free(g->edge_len); free(g->edge_bases); free(g->edge_vertices); free(g->fwd_xlat); free(g->rev_xlat);
+    free(g->edge_off); free(g->edge_len); free(g->edge_bases); free(g->edge_vertices); free(g->fwd_xlat); free(g->rev_xlat); free(g->involution);
     free(g->path_offset); free(g->path_off); free(g->path_edges); free(g->dump);
     memset(g, 0, sizeof(*g));
 }

@@ -1,8 +1,8 @@
 """Worker of tests/test_sharded_gloo.py: one rank of the sharded step-2 PROTOCOL on CPU over torch.distributed (gloo).
 
 The device stages are stood in for by the host-compiled device functions (tests/hostcheck); what is under test is the
-multi-rank logic: read sharding by index, routing of k-mer records to the owner of their hash partition (the product's own
-part_of_hash / owner_of_partition, csrc/shard.cuh), counting by owners, all-gather of the counted k-mers, identical graph on
+multi-rank logic: read sharding by index, routing of super-k-mer records to the owner of their minimiser partition (the product's own
+mini_part / owner_of_partition, csrc/extract.cuh, csrc/shard.cuh), counting by owners, all-gather of the counted k-mers, identical graph on
 every rank, paths by shard.  The GPU implementation of the same protocol (NCCL) is tested in tests/test_gpu_sharded.py.
 """
 import ctypes as C
@@ -36,7 +36,7 @@ def main():
     recs_p, own_p, nrec = C.c_void_p(), C.c_void_p(), C.c_uint64()
     reads = shard.c()
     assert hc.hc_extract_records(C.byref(reads), 7, logP, world, C.byref(recs_p), C.byref(own_p), C.byref(nrec)) == 0
-    recs = T._arr(recs_p.value, 2 * nrec.value, "<u8").reshape(-1, 2)
+    recs = T._arr(recs_p.value, 4 * nrec.value, "<u8").reshape(-1, 4)      # super-k-mer records (csrc/extract.cuh: SkmRec)
     owner = T._arr(own_p.value, nrec.value, "<u4")
     hc.hc_free(recs_p); hc.hc_free(own_p)
     # swizzle: all-to-all by owner
@@ -59,7 +59,7 @@ def main():
     assert hc.hc_graph(allk.ctypes.data, len(allk), 4, C.byref(reads), 1, 1, 24, 8, C.byref(g)) == 0
     d = T.graph_to_dict(g)
     hc.hc_graph_free(C.byref(g))
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=bounds[rank], hi=bounds[rank + 1], n_total_inst=sum(len(x) for x in outgoing),
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), lo=bounds[rank], hi=bounds[rank + 1], n_total_inst=int(sum(int((((x[:, 3] >> np.uint64(56)) & np.uint64(31)) + np.uint64(1)).sum()) for x in outgoing)),
              **{k: d[k] for k in ("hist", "edge_len", "edge_off", "edge_bases", "edge_vertices", "fwd_xlat", "rev_xlat", "path_offset", "path_off",
                                   "path_edges", "dump")}, allk=allk)
     dist.barrier()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(T):
     lib = T.product_lib()
     for s in declared_symbols():
         assert hasattr(lib, s), "missing export " + s
-    assert lib.w2rap_step2_abi_version() == 1
+    assert lib.w2rap_step2_abi_version() == 2
     assert b"sm_100a" in lib.w2rap_step2_build_info()
 
 

@@ -18,7 +18,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def both(T, rs, **kw):
     got = T.run_product(rs, T.default_params(**kw))
-    want = T.run_oracle(rs, T.default_params(**{k: v for k, v in kw.items() if k not in ("table_slots", "device")}))
+    want = T.run_oracle(rs, T.default_params(**{k: v for k, v in kw.items() if k not in ("table_slots", "device", "force_passes")}))
     return want, got
 
 
@@ -80,8 +80,19 @@ def test_golden_reference_outputs(T, case):
     assert rep["path_mismatches"] == [] and rep["path_ties"] <= 3, rep
 
 
+@pytest.mark.parametrize("npass", [2, 3])
+def test_forced_hash_range_passes(T, npass):
+    """The replacement of the reference's disk batches (BuildReadQGraph.cc:1120-1250): when the records of the whole job do not fit
+    in device memory the k-mer space is counted in hash-range passes.  Forced here: every pass filter, the cross-pass accumulation
+    of solid records and the histogram must give the single-pass answer, k-mer for k-mer."""
+    rs = T.rich_set(seed=14, genome=60000, cov=40)
+    want, got = both(T, rs, dump_kmers=2, force_passes=npass)
+    T.assert_graph_equal(want, got)
+    assert got["timings"]["count_passes"] >= npass
+
+
 def test_small_counting_region_many_groups(T):
-    """A forced small counting region: thousands of partitions / groups must give the same answer as one."""
+    """Forced small counting tables: every partition fails the shared-memory count and goes through a small L2 region in groups."""
     rs = T.rich_set(seed=6, genome=50000, cov=40)
     want, got = both(T, rs, dump_kmers=2, table_slots=60000)
     assert got["timings"]["count_passes"] > 3
@@ -89,8 +100,8 @@ def test_small_counting_region_many_groups(T):
 
 
 def test_tiny_counting_region_overflow_paths(T):
-    """A 64-slot region: group estimates are wrong all the time and some partitions exceed the region, so the per-partition
-    retry and the hash sub-range split (with roll-back of partial output) are exercised."""
+    """A 4-slot shared-memory table and a 64-slot region: every partition exceeds both, so the per-partition retry and the hash
+    sub-range split (with roll-back of partial output) are exercised."""
     rs = T.rich_set(seed=6, genome=12000, cov=30, families=2, palindromes=1, plasmid=600)
     want, got = both(T, rs, dump_kmers=2, table_slots=64)
     assert got["timings"]["count_passes"] > 1000
@@ -126,6 +137,19 @@ def test_edge_cases(T):
     want, got = both(T, rs, min_freq=200)
     T.assert_graph_equal(want, got)
     assert got["n_solid"] == 0 and got["n_pathed"] == 0
+
+
+def test_corrupt_quality_stream_is_rejected(T):
+    """A PQVec block whose payload would run past its stream (truncated / corrupted .qualp) is a clean W2RAP_ERR_BAD_ARG, not
+    an out-of-bounds walk on the device (the decoders are bounded by qual_off[i+1])."""
+    rs = T.smoke_set(seed=3, genome=3000, cov=10)
+    o = int(rs.qual_off[rs.n - 1])
+    rs.quals[o] = 255                    # the last read's first block claims 255 qualities ...
+    rs.quals[o + 1] |= 7                 # ... of 7 bits each: 225 bytes of payload in a ~100-byte stream
+    with pytest.raises(RuntimeError, match=r"failed \(1\)"):
+        T.run_product(rs)
+    got = T.run_product(T.smoke_set(seed=3, genome=3000, cov=10))      # and the library is still usable afterwards
+    assert got["n_pathed"] > 0
 
 
 def test_saturating_counts(T):

@@ -67,6 +67,15 @@ def test_sharded_equals_oracle(T, world):
     assert res[0]["timings"]["exchange_ms"] > 0
 
 
+def test_sharded_forced_passes(T):
+    """Hash-range counting passes under sharding: the pass filter, the per-pass exchange and the accumulation of solid records."""
+    rs = T.rich_set(seed=15, genome=50000, cov=40, families=3, palindromes=2, plasmid=900)
+    want = T.run_oracle(rs, T.default_params(dump_kmers=1))
+    res, _ = run_sharded(T, rs, 2, dump_kmers=1, force_passes=3)
+    for got in res:
+        T.assert_graph_equal(want, dict(got, n_reads=want["n_reads"], n_bases=want["n_bases"]), "forced passes", check_paths=False)
+
+
 def test_sharded_small_region_and_skew(T):
     """Tiny counting region (many groups, overflow fallbacks) and a high-multiplicity k-mer family under sharding."""
     rng = np.random.default_rng(5)

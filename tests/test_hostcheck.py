@@ -19,13 +19,14 @@ SO = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
 @pytest.fixture(scope="session")
 def hc(T):
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
+    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh", "shard.cuh", "shardgraph.cuh")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, src], check=True)
     lib = C.CDLL(SO)
     lib.hc_count.argtypes = [C.POINTER(T.Reads), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.hc_graph.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(T.Reads), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(T.Graph)]
+    lib.hc_graph_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(T.Reads), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(T.Graph)]
     lib.hc_free.argtypes = [C.c_void_p]
     lib.hc_graph_free.argtypes = [C.POINTER(T.Graph)]
     return lib
@@ -100,3 +101,41 @@ def test_minimizer_partition_key_is_strand_symmetric(T, hc):
     n = C.c_uint64(0)
     assert hc.hc_minimizer_symmetry(C.byref(reads), C.byref(n)) == 0
     assert n.value > 1000
+
+
+def test_super_kmer_records_round_trip(T, hc):
+    """The map's 32-byte super-k-mer records (extract.cuh: skm_build) expanded by the reduce (skm_kmer_at) give exactly the
+    (canonical k-mer, context) stream of the reference's leaf loop, for every read: short, exactly-K, variable-length and long ones."""
+    hc.hc_skm_roundtrip.restype = C.c_uint64
+    hc.hc_skm_roundtrip.argtypes = [C.POINTER(T.Reads), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    for rs, logP in ((T.rich_set(seed=4, genome=30000, cov=20, vary_len=True), 6), (T.rich_set(seed=9, genome=20000, cov=10, read_len=600, vary_len=True), 10),
+                     (T.smoke_set(seed=1, genome=5000, cov=10, read_len=61), 3)):
+        nrec, ninst = C.c_uint64(), C.c_uint64()
+        reads = rs.c()
+        bad = hc.hc_skm_roundtrip(C.byref(reads), 7, logP, C.byref(nrec), C.byref(ninst))
+        assert bad == 0 and ninst.value > 0
+        assert nrec.value <= ninst.value
+
+
+@pytest.mark.parametrize("world,logP", [(2, 5), (4, 7), (8, 9)])
+def test_sharded_graph_stage_simulated_ranks(T, hc, world, logP):
+    """csrc/shardgraph.cuh with `world` simulated ranks: dictionary sharded by minimiser owner, neighbour queries -> ghost entries,
+    local chains ranked per rank, one record per chain piece gathered and ranked, strands/edges/offsets derived per owner — must give
+    the oracle's graph bit for bit (pruned contexts, edge + offset of every k-mer, edge bytes, vertices, paths), including circles
+    that span ranks (the plasmid) and palindromes."""
+    rs = T.rich_set(seed=11, genome=40000, cov=40, families=4, palindromes=3, plasmid=1500)
+    ptr, n, ninst = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    reads = rs.c()
+    assert hc.hc_count(C.byref(reads), 7, C.byref(ptr), C.byref(n), C.byref(ninst)) == 0
+    g = T.Graph()
+    rc = hc.hc_graph_sharded(ptr, n, 4, world, logP, C.byref(reads), 1, 1, 24, 8, C.byref(g))
+    hc.hc_free(ptr)
+    assert rc == 0, "sharded hostcheck failure %d" % rc
+    d = T.graph_to_dict(g)
+    n_pieces = g.timings.count_passes
+    hc.hc_graph_free(C.byref(g))
+    want = T.run_oracle(rs, T.default_params(dump_kmers=1, apply_fixpaths=1))
+    for k in ("n_kmer_instances", "n_bases", "n_reads", "hist"):
+        d[k] = want[k]
+    T.assert_graph_equal(want, d, "sharded hostcheck (world %d) vs oracle" % world)
+    assert n_pieces > 2 * want["n_edges"]           # the chains really were cut into pieces at rank boundaries

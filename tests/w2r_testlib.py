@@ -31,13 +31,18 @@ class Params(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("K", C.c_uint32), ("min_qual", C.c_uint32), ("min_freq", C.c_uint32),
                 ("want_paths", C.c_uint32), ("apply_fixpaths", C.c_uint32), ("dump_kmers", C.c_uint32),
                 ("device", C.c_int32), ("workdir", C.c_char_p), ("table_slots", C.c_uint64), ("verbose", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("force_passes", C.c_uint32)]
 
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "count_ms", "solid_ms", "adjacency_ms", "unipath_ms", "hbv_ms",
                                          "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms", "exchange_ms", "host_pre_ms", "host_post_ms", "wall_ms")] + \
-               [(n, C.c_uint32) for n in ("count_launches", "kernel_launches", "count_passes", "reserved")]
+               [(n, C.c_uint32) for n in ("count_launches", "kernel_launches", "count_passes", "reserved")] + \
+               [("dict_ms", C.c_float), ("graph_exchange_ms", C.c_float), ("exchange_bytes", C.c_uint64), ("kernel_ms", C.c_float * 16)]
+
+
+KERNEL_NAMES = ["k_good_len", "k_minimizer_map<count>", "k_minimizer_map<store>", "k_count_smem", "k_insert_solid", "k_adjacency", "k_links",
+                "k_splitter_walk", "k_splitter_finish", "k_emit_edges", "k_bloom_build", "k_path_reads"]
 
 
 class KmerRec(C.Structure):
@@ -55,10 +60,10 @@ class Graph(C.Structure):
                 ("n_edges", C.c_uint64), ("n_edge_bases", C.c_uint64), ("edge_off", C.c_void_p),
                 ("edge_len", C.c_void_p), ("edge_bases", C.c_void_p),
                 ("n_vertices", C.c_uint64), ("n_hbv_edges", C.c_uint64), ("edge_vertices", C.c_void_p),
-                ("fwd_xlat", C.c_void_p), ("rev_xlat", C.c_void_p),
+                ("fwd_xlat", C.c_void_p), ("rev_xlat", C.c_void_p), ("involution", C.c_void_p),
                 ("n_paths", C.c_uint64), ("n_path_edges", C.c_uint64), ("path_offset", C.c_void_p),
                 ("path_off", C.c_void_p), ("path_edges", C.c_void_p), ("n_pathed", C.c_uint64),
-                ("n_multipathed", C.c_uint64),
+                ("n_multipathed", C.c_uint64), ("digest_graph", C.c_uint64), ("digest_paths", C.c_uint64),
                 ("n_dump", C.c_uint64), ("dump", C.c_void_p),
                 ("timings", Timings), ("_owner", C.c_void_p)]
 
@@ -68,10 +73,13 @@ class SynthParams(C.Structure):
                 ("het_per_10k", C.c_uint32), ("reserved", C.c_uint32), ("n_reads", C.c_uint64), ("first_read", C.c_uint64)]
 
 
+ABI_VERSION = 2
+
+
 def default_params(min_qual=7, min_freq=4, want_paths=1, apply_fixpaths=0, dump_kmers=0, workdir=None,
-                   table_slots=0, device=-1, verbose=0):
-    return Params(1, K, min_qual, min_freq, want_paths, apply_fixpaths, dump_kmers, device,
-                  workdir.encode() if workdir else None, table_slots, verbose, 0)
+                   table_slots=0, device=-1, verbose=0, force_passes=0):
+    return Params(ABI_VERSION, K, min_qual, min_freq, want_paths, apply_fixpaths, dump_kmers, device,
+                  workdir.encode() if workdir else None, table_slots, verbose, force_passes)
 
 
 def _arr(ptr, n, dtype):
@@ -96,11 +104,12 @@ def graph_to_dict(g):
         n_vertices=int(g.n_vertices), n_hbv_edges=int(g.n_hbv_edges),
         edge_vertices=_arr(g.edge_vertices, 4 * ne, "<i4").reshape(-1, 4),
         fwd_xlat=_arr(g.fwd_xlat, ne, "<i4"), rev_xlat=_arr(g.rev_xlat, ne, "<i4"),
+        involution=_arr(g.involution, g.n_hbv_edges, "<i4"), digest_graph=int(g.digest_graph), digest_paths=int(g.digest_paths),
         n_paths=npth, n_path_edges=int(g.n_path_edges), path_offset=_arr(g.path_offset, npth, "<i4"),
         path_off=_arr(g.path_off, npth + 1 if npth else 0, "<u8"), path_edges=_arr(g.path_edges, g.n_path_edges, "<i4"),
         n_pathed=int(g.n_pathed), n_multipathed=int(g.n_multipathed),
         dump=_arr(g.dump, g.n_dump, KMER_REC_DTYPE),
-        timings={n: getattr(g.timings, n) for n, _ in Timings._fields_},
+        timings={n: (list(getattr(g.timings, n)) if n == "kernel_ms" else getattr(g.timings, n)) for n, _ in Timings._fields_},
     )
     return d
 
@@ -585,7 +594,7 @@ def assert_graph_equal(a, b, what="graph", check_paths=True, check_dump=True):
     for k in ("n_reads", "n_bases", "n_kmer_instances", "n_distinct", "n_solid", "n_edges", "n_edge_bases", "n_vertices",
               "n_hbv_edges"):
         assert a[k] == b[k], "%s: %s differs: %s vs %s" % (what, k, a[k], b[k])
-    for k in ("hist", "edge_len", "edge_off", "edge_bases", "edge_vertices", "fwd_xlat", "rev_xlat"):
+    for k in ("hist", "edge_len", "edge_off", "edge_bases", "edge_vertices", "fwd_xlat", "rev_xlat", "involution"):
         assert np.array_equal(a[k], b[k]), "%s: array %s differs" % (what, k)
     if check_dump and (len(a["dump"]) or len(b["dump"])):
         assert len(a["dump"]) == len(b["dump"]), "%s: dump sizes differ %d vs %d" % (what, len(a["dump"]), len(b["dump"]))

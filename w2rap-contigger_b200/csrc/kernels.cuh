@@ -81,8 +81,8 @@ __global__ void k_good_len(ReadsView r, uint64_t first, uint64_t count, uint32_t
         unsigned long long mine = 0;
         if (i < end) {
             uint32_t nq = 0;
-            uint32_t gl = pq_good_length(r.quals + r.qual_off[i], min_qual, &nq);
-            if (nq != r.len[i]) atomicExch(bad, 1);              // a valid store has one quality per base
+            uint32_t gl = pq_good_length(r.quals + r.qual_off[i], r.quals + r.qual_off[i + 1], min_qual, &nq);
+            if (nq != r.len[i]) atomicExch(bad, 1);              // a valid store has one quality per base, framed inside its stream
             if (gl > r.len[i]) gl = r.len[i];
             good[i] = (uint16_t)gl;
             if (gl > (uint32_t)K) mine = gl - K + 1;
@@ -198,13 +198,20 @@ __global__ void k_rank_step_inplace(const uint32_t* __restrict__ list, uint64_t 
     }
 }
 // Splitter-based list ranking (see unipath.cuh).
-__global__ void k_splitter_walk(const uint32_t* __restrict__ next0, uint64_t nn, RankState* __restrict__ label, RankState* __restrict__ S,
-                                uint32_t* __restrict__ list, unsigned long long* cursor) {
+__global__ void k_count_splitters(const uint32_t* __restrict__ next0, const uint8_t* __restrict__ ghead, uint64_t nn, unsigned long long* __restrict__ count) {
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t x = base + threadIdx.x;
-        bool sp = x < nn && node_is_splitter(next0, (uint32_t)x);
+        const unsigned m = __ballot_sync(__activemask(), x < nn && node_is_splitter(next0, ghead, (uint32_t)x));
+        if (lane_id() == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+    }
+}
+__global__ void k_splitter_walk(const uint32_t* __restrict__ next0, const uint8_t* __restrict__ ghead, uint64_t nn, RankState* __restrict__ label, RankState* __restrict__ S,
+                                uint32_t* __restrict__ list, uint64_t list_cap, unsigned long long* cursor) {
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = base + threadIdx.x;
+        bool sp = x < nn && node_is_splitter(next0, ghead, (uint32_t)x);
         uint64_t pos = warp_append(cursor, sp);
-        if (sp) { list[pos] = (uint32_t)x; splitter_walk(next0, (uint32_t)x, label, S); }
+        if (sp) { if (pos < list_cap) list[pos] = (uint32_t)x; splitter_walk(next0, (uint32_t)x, label, S); }
     }
 }
 __global__ void k_splitter_finish(const uint32_t* __restrict__ next0, uint64_t nn, RankState* __restrict__ label_then_rank, const RankState* __restrict__ S,
@@ -337,13 +344,18 @@ __global__ void k_pal_widths(const uint8_t* __restrict__ is_pal, uint64_t E, uin
 }
 // HBV edge ids: canonical edge i -> fwd id, then rc id (one id for a palindrome) (HBVFromEdges.cc:137-151).
 __global__ void k_hbv_edges(uint64_t E, const uint8_t* __restrict__ is_pal, const uint32_t* __restrict__ xl, const int32_t* __restrict__ edge_vertices,
-                            int32_t* __restrict__ fwd_xlat, int32_t* __restrict__ rev_xlat, uint32_t* __restrict__ hcanon, int32_t* __restrict__ hleft, int32_t* __restrict__ hright) {
+                            int32_t* __restrict__ fwd_xlat, int32_t* __restrict__ rev_xlat, uint32_t* __restrict__ hcanon, int32_t* __restrict__ hleft, int32_t* __restrict__ hright,
+                            int32_t* __restrict__ involution) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t f = xl[i];
         fwd_xlat[i] = (int32_t)f;
         hcanon[f] = (uint32_t)(i << 1); hleft[f] = edge_vertices[4 * i]; hright[f] = edge_vertices[4 * i + 1];
-        if (is_pal[i]) rev_xlat[i] = (int32_t)f;
-        else { rev_xlat[i] = (int32_t)f + 1; hcanon[f + 1] = (uint32_t)(i << 1) | 1u; hleft[f + 1] = edge_vertices[4 * i + 2]; hright[f + 1] = edge_vertices[4 * i + 3]; }
+        // the involution step 3 asks for (paths/HyperBasevector.cc:648-660) is the fwd/rc pairing itself
+        if (is_pal[i]) { rev_xlat[i] = (int32_t)f; involution[f] = (int32_t)f; }
+        else {
+            rev_xlat[i] = (int32_t)f + 1; hcanon[f + 1] = (uint32_t)(i << 1) | 1u; hleft[f + 1] = edge_vertices[4 * i + 2]; hright[f + 1] = edge_vertices[4 * i + 3];
+            involution[f] = (int32_t)f + 1; involution[f + 1] = (int32_t)f;
+        }
     }
 }
 __global__ void k_adj_fill(uint64_t nh, const int32_t* __restrict__ hleft, const int32_t* __restrict__ hright, int32_t* __restrict__ from_e, int32_t* __restrict__ to_e,
@@ -492,6 +504,44 @@ __global__ void k_collect_overflow(const PathMeta* __restrict__ meta, uint64_t n
         uint64_t pos = warp_append(cursor, want);
         if (want) list[pos] = (uint32_t)i;
     }
+}
+
+// ================================================================ result digests (w2rap_graph.digest_*)
+__device__ __forceinline__ uint64_t digest_mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
+// *out += sum over i of mix(mix(i + salt) ^ word[i]) for the n_bytes at p (4-byte aligned; the last word is zero-extended)
+__global__ void k_digest_words(const uint8_t* __restrict__ p, uint64_t n_bytes, uint64_t salt, unsigned long long* out) {
+    const uint64_t nw = (n_bytes + 3) / 4;
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w = 0;
+        if (4 * i + 4 <= n_bytes) w = reinterpret_cast<const uint32_t*>(p)[i];
+        else for (uint64_t b = 4 * i; b < n_bytes; ++b) w |= (uint32_t)p[b] << (8 * (b - 4 * i));
+        acc += digest_mix(digest_mix(i + salt) ^ w);
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane_id() == 0 && acc) atomicAdd(out, acc);
+}
+// one term per read: the read's sequence bound to its path (offset, edges).  A sum, so it does not depend on how the reads are
+// sharded over GPUs.
+__global__ void k_digest_paths(ReadsView r, const int32_t* __restrict__ path_offset, const uint64_t* __restrict__ path_off, const int32_t* __restrict__ path_edges,
+                               unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t len = r.len[i];
+        const uint8_t* b = r.bases + r.base_off[i];
+        uint64_t h = digest_mix(len);
+        const uint32_t nb = (len + 3) / 4;
+        for (uint32_t j = 0; j < nb; ++j) {
+            uint32_t v = b[j];
+            if (j + 1 == nb && (len & 3u)) v &= (1u << (2u * (len & 3u))) - 1u;      // bits past the last base are not part of the read
+            h = digest_mix(h ^ v) + j;
+        }
+        h = digest_mix(h ^ (uint64_t)(uint32_t)path_offset[i]);
+        for (uint64_t e = path_off[i]; e < path_off[i + 1]; ++e) h = digest_mix(h ^ (uint64_t)(uint32_t)path_edges[e]) + 0x9e3779b97f4a7c15ull;
+        acc += h;
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane_id() == 0 && acc) atomicAdd(out, acc);
 }
 
 }  // namespace w2r

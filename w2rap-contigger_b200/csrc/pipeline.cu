@@ -2,7 +2,7 @@
 //
 // Mirrors buildReadQGraph (paths/long/BuildReadQGraph.cc:1253-1327) stage by stage:
 //   createDictOMPRecursive  -> count_stage()      (k_good_len, k_minimizer_map x2, [NCCL exchange], k_count_smem, k_count_region + k_scan_region as
-//                                                  fallback / legacy path, k_insert_solid)
+//                                                  fallback, k_insert_solid)
 //   recomputeAdjacencies    -> k_adjacency
 //   buildEdges              -> unipath_stage()    (k_links, pointer-jumping list ranking, circles, edge emission)
 //   buildHBVFromEdges       -> hbv_stage()        (end keys, radix sort, vertex ids, incidence)
@@ -140,6 +140,26 @@ struct StageTimer {
     float stop() { cudaEventRecord(ev[1], c.stream); cudaEventSynchronize(ev[1]); float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); return ms; }
 };
 
+// CUDA-event time of individual kernels without stalling the queue: events are recorded around the launches and read once the
+// stream has drained (w2rap_timings.kernel_ms).
+struct KernelTimers {
+    struct Span { int idx; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    cudaStream_t s = nullptr;
+    void begin(int idx) { Span sp{idx, nullptr, nullptr}; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); cudaEventRecord(sp.a, s); spans.push_back(sp); }
+    void end() { cudaEventRecord(spans.back().b, s); }
+    void resolve(float* kernel_ms) {
+        for (Span& sp : spans) {
+            float ms = 0;
+            if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) kernel_ms[sp.idx] += ms; else cudaGetLastError();
+            cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+        }
+        spans.clear();
+    }
+    ~KernelTimers() { for (Span& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } }
+};
+#define W2R_TIMED(idx, ...) do { kt_.begin(idx); __VA_ARGS__; kt_.end(); } while (0)
+
 static void say(const Ctx& c, const char* fmt, ...) {
     if (!c.verbose) return;
     va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap); printf("\n"); fflush(stdout);
@@ -153,6 +173,7 @@ struct Pipeline {
     w2rap_graph* out;
     GraphOwner* owner;
     std::vector<DumpRec> dump_host;
+    KernelTimers kt_;
 
     // persistent device state between stages
     SBuf<uint16_t> good;
@@ -160,7 +181,7 @@ struct Pipeline {
     SolidTable st{nullptr, 0};
     uint64_t E = 0, nv = 0, nh = 0;
     SBuf<uint8_t> edge_bases; SBuf<uint64_t> edge_off; SBuf<uint32_t> edge_len;
-    SBuf<int32_t> edge_vertices, fwd_xlat, rev_xlat, hleft, hright, from_e, to_e;
+    SBuf<int32_t> edge_vertices, fwd_xlat, rev_xlat, involution, hleft, hright, from_e, to_e;
     SBuf<uint32_t> hcanon;
     SBuf<uint8_t> from_n, to_n;
     uint64_t edge_bytes = 0;
@@ -225,395 +246,368 @@ struct Pipeline {
         if (scnt[rank]) W2R_CUDA(cudaMemcpyAsync((char*)recv + roff[rank], (const char*)send + soff[rank], scnt[rank], cudaMemcpyDeviceToDevice, c.stream));
     }
 
-    // ---- createDictOMPRecursive (BuildReadQGraph.cc:1000-1108): quality floor, k-mer counting, min-frequency filter, dictionary
-    void count_stage() {
+    // ---- createDictOMPRecursive (BuildReadQGraph.cc:1000-1108): quality floor, k-mer counting, min-frequency filter, dictionary.
+    // map (k_good_len, k_minimizer_map x2 per read batch) -> [NCCL exchange of the records to the partition owners] ->
+    // reduce (k_count_smem; k_count_region/k_scan_region for partitions that do not fit shared memory) -> solid records.
+    struct Batch { uint64_t first, count; cudaEvent_t ready; };      // reads [first, first+count) with an event to wait for (nullptr = resident)
+    struct CountPlan {
+        uint32_t logP = 0, npass = 1, nmap = 1, nslab = 1;
+        uint64_t P = 1, Pown = 1;
+        uint64_t n_inst = 0, n_inst_local = 0;        // upper bounds: whole job / this rank
+    };
+    // device state of one counting attempt
+    struct CountBufs {
+        SBuf<SkmRec> recs, xrecs;                      // local record area; sharded: the records this rank owns after the exchange
+        SBuf<uint32_t> part_count, part_kcount, cursor;   // [nmap][P]
+        SBuf<uint64_t> part_base, batch_total, batch_ktotal;
+        SBuf<unsigned long long> batch_off;            // [nmap + 1]
+        SBuf<uint32_t> xcount, xkcount;                // sharded: [world][Pown] records / k-mers of my partitions held by each rank
+        SBuf<uint64_t> xbase, xtot, xktot;
+        SBuf<unsigned long long> xoff;                 // [world + 1]
+    };
+    SBuf<unsigned long long> cs_scal;                  // [0] k-mer instances, [1] solid cursor, [2] dump cursor, [4], [5] failed-partition cursors
+    SBuf<int> cs_flags;                                // [0] malformed quality vector, [1] record buffer overflow, [2] solid staging overflow
+    SBuf<unsigned long long> cs_hist;
+    SBuf<CountSlot> cs_region;                         // two L2-resident counting regions (fallback reduce)
+    SBuf<DumpRec> cs_dump;
+    SBuf<ulonglong2> cs_solid; uint64_t cs_solid_cap = 0;
+    uint64_t cs_R = 0; uint32_t cs_logR = 0;
+    bool good_done = false;
+    float map_ms = 0, reduce_ms = 0, xchg_ms = 0;
+    uint32_t n_groups = 0;
+    uint64_t xchg_bytes = 0;
+
+    void run_good_len(const Batch& bt) {
+        if (bt.ready) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
+        if (bt.count) W2R_TIMED(W2RAP_KT_GOOD_LEN, W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, dr.view(), bt.first, bt.count, prm.min_qual, good.p, cs_scal.p, cs_flags.p));
+    }
+
+    // map: per read batch  quality floor -> counting launch -> scan -> store launch (all queued without a host round trip, so a
+    // batch is mapped as soon as it has crossed PCIe).  Returns false if the record area was too small (need = exact size).
+    bool map_records(const CountPlan& pl, CountBufs& cb, const std::vector<Batch>& batches, uint32_t pass, uint64_t* need) {
+        static const unsigned map_ctas = getenv("W2RAP_MAP_CTAS") ? (unsigned)atoi(getenv("W2RAP_MAP_CTAS")) : 6u;
         const ReadsView rv = dr.view();
+        const uint64_t P = pl.P;
+        cb.cursor.zero(); cb.part_count.zero(); cb.part_kcount.zero();
+        W2R_CUDA(cudaMemsetAsync(cb.batch_off.p, 0, sizeof(unsigned long long), c.stream));
+        std::vector<Batch> mb = batches;
+        if (world > 1) {        // sharded: one map batch (the layout must be by owner rank), after the whole shard has arrived
+            if (!good_done) for (const Batch& bt : batches) run_good_len(bt);
+            good_done = true;
+            mb.assign(1, Batch{0, dr.n, nullptr});
+        }
+        std::vector<cudaEvent_t> ev(2 * pl.nmap, nullptr);                 // the map launches are timed without stalling the queue
+        struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); } } evg{ev};
+        for (uint32_t bi = 0; bi < pl.nmap; ++bi) {
+            const Batch& bt = mb[bi];
+            MiniParams mp{pl.logP, pl.npass, pass, cb.part_count.p + bi * P, cb.part_kcount.p + bi * P, cb.part_base.p + bi * P, cb.cursor.p + bi * P, cb.recs.p,
+                          cb.batch_off.p + bi, cb.recs.n, cs_flags.p + 1};
+            if (!good_done) run_good_len(bt);
+            W2R_CUDA(cudaEventCreate(&ev[2 * bi])); W2R_CUDA(cudaEventCreate(&ev[2 * bi + 1]));
+            W2R_CUDA(cudaEventRecord(ev[2 * bi], c.stream));
+            if (bt.count && pl.n_inst_local) W2R_TIMED(W2RAP_KT_MAP_COUNT, W2R_LAUNCH(c, k_minimizer_map<true>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp));
+            exclusive_scan<uint32_t, uint64_t>(c, cb.part_count.p + bi * P, P, cb.part_base.p + bi * P, cb.batch_total.p + bi);
+            W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, cb.batch_off.p + bi, cb.batch_total.p + bi);
+            if (bt.count && pl.n_inst_local) { W2R_TIMED(W2RAP_KT_MAP_STORE, W2R_LAUNCH(c, k_minimizer_map<false>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp)); c.count_launches++; }
+            W2R_CUDA(cudaEventRecord(ev[2 * bi + 1], c.stream));
+        }
+        good_done = true;
+        unsigned long long total = 0;
+        W2R_CUDA(cudaMemcpyAsync(&total, cb.batch_off.p + pl.nmap, 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        for (uint32_t bi = 0; bi < pl.nmap; ++bi) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * bi], ev[2 * bi + 1]); map_ms += ms; }
+        if (d2h_scalar(c, cs_flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
+        *need = total;
+        std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, cs_flags.p + 1)};
+        allreduce_u64(of, ncclMax);               // every rank must take the same branch
+        if (of[0]) { W2R_CUDA(cudaMemsetAsync(cs_flags.p + 1, 0, sizeof(int), c.stream)); return false; }
+        return true;
+    }
+
+    // sharded: route every record to the rank that owns its partition.  The local area is laid out by partition = by owner, so
+    // "everything rank d owns" is one contiguous piece: exchange the per-partition counts, scan them into the receive layout,
+    // then one grouped ncclSend/ncclRecv per peer (MapReduceEngine's swizzle, MapReduceEngine.h:337-358, over NVLink).
+    void exchange_records(const CountPlan& pl, CountBufs& cb) {
+        EventTimer kt(c.stream);
+        kt.start();
+        const uint64_t Pown = pl.Pown;
+        alltoall_slabs(cb.part_count.p, cb.xcount.p, Pown * sizeof(uint32_t));          // xcount[s][q] = records of my partition q held by rank s
+        alltoall_slabs(cb.part_kcount.p, cb.xkcount.p, Pown * sizeof(uint32_t));
+        W2R_CUDA(cudaMemsetAsync(cb.xoff.p, 0, sizeof(unsigned long long), c.stream));
+        for (int sidx = 0; sidx < world; ++sidx) {
+            exclusive_scan<uint32_t, uint64_t>(c, cb.xcount.p + (uint64_t)sidx * Pown, Pown, cb.xbase.p + (uint64_t)sidx * Pown, cb.xtot.p + sidx);
+            W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, cb.xoff.p + sidx, cb.xtot.p + sidx);
+        }
+        std::vector<uint64_t> sbeg(world + 1, 0), rtot(world, 0);
+        for (int d = 0; d < world; ++d) W2R_CUDA(cudaMemcpyAsync(&sbeg[d], cb.part_base.p + (uint64_t)d * Pown, 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaMemcpyAsync(&sbeg[world], cb.batch_total.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaMemcpyAsync(rtot.data(), cb.xtot.p, world * 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        std::vector<size_t> soff(world), scnt(world), roff(world), rcnt(world);
+        size_t racc = 0;
+        for (int d = 0; d < world; ++d) {
+            soff[d] = sbeg[d] * sizeof(SkmRec); scnt[d] = (sbeg[d + 1] - sbeg[d]) * sizeof(SkmRec);
+            roff[d] = racc * sizeof(SkmRec); rcnt[d] = rtot[d] * sizeof(SkmRec); racc += rtot[d];
+            if (d != rank) xchg_bytes += scnt[d];
+        }
+        cb.xrecs.alloc(c, racc + 1);
+        alltoall_v(cb.recs.p, soff, scnt, cb.xrecs.p, roff, rcnt);
+        xchg_ms += kt.stop();
+    }
+
+    // reduce: what this rank counts is `nslab` runs per owned partition (read batches on one GPU, source ranks when sharded)
+    void reduce_records(const CountPlan& pl, const SkmRec* xrecs, const uint32_t* xcur, const uint32_t* xkcur, RunView runs, cudaStream_t s2, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+        static const uint32_t smem_log_env = getenv("W2RAP_SMEM_LOG") ? (uint32_t)atoi(getenv("W2RAP_SMEM_LOG")) : 13u;
+        const uint64_t Pown = pl.Pown, R = cs_R;
+        const uint32_t nslab = pl.nslab;
+        EventTimer kt(c.stream);
+        kt.start();
+        SBuf<uint32_t> failed(c, Pown), failed2(c, Pown);
+        W2R_CUDA(cudaMemsetAsync(cs_scal.p + 4, 0, 16, c.stream));
+        // (a per-device attribute: set on every call — ranks driven from threads of one process each have their own device)
+        const size_t stage_bytes = (size_t)2 * SKM_CHUNK * sizeof(SkmRec);
+        W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((20u << SMEM_LOG_SLOTS_MAX) + stage_bytes)));
+        // the table_slots test hook shrinks the first table as well, so that partitions really take the fallback path
+        uint32_t log1 = std::max(2u, std::min(smem_log_env, SMEM_LOG_SLOTS_MAX));
+        if (prm.table_slots) log1 = (uint32_t)std::max(2, std::min((int)SMEM_LOG_SLOTS_MAX, (int)cs_logR - 6));
+        SmemCountParams sc{xrecs, xcur, runs.part_base, runs.slab_off, nslab, (uint32_t)Pown, prm.min_freq, cs_hist.p, cs_solid.p, cs_scal.p + 1, cs_solid_cap, cs_flags.p + 2,
+                           prm.dump_kmers == 2 ? cs_dump.p : nullptr, cs_scal.p + 2, failed.p, cs_scal.p + 4, log1, nullptr, 0};
+        kt_.begin(W2RAP_KT_REDUCE);
+        k_count_smem<<<(unsigned)std::min<uint64_t>(Pown, (uint64_t)c.sm_count), 1024, ((size_t)20u << log1) + stage_bytes, c.stream>>>(sc); c.launches++; ++n_groups;
+        kt_.end();
+        W2R_CUDA(cudaGetLastError());
+        const uint64_t nfail1 = (log1 < SMEM_LOG_SLOTS_MAX && !prm.table_slots) ? d2h_scalar(c, cs_scal.p + 4) : 0;
+        if (nfail1) {
+            SmemCountParams sc2 = sc;
+            sc2.failed = failed2.p; sc2.failed_cursor = cs_scal.p + 5; sc2.log_slots = SMEM_LOG_SLOTS_MAX; sc2.plist = failed.p; sc2.nlist = (uint32_t)nfail1;
+            k_count_smem<<<(unsigned)std::min<uint64_t>(nfail1, (uint64_t)c.sm_count), 1024, ((size_t)20u << SMEM_LOG_SLOTS_MAX) + stage_bytes, c.stream>>>(sc2); c.launches++; ++n_groups;
+            W2R_CUDA(cudaGetLastError());
+        }
+        const SBuf<uint32_t>& failed_final = nfail1 ? failed2 : failed;
+        const uint64_t nfail = d2h_scalar(c, nfail1 ? cs_scal.p + 5 : cs_scal.p + 4);
+        if (nfail) {
+            say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)Pown);
+            std::vector<uint32_t> fl(nfail);
+            W2R_CUDA(cudaMemcpyAsync(fl.data(), failed_final.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream));
+            // per owned partition: largest run in records (sizes the grid) and k-mer instances (bounds its distinct k-mers)
+            std::vector<uint32_t> raw((size_t)nslab * Pown), rawk((size_t)nslab * Pown);
+            W2R_CUDA(cudaMemcpyAsync(raw.data(), xcur, raw.size() * 4, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaMemcpyAsync(rawk.data(), xkcur, rawk.size() * 4, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            std::vector<uint32_t> sizes(Pown, 0);
+            std::vector<uint64_t> totals(Pown, 0);
+            for (uint32_t sidx = 0; sidx < nslab; ++sidx)
+                for (uint64_t q = 0; q < Pown; ++q) { sizes[q] = std::max(sizes[q], raw[sidx * Pown + q]); totals[q] += rawk[sidx * Pown + q]; }
+            // the persisting carve-out is taken from the normal L2, which the map needs for write combining: hold it only while it is used
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(2 * R * sizeof(CountSlot), 80u << 20)) != cudaSuccess) cudaGetLastError();
+            set_l2_window(cs_region.p, 2 * R * sizeof(CountSlot));
+            {   // the second stream gets the same L2 window
+                cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+                attr.accessPolicyWindow.base_ptr = cs_region.p; attr.accessPolicyWindow.num_bytes = 2 * R * sizeof(CountSlot);
+                attr.accessPolicyWindow.hitRatio = 1.0f; attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(s2, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+            }
+            SBuf<int> gflag(c, nfail + 1); gflag.zero();
+            uint32_t group_parity = 0;
+            auto fork = [&] { W2R_CUDA(cudaEventRecord(ev_fork, c.stream)); W2R_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0)); };
+            auto join = [&] { W2R_CUDA(cudaEventRecord(ev_join, s2)); W2R_CUDA(cudaStreamWaitEvent(c.stream, ev_join, 0)); };
+            // entries [i0, i0+g) of the failed list go through one counting region together (two regions on two streams alternate)
+            auto run_group = [&](uint32_t i0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag) {
+                ++n_groups;
+                uint32_t mxg = 0;
+                for (uint32_t q = i0; q < i0 + g; ++q) mxg = std::max(mxg, sizes[fl[q]]);
+                cudaStream_t gs = (group_parity & 1u) ? s2 : c.stream;
+                CountSlot* greg = cs_region.p + ((group_parity & 1u) ? R : 0);
+                ++group_parity;
+                if (mxg) {
+                    RegionParams rp{greg, cs_logR, sub_mask, sub_id, flag};
+                    RunView rv2 = runs;
+                    rv2.plist = failed_final.p;
+                    dim3 gr(std::max(1u, std::min<unsigned>((mxg + 7) / 8, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(g * nslab, 8u))))), g * nslab);
+                    k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, i0, g, rv2, rp); c.launches++;
+                    W2R_CUDA(cudaGetLastError());
+                }
+                ScanParams sp{greg, R, prm.min_freq, cs_hist.p, cs_solid.p, cs_scal.p + 1, cs_solid_cap, prm.dump_kmers == 2 ? cs_dump.p : nullptr, cs_scal.p + 2, flag, cs_flags.p + 2};
+                k_scan_region<<<grid(R, 256, 4), 256, 0, gs>>>(sp); c.launches++;
+                W2R_CUDA(cudaGetLastError());
+            };
+            // in bulk: as many listed partitions per region pass as fit it even if every k-mer were distinct (load <= 0.6), no host
+            // round trip per group; a group that overflows all the same is redone partition by partition below
+            std::vector<std::pair<uint32_t, uint32_t>> lgroups;        // (offset into fl, count)
+            const uint32_t gmax = std::max(1u, 4000u / nslab);          // gridDim.y = g * nslab <= 65535
+            for (size_t i0 = 0; i0 < fl.size();) {
+                uint64_t acc = 0; size_t j = i0;
+                while (j < fl.size() && j - i0 < gmax && (j == i0 || (double)(acc + totals[fl[j]]) <= 0.6 * (double)R)) { acc += totals[fl[j]]; ++j; }
+                lgroups.push_back({(uint32_t)i0, (uint32_t)(j - i0)});
+                i0 = j;
+            }
+            if (lgroups.size() > nfail) W2R_FAIL(W2RAP_ERR_INTERNAL, "more fallback groups than failed partitions");
+            fork();
+            for (size_t gi = 0; gi < lgroups.size(); ++gi) run_group(lgroups[gi].first, lgroups[gi].second, 0, 0, gflag.p + gi);
+            join();
+            std::vector<int> lgf(lgroups.size());
+            W2R_CUDA(cudaMemcpyAsync(lgf.data(), gflag.p, lgroups.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            int* one_flag = gflag.p + nfail;
+            for (size_t gi = 0; gi < lgroups.size(); ++gi) {
+                if (!lgf[gi]) continue;
+                // the group did not fit together: its partitions one by one, and a partition that still fails in hash sub-ranges
+                for (uint32_t k = lgroups[gi].first; k < lgroups[gi].first + lgroups[gi].second; ++k) {
+                    unsigned long long snapshot[2];
+                    std::vector<unsigned long long> hist_snapshot(104);
+                    W2R_CUDA(cudaMemcpyAsync(snapshot, cs_scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaMemcpyAsync(hist_snapshot.data(), cs_hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaMemsetAsync(one_flag, 0, sizeof(int), c.stream));
+                    fork(); run_group(k, 1, 0, 0, one_flag); join();
+                    if (!d2h_scalar(c, one_flag)) continue;
+                    for (uint32_t S = 2;; S *= 2) {
+                        if (S > 4096) W2R_FAIL(W2RAP_ERR_INTERNAL, "a k-mer partition does not fit the counting region even in 4096 hash sub-ranges");
+                        bool ok = true;
+                        for (uint32_t sid = 0; sid < S && ok; ++sid) {
+                            W2R_CUDA(cudaMemsetAsync(one_flag, 0, sizeof(int), c.stream));
+                            fork(); run_group(k, 1, S - 1, sid, one_flag); join();
+                            if (d2h_scalar(c, one_flag)) ok = false;
+                        }
+                        if (ok) break;
+                        // roll back what the successful sub-ranges of this split emitted, then split finer
+                        W2R_CUDA(cudaMemcpyAsync(cs_scal.p + 1, snapshot, 16, cudaMemcpyHostToDevice, c.stream));
+                        W2R_CUDA(cudaMemcpyAsync(cs_hist.p, hist_snapshot.data(), 104 * 8, cudaMemcpyHostToDevice, c.stream));
+                        W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    }
+                }
+            }
+            set_l2_window(nullptr, 0);
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
+        }
+        reduce_ms += kt.stop();
+    }
+
+    void count_stage() {
         good.alloc(c, dr.n);
-        SBuf<unsigned long long> scal(c, 8);       // [0] k-mer instances, [1] solid cursor, [2] dump cursor, [4], [5] failed-partition cursors
-        scal.zero();
-        SBuf<int> flags(c, 4);                     // [0] malformed quality vector, [1] record buffer overflow, [2] solid staging overflow
-        flags.zero();
+        cs_scal.alloc(c, 8); cs_scal.zero();
+        cs_flags.alloc(c, 4); cs_flags.zero();
+        cs_hist.alloc(c, 104); cs_hist.zero();
+        CountPlan pl;
         // Everything is sized from an upper bound of the instance count that needs no qualities (sum of len-59), so that the
         // quality floor + map of the first read batch can start while later batches are still crossing PCIe.
-        const unsigned long long n_inst_local = dr.n_inst_upper;
-        std::vector<unsigned long long> agg = {n_inst_local};
+        pl.n_inst_local = dr.n_inst_upper;
+        std::vector<unsigned long long> agg = {pl.n_inst_local};
         allreduce_u64(agg, ncclSum);
-        std::vector<unsigned long long> mx = {n_inst_local};
-        allreduce_u64(mx, ncclMax);
-        const unsigned long long n_inst = agg[0], n_inst_max = mx[0];      // whole job / largest shard (upper bounds)
-        // read batches: [first, first+count) with an event to wait for (nullptr = already resident)
-        struct Batch { uint64_t first, count; cudaEvent_t ready; };
+        pl.n_inst = agg[0];
         std::vector<Batch> batches;
         if (!dr.batch_ready.empty()) for (size_t b = 0; b < dr.batch_ready.size(); ++b) batches.push_back(Batch{dr.batch_first[b], dr.batch_first[b + 1] - dr.batch_first[b], dr.batch_ready[b]});
         else batches.push_back(Batch{0, dr.n, nullptr});
-        bool good_done = false;
 
-        // region: the L2-resident counting table.  1 Mi slots x 32 B = 32 MB of the 126 MB L2 (smaller for tiny inputs / the test hook).
-        uint32_t logR = 20;
-        while (logR > 8 && (1ull << (logR - 1)) >= 2 * n_inst + 64) --logR;
-        if (prm.table_slots) { logR = 6; while ((2ull << logR) <= prm.table_slots && logR < 24) ++logR; }
-        const uint64_t R = 1ull << logR;
-        // Default: FINE partitions keyed by minimiser (count_part.cuh: k_minimizer_map), each small enough for one CTA to count in
-        // shared memory (k_count_smem); the k-mer hash bits are then all free for the slot inside the table.  Rank r owns the
-        // contiguous partition range [r*P/world, (r+1)*P/world).
-        // Legacy (the table_slots test hook, W2RAP_STATIC_PARTITIONS): hash partitions in static sub-buffers, counted through the
-        // L2 region; few enough records each that even an all-distinct partition fits the region.
-        const bool mini = !prm.table_slots && !getenv("W2RAP_STATIC_PARTITIONS");
-        // table size of the first k_count_smem launch: 8192 slots and partitions of ~24 k records (measured, config 2: 73 ms; 4096
-        // slots with two 512-thread CTAs per SM and ~12 k records: 79 ms)
-        static const uint32_t smem_log = getenv("W2RAP_SMEM_LOG") ? (uint32_t)atoi(getenv("W2RAP_SMEM_LOG")) : 13u;
-        static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : (smem_log <= 12 ? 12000.0 : 24000.0);
-        uint32_t logP = 0;
-        if (mini) { while (((double)n_inst / (double)(1ull << logP) > fine_recs || (1ull << logP) < (uint64_t)world) && logP < 22) ++logP; }
-        else
-        // (n_inst is an upper bound, and real read sets are far from all-distinct: 0.9 R records per partition; a partition that
-        //  does not fit is handled by the hash sub-range fallback)
-        while (((double)n_inst / (double)(1ull << logP) > 0.9 * (double)R || (1ull << logP) < (uint64_t)world) && logP < 24) ++logP;
-        size_t budget = (size_t)(device_budget(c) * 0.80);
+        // fallback region: 1 Mi slots x 32 B = 32 MB of the 126 MB L2, twice (smaller for tiny inputs / the test hook)
+        cs_logR = 20;
+        while (cs_logR > 8 && (1ull << (cs_logR - 1)) >= 2 * pl.n_inst + 64) --cs_logR;
+        if (prm.table_slots) { cs_logR = 6; while ((2ull << cs_logR) <= prm.table_slots && cs_logR < 24) ++cs_logR; }
+        cs_R = 1ull << cs_logR;
+        // FINE partitions keyed by minimiser, each small enough for one CTA to count in shared memory: ~24 k k-mer instances
+        // (measured, config 2, 8192-slot table).  Rank r owns the contiguous partition range [r*P/world, (r+1)*P/world).
+        static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : 24000.0;
+        while (((double)pl.n_inst / (double)(1ull << pl.logP) > fine_recs || (1ull << pl.logP) < (uint64_t)world) && pl.logP < 22) ++pl.logP;
+        pl.P = 1ull << pl.logP; pl.Pown = pl.P / world;
+        pl.nmap = world > 1 ? 1u : (uint32_t)batches.size();
+        pl.nslab = world > 1 ? (uint32_t)world : pl.nmap;
+        if (pl.nslab > SMEM_MAX_BATCH) W2R_FAIL(W2RAP_ERR_INTERNAL, "more record runs per partition than the reduce kernel handles");
         if (prm.dump_kmers == 2 && world > 1) W2R_FAIL(W2RAP_ERR_BAD_ARG, "dump level 2 is a single-GPU test hook");
-        const size_t fixed_bytes = R * sizeof(CountSlot) + (prm.dump_kmers == 2 ? n_inst * sizeof(DumpRec) : 0) +
-                                   (size_t)((double)n_inst / world / std::max<uint32_t>(1, prm.min_freq) * 1.3) * sizeof(ulonglong2);
-        if (fixed_bytes + (64u << 20) > budget) W2R_FAIL(W2RAP_ERR_OOM, "not enough device memory for the solid k-mer staging buffer");
-        SBuf<ulonglong2> solid;                       // solid records of the partitions this rank owns
-        uint64_t solid_cap = 0;
-        // Two regions on two streams: groups alternate between them, so the scan/reset of one group overlaps the inserts of the next.
-        SBuf<CountSlot> region(c, 2 * R);
-        SBuf<DumpRec> dump_dev(c, prm.dump_kmers == 2 ? n_inst : 0);
-        SBuf<unsigned long long> hist(c, 104); hist.zero();
-        W2R_LAUNCH(c, k_init_count_table, grid(4 * R, 256), 256, 0, region.p, 2 * R);
+        const size_t budget = (size_t)(device_budget(c) * 0.80);
+        cs_region.alloc(c, 2 * cs_R);
+        cs_dump.alloc(c, prm.dump_kmers == 2 ? pl.n_inst : 0);
+        W2R_LAUNCH(c, k_init_count_table, grid(4 * cs_R, 256), 256, 0, cs_region.p, 2 * cs_R);
         cudaStream_t s2 = nullptr;
         W2R_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
         struct StreamGuard { cudaStream_t s; ~StreamGuard() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } } s2_guard{s2};
         cudaEvent_t ev_fork, ev_join;
         cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
         struct EventGuard { cudaEvent_t a, b; ~EventGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_guard{ev_fork, ev_join};
-        uint32_t group_parity = 0;
-        float part_ms = 0, region_ms = 0, xchg_ms = 0;
-        uint32_t npass = 1;
-        double slack = 1.06;
-        uint64_t n_distinct_seen = 0;
-        uint32_t n_groups = 0;
-        EventTimer kt(c.stream);
+
+        // Records per k-mer instance: ~1/13 on 250-base reads; short reads approach 1.  The area is sized from an estimate and, if
+        // the store launch reports an overflow, re-sized to the exact need the counting launch computed.
+        double rec_per_inst = 1.0 / 6.0;
+        uint64_t need_exact = 0;
+        pl.npass = prm.force_passes ? prm.force_passes : 1u;
         for (int attempt = 0;; ++attempt) {
-            if (attempt > 8) W2R_FAIL(W2RAP_ERR_INTERNAL, "k-mer partitioning did not converge");
-            const uint64_t P = 1ull << logP, Pown = P / world;
-            // legacy layout: 8 sub-buffers per partition with cursors on separate L2 lines; minimiser layout: one cursor per partition
-            const uint32_t nsub = (!mini && n_inst_max / P >= 65536 && !prm.table_slots) ? 8u : 1u;
-            const uint32_t cstride = mini ? 1 : 32;
-            const uint64_t NB = P * nsub, NBown = Pown * nsub;
-            const uint64_t per_part = (uint64_t)((double)n_inst_max / (double)NB / (double)npass);
-            const uint64_t cap = mini ? (1ull << 40) : (uint64_t)((double)per_part * slack) + 1024;
-            // minimiser layout: the local record area is sized from the upper bound (exact sizes come from the counting launch, but
-            // only on the device); with several passes the k-mer space is split by minimiser hash, so allow for uneven passes.
-            // Sharded: plus the records this rank owns (allocated exactly once the counts have been exchanged).
-            const size_t local_recs = mini ? (size_t)((double)n_inst_local / npass * (npass > 1 ? slack * 1.2 : 1.0)) + 64 : NB * cap;
-            const size_t rec_bytes = mini ? (local_recs + (world > 1 ? (size_t)((double)n_inst / world / npass * 1.25) : 0)) * sizeof(ulonglong2)
-                                          : NB * cap * sizeof(ulonglong2) * (world > 1 ? 2 : 1);   // + the receive slabs
-            // Legacy layout: scattered single-record appends over tens of GB run into TLB misses (measured: 2x slower per record on
-            // an 82 GB buffer than on a 41 GB one), so that buffer is capped and the k-mer space split into hash-range passes.
-            static const double rec_cap_gb = getenv("W2RAP_REC_BUDGET_GB") ? atof(getenv("W2RAP_REC_BUDGET_GB")) : 48.0;
-            std::vector<unsigned long long> too_big = {(rec_bytes + fixed_bytes > budget || (!mini && (double)(NB * cap * sizeof(ulonglong2)) > rec_cap_gb * 1e9)) ? 1ull : 0ull};
+            if (attempt > 12) W2R_FAIL(W2RAP_ERR_INTERNAL, "k-mer partitioning did not converge");
+            const uint64_t P = pl.P, Pown = pl.Pown;
+            // with several passes the k-mer space is split by minimiser hash: allow for uneven passes
+            const size_t local_recs = std::max<uint64_t>(need_exact + need_exact / 64, (uint64_t)((double)pl.n_inst_local * rec_per_inst / pl.npass * (pl.npass > 1 ? 1.25 : 1.0))) + 1024;
+            const size_t solid_est = (size_t)((double)pl.n_inst / world / pl.npass / std::max<uint32_t>(1, prm.min_freq) * 1.3) * sizeof(ulonglong2);
+            const size_t rec_bytes = (local_recs + (world > 1 ? (size_t)((double)pl.n_inst * rec_per_inst / world / pl.npass * 1.25) : 0)) * sizeof(SkmRec);
+            std::vector<unsigned long long> too_big = {(rec_bytes + solid_est + cs_dump.bytes() + (64u << 20) > budget) ? 1ull : 0ull};
             allreduce_u64(too_big, ncclMax);                     // every rank must run the same number of passes
-            if (too_big[0] && npass < 4096) { npass *= 2; continue; }
-            const double t_alloc0 = now_ms();
-            SBuf<ulonglong2> recs(c, local_recs), xrecs_buf(c, (!mini && world > 1) ? NB * cap : 0);
-            if (getenv("W2RAP_TRACE")) fprintf(stderr, "[w2rap] count: record buffer %.2f GB allocated in %.1f ms (host)\n", recs.bytes() / 1e9, now_ms() - t_alloc0);
-            // Minimiser layout, one GPU: every read batch gets its own exactly sized record area, so that a batch is mapped as soon
-            // as it has arrived; a partition is then one run per batch.  Sharded: one local area, laid out by partition = by owner,
-            // and after the exchange a partition is one run per source rank.  Either way the reduce sees `nslab` runs per partition.
-            const uint32_t nmap = mini ? (world > 1 ? 1u : (uint32_t)batches.size()) : 0u;
-            const uint32_t nslab = mini ? (world > 1 ? (uint32_t)world : nmap) : (uint32_t)world;
-            if (mini && nslab > SMEM_MAX_BATCH) W2R_FAIL(W2RAP_ERR_INTERNAL, "more record slabs per partition than the reduce kernel handles");
-            SBuf<uint32_t> part_count(c, nmap * P);
-            SBuf<uint64_t> part_base(c, nmap * P), batch_total(c, nmap);
-            SBuf<unsigned long long> batch_off(c, mini ? nmap + 1 : 0);
-            SBuf<uint32_t> cursor(c, mini ? nmap * P : NB * cstride), xcur_buf(c, world > 1 ? (mini ? world * Pown : NB * cstride) : 0);
-            SBuf<uint64_t> xbase(c, (mini && world > 1) ? world * Pown : 0), xtot(c, (mini && world > 1) ? world : 0);
-            SBuf<unsigned long long> xoff(c, (mini && world > 1) ? world + 1 : 0);
-            const uint64_t slab_recs = NBown * cap, slab_cur = NBown * cstride;
-            // what this rank reduces: records, per-slab partition sizes, and (minimiser layout) where the runs start
-            const ulonglong2* xrecs = world > 1 ? xrecs_buf.p : recs.p;
-            const uint32_t* xcur = world > 1 ? xcur_buf.p : cursor.p;            // [nslab][NBown][cstride]
-            RunView runs{nullptr, nullptr, Pown, nullptr};
-            if (mini) runs = world > 1 ? RunView{xbase.p, xoff.p, Pown, nullptr} : RunView{part_base.p, batch_off.p, Pown, nullptr};
-            std::vector<uint32_t> sizes(Pown), raw_sizes((size_t)nslab * slab_cur);
-            std::vector<uint64_t> totals(Pown);
-            bool retry = false;
-            W2R_CUDA(cudaMemsetAsync(scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
-            hist.zero();
-            uint64_t solid_used_before = 0;
-            for (uint32_t pass = 0; pass < npass && !retry; ++pass) {
-                cursor.zero();
-                if (mini) {
-                    // launch 1 sizes the partitions exactly (per read batch, under the upload), the scan lays them out, launch 2 stores
-                    static const unsigned map_ctas = getenv("W2RAP_MAP_CTAS") ? (unsigned)atoi(getenv("W2RAP_MAP_CTAS")) : 8u;
-                    part_count.zero();
-                    W2R_CUDA(cudaMemsetAsync(batch_off.p, 0, sizeof(unsigned long long), c.stream));
-                    std::vector<Batch> mb = batches;
-                    if (world > 1) {        // sharded: one map batch (the layout must be by owner rank), after the whole shard has arrived
-                        for (const Batch& bt : batches) {
-                            if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
-                            if (bt.count && !good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
-                        }
-                        good_done = true;
-                        mb.assign(1, Batch{0, dr.n, nullptr});
-                    }
-                    std::vector<cudaEvent_t> ev(2 * nmap, nullptr);                 // the store launches are timed without stalling the queue
-                    struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); } } evg{ev};
-                    for (uint32_t bi = 0; bi < nmap; ++bi) {
-                        const Batch& bt = mb[bi];
-                        MiniParams mp{logP, npass, pass, part_count.p + bi * P, part_base.p + bi * P, cursor.p + bi * P, recs.p, batch_off.p + bi, recs.n, flags.p + 1};
-                        if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
-                        if (bt.count && !good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
-                        if (bt.count && n_inst_local) W2R_LAUNCH(c, k_minimizer_map<true>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp);
-                        exclusive_scan<uint32_t, uint64_t>(c, part_count.p + bi * P, P, part_base.p + bi * P, batch_total.p + bi);
-                        W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, batch_off.p + bi, batch_total.p + bi);
-                        W2R_CUDA(cudaEventCreate(&ev[2 * bi])); W2R_CUDA(cudaEventCreate(&ev[2 * bi + 1]));
-                        W2R_CUDA(cudaEventRecord(ev[2 * bi], c.stream));
-                        if (bt.count && n_inst_local) { W2R_LAUNCH(c, k_minimizer_map<false>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp); c.count_launches++; }
-                        W2R_CUDA(cudaEventRecord(ev[2 * bi + 1], c.stream));
-                    }
-                    good_done = true;
-                    W2R_CUDA(cudaStreamSynchronize(c.stream));
-                    for (uint32_t bi = 0; bi < nmap; ++bi) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * bi], ev[2 * bi + 1]); part_ms += ms; }
-                } else {
-                    PartParams pp{recs.p, cursor.p, cap, logP, nsub, cstride, npass, pass, flags.p + 1};
-                    kt.start();
-                    for (const Batch& bt : batches) {
-                        if (!bt.count) continue;
-                        if (bt.ready && !good_done) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
-                        if (!good_done) W2R_LAUNCH(c, k_good_len, grid(bt.count, 128), 128, 0, rv, bt.first, bt.count, prm.min_qual, good.p, scal.p, flags.p);
-                        if (n_inst_local) { W2R_LAUNCH(c, k_extract_partition, grid(bt.count, 256, 8), 256, 0, rv, bt.first, bt.count, good.p, pp); c.count_launches++; }
-                    }
-                    good_done = true;
-                    part_ms += kt.stop();
-                }
-                if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
-                std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, flags.p + 1)};
-                allreduce_u64(of, ncclSum);
-                if (of[0]) {        // a record buffer overflowed somewhere (legacy: skewed k-mer multiplicities; minimiser: an uneven pass): more slack, on every rank
-                    W2R_CUDA(cudaMemsetAsync(flags.p + 1, 0, sizeof(int), c.stream));
-                    slack *= 1.5; retry = true; break;
-                }
-                if (world > 1 && !mini) {    // route every record to the rank that owns its partition: fixed-size slabs
-                    kt.start();
-                    alltoall_slabs(recs.p, xrecs_buf.p, slab_recs * sizeof(ulonglong2));
-                    alltoall_slabs(cursor.p, xcur_buf.p, slab_cur * sizeof(uint32_t));
-                    xchg_ms += kt.stop();
-                }
-                if (world > 1 && mini) {     // ... exactly sized runs: counts first, then the records
-                    kt.start();
-                    alltoall_slabs(part_count.p, xcur_buf.p, Pown * sizeof(uint32_t));          // xcur[s][q] = records of my partition q held by rank s
-                    W2R_CUDA(cudaMemsetAsync(xoff.p, 0, sizeof(unsigned long long), c.stream));
-                    for (int sidx = 0; sidx < world; ++sidx) {
-                        exclusive_scan<uint32_t, uint64_t>(c, xcur_buf.p + (uint64_t)sidx * Pown, Pown, xbase.p + (uint64_t)sidx * Pown, xtot.p + sidx);
-                        W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, xoff.p + sidx, xtot.p + sidx);
-                    }
-                    std::vector<uint64_t> sbeg(world + 1, 0), rtot(world, 0);
-                    for (int d = 0; d < world; ++d) W2R_CUDA(cudaMemcpyAsync(&sbeg[d], part_base.p + (uint64_t)d * Pown, 8, cudaMemcpyDeviceToHost, c.stream));
-                    W2R_CUDA(cudaMemcpyAsync(&sbeg[world], batch_total.p, 8, cudaMemcpyDeviceToHost, c.stream));
-                    W2R_CUDA(cudaMemcpyAsync(rtot.data(), xtot.p, world * 8, cudaMemcpyDeviceToHost, c.stream));
-                    W2R_CUDA(cudaStreamSynchronize(c.stream));
-                    std::vector<size_t> soff(world), scnt(world), roff(world), rcnt(world);
-                    size_t racc = 0;
-                    for (int d = 0; d < world; ++d) {
-                        soff[d] = sbeg[d] * sizeof(ulonglong2); scnt[d] = (sbeg[d + 1] - sbeg[d]) * sizeof(ulonglong2);
-                        roff[d] = racc * sizeof(ulonglong2); rcnt[d] = rtot[d] * sizeof(ulonglong2); racc += rtot[d];
-                    }
-                    xrecs_buf.alloc(c, racc + 1);
-                    xrecs = xrecs_buf.p;
-                    alltoall_v(recs.p, soff, scnt, xrecs_buf.p, roff, rcnt);
-                    xchg_ms += kt.stop();
-                }
-                W2R_CUDA(cudaMemcpyAsync(raw_sizes.data(), xcur, raw_sizes.size() * 4, cudaMemcpyDeviceToHost, c.stream));
-                W2R_CUDA(cudaStreamSynchronize(c.stream));
-                uint64_t owned_records = 0;
-                for (uint64_t q = 0; q < Pown; ++q) {
-                    uint32_t mxs = 0;
-                    uint64_t tq = 0;
-                    for (uint32_t sidx = 0; sidx < nslab; ++sidx)
-                        for (uint32_t u = 0; u < nsub; ++u) { uint32_t v = raw_sizes[sidx * slab_cur + (q * nsub + u) * cstride]; mxs = std::max(mxs, v); tq += v; }
-                    sizes[q] = mxs;      // largest run / sub-buffer of the partition (sizes the grid)
-                    totals[q] = tq;
-                    owned_records += tq;
-                }
-                {   // staging for this pass's solid records (each needs >= min_freq instances)
-                    uint64_t need = solid_used_before + owned_records / std::max<uint32_t>(1, prm.min_freq) + 1024;
-                    if (need > solid_cap) {
-                        SBuf<ulonglong2> bigger(c, need + need / 4);
-                        if (solid_used_before) W2R_CUDA(cudaMemcpyAsync(bigger.p, solid.p, solid_used_before * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, c.stream));
-                        solid = std::move(bigger);
-                        solid_cap = solid.n;
-                    }
-                }
-                // ---- reduce
-                kt.start();
-                // the persisting carve-out is taken from the normal L2, which the map needs for write combining: hold it only while reducing
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(2 * R * sizeof(CountSlot), 80u << 20)) != cudaSuccess) cudaGetLastError();
-                set_l2_window(region.p, 2 * R * sizeof(CountSlot));
-                {   // the second stream gets the same L2 window and starts after everything queued so far
-                    cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
-                    attr.accessPolicyWindow.base_ptr = region.p; attr.accessPolicyWindow.num_bytes = 2 * R * sizeof(CountSlot);
-                    attr.accessPolicyWindow.hitRatio = 1.0f; attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                    if (cudaStreamSetAttribute(s2, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-                }
-                SBuf<int> gflag(c, Pown + 1); gflag.zero();
-                auto fork = [&] { W2R_CUDA(cudaEventRecord(ev_fork, c.stream)); W2R_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0)); };
-                auto join = [&] { W2R_CUDA(cudaEventRecord(ev_join, s2)); W2R_CUDA(cudaStreamWaitEvent(c.stream, ev_join, 0)); };
-                fork();
-                // a group of owned partitions goes through one counting region: the consecutive range [p0, p0+g), or entries
-                // [p0, p0+g) of a partition list (hlist on the host, dlist on the device)
-                auto run_group = [&](uint32_t p0, uint32_t g, uint32_t sub_mask, uint32_t sub_id, int* flag, const uint32_t* dlist = nullptr, const uint32_t* hlist = nullptr) {
-                    ++n_groups;
-                    uint32_t mxg = 0;
-                    for (uint32_t q = p0; q < p0 + g; ++q) mxg = std::max(mxg, sizes[hlist ? hlist[q] : q]);
-                    cudaStream_t gs = (group_parity & 1u) ? s2 : c.stream;
-                    CountSlot* greg = region.p + ((group_parity & 1u) ? R : 0);
-                    ++group_parity;
-                    if (mxg) {
-                        RegionParams rp{greg, logR, mini ? 0u : logP, sub_mask, sub_id, flag};
-                        const uint32_t gy = g * nsub;
-                        dim3 gr(std::max(1u, std::min<unsigned>((mxg + 511) / 512, (unsigned)(c.sm_count * 8 / std::max(1u, std::min(gy * nslab, 8u))))), gy * nslab);
-                        RunView rv2 = runs;
-                        rv2.plist = dlist;
-                        k_count_region<<<gr, 256, 0, gs>>>(xrecs, xcur, cstride, cap, p0 * nsub, gy, slab_recs, slab_cur, rv2, rp); c.launches++;
-                        W2R_CUDA(cudaGetLastError());
-                    }
-                    ScanParams sp{greg, R, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, flag, flags.p + 2};
-                    k_scan_region<<<grid(R, 256, 4), 256, 0, gs>>>(sp); c.launches++;
-                    W2R_CUDA(cudaGetLastError());
-                };
-                std::vector<std::pair<uint32_t, uint32_t>> groups;   // (first owned partition, count)
-                std::vector<int> gf(Pown + 1, 0);
-                if (mini) {
-                    // every partition is counted by one CTA in shared memory; the few that do not fit are retried with the largest
-                    // table, and what still fails is redone through the region below
-                    SBuf<uint32_t> failed(c, Pown), failed2(c, Pown);
-                    W2R_CUDA(cudaMemsetAsync(scal.p + 4, 0, 16, c.stream));
-                    // (a per-device attribute: set on every call — ranks driven from threads of one process each have their own device)
-                    W2R_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((20u << SMEM_LOG_SLOTS_MAX))));
-                    const uint32_t log1 = std::min(std::max(smem_log, 10u), SMEM_LOG_SLOTS_MAX);
-                    SmemCountParams sc{xrecs, xcur, runs.part_base, runs.slab_off, nslab, (uint32_t)Pown, 0u, prm.min_freq, hist.p, solid.p, scal.p + 1, solid_cap, flags.p + 2,
-                                       prm.dump_kmers == 2 ? dump_dev.p : nullptr, scal.p + 2, failed.p, scal.p + 4, log1, nullptr, 0};
-                    const bool two_per_sm = log1 <= 12;
-                    k_count_smem<<<(unsigned)std::min<uint64_t>(Pown, (uint64_t)c.sm_count * (two_per_sm ? 2 : 1)), two_per_sm ? 512 : 1024, (size_t)20u << log1, c.stream>>>(sc); c.launches++; ++n_groups;
-                    W2R_CUDA(cudaGetLastError());
-                    const uint64_t nfail1 = log1 < SMEM_LOG_SLOTS_MAX ? d2h_scalar(c, scal.p + 4) : 0;
-                    if (nfail1) {
-                        SmemCountParams sc2 = sc;
-                        sc2.failed = failed2.p; sc2.failed_cursor = scal.p + 5; sc2.log_slots = SMEM_LOG_SLOTS_MAX; sc2.plist = failed.p; sc2.nlist = (uint32_t)nfail1;
-                        k_count_smem<<<(unsigned)std::min<uint64_t>(nfail1, (uint64_t)c.sm_count), 1024, (size_t)20u << SMEM_LOG_SLOTS_MAX, c.stream>>>(sc2); c.launches++; ++n_groups;
-                        W2R_CUDA(cudaGetLastError());
-                    }
-                    const SBuf<uint32_t>& failed_final = nfail1 ? failed2 : failed;
-                    const uint64_t nfail = d2h_scalar(c, nfail1 ? scal.p + 5 : scal.p + 4);
-                    std::vector<uint32_t> fl(nfail);
-                    if (nfail) { W2R_CUDA(cudaMemcpyAsync(fl.data(), failed_final.p, nfail * 4, cudaMemcpyDeviceToHost, c.stream)); W2R_CUDA(cudaStreamSynchronize(c.stream)); }
-                    if (nfail) {
-                        say(c, "%llu of %llu k-mer partitions did not fit shared memory; counting them through the L2 region", (unsigned long long)nfail, (unsigned long long)Pown);
-                        // in bulk: as many listed partitions per region pass as fit it even if every record were distinct (load <= 0.6),
-                        // alternating regions/streams, no host round trip per group; a group that overflows all the same is redone
-                        // partition by partition below
-                        std::vector<std::pair<uint32_t, uint32_t>> lgroups;        // (offset into fl, count)
-                        const uint32_t gmax = std::max(1u, 4000u / nslab);          // gridDim.y = g * nslab <= 65535
-                        for (size_t i0 = 0; i0 < fl.size();) {
-                            uint64_t acc = 0; size_t j = i0;
-                            while (j < fl.size() && j - i0 < gmax && (j == i0 || (double)(acc + totals[fl[j]]) <= 0.6 * (double)R)) { acc += totals[fl[j]]; ++j; }
-                            lgroups.push_back({(uint32_t)i0, (uint32_t)(j - i0)});
-                            i0 = j;
-                        }
-                        fork();
-                        for (size_t gi = 0; gi < lgroups.size(); ++gi) run_group(lgroups[gi].first, lgroups[gi].second, 0, 0, gflag.p + gi, failed_final.p, fl.data());
-                        join();
-                        std::vector<int> lgf(lgroups.size());
-                        W2R_CUDA(cudaMemcpyAsync(lgf.data(), gflag.p, lgroups.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-                        W2R_CUDA(cudaStreamSynchronize(c.stream));
-                        for (size_t gi = 0; gi < lgroups.size(); ++gi)
-                            if (lgf[gi]) for (uint32_t k = lgroups[gi].first; k < lgroups[gi].first + lgroups[gi].second; ++k) { groups.push_back({fl[k], 1u}); gf[fl[k]] = 1; }
-                    }
-                } else {
-                    // groups of consecutive owned partitions share the region; the group size comes from the first partition's distinct count
-                    run_group(0, 1, 0, 0, gflag.p + 0);
-                    groups.push_back({0u, 1u});
-                    if (Pown > 1) {
-                        std::vector<unsigned long long> hh(104);
-                        W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
-                        W2R_CUDA(cudaStreamSynchronize(c.stream));
-                        unsigned long long d0 = 0;
-                        for (int i = 1; i <= 100; ++i) d0 += hh[i];
-                        d0 -= std::min<unsigned long long>(d0, n_distinct_seen);
-                        uint32_t g = (uint32_t)std::max<double>(1.0, std::min<double>(4096.0, 0.5 * (double)R / ((double)d0 * 1.15 + 1.0)));
-                        g = std::max<uint32_t>(1u, std::min<uint32_t>(g, 32768u / (nsub * world)));
-                        for (uint64_t p0 = 1; p0 < Pown; p0 += g) {
-                            uint32_t gg = (uint32_t)std::min<uint64_t>(g, Pown - p0);
-                            run_group((uint32_t)p0, gg, 0, 0, gflag.p + p0);
-                            groups.push_back({(uint32_t)p0, gg});
-                        }
-                    }
-                    join();
-                    W2R_CUDA(cudaMemcpyAsync(gf.data(), gflag.p, (Pown + 1) * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-                    W2R_CUDA(cudaStreamSynchronize(c.stream));
-                }
-                for (auto& gr : groups) {
-                    if (!gf[gr.first]) continue;
-                    // the group did not fit together: its partitions one by one, and a partition that still fails in hash sub-ranges
-                    for (uint32_t q = gr.first; q < gr.first + gr.second; ++q) {
-                        unsigned long long snapshot[2];
-                        std::vector<unsigned long long> hist_snapshot(104);
-                        W2R_CUDA(cudaMemcpyAsync(snapshot, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
-                        W2R_CUDA(cudaMemcpyAsync(hist_snapshot.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
-                        W2R_CUDA(cudaMemsetAsync(gflag.p + Pown, 0, sizeof(int), c.stream));
-                        fork(); run_group(q, 1, 0, 0, gflag.p + Pown); join();
-                        if (!d2h_scalar(c, gflag.p + Pown)) continue;
-                        for (uint32_t S = 2;; S *= 2) {
-                            if (S > 4096) W2R_FAIL(W2RAP_ERR_INTERNAL, "a k-mer partition does not fit the counting region even in 4096 hash sub-ranges");
-                            bool ok = true;
-                            for (uint32_t sid = 0; sid < S && ok; ++sid) {
-                                W2R_CUDA(cudaMemsetAsync(gflag.p + Pown, 0, sizeof(int), c.stream));
-                                fork(); run_group(q, 1, S - 1, sid, gflag.p + Pown); join();
-                                if (d2h_scalar(c, gflag.p + Pown)) ok = false;
-                            }
-                            if (ok) break;
-                            // roll back what the successful sub-ranges of this split emitted, then split finer
-                            W2R_CUDA(cudaMemcpyAsync(scal.p + 1, snapshot, 16, cudaMemcpyHostToDevice, c.stream));
-                            W2R_CUDA(cudaMemcpyAsync(hist.p, hist_snapshot.data(), 104 * 8, cudaMemcpyHostToDevice, c.stream));
-                            W2R_CUDA(cudaStreamSynchronize(c.stream));
-                        }
-                    }
-                }
-                set_l2_window(nullptr, 0);
-                region_ms += kt.stop();
-                if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
-                {
-                    std::vector<unsigned long long> hh(104);
-                    W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
-                    W2R_CUDA(cudaStreamSynchronize(c.stream));
-                    n_distinct_seen = 0;
-                    for (int i = 1; i <= 100; ++i) n_distinct_seen += hh[i];
-                    solid_used_before = d2h_scalar(c, scal.p + 1);
-                }
-                if (mini && world > 1) { xrecs_buf.release(); xrecs = nullptr; }
+            if (too_big[0] && !prm.force_passes) {
+                if (pl.npass >= 4096) W2R_FAIL(W2RAP_ERR_OOM, "not enough device memory for the k-mer records even in 4096 passes");
+                pl.npass *= 2; --attempt; continue;              // (more passes are not a failed attempt)
             }
-            if (retry) { n_distinct_seen = 0; n_groups = 0; continue; }
-            if (d2h_scalar(c, flags.p + 2)) W2R_FAIL(W2RAP_ERR_INTERNAL, "solid staging buffer overflow");
+            CountBufs cb;
+            cb.recs.alloc(c, local_recs);
+            cb.part_count.alloc(c, pl.nmap * P); cb.part_kcount.alloc(c, pl.nmap * P); cb.cursor.alloc(c, pl.nmap * P);
+            cb.part_base.alloc(c, pl.nmap * P); cb.batch_total.alloc(c, pl.nmap); cb.batch_ktotal.alloc(c, pl.nmap);
+            cb.batch_off.alloc(c, pl.nmap + 1);
+            if (world > 1) {
+                cb.xcount.alloc(c, world * Pown); cb.xkcount.alloc(c, world * Pown); cb.xbase.alloc(c, world * Pown);
+                cb.xtot.alloc(c, world); cb.xktot.alloc(c, world); cb.xoff.alloc(c, world + 1);
+            }
+            bool retry = false;
+            W2R_CUDA(cudaMemsetAsync(cs_scal.p + 1, 0, 16, c.stream));       // solid cursor, dump cursor
+            cs_hist.zero();
+            n_groups = 0;
+            uint64_t solid_used = 0;
+            for (uint32_t pass = 0; pass < pl.npass && !retry; ++pass) {
+                uint64_t need = 0;
+                if (!map_records(pl, cb, batches, pass, &need)) {
+                    std::vector<unsigned long long> nd = {need};
+                    allreduce_u64(nd, ncclMax);
+                    need_exact = std::max<uint64_t>(need_exact, nd[0]);
+                    retry = true; break;
+                }
+                if (world > 1) exchange_records(pl, cb);
+                const uint32_t* xcur = world > 1 ? cb.xcount.p : cb.part_count.p;
+                const uint32_t* xkcur = world > 1 ? cb.xkcount.p : cb.part_kcount.p;
+                const SkmRec* xrecs = world > 1 ? cb.xrecs.p : cb.recs.p;
+                RunView runs = world > 1 ? RunView{cb.xbase.p, cb.xoff.p, Pown, nullptr} : RunView{cb.part_base.p, cb.batch_off.p, Pown, nullptr};
+                {   // staging for this pass's solid records: each needs >= min_freq of the k-mer instances this rank reduces
+                    SBuf<uint64_t> ktot(c, pl.nslab), kscan(c, Pown);
+                    for (uint32_t sidx = 0; sidx < pl.nslab; ++sidx) exclusive_scan<uint32_t, uint64_t>(c, xkcur + (uint64_t)sidx * Pown, Pown, kscan.p, ktot.p + sidx);
+                    std::vector<uint64_t> kt_h(pl.nslab);
+                    W2R_CUDA(cudaMemcpyAsync(kt_h.data(), ktot.p, pl.nslab * 8, cudaMemcpyDeviceToHost, c.stream));
+                    W2R_CUDA(cudaStreamSynchronize(c.stream));
+                    uint64_t owned = 0;
+                    for (uint64_t v : kt_h) owned += v;
+                    const uint64_t want = solid_used + owned / std::max<uint32_t>(1, prm.min_freq) + 1024;
+                    if (want > cs_solid_cap) {
+                        SBuf<ulonglong2> bigger(c, want + want / 4);
+                        if (solid_used) W2R_CUDA(cudaMemcpyAsync(bigger.p, cs_solid.p, solid_used * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, c.stream));
+                        cs_solid = std::move(bigger);
+                        cs_solid_cap = cs_solid.n;
+                    }
+                }
+                reduce_records(pl, xrecs, xcur, xkcur, runs, s2, ev_fork, ev_join);
+                solid_used = d2h_scalar(c, cs_scal.p + 1);
+                if (world > 1) cb.xrecs.release();
+            }
+            if (retry) continue;
+            if (d2h_scalar(c, cs_flags.p + 2)) W2R_FAIL(W2RAP_ERR_INTERNAL, "solid staging buffer overflow");
             break;
         }
-        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
         {   // the exact instance count of the whole job (the bound above only sized buffers)
-            std::vector<unsigned long long> exact = {(unsigned long long)d2h_scalar(c, scal.p)};
+            std::vector<unsigned long long> exact = {(unsigned long long)d2h_scalar(c, cs_scal.p)};
             allreduce_u64(exact, ncclSum);
             out->n_kmer_instances = exact[0];
             say(c, "%llu k-mer instances in quality-floored reads", exact[0]);
         }
-        out->timings.count_kernel_ms = part_ms;
-        out->timings.region_ms = region_ms;
+        out->timings.count_kernel_ms = map_ms;
+        out->timings.region_ms = reduce_ms;
         out->timings.exchange_ms = xchg_ms;
         out->timings.count_passes = n_groups;
         std::vector<unsigned long long> hh(104);
-        W2R_CUDA(cudaMemcpyAsync(hh.data(), hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaMemcpyAsync(hh.data(), cs_hist.p, 104 * 8, cudaMemcpyDeviceToHost, c.stream));
         unsigned long long cursors[2];
-        W2R_CUDA(cudaMemcpyAsync(cursors, scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaMemcpyAsync(cursors, cs_scal.p + 1, 16, cudaMemcpyDeviceToHost, c.stream));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         allreduce_u64(hh, ncclSum);                          // histogram of the whole job
         uint64_t n_distinct = 0;
@@ -621,44 +615,52 @@ struct Pipeline {
         const uint64_t n_solid_local = cursors[0];
         if (prm.dump_kmers == 2 && cursors[1]) {
             dump_host.resize(cursors[1]);
-            W2R_CUDA(cudaMemcpyAsync(dump_host.data(), dump_dev.p, cursors[1] * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaMemcpyAsync(dump_host.data(), cs_dump.p, cursors[1] * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
             W2R_CUDA(cudaStreamSynchronize(c.stream));
         }
-        region.release(); dump_dev.release();
-        // every rank needs the whole dictionary for adjacency, unipaths and pathing: all-gather the solid records
+        cs_region.release(); cs_dump.release();
+        build_dictionary(n_solid_local, n_distinct);
+    }
+
+    // every rank needs the whole dictionary for adjacency, unipaths and pathing: all-gather the solid records, then
+    // the dictionary (kmers/ReadPather.h:176-349) as an open-addressing table at load <= 0.5
+    void build_dictionary(uint64_t n_solid_local, uint64_t n_distinct) {
         std::vector<unsigned long long> per_rank(world, 0ull);
         per_rank[rank] = n_solid_local;
         allreduce_u64(per_rank, ncclSum);
         uint64_t n_solid = 0;
         for (auto v : per_rank) n_solid += v;
         SBuf<ulonglong2> solid_all;
-        const ulonglong2* solid_src = solid.p;
+        const ulonglong2* solid_src = cs_solid.p;
         if (world > 1) {
+            EventTimer kt(c.stream);
             kt.start();
             solid_all.alloc(c, n_solid);
             uint64_t off = 0;
+            NcclApi& n = NcclApi::get();
+            nccl_check(n.GroupStart(), "group start");             // one grouped all-gather of variable-size pieces
             for (int sidx = 0; sidx < world; ++sidx) {
-                if (per_rank[sidx]) nccl_check(NcclApi::get().Broadcast(sidx == rank ? (const void*)solid.p : (const void*)(solid_all.p + off), solid_all.p + off,
-                                                                         per_rank[sidx] * sizeof(ulonglong2), ncclUint8, sidx, comm, c.stream), "broadcast");
+                if (per_rank[sidx]) nccl_check(n.Broadcast(sidx == rank ? (const void*)cs_solid.p : (const void*)(solid_all.p + off), solid_all.p + off,
+                                                           per_rank[sidx] * sizeof(ulonglong2), ncclUint8, sidx, comm, c.stream), "broadcast");
                 off += per_rank[sidx];
             }
+            nccl_check(n.GroupEnd(), "group end");
             out->timings.exchange_ms += kt.stop();
             solid_src = solid_all.p;
-            solid.release();
+            cs_solid.release();
         }
         out->n_distinct = n_distinct; out->n_solid = n_solid;
         say(c, "%llu kmers counted, filtering...", (unsigned long long)n_distinct);
         say(c, "%llu / %llu kmers with Freq >= %u", (unsigned long long)n_solid, (unsigned long long)n_distinct, prm.min_freq);
-
-        // dictionary (kmers/ReadPather.h:176-349) as an open-addressing table at load <= 0.5
         uint32_t lg = 10;
         while ((1ull << lg) < 2 * n_solid) ++lg;
         if (lg > 31) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^30 solid k-mers on one device");
         solid_slots.alloc(c, 1ull << lg);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, lg};
-        if (n_solid) W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, solid_src, n_solid, st);
-        W2R_CUDA(cudaStreamSynchronize(c.stream));   // solid / solid_all are released when this function returns
+        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, solid_src, n_solid, st));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));   // the solid staging buffers are released when this function returns
+        cs_solid.release();
     }
 
     // ---- buildEdges (BuildReadQGraph.cc:314-339)
@@ -667,16 +669,19 @@ struct Pipeline {
         SBuf<uint32_t> next0(c, nn);
         SBuf<int> flags(c, 4); flags.zero();
         SBuf<unsigned long long> scal(c, 4); scal.zero();
-        W2R_LAUNCH(c, k_links, grid(nn, 256), 256, 0, st, next0.p, flags.p);
+        W2R_TIMED(W2RAP_KT_LINKS, W2R_LAUNCH(c, k_links, grid(nn, 256), 256, 0, st, next0.p, flags.p));
         // list ranking: splitters walk to the next splitter, the splitters alone are ranked by pointer jumping (unipath.cuh)
         SBuf<RankState> A(c, nn), B(c, nn);          // A: label, then the final (tail, distance) of every node; B: splitter states
-        SBuf<uint32_t> splist(c, nn / 16 + out->n_solid / 2 + 1024);
-        W2R_CUDA(cudaMemsetAsync(A.p, 0xff, A.bytes(), c.stream));     // label = {NIL, ...}
+        // every strand head is a splitter (two per edge: up to 2 * n_solid on a graph of one-k-mer edges) plus ~1/64 of all nodes
+        // by the hash rule: count them first, then size the list exactly
         W2R_CUDA(cudaMemsetAsync(scal.p + 3, 0, 8, c.stream));
-        W2R_LAUNCH(c, k_splitter_walk, grid(nn, 256), 256, 0, next0.p, nn, A.p, B.p, splist.p, scal.p + 3);
+        W2R_LAUNCH(c, k_count_splitters, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)nullptr, nn, scal.p + 3);
         if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a neighbour k-mer promised by a pruned context is missing (reference: ForceAssert in EdgeBuilder::lookup)");
         const uint64_t nsp = d2h_scalar(c, scal.p + 3);
-        if (nsp > splist.n) W2R_FAIL(W2RAP_ERR_INTERNAL, "splitter list overflow");
+        SBuf<uint32_t> splist(c, nsp);
+        W2R_CUDA(cudaMemsetAsync(A.p, 0xff, A.bytes(), c.stream));     // label = {NIL, ...}
+        W2R_CUDA(cudaMemsetAsync(scal.p + 3, 0, 8, c.stream));
+        W2R_TIMED(W2RAP_KT_SPLITTER_WALK, W2R_LAUNCH(c, k_splitter_walk, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)nullptr, nn, A.p, B.p, splist.p, nsp, scal.p + 3));
         unsigned long long prev_un = ~0ull;
         if (nsp) {
             for (int round = 0; round < 48; ++round) {
@@ -688,7 +693,7 @@ struct Pipeline {
             }
         }
         W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
-        W2R_LAUNCH(c, k_splitter_finish, grid(nn, 256), 256, 0, next0.p, nn, A.p, (const RankState*)B.p, scal.p);
+        W2R_TIMED(W2RAP_KT_SPLITTER_FINISH, W2R_LAUNCH(c, k_splitter_finish, grid(nn, 256), 256, 0, next0.p, nn, A.p, (const RankState*)B.p, scal.p));
         prev_un = d2h_scalar(c, scal.p);
         RankState* cur = A.p; RankState* oth = B.p;
         if (prev_un) {   // smooth circles (:332-335)
@@ -754,14 +759,14 @@ struct Pipeline {
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         edge_bases.alloc(c, (edge_bytes + 3 + 32) & ~3ull);
         edge_bases.zero();
-        W2R_LAUNCH(c, k_emit_edges, grid(nn, 256), 256, 0, st, R, edge_of_head.p, edge_off.p, edge_bases.p);
+        W2R_TIMED(W2RAP_KT_EMIT_EDGES, W2R_LAUNCH(c, k_emit_edges, grid(nn, 256), 256, 0, st, R, edge_of_head.p, edge_off.p, edge_bases.p));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
     }
 
     // ---- buildHBVFromEdges (paths/long/HBVFromEdges.cc:76-154)
     void hbv_stage() {
         edge_vertices.alloc(c, 4 * E); fwd_xlat.alloc(c, E); rev_xlat.alloc(c, E);
-        if (!E) { nv = nh = 0; return; }
+        if (!E) { nv = nh = 0; involution.alloc(c, 0); return; }
         const uint64_t n4 = 4 * E;
         if (n4 >= (1ull << 32)) W2R_FAIL(W2RAP_ERR_OOM, "too many edges for 32-bit end indices");
         SBuf<uint64_t> kh(c, n4), k0(c, n4), k1(c, n4);
@@ -780,8 +785,8 @@ struct Pipeline {
         W2R_LAUNCH(c, k_pal_widths, grid(E, 256), 256, 0, is_pal.p, E, width.p);
         exclusive_scan<uint32_t, uint32_t>(c, width.p, E, xl.p, tot.p);
         nh = d2h_scalar(c, tot.p);
-        hcanon.alloc(c, nh); hleft.alloc(c, nh); hright.alloc(c, nh);
-        W2R_LAUNCH(c, k_hbv_edges, grid(E, 256), 256, 0, E, is_pal.p, xl.p, edge_vertices.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p);
+        hcanon.alloc(c, nh); hleft.alloc(c, nh); hright.alloc(c, nh); involution.alloc(c, nh);
+        W2R_LAUNCH(c, k_hbv_edges, grid(E, 256), 256, 0, E, is_pal.p, xl.p, edge_vertices.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, involution.p);
         from_e.alloc(c, 4 * nv); to_e.alloc(c, 4 * nv); from_n.alloc(c, nv); to_n.alloc(c, nv);
         SBuf<uint32_t> fc(c, nv), tc(c, nv); fc.zero(); tc.zero();
         SBuf<int> bad(c, 1); bad.zero();
@@ -808,7 +813,7 @@ struct Pipeline {
             if (bytes * 8 >= 2 * out->n_solid) {          // below ~2 bits per key the filter passes most queries: not worth its L2
                 bloom_words.alloc(c, bytes / 4); bloom_words.zero();
                 bloom = KmerBloom{bloom_words.p, bytes / 4};
-                W2R_LAUNCH(c, k_bloom_build, grid(st.size(), 256), 256, 0, st, bloom);
+                W2R_TIMED(W2RAP_KT_BLOOM_BUILD, W2R_LAUNCH(c, k_bloom_build, grid(st.size(), 256), 256, 0, st, bloom));
                 if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) cudaGetLastError();
                 set_l2_window(bloom_words.p, bytes);
             }
@@ -835,7 +840,7 @@ struct Pipeline {
             else if (path_occ >= 10) W2R_LAUNCH(c, k_path_reads<10>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
             else W2R_LAUNCH(c, k_path_reads<8>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
         };
-        launch_path(gr, nullptr, n, stage.p, cap, left_cap, row_off.p, meta.p);
+        W2R_TIMED(W2RAP_KT_PATH_READS, launch_path(gr, nullptr, n, stage.p, cap, left_cap, row_off.p, meta.p));
         W2R_LAUNCH(c, k_path_lens, grid(n, 256), 256, 0, meta.p, (const uint32_t*)nullptr, n, lens.p, counters.p);
         unsigned long long cnt[3];
         W2R_CUDA(cudaMemcpyAsync(cnt, counters.p, 24, cudaMemcpyDeviceToHost, c.stream));
@@ -849,7 +854,7 @@ struct Pipeline {
         if (n_ovf) {
             W2R_CUDA(cudaMemsetAsync(counters.p + 3, 0, 8, c.stream));
             W2R_LAUNCH(c, k_collect_overflow, grid(n, 256), 256, 0, meta.p, n, olist.p, counters.p + 3);
-            launch_path(grid(n_ovf, block, 12), olist.p, n_ovf, stage2.p, cap2, left2, row_off2.p, meta2.p);
+            W2R_TIMED(W2RAP_KT_PATH_READS, launch_path(grid(n_ovf, block, 12), olist.p, n_ovf, stage2.p, cap2, left2, row_off2.p, meta2.p));
             W2R_CUDA(cudaMemsetAsync(counters.p + 2, 0, 8, c.stream));
             W2R_LAUNCH(c, k_path_lens, grid(n_ovf, 256), 256, 0, meta2.p, (const uint32_t*)olist.p, n_ovf, lens.p, counters.p);
             W2R_CUDA(cudaMemcpyAsync(cnt, counters.p, 24, cudaMemcpyDeviceToHost, c.stream));
@@ -883,6 +888,7 @@ struct Pipeline {
 
     void run() {
         W2R_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        kt_.s = c.stream;
         c.verbose = prm.verbose != 0;
         StageTimer total(c), st_t(c);
         total.start();
@@ -893,7 +899,7 @@ struct Pipeline {
         good.release();
         say(c, "updating adjacencies");
         st_t.start();
-        W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st);
+        W2R_TIMED(W2RAP_KT_ADJACENCY, W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st));
         out->timings.adjacency_ms = st_t.stop();
         say(c, "finding edges (unique paths)");
         st_t.start(); unipath_stage(); out->timings.unipath_ms = st_t.stop();
@@ -915,6 +921,16 @@ struct Pipeline {
         out->edge_vertices = to_host<int32_t>(edge_vertices.p, 4 * E);
         out->fwd_xlat = to_host<int32_t>(fwd_xlat.p, E);
         out->rev_xlat = to_host<int32_t>(rev_xlat.p, E);
+        out->involution = to_host<int32_t>(involution.p, nh);
+        SBuf<unsigned long long> dig(c, 2); dig.zero();
+        {   // digest of the graph: every array at its own salt
+            struct Part { const void* p; size_t bytes; } parts[] = {{edge_len.p, E * 4}, {edge_bases.p, edge_bytes}, {edge_vertices.p, 4 * E * 4}, {fwd_xlat.p, E * 4}, {rev_xlat.p, E * 4}};
+            uint64_t salt = 1;
+            for (const Part& pt : parts) { if (pt.bytes) W2R_LAUNCH(c, k_digest_words, grid((pt.bytes + 3) / 4, 256, 4), 256, 0, (const uint8_t*)pt.p, pt.bytes, salt << 40, dig.p); ++salt; }
+            if (prm.want_paths && dr.n) W2R_LAUNCH(c, k_digest_paths, grid(dr.n, 256, 8), 256, 0, dr.view(), d_offset.p, d_path_off.p, d_path_edges.p, dig.p + 1);
+        }
+        unsigned long long dig_h[2] = {0, 0};
+        W2R_CUDA(cudaMemcpyAsync(dig_h, dig.p, 16, cudaMemcpyDeviceToHost, c.stream));
         if (prm.want_paths) {
             out->n_paths = dr.n; out->n_path_edges = npe; out->n_pathed = pathed; out->n_multipathed = multi;
             out->path_offset = to_host<int32_t>(d_offset.p, dr.n);
@@ -942,7 +958,17 @@ struct Pipeline {
             static_assert(sizeof(DumpRec) == sizeof(w2rap_kmer_rec), "dump record layout");
             memcpy(out->dump, dump_host.data(), dump_host.size() * sizeof(DumpRec));
         }
+        {   // digests (the histogram is folded in on the host: 101 words)
+            uint64_t hd = 0;
+            for (int i = 0; i <= 100; ++i) { uint64_t x = out->hist[i] + 0x9e3779b97f4a7c15ull * (uint64_t)(i + 1); x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; hd += x; }
+            out->digest_graph = dig_h[0] + hd;
+            std::vector<unsigned long long> dp = {dig_h[1]};
+            allreduce_u64(dp, ncclSum);           // paths: summed over the shards
+            out->digest_paths = dp[0];
+        }
         out->timings.total_ms = total.stop();
+        kt_.resolve(out->timings.kernel_ms);
+        out->timings.exchange_bytes = xchg_bytes;
         out->timings.kernel_launches = c.launches;
         out->timings.count_launches = c.count_launches;
         say(c, "%llu edges of total length %llu; %llu vertices", (unsigned long long)E, (unsigned long long)neb, (unsigned long long)nv);
@@ -951,7 +977,8 @@ struct Pipeline {
     ~Pipeline() {
         // free stream-ordered buffers before the stream goes away
         good.release(); solid_slots.release(); edge_bases.release(); edge_off.release(); edge_len.release();
-        edge_vertices.release(); fwd_xlat.release(); rev_xlat.release(); hleft.release(); hright.release(); from_e.release(); to_e.release();
+        edge_vertices.release(); fwd_xlat.release(); rev_xlat.release(); involution.release(); hleft.release();
+        cs_scal.release(); cs_flags.release(); cs_hist.release(); cs_region.release(); cs_dump.release(); cs_solid.release(); hright.release(); from_e.release(); to_e.release();
         hcanon.release(); from_n.release(); to_n.release();
         if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
     }
@@ -1075,6 +1102,7 @@ static void check_params(const w2rap_params* p) {
     if (p->abi_version != W2RAP_STEP2_ABI_VERSION) W2R_FAIL(W2RAP_ERR_BAD_ARG, "ABI version %u, library has %d", p->abi_version, W2RAP_STEP2_ABI_VERSION);
     if (p->K != W2RAP_K) W2R_FAIL(W2RAP_ERR_BAD_ARG, "K=%u: only K=60 is built (the reference hard-wires it, BuildReadQGraph.cc:51)", p->K);
     if (p->min_freq == 0 || p->min_freq > 255) W2R_FAIL(W2RAP_ERR_BAD_ARG, "min_freq must be in 1..255 (counts saturate at 255)");
+    if (p->force_passes > 4096) W2R_FAIL(W2RAP_ERR_BAD_ARG, "force_passes must be <= 4096");
 }
 
 }  // namespace w2r
@@ -1180,9 +1208,9 @@ int w2rap_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* o
         run_on_device(d, p, out, 0.f, nullptr, t_entry);          // consumes the batches as they land
         cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
         out->timings.h2d_ms = h2d;              // overlapped with the quality floor + extraction, already inside total_ms
-    } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    } catch (...) { cudaStreamSynchronize(us); d.release(); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
     const double t_post = now_ms();
-    d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamSynchronize(us); d.release(); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
     out->timings.host_post_ms = (float)(now_ms() - t_post);
     out->timings.wall_ms = (float)(now_ms() - t_entry);
     if (p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
@@ -1253,8 +1281,8 @@ int w2rap_step2_run_sharded(const w2rap_reads* shard, const w2rap_params* p, w2r
         run_on_device(d, p, out, 0.f, comm);
         cudaEventSynchronize(e1); cudaEventElapsedTime(&h2d, e0, e1);
         out->timings.h2d_ms = h2d;
-    } catch (...) { d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
-    d.release(); cudaStreamSynchronize(us); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } catch (...) { cudaStreamSynchronize(us); d.release(); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    cudaStreamSynchronize(us); d.release(); cudaStreamDestroy(us); cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (comm->rank == 0 && p->workdir && p->workdir[0]) { std::string f = std::string(p->workdir) + "/small_K.freqs"; int rc = w2rap_write_freqs(f.c_str(), out, err, errlen); if (rc) return rc; }
     W2R_API_END
 }

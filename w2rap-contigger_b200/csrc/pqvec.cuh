@@ -43,14 +43,19 @@ struct PQReader {
 // and stops at the first position where K consecutive quals >= minQual have been seen; that is the end of the right-most
 // maximal run of >= K good quals, which a forward scan finds as "the last position at which the current run is >= K".
 // The result is stored in a uint16_t by the reference.  *n_quals receives the number of qualities in the stream.
-W2R_HD uint32_t pq_good_length(const uint8_t* stream, uint32_t min_qual, uint32_t* n_quals) {
+// `end` = one past the last byte of the stream (qual_off[i+1]): a block header or payload that would cross it (a truncated or
+// corrupted .qualp) stops the walk and reports 0xffffffff qualities, which the caller turns into W2RAP_ERR_BAD_ARG.
+W2R_HD uint32_t pq_good_length(const uint8_t* stream, const uint8_t* end, uint32_t min_qual, uint32_t* n_quals) {
     const uint8_t* p = stream;
     uint32_t run = 0, good = 0, i = 0;
     for (;;) {
+        if (p >= end) { i = 0xffffffffu; break; }               // no terminator inside the stream
         const uint32_t nq = *p++;
         if (!nq) break;
+        if (p + 2 > end) { i = 0xffffffffu; break; }
         const uint32_t hdr = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
         const uint32_t nbits = hdr & 7u, minq = (hdr >> 3) & 63u;
+        if (p + ((9u + nq * nbits + 7u) >> 3) > end) { i = 0xffffffffu; break; }
         if (nbits == 0) {                       // a constant block is one step: the run grows by nq or is reset
             p += 2;
             i += nq;
@@ -79,6 +84,9 @@ W2R_HD uint32_t pq_good_length(const uint8_t* stream, uint32_t min_qual, uint32_
     }
     if (n_quals) *n_quals = i;
     return good & 0xffffu;
+}
+W2R_HD uint32_t pq_good_length(const uint8_t* stream, uint32_t min_qual, uint32_t* n_quals) {      // trusted stream (tests)
+    return pq_good_length(stream, (const uint8_t*)~(uintptr_t)0, min_qual, n_quals);
 }
 
 // Decodes up to `cap` quals into out; returns the number of quals in the stream.

@@ -17,6 +17,9 @@ namespace w2r {
 
 constexpr uint32_t RANK_RESOLVED = 0x80000000u;
 constexpr uint32_t EMPTY_NODE = 0xfffffffeu;   // next0[] of a node whose slot holds no k-mer
+constexpr uint32_t GHOST_TAIL = 0xfffffffdu;   // next0[] of a GHOST node (sharded graph stage, shardgraph.cuh): a copy of a k-mer another
+                                               // rank owns.  A node whose successor is a ghost is the tail of its LOCAL chain piece.
+W2R_HD bool slot_is_ghost(const SolidSlot& s) { return s.pad != 0; }      // pad = owner rank + 1, edge = slot on the owner
 
 W2R_HD Kmer node_kmer(const SolidTable& t, uint32_t x) {
     const SolidSlot& s = t.slots[x >> 1];
@@ -26,9 +29,12 @@ W2R_HD Kmer node_kmer(const SolidTable& t, uint32_t x) {
 
 // Successor link of oriented node x, or NIL.  *missing is set if a neighbour that the pruned context promises is absent
 // (the reference would ForceAssert, :265).
-W2R_HD uint32_t unipath_succ_link(const SolidTable& t, uint32_t x, int* missing) {
+// *to_ghost (optional) is set if the successor is a ghost node.
+W2R_HD uint32_t unipath_succ_link(const SolidTable& t, uint32_t x, int* missing, bool* to_ghost = nullptr) {
     const SolidSlot& s = t.slots[x >> 1];
+    if (to_ghost) *to_ghost = false;
     if (s.w0 == EMPTY_W0) return EMPTY_NODE;
+    if (slot_is_ghost(s)) return GHOST_TAIL;
     Kmer k{s.w0, s.w1};
     Kmer rc = kmer_rc(k);
     if (rc == k) return NIL;                                   // :105 palindromes are one-k-mer edges
@@ -45,6 +51,7 @@ W2R_HD uint32_t unipath_succ_link(const SolidTable& t, uint32_t x, int* missing)
     uint32_t c2 = t.slots[ts].ctx & 0xffu;
     if (rev) c2 = ctx_rc(c2);
     if (nib_count(c2 >> 4) != 1) return NIL;                    // :242
+    if (to_ghost) *to_ghost = slot_is_ghost(t.slots[ts]);
     return (uint32_t)(2 * ts) + (rev ? 1u : 0u);
 }
 
@@ -65,7 +72,7 @@ struct alignas(8) RankState { uint32_t x, y; };
 
 W2R_HD RankState rank_init_node(const uint32_t* next0, uint32_t x) {
     uint32_t nx = next0[x];
-    return nx >= EMPTY_NODE ? RankState{x, RANK_RESOLVED} : RankState{nx, 1u};
+    return nx >= GHOST_TAIL ? RankState{x, RANK_RESOLVED} : RankState{nx, 1u};
 }
 
 // ---- list ranking with splitters (Helman-JaJa): O(N) work instead of O(N log N) pointer jumping over every node.
@@ -75,22 +82,29 @@ W2R_HD RankState rank_init_node(const uint32_t* next0, uint32_t x) {
 // Nodes of cycles that contain no splitter stay unlabelled; splitters on a cycle never resolve: both are "circle" nodes.
 constexpr uint32_t SPLITTER_MASK = 63u;
 W2R_HD bool hash_splitter(uint32_t x) { uint32_t h = x * 0x9e3779b1u; h ^= h >> 15; h *= 0x85ebca77u; h ^= h >> 13; return (h & SPLITTER_MASK) == 0; }
-W2R_HD bool node_is_splitter(const uint32_t* next0, uint32_t x) { return next0[x] != EMPTY_NODE && (next0[x ^ 1u] == NIL || hash_splitter(x)); }
+// ghead (may be null): ghead[x] != 0 marks a node whose PREDECESSOR is a ghost: the head of a local chain piece.
+W2R_HD bool node_is_splitter(const uint32_t* next0, const uint8_t* ghead, uint32_t x) {
+    const uint32_t nx = next0[x];
+    if (nx == EMPTY_NODE || nx == GHOST_TAIL) return false;
+    return next0[x ^ 1u] == NIL || (ghead && ghead[x]) || hash_splitter(x);
+}
 // label[] must be initialised to {NIL, 0}.  Writes label[y] for every node of the segment and the splitter's own state S[s].
+// A chain ends at a node without successor or at a node whose successor is a ghost (next0[next0[y]] == GHOST_TAIL).
 W2R_HD void splitter_walk(const uint32_t* next0, uint32_t s, RankState* label, RankState* S) {
-    uint32_t y = s, o = 0;
+    uint32_t y = s, o = 0, ny = next0[s];
     for (;;) {
         label[y] = RankState{s, o};
-        uint32_t nx = next0[y];
-        if (nx == NIL) { S[s] = RankState{y, o | RANK_RESOLVED}; return; }          // reached the tail: resolved
+        if (ny == NIL) { S[s] = RankState{y, o | RANK_RESOLVED}; return; }          // reached the tail: resolved
+        const uint32_t nny = next0[ny];
+        if (nny == GHOST_TAIL) { S[s] = RankState{y, o | RANK_RESOLVED}; return; }  // the chain goes on on another rank: local tail
         ++o;
-        if (hash_splitter(nx) || nx == s) { S[s] = RankState{nx, o}; return; }       // next splitter (nx == s: a cycle with one splitter)
-        y = nx;
+        if (hash_splitter(ny) || ny == s) { S[s] = RankState{ny, o}; return; }       // next splitter (ny == s: a cycle with one splitter)
+        y = ny; ny = nny;
     }
 }
 // After the splitters are ranked: node y -> (tail, distance to tail | RESOLVED), or unresolved if y lies on a circle.
 W2R_HD RankState splitter_finish_node(const uint32_t* next0, const RankState* label, const RankState* S, uint32_t y) {
-    if (next0[y] == EMPTY_NODE) return RankState{y, RANK_RESOLVED};
+    if (next0[y] == EMPTY_NODE || next0[y] == GHOST_TAIL) return RankState{y, RANK_RESOLVED};
     RankState l = label[y];
     if (l.x == NIL) return RankState{y, 0};                                          // never labelled: a circle without splitter
     RankState st = S[l.x];
