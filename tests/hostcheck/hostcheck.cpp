@@ -30,6 +30,7 @@ struct Collect {
     std::vector<Rec>* v;
     void operator()(Kmer k, uint32_t ctx) const { v->push_back(Rec{k.w0, k.w1, ctx}); }
 };
+uint64_t table_slots_for(uint64_t n) { return solid_table_slots(n); }      // the product's sizing rule (kmer.cuh)
 template <class T> T* dup(const std::vector<T>& v) { T* p = (T*)malloc((v.size() ? v.size() : 1) * sizeof(T)); if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T)); return p; }
 }  // namespace
 
@@ -293,18 +294,17 @@ int finish_graph(const SolidTable& st, EdgeSet& es, uint64_t n_solid, const w2ra
     const uint64_t n = in->n_reads;
     uint32_t maxlen = 0;
     for (uint64_t r = 0; r < n; ++r) maxlen = std::max(maxlen, in->len[r]);
-    std::vector<uint8_t> qs(maxlen + 16);
     std::vector<int32_t> row(cap), row2(3 * maxlen + 32), poff(n), pedges;
     std::vector<uint64_t> path_off(n + 1, 0);
     uint64_t n_ovf = 0;
     for (uint64_t r = 0; r < n; ++r) {
         const uint8_t* b = in->bases + in->base_off[r];
         const uint8_t* q = in->quals + in->qual_off[r];
-        PathResult pr = path_one_read(g, b, in->len[r], q, qs.data(), row.data(), cap, left_cap, apply_fixpaths != 0);
+        PathResult pr = path_one_read(g, b, in->len[r], q, row.data(), cap, left_cap, apply_fixpaths != 0);
         const int32_t* src = row.data();
         if (pr.overflow) {
             ++n_ovf;
-            pr = path_one_read(g, b, in->len[r], q, qs.data(), row2.data(), 3 * maxlen + 32, maxlen + 16, apply_fixpaths != 0);
+            pr = path_one_read(g, b, in->len[r], q, row2.data(), 3 * maxlen + 32, maxlen + 16, apply_fixpaths != 0);
             if (pr.overflow) return 105;
             src = row2.data();
         }
@@ -334,17 +334,15 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     // ---- k_insert_solid
     uint64_t n_solid = 0;
     for (uint64_t i = 0; i < n_all; ++i) if (all[i].count >= min_freq) ++n_solid;
-    uint32_t lg = 10;
-    while ((1ull << lg) < 2 * n_solid) ++lg;
-    std::vector<SolidSlot> slots(1ull << lg);
+    std::vector<SolidSlot> slots(table_slots_for(n_solid));
     memset(slots.data(), 0xff, slots.size() * sizeof(SolidSlot));
-    SolidTable st{slots.data(), lg};
-    const uint64_t T = st.size(), mask = T - 1, nn = 2 * T;
+    SolidTable st{slots.data(), slots.size()};
+    const uint64_t T = st.size(), nn = 2 * T;
     for (uint64_t i = 0; i < n_all; ++i) {
         if (all[i].count < min_freq) continue;
         Kmer k{all[i].w0, all[i].w1};
         uint64_t h = st.home(k);
-        while (slots[h].w0 != EMPTY_W0) h = (h + 1) & mask;
+        while (slots[h].w0 != EMPTY_W0) h = st.next(h);
         slots[h].w0 = k.w0; slots[h].w1 = k.w1; slots[h].ctx = all[i].ctx; slots[h].edge = NIL; slots[h].off = 0; slots[h].pad = 0;
     }
     out->n_solid = n_solid; out->n_distinct = n_all;
@@ -415,15 +413,12 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         uint64_t nq = 0;
         for (const w2rap_kmer_rec& e : me.owned) neighbour_queries(Kmer{e.w0, e.w1}, e.ctx & 0xffu, logP, world, r, emit);
         for (auto& v : me.q) nq += v.size();
-        uint32_t lg = 6;
-        while ((1ull << lg) < 2 * (me.owned.size() + nq)) ++lg;
-        me.slots.resize(1ull << lg);
+        me.slots.resize(table_slots_for(me.owned.size() + nq));
         memset(me.slots.data(), 0xff, me.slots.size() * sizeof(SolidSlot));
-        me.st = SolidTable{me.slots.data(), lg};
-        const uint64_t mask = me.st.size() - 1;
+        me.st = SolidTable{me.slots.data(), me.slots.size()};
         for (const w2rap_kmer_rec& e : me.owned) {
             uint64_t h = me.st.home(Kmer{e.w0, e.w1});
-            while (me.slots[h].w0 != EMPTY_W0) h = (h + 1) & mask;
+            while (me.slots[h].w0 != EMPTY_W0) h = me.st.next(h);
             me.slots[h] = SolidSlot{e.w0, e.w1, e.ctx & 0xffu, NIL, 0, 0};
         }
     }
@@ -436,13 +431,12 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         }
     for (uint32_t r = 0; r < world; ++r) {
         Rank& me = rk[r];
-        const uint64_t mask = me.st.size() - 1;
         for (uint32_t d = 0; d < world; ++d)
             for (size_t i = 0; i < me.q[d].size(); ++i) {
                 if (me.reply[d][i] == NIL) continue;
                 const Kmer k = me.q[d][i];
                 uint64_t h = me.st.home(k);
-                while (me.slots[h].w0 != EMPTY_W0 && !(me.slots[h].w0 == k.w0 && me.slots[h].w1 == k.w1)) h = (h + 1) & mask;
+                while (me.slots[h].w0 != EMPTY_W0 && !(me.slots[h].w0 == k.w0 && me.slots[h].w1 == k.w1)) h = me.st.next(h);
                 if (me.slots[h].w0 == EMPTY_W0) { me.slots[h] = SolidSlot{k.w0, k.w1, 0, me.reply[d][i], 0, d + 1u}; ++n_ghost; }
             }
     }
@@ -598,17 +592,15 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
             if (e != NIL) emit_node_sharded(me.st, pos, e, es.edge_off.data(), (uint32_t)x, put);
         }
     // ---- all-gather of the owned entries (with pruned context, edge, offset): the whole dictionary for pathing
-    uint32_t lg = 10;
-    while ((1ull << lg) < 2 * n_solid) ++lg;
-    std::vector<SolidSlot> full(1ull << lg);
+    std::vector<SolidSlot> full(table_slots_for(n_solid));
     memset(full.data(), 0xff, full.size() * sizeof(SolidSlot));
-    SolidTable fst{full.data(), lg};
+    SolidTable fst{full.data(), full.size()};
     for (Rank& me : rk)
         for (uint64_t i = 0; i < me.st.size(); ++i) {
             const SolidSlot& sl = me.slots[i];
             if (sl.w0 == EMPTY_W0 || slot_is_ghost(sl)) continue;
             uint64_t h = fst.home(Kmer{sl.w0, sl.w1});
-            while (full[h].w0 != EMPTY_W0) h = (h + 1) & (fst.size() - 1);
+            while (full[h].w0 != EMPTY_W0) h = fst.next(h);
             full[h] = sl;
         }
     const uint32_t keep_passes = out->timings.count_passes, keep_res = out->timings.reserved;

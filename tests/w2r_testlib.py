@@ -459,12 +459,13 @@ def parse_freqs(path):
     return h
 
 
-def run_reference_step2(dirname, threads=1, min_freq=4, min_qual=7, timeout=3600):
+def run_reference_step2(dirname, threads=1, min_freq=4, min_qual=7, timeout=3600, binary=None):
     """Runs the reference's own step 2 (+FixPaths, +dump) on <dirname>/frag_reads_orig.{fastb,qualp}."""
-    if not os.path.exists(REF_BIN):
+    binary = binary or REF_BIN
+    if not os.path.exists(binary):
         raise RuntimeError("reference binary missing: make -C oracle")
     env = dict(os.environ, OMP_PROC_BIND="spread", MALLOC_PER_THREAD="1")
-    out = _run([REF_BIN, "-t", str(threads), "-o", dirname, "-p", "x", "-r", "dummy", "--from_step", "2", "--to_step", "2",
+    out = _run([binary, "-t", str(threads), "-o", dirname, "-p", "x", "-r", "dummy", "--from_step", "2", "--to_step", "2",
                 "--dump_perf", "1", "--min_freq", str(min_freq), "--min_qual", str(min_qual)], env=env, timeout=timeout)
     perf = {}
     pf = os.path.join(dirname, "x.perf")

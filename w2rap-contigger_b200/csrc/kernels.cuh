@@ -108,7 +108,6 @@ __global__ void k_dump_solid(SolidTable st, DumpRec* __restrict__ out, unsigned 
 
 // Dictionary build (BuildReadQGraph.cc:1096-1104 insertEntryNoLocking, in parallel): keys are unique, so a successful CAS owns the slot.
 __global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, SolidTable st) {
-    const uint64_t mask = st.size() - 1;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         ulonglong2 rec = __ldcs(recs + i);
         Kmer k{rec.x, rec.y & ~0xffull};
@@ -118,7 +117,21 @@ __global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, 
             SolidSlot* p = st.slots + h;
             U128 old = cas128(p, ~0ull, ~0ull, k.w0, k.w1);
             if (old.lo == ~0ull && old.hi == ~0ull) { p->ctx = ctx; p->edge = NIL; p->off = 0; p->pad = 0; break; }
-            h = (h + 1) & mask;
+            h = st.next(h);
+        }
+    }
+}
+// The same from whole entries (k-mer, pruned context, edge, offset): the pathing dictionary of a sharded run is built from the
+// entries the owner ranks finished (shardgraph.cuh), gathered from all ranks.
+__global__ void k_insert_entries(const SolidSlot* __restrict__ recs, uint64_t n, SolidTable st) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const SolidSlot e = recs[i];
+        uint64_t h = st.home(Kmer{e.w0, e.w1});
+        for (;;) {
+            SolidSlot* p = st.slots + h;
+            U128 old = cas128(p, ~0ull, ~0ull, e.w0, e.w1);
+            if (old.lo == ~0ull && old.hi == ~0ull) { p->ctx = e.ctx; p->edge = e.edge; p->off = e.off; p->pad = 0; break; }
+            h = st.next(h);
         }
     }
 }
@@ -138,7 +151,7 @@ __global__ void k_adjacency(SolidTable st) {
     const uint64_t T = st.size();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) {
         SolidSlot* s = st.slots + i;
-        if (s->w0 == EMPTY_W0) continue;
+        if (s->w0 == EMPTY_W0 || slot_is_ghost(*s)) continue;      // (ghosts: copies of k-mers other ranks own; they only answer membership)
         uint32_t c = s->ctx & 0xffu;
         uint32_t c2 = pruned_context(st, Kmer{s->w0, s->w1}, c);
         if (c2 != c) s->ctx = c2;     // other threads only test membership (keys), never contexts, during this kernel
@@ -399,10 +412,9 @@ struct alignas(8) PathMeta { uint32_t x, y; };   // x = first id in the staging 
 // (all requesters at once), and continues along its read.
 constexpr int PATH_GAP_BATCH = 4;
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, GraphView g, const uint32_t* __restrict__ list, uint64_t n_rows, uint8_t* __restrict__ qscratch,
-                                                    uint32_t qstride, int32_t* __restrict__ stage, uint32_t cap, uint32_t left_cap, int32_t* __restrict__ out_offset,
+__global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, GraphView g, const uint32_t* __restrict__ list, uint64_t n_rows,
+                                                    int32_t* __restrict__ stage, uint32_t cap, uint32_t left_cap, int32_t* __restrict__ out_offset,
                                                     PathMeta* __restrict__ out_meta, uint32_t apply_fixpaths) {
-    uint8_t* myq = qscratch + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * qstride;
     const uint32_t lane = lane_id();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t row0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); row0 < n_rows; row0 += stride) {   // warp-uniform trip count
@@ -465,7 +477,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
             }
         }
         if (live) {
-            PathResult pr = w.finish(r.quals + r.qual_off[i], myq, apply_fixpaths != 0);
+            PathResult pr = w.finish(r.quals + r.qual_off[i], apply_fixpaths != 0);
             out_offset[row] = pr.offset;
             out_meta[row] = PathMeta{pr.start, pr.overflow ? 0x80000000u : pr.len};
         }

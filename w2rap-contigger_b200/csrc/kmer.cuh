@@ -169,14 +169,20 @@ struct __attribute__((aligned(32))) SolidSlot { uint64_t w0, w1; uint32_t ctx, e
 
 struct SolidTable {
     SolidSlot* slots;
-    uint32_t log2n;            // slots = 1 << log2n  (<= 2^31 so that oriented node ids 2*slot+o fit in 32 bits)
-    W2R_HD uint64_t size() const { return 1ull << log2n; }
-    W2R_HD uint64_t home(Kmer k) const { return kmer_hash(k) >> (64 - log2n); }
+    uint64_t nslots;           // any size (not only powers of two): the home slot is the hash scaled to [0, nslots).  Tables whose slots
+                               // become 32-bit oriented node ids (2*slot+o: the graph stage) hold <= 2^31 slots; the pathing table any number
+    W2R_HD uint64_t size() const { return nslots; }
+    W2R_HD uint64_t home_of_hash(uint64_t h) const { return mulhi64(h, nslots); }
+    W2R_HD uint64_t home(Kmer k) const { return home_of_hash(kmer_hash(k)); }
+    W2R_HD uint64_t next(uint64_t h) const { return h + 1 == nslots ? 0 : h + 1; }
 };
 
-// Canonical lookup; returns slot or -1.
-W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) {
-    uint64_t mask = t.size() - 1, h = t.home(k);
+// slots for n keys: load ~0.6 (linear probing: ~1.8 probes per hit, ~3.6 per miss; pathing screens misses with the Bloom filter)
+W2R_HD uint64_t solid_table_slots(uint64_t n) { return n + (n >> 1) + (n >> 3) + 1024; }
+
+// Canonical lookup with the k-mer's hash already known; returns slot or -1.
+W2R_HD int64_t solid_find_hashed(const SolidTable& t, Kmer k, uint64_t hh) {
+    uint64_t h = t.home_of_hash(hh);
     for (;;) {
         const SolidSlot* s = t.slots + h;
 #if defined(__CUDA_ARCH__)
@@ -187,9 +193,10 @@ W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) {
 #endif
         if (a == k.w0 && b == k.w1) return (int64_t)h;
         if (a == EMPTY_W0) return -1;
-        h = (h + 1) & mask;
+        h = t.next(h);
     }
 }
+W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) { return solid_find_hashed(t, k, kmer_hash(k)); }
 // Blocked Bloom filter over the dictionary keys (two bits in one 32-bit word per key).  Read pathing looks up every k-mer of
 // a read's error-laden tail, almost all of them absent; the filter is small enough to stay in L2, so a negative lookup costs
 // one L2 hit instead of a random DRAM sector (+ a TLB miss) in the multi-GB table.  No false negatives.
@@ -207,22 +214,6 @@ W2R_HD bool bloom_may_contain(const KmerBloom& b, uint64_t h) {
 #else
     return (b.words[bloom_word(b, h)] & m) == m;
 #endif
-}
-// Canonical lookup with the k-mer's hash already known.
-W2R_HD int64_t solid_find_hashed(const SolidTable& t, Kmer k, uint64_t hh) {
-    uint64_t mask = t.size() - 1, h = hh >> (64 - t.log2n);
-    for (;;) {
-        const SolidSlot* s = t.slots + h;
-#if defined(__CUDA_ARCH__)
-        ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(s));
-        uint64_t a = kk.x, bb = kk.y;
-#else
-        uint64_t a = s->w0, bb = s->w1;
-#endif
-        if (a == k.w0 && bb == k.w1) return (int64_t)h;
-        if (a == EMPTY_W0) return -1;
-        h = (h + 1) & mask;
-    }
 }
 // Canonical lookup through the filter.
 W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer k) {

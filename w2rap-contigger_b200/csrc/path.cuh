@@ -40,41 +40,89 @@ W2R_HD uint32_t hbv_edge_base(const GraphView& g, int32_t he, uint64_t pos) { ui
 W2R_HD uint32_t hbv_edge_len(const GraphView& g, int32_t he) { return g.edge_len[g.hcanon[he] >> 1]; }
 W2R_HD bool part_same_edge(const PathPart& a, const PathPart& b) { return a.edge == b.edge && a.rc == b.rc; }
 
-// BuildReadQGraph.cc:552-558 isJoinable: same edge id, or equal LAST (K-1)-mers of the two oriented edges.
+// n <= 32 bases of an ORIENTED edge starting at oriented position pos, LSB-first (base pos in bits 1:0), bits above 2n clear.
+// rc: oriented positions pos..pos+n-1 are canonical positions len-pos-n..len-pos-1, reversed and complemented.
+W2R_HD uint64_t oriented_bases(const uint8_t* ep, uint64_t len, uint32_t rc, uint64_t pos, uint32_t n) {
+    uint64_t w = rc ? rev2(~bases32_at(ep, len - pos - n)) >> (2u * (32u - n)) : bases32_at(ep, pos);
+    if (n < 32u) w &= (1ull << (2u * n)) - 1ull;
+    return w;
+}
+W2R_HD uint64_t read_bases(const uint8_t* bases, uint64_t pos, uint32_t n) {
+    uint64_t w = bases32_at(bases, pos);
+    if (n < 32u) w &= (1ull << (2u * n)) - 1ull;
+    return w;
+}
+
+// BuildReadQGraph.cc:552-558 isJoinable: same edge id, or equal LAST (K-1)-mers of the two oriented edges (32 + 27 bases: two words).
 W2R_HD bool part_joinable(const GraphView& g, const PathPart& a, const PathPart& b) {
     if (a.edge == b.edge) return true;
-    uint64_t la = g.edge_len[a.edge], lb = g.edge_len[b.edge];
-    for (int i = 0; i < K - 1; ++i)
-        if (edge_base_oriented(g, a.edge, a.rc, la - (K - 1) + i) != edge_base_oriented(g, b.edge, b.rc, lb - (K - 1) + i)) return false;
-    return true;
+    const uint64_t la = g.edge_len[a.edge], lb = g.edge_len[b.edge];
+    const uint8_t* pa = g.edge_bases + g.edge_off[a.edge];
+    const uint8_t* pb = g.edge_bases + g.edge_off[b.edge];
+    if (oriented_bases(pa, la, a.rc, la - (K - 1), 32) != oriented_bases(pb, lb, b.rc, lb - (K - 1), 32)) return false;
+    return oriented_bases(pa, la, a.rc, la - (K - 1) + 32, K - 1 - 32) == oriented_bases(pb, lb, b.rc, lb - (K - 1) + 32, K - 1 - 32);
 }
 
 // paths/long/ExtendReadPath.cc:15-109.  penalty -= 0.2*penalty (unsigned -= double) == 4*penalty/5 in integers.
-W2R_HD uint32_t score_left_overlap(const GraphView& g, const uint8_t* bases, const uint8_t* quals, uint32_t start, int32_t he) {
+// Read and edge are compared 32 bases per step (XOR of packed words); only mismatches cost a quality lookup, and a run of matches
+// decays the penalty until it reaches zero.
+struct OverlapScore {
     uint32_t qsum = 0, pen = 0;
-    int64_t b = (int64_t)start - 1, e = (int64_t)hbv_edge_len(g, he) - K;
+    W2R_HD void matches(uint32_t m) { while (m-- && pen) pen = 4u * pen / 5u; }
+    W2R_HD void mismatch(uint32_t q) { pen += q == 2u ? 20u : q; qsum += pen; }
+};
+W2R_HD uint32_t score_left_overlap(const GraphView& g, const uint8_t* bases, const uint8_t* qstream, uint32_t start, int32_t he) {
+    const uint32_t hc = g.hcanon[he], canon = hc >> 1, rc = hc & 1u;
+    const uint64_t elen = g.edge_len[canon];
+    const uint8_t* ep = g.edge_bases + g.edge_off[canon];
+    OverlapScore sc;
+    int64_t b = (int64_t)start - 1, e = (int64_t)elen - K;        // read index downwards from start-1 against edge index downwards from |e|-K
     while (b >= 0 && e >= 0) {
-        if (packed_base(bases, (uint64_t)b) != hbv_edge_base(g, he, (uint64_t)e)) { uint32_t q = quals[b] == 2 ? 20u : quals[b]; pen += q; qsum += pen; }
-        else if (pen > 0) pen = 4u * pen / 5u;
-        --b; --e;
+        const uint32_t n = (uint32_t)((b < e ? b : e) + 1 < 32 ? (b < e ? b : e) + 1 : 32);
+        // positions b-n+1..b of the read against e-n+1..e of the edge; reversed so that the walk order (downwards) is bit order
+        uint64_t x = read_bases(bases, (uint64_t)(b - n + 1), n) ^ oriented_bases(ep, elen, rc, (uint64_t)(e - n + 1), n);
+        x = rev2(x) >> (2u * (32u - n));
+        uint32_t done = 0;
+        while (x) {
+            const uint32_t j = (uint32_t)ctz64(x) >> 1;
+            sc.matches(j - done);
+            sc.mismatch(pq_qual_at(qstream, (uint32_t)(b - j)));
+            done = j + 1;
+            x &= ~(3ull << (2u * j));
+        }
+        sc.matches(n - done);
+        b -= n; e -= n;
     }
-    if (b >= 0) qsum += 10u * (uint32_t)(b + 1);
-    return qsum;
+    if (b >= 0) sc.qsum += 10u * (uint32_t)(b + 1);
+    return sc.qsum;
 }
-W2R_HD uint32_t score_right_overlap(const GraphView& g, const uint8_t* bases, const uint8_t* quals, uint32_t rlen, uint32_t start, int32_t he) {
-    uint32_t qsum = 0, pen = 0;
-    uint64_t b = rlen - start, e = K - 1, elen = hbv_edge_len(g, he);
+W2R_HD uint32_t score_right_overlap(const GraphView& g, const uint8_t* bases, const uint8_t* qstream, uint32_t rlen, uint32_t start, int32_t he) {
+    const uint32_t hc = g.hcanon[he], canon = hc >> 1, rc = hc & 1u;
+    const uint64_t elen = g.edge_len[canon];
+    const uint8_t* ep = g.edge_bases + g.edge_off[canon];
+    OverlapScore sc;
+    uint64_t b = rlen - start, e = K - 1;
     while (b < rlen && e < elen) {
-        if (packed_base(bases, b) != hbv_edge_base(g, he, e)) { uint32_t q = quals[b] == 2 ? 20u : quals[b]; pen += q; qsum += pen; }
-        else if (pen > 0) pen = 4u * pen / 5u;
-        ++b; ++e;
+        uint64_t m = rlen - b < elen - e ? rlen - b : elen - e;
+        const uint32_t n = m < 32 ? (uint32_t)m : 32u;
+        uint64_t x = read_bases(bases, b, n) ^ oriented_bases(ep, elen, rc, e, n);
+        uint32_t done = 0;
+        while (x) {
+            const uint32_t j = (uint32_t)ctz64(x) >> 1;
+            sc.matches(j - done);
+            sc.mismatch(pq_qual_at(qstream, (uint32_t)(b + j)));
+            done = j + 1;
+            x &= ~(3ull << (2u * j));
+        }
+        sc.matches(n - done);
+        b += n; e += n;
     }
-    if (b < rlen) qsum += 10u * (uint32_t)(rlen - b);
-    return qsum;
+    if (b < rlen) sc.qsum += 10u * (uint32_t)(rlen - b);
+    return sc.qsum;
 }
 
 // ExtendReadPath.cc:150-212 (left) / :262-318 (right): classify candidates, then score.  Returns the chosen hbv edge or -1.
-W2R_HD int32_t choose_extension(const GraphView& g, int32_t v, bool leftward, uint32_t last_gap, const uint8_t* bases, const uint8_t* quals, uint32_t rlen) {
+W2R_HD int32_t choose_extension(const GraphView& g, int32_t v, bool leftward, uint32_t last_gap, const uint8_t* bases, const uint8_t* quals /* PQVec stream */, uint32_t rlen) {
     const int32_t* cand = (leftward ? g.to_e : g.from_e) + 4 * (int64_t)v;
     const uint32_t nc = leftward ? g.to_n[v] : g.from_n[v];
     const bool solo = nc == 1;
@@ -228,7 +276,7 @@ struct PathWalker {
         pending_gap = true;
         if (slot < 0 || !seed(slot)) scan_done = true;
     }
-    W2R_HD PathResult finish(const uint8_t* qstream, uint8_t* qscratch, bool apply_fixpaths) {
+    W2R_HD PathResult finish(const uint8_t* qstream, bool apply_fixpaths) {
         PathResult res{0, left_cap, 0, false};
         // :904-918 a trailing seed that only reached <= 5 k-mers into an edge from its very start is dropped
         if (last_is_gap) {
@@ -243,12 +291,10 @@ struct PathWalker {
         int32_t offset = first_is_gap ? (int32_t)first_hit_off - (int32_t)gap0_len : (int32_t)first_hit_off;   // :816-826
 
         // :922-923 quality-aware extension (ExtendReadPath.cc:115-348); all left extensions first, then right
-        bool have_quals = false;
         uint32_t nl = 0;
         int32_t front = row[left_cap], back = row[left_cap + n_ids - 1];
         while (offset < 0 && (uint32_t)(-offset) >= 10u) {
-            if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
-            int32_t e = choose_extension(*g, g->hleft[front], true, (uint32_t)(-offset), bases, qscratch, rlen);
+            int32_t e = choose_extension(*g, g->hleft[front], true, (uint32_t)(-offset), bases, qstream, rlen);
             if (e < 0) break;
             uint32_t ek = hbv_edge_len(*g, e) - K + 1;
             offset += (int32_t)ek; sum_kmers += ek;
@@ -258,9 +304,8 @@ struct PathWalker {
         for (;;) {
             int32_t lastg = (int32_t)rlen + offset - (int32_t)sum_kmers - (K - 1);
             if (lastg < 10) break;
-            if (!have_quals) { pq_decode(qstream, qscratch, rlen); have_quals = true; }
             // the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
-            int32_t e = choose_extension(*g, g->hleft[back], false, (uint32_t)lastg, bases, qscratch, rlen);
+            int32_t e = choose_extension(*g, g->hleft[back], false, (uint32_t)lastg, bases, qstream, rlen);
             if (e < 0) break;
             sum_kmers += hbv_edge_len(*g, e) - K + 1;
             if (n_ids < right_cap) row[left_cap + n_ids] = e; else res.overflow = true;
@@ -280,8 +325,8 @@ struct PathWalker {
 };
 
 // Paths one read, serially (the host check; the device kernel drives the walker itself and resolves gaps with the whole warp).
-// `row` is this read's staging row of `cap` ints; `qscratch` holds >= rlen bytes for lazily decoded quals.
-W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32_t rlen, const uint8_t* qstream, uint8_t* qscratch,
+// `row` is this read's staging row of `cap` ints; qualities are looked up in the PQVec stream where an extension needs them.
+W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32_t rlen, const uint8_t* qstream,
                                 int32_t* row, uint32_t cap, uint32_t left_cap, bool apply_fixpaths) {
     PathWalker w;
     w.init(g, bases, rlen, row, cap, left_cap);
@@ -303,7 +348,7 @@ W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32
         }
         w.gap_found(p, slot);
     }
-    return w.finish(qstream, qscratch, apply_fixpaths);
+    return w.finish(qstream, apply_fixpaths);
 }
 
 }  // namespace w2r

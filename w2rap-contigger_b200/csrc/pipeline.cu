@@ -19,6 +19,7 @@
 #include "device_reads.cuh"
 #include "count_part.cuh"
 #include "kernels.cuh"
+#include "shardgraph_kernels.cuh"
 #include "nccl_dl.h"
 #include "prims.cuh"
 
@@ -510,6 +511,7 @@ struct Pipeline {
         static const double fine_recs = getenv("W2RAP_FINE_RECS") ? atof(getenv("W2RAP_FINE_RECS")) : 24000.0;
         while (((double)pl.n_inst / (double)(1ull << pl.logP) > fine_recs || (1ull << pl.logP) < (uint64_t)world) && pl.logP < 22) ++pl.logP;
         pl.P = 1ull << pl.logP; pl.Pown = pl.P / world;
+        count_logP_ = pl.logP;
         pl.nmap = world > 1 ? 1u : (uint32_t)batches.size();
         pl.nslab = world > 1 ? (uint32_t)world : pl.nmap;
         if (pl.nslab > SMEM_MAX_BATCH) W2R_FAIL(W2RAP_ERR_INTERNAL, "more record runs per partition than the reduce kernel handles");
@@ -622,66 +624,45 @@ struct Pipeline {
         build_dictionary(n_solid_local, n_distinct);
     }
 
-    // every rank needs the whole dictionary for adjacency, unipaths and pathing: all-gather the solid records, then
-    // the dictionary (kmers/ReadPather.h:176-349) as an open-addressing table at load <= 0.5
+    // One GPU: the dictionary (kmers/ReadPather.h:176-349) as an open-addressing table over all solid k-mers.  Sharded: every rank keeps
+    // the solid k-mers it counted; graph_stage_sharded() builds its local table from them.
+    uint64_t n_solid_local_ = 0;
+    uint32_t count_logP_ = 0;
     void build_dictionary(uint64_t n_solid_local, uint64_t n_distinct) {
-        std::vector<unsigned long long> per_rank(world, 0ull);
-        per_rank[rank] = n_solid_local;
-        allreduce_u64(per_rank, ncclSum);
-        uint64_t n_solid = 0;
-        for (auto v : per_rank) n_solid += v;
-        SBuf<ulonglong2> solid_all;
-        const ulonglong2* solid_src = cs_solid.p;
-        if (world > 1) {
-            EventTimer kt(c.stream);
-            kt.start();
-            solid_all.alloc(c, n_solid);
-            uint64_t off = 0;
-            NcclApi& n = NcclApi::get();
-            nccl_check(n.GroupStart(), "group start");             // one grouped all-gather of variable-size pieces
-            for (int sidx = 0; sidx < world; ++sidx) {
-                if (per_rank[sidx]) nccl_check(n.Broadcast(sidx == rank ? (const void*)cs_solid.p : (const void*)(solid_all.p + off), solid_all.p + off,
-                                                           per_rank[sidx] * sizeof(ulonglong2), ncclUint8, sidx, comm, c.stream), "broadcast");
-                off += per_rank[sidx];
-            }
-            nccl_check(n.GroupEnd(), "group end");
-            out->timings.exchange_ms += kt.stop();
-            solid_src = solid_all.p;
-            cs_solid.release();
-        }
+        std::vector<unsigned long long> tot = {n_solid_local};
+        allreduce_u64(tot, ncclSum);
+        const uint64_t n_solid = tot[0];
+        n_solid_local_ = n_solid_local;
         out->n_distinct = n_distinct; out->n_solid = n_solid;
         say(c, "%llu kmers counted, filtering...", (unsigned long long)n_distinct);
         say(c, "%llu / %llu kmers with Freq >= %u", (unsigned long long)n_solid, (unsigned long long)n_distinct, prm.min_freq);
-        uint32_t lg = 10;
-        while ((1ull << lg) < 2 * n_solid) ++lg;
-        if (lg > 31) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^30 solid k-mers on one device");
-        solid_slots.alloc(c, 1ull << lg);
+        if (world > 1) return;
+        EventTimer kt(c.stream);
+        kt.start();
+        const uint64_t nslots = solid_table_slots(n_solid);
+        if (nslots > (1ull << 31) - 8) W2R_FAIL(W2RAP_ERR_OOM, "too many solid k-mers for one device's graph stage (32-bit oriented node ids); shard over more GPUs");
+        solid_slots.alloc(c, nslots);
         solid_slots.fill_ff();
-        st = SolidTable{solid_slots.p, lg};
-        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, solid_src, n_solid, st));
-        W2R_CUDA(cudaStreamSynchronize(c.stream));   // the solid staging buffers are released when this function returns
+        st = SolidTable{solid_slots.p, nslots};
+        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, (const ulonglong2*)cs_solid.p, n_solid, st));
+        out->timings.dict_ms = kt.stop();
         cs_solid.release();
     }
 
-    // ---- buildEdges (BuildReadQGraph.cc:314-339)
-    void unipath_stage() {
-        const uint64_t T = st.size(), nn = 2 * T;
-        SBuf<uint32_t> next0(c, nn);
+    // ---- list ranking of the oriented nodes (unipath.cuh): splitters walk to the next splitter, the splitters alone are ranked by
+    // pointer jumping, circles are cut at their minimum k-mer and ranked as paths.  On return *cur holds (tail, distance | RESOLVED)
+    // of every node and *oth is scratch.  ghead (sharded runs): nodes whose predecessor lives on another rank.
+    void list_ranking(SBuf<uint32_t>& next0, const uint8_t* ghead, uint64_t nn, SBuf<RankState>& A, SBuf<RankState>& B, RankState** cur_out, RankState** oth_out) {
         SBuf<int> flags(c, 4); flags.zero();
         SBuf<unsigned long long> scal(c, 4); scal.zero();
-        W2R_TIMED(W2RAP_KT_LINKS, W2R_LAUNCH(c, k_links, grid(nn, 256), 256, 0, st, next0.p, flags.p));
-        // list ranking: splitters walk to the next splitter, the splitters alone are ranked by pointer jumping (unipath.cuh)
-        SBuf<RankState> A(c, nn), B(c, nn);          // A: label, then the final (tail, distance) of every node; B: splitter states
         // every strand head is a splitter (two per edge: up to 2 * n_solid on a graph of one-k-mer edges) plus ~1/64 of all nodes
         // by the hash rule: count them first, then size the list exactly
-        W2R_CUDA(cudaMemsetAsync(scal.p + 3, 0, 8, c.stream));
-        W2R_LAUNCH(c, k_count_splitters, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)nullptr, nn, scal.p + 3);
-        if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a neighbour k-mer promised by a pruned context is missing (reference: ForceAssert in EdgeBuilder::lookup)");
+        W2R_LAUNCH(c, k_count_splitters, grid(nn, 256), 256, 0, next0.p, ghead, nn, scal.p + 3);
         const uint64_t nsp = d2h_scalar(c, scal.p + 3);
         SBuf<uint32_t> splist(c, nsp);
         W2R_CUDA(cudaMemsetAsync(A.p, 0xff, A.bytes(), c.stream));     // label = {NIL, ...}
         W2R_CUDA(cudaMemsetAsync(scal.p + 3, 0, 8, c.stream));
-        W2R_TIMED(W2RAP_KT_SPLITTER_WALK, W2R_LAUNCH(c, k_splitter_walk, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)nullptr, nn, A.p, B.p, splist.p, nsp, scal.p + 3));
+        W2R_TIMED(W2RAP_KT_SPLITTER_WALK, W2R_LAUNCH(c, k_splitter_walk, grid(nn, 256), 256, 0, next0.p, ghead, nn, A.p, B.p, splist.p, nsp, scal.p + 3));
         unsigned long long prev_un = ~0ull;
         if (nsp) {
             for (int round = 0; round < 48; ++round) {
@@ -728,6 +709,42 @@ struct Pipeline {
             W2R_LAUNCH(c, k_copy_list, grid(ncyc, 256), 256, 0, list.p, ncyc, x0, cur);
             W2R_CUDA(cudaStreamSynchronize(c.stream));
         }
+        *cur_out = cur; *oth_out = oth;
+    }
+
+    // Edge ids, lengths and byte offsets from the heads of the kept strands (E of them, in any order): deterministic edge order =
+    // sorted by sequence == sorted by the first 60 bases (each oriented k-mer heads at most one edge).  edge_of[h_idx] = edge id.
+    void edges_from_heads(SBuf<uint32_t>& h_idx, SBuf<uint32_t>& h_n, SBuf<uint64_t>& h_w0, SBuf<uint64_t>& h_w1, SBuf<uint32_t>& edge_of) {
+        SBuf<uint32_t> perm(c, E), tmp(c, E);
+        if (E) {
+            W2R_LAUNCH(c, k_rs_iota, grid(E, 256), 256, 0, perm.p, (uint32_t)E);
+            SortWord words[2] = {{h_w1.p, 8, 64}, {h_w0.p, 0, 64}};
+            radix_sort_perm(c, perm.p, tmp.p, (uint32_t)E, words, 2);
+        }
+        edge_len.alloc(c, E);
+        SBuf<uint32_t> nbytes(c, E);
+        if (E) W2R_LAUNCH(c, k_assign_edges, grid(E, 256), 256, 0, perm.p, E, h_idx.p, h_n.p, edge_of.p, edge_len.p, nbytes.p);
+        edge_off.alloc(c, E + 1);
+        SBuf<unsigned long long> tot(c, 1);
+        exclusive_scan<uint32_t, unsigned long long>(c, nbytes.p, E, (unsigned long long*)edge_off.p, tot.p);
+        edge_bytes = E ? d2h_scalar(c, tot.p) : 0;
+        W2R_CUDA(cudaMemcpyAsync(edge_off.p + E, &edge_bytes, 8, cudaMemcpyHostToDevice, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        edge_bases.alloc(c, (edge_bytes + 3 + 32) & ~3ull);
+        edge_bases.zero();
+    }
+
+    // ---- buildEdges (BuildReadQGraph.cc:314-339)
+    void unipath_stage() {
+        const uint64_t T = st.size(), nn = 2 * T;
+        SBuf<uint32_t> next0(c, nn);
+        SBuf<int> flags(c, 4); flags.zero();
+        SBuf<unsigned long long> scal(c, 4); scal.zero();
+        W2R_TIMED(W2RAP_KT_LINKS, W2R_LAUNCH(c, k_links, grid(nn, 256), 256, 0, st, next0.p, flags.p));
+        if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a neighbour k-mer promised by a pruned context is missing (reference: ForceAssert in EdgeBuilder::lookup)");
+        SBuf<RankState> A(c, nn), B(c, nn);          // A: label, then the final (tail, distance) of every node; B: splitter states
+        RankState* cur = nullptr; RankState* oth = nullptr;
+        list_ranking(next0, nullptr, nn, A, B, &cur, &oth);
         const RankState* R = cur;
         SBuf<uint8_t> keep(c, nn); keep.zero();
         W2R_LAUNCH(c, k_strand_decide, grid(nn, 256), 256, 0, st, R, keep.p, flags.p + 2);
@@ -740,27 +757,246 @@ struct Pipeline {
         W2R_LAUNCH(c, k_collect_heads, grid(nn, 256), 256, 0, st, R, keep.p, h_node.p, h_w0.p, h_w1.p, h_n.p, scal.p + 2, cap);
         E = d2h_scalar(c, scal.p + 2);
         if (E > cap) W2R_FAIL(W2RAP_ERR_INTERNAL, "more edges than solid k-mers");
-        // deterministic edge order: sorted by sequence == sorted by the first 60 bases (each oriented k-mer heads at most one edge)
-        SBuf<uint32_t> perm(c, E), tmp(c, E);
-        if (E) {
-            W2R_LAUNCH(c, k_rs_iota, grid(E, 256), 256, 0, perm.p, (uint32_t)E);
-            SortWord words[2] = {{h_w1.p, 8, 64}, {h_w0.p, 0, 64}};
-            radix_sort_perm(c, perm.p, tmp.p, (uint32_t)E, words, 2);
-        }
         SBuf<uint32_t> edge_of_head(c, nn); edge_of_head.fill_ff();
-        edge_len.alloc(c, E);
-        SBuf<uint32_t> nbytes(c, E);
-        if (E) W2R_LAUNCH(c, k_assign_edges, grid(E, 256), 256, 0, perm.p, E, h_node.p, h_n.p, edge_of_head.p, edge_len.p, nbytes.p);
-        edge_off.alloc(c, E + 1);
-        SBuf<unsigned long long> tot(c, 1);
-        exclusive_scan<uint32_t, unsigned long long>(c, nbytes.p, E, (unsigned long long*)edge_off.p, tot.p);
-        edge_bytes = E ? d2h_scalar(c, tot.p) : 0;
-        W2R_CUDA(cudaMemcpyAsync(edge_off.p + E, &edge_bytes, 8, cudaMemcpyHostToDevice, c.stream));
-        W2R_CUDA(cudaStreamSynchronize(c.stream));
-        edge_bases.alloc(c, (edge_bytes + 3 + 32) & ~3ull);
-        edge_bases.zero();
+        edges_from_heads(h_node, h_n, h_w0, h_w1, edge_of_head);
         W2R_TIMED(W2RAP_KT_EMIT_EDGES, W2R_LAUNCH(c, k_emit_edges, grid(nn, 256), 256, 0, st, R, edge_of_head.p, edge_off.p, edge_bases.p));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
+    }
+
+    // ---- multi-GPU plumbing of the sharded graph stage
+    // all-gather of variable-size contributions (n_mine elements of T from every rank, in rank order).  off[r] = first element of
+    // rank r, off[world] = total.
+    template <class T>
+    void allgather_v(const T* mine, uint64_t n_mine, SBuf<T>& all, std::vector<uint64_t>& off) {
+        std::vector<unsigned long long> per(world, 0ull);
+        per[rank] = n_mine;
+        allreduce_u64(per, ncclSum);
+        off.assign(world + 1, 0);
+        for (int r = 0; r < world; ++r) off[r + 1] = off[r] + per[r];
+        all.alloc(c, off[world] + 1);
+        NcclApi& n = NcclApi::get();
+        nccl_check(n.GroupStart(), "group start");
+        for (int r = 0; r < world; ++r)
+            if (per[r]) nccl_check(n.Broadcast(r == rank ? (const void*)mine : (const void*)(all.p + off[r]), all.p + off[r], per[r] * sizeof(T), ncclUint8, r, comm, c.stream), "broadcast");
+        nccl_check(n.GroupEnd(), "group end");
+        xchg_bytes += n_mine * sizeof(T) * (uint64_t)(world - 1);
+    }
+
+    // ---- recomputeAdjacencies + buildEdges (kmers/ReadPather.h:307-346, BuildReadQGraph.cc:99-339) over a dictionary that stays
+    // sharded by minimiser owner (shardgraph.cuh): neighbour queries -> ghost entries, local list ranking, chain-end records
+    // gathered and ranked on every rank, edge ids from a global sort, edge bases by all-reduce; finally the finished entries are
+    // gathered into the pathing dictionary.  `solid` = the solid records {w0, w1 | raw ctx} this rank owns.
+    void graph_stage_sharded(SBuf<ulonglong2>& solid, uint64_t n_local, uint32_t logP) {
+        EventTimer xt(c.stream);
+        float xms = 0;
+        const uint32_t me = (uint32_t)rank, W = (uint32_t)world;
+        SBuf<int> flags(c, 8); flags.zero();
+        SBuf<unsigned long long> scal(c, 8); scal.zero();
+        // -- round 1: neighbour queries from the solid records
+        uint64_t qcap = std::max<uint64_t>(1024, n_local / 4);
+        SBuf<ulonglong2> qkeys;
+        SBuf<unsigned long long> qcount(c, W);
+        SBuf<uint64_t> qbase(c, W);
+        std::vector<unsigned long long> qn(W, 0);
+        for (int attempt = 0;; ++attempt) {
+            if (attempt > 2) W2R_FAIL(W2RAP_ERR_INTERNAL, "neighbour query buffers did not converge");
+            qkeys.alloc(c, W * qcap);
+            std::vector<uint64_t> qb(W);
+            for (uint32_t d = 0; d < W; ++d) qb[d] = d * qcap;
+            W2R_CUDA(cudaMemcpyAsync(qbase.p, qb.data(), W * 8, cudaMemcpyHostToDevice, c.stream));
+            qcount.zero();
+            if (n_local) W2R_LAUNCH(c, k_neighbour_queries, grid(n_local, 256), 256, 0, solid.p, n_local, logP, W, me, QueryOut{qkeys.p, qbase.p, qcount.p, qcap});
+            W2R_CUDA(cudaMemcpyAsync(qn.data(), qcount.p, W * 8, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            unsigned long long mx = 0;
+            for (auto v : qn) mx = std::max(mx, v);
+            if (mx <= qcap) break;
+            qcap = mx + mx / 32 + 64;
+        }
+        uint64_t nq_total = 0;
+        for (auto v : qn) nq_total += v;
+        // -- the local table: owned entries now, ghosts later
+        const uint64_t nslots = solid_table_slots(n_local + nq_total);
+        if (nslots > (1ull << 31) - 8) W2R_FAIL(W2RAP_ERR_OOM, "too many solid k-mers per GPU for 32-bit oriented node ids; shard over more GPUs");
+        solid_slots.alloc(c, nslots);
+        solid_slots.fill_ff();
+        st = SolidTable{solid_slots.p, nslots};
+        if (n_local) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_local, 256), 256, 0, (const ulonglong2*)solid.p, n_local, st));
+        solid.release();
+        // -- keys to the owners, slots back
+        xt.start();
+        SBuf<unsigned long long> rcount(c, W);
+        alltoall_slabs(qcount.p, rcount.p, sizeof(unsigned long long));
+        std::vector<unsigned long long> rn(W, 0);
+        W2R_CUDA(cudaMemcpyAsync(rn.data(), rcount.p, W * 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        std::vector<size_t> q_off(W), q_cnt(W), r_off(W), r_cnt(W);
+        uint64_t nr_total = 0;
+        for (uint32_t d = 0; d < W; ++d) { q_off[d] = d * qcap; q_cnt[d] = qn[d]; r_off[d] = nr_total; r_cnt[d] = rn[d]; nr_total += rn[d]; if (d != me) xchg_bytes += qn[d] * 16 + rn[d] * 8; }
+        auto scaled = [](const std::vector<size_t>& v, size_t k) { std::vector<size_t> o(v.size()); for (size_t i = 0; i < v.size(); ++i) o[i] = v[i] * k; return o; };
+        SBuf<ulonglong2> rkeys(c, nr_total + 1);
+        alltoall_v(qkeys.p, scaled(q_off, 16), scaled(q_cnt, 16), rkeys.p, scaled(r_off, 16), scaled(r_cnt, 16));
+        SBuf<uint32_t> rreply(c, nr_total + 1), qreply(c, W * qcap), gslot(c, W * qcap);
+        if (nr_total) W2R_LAUNCH(c, k_answer_queries, grid(nr_total, 256), 256, 0, st, (const ulonglong2*)rkeys.p, nr_total, rreply.p);
+        alltoall_v(rreply.p, scaled(r_off, 4), scaled(r_cnt, 4), qreply.p, scaled(q_off, 4), scaled(q_cnt, 4));
+        xms += xt.stop();
+        rkeys.release();
+        for (uint32_t d = 0; d < W; ++d)
+            if (qn[d]) W2R_LAUNCH(c, k_insert_ghosts, grid(qn[d], 256), 256, 0, st, (const ulonglong2*)qkeys.p + d * qcap, (const uint32_t*)qreply.p + d * qcap, (uint64_t)qn[d], d, gslot.p + d * qcap);
+        qkeys.release();
+        // -- adjacency pruning of the owned entries (ghosts only answer membership); then the ghosts' pruned contexts
+        W2R_TIMED(W2RAP_KT_ADJACENCY, W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st));
+        xt.start();
+        SBuf<uint32_t> rctx(c, nr_total + 1), qctx(c, W * qcap);
+        if (nr_total) W2R_LAUNCH(c, k_gather_ctx, grid(nr_total, 256), 256, 0, st, (const uint32_t*)rreply.p, nr_total, rctx.p);
+        alltoall_v(rctx.p, scaled(r_off, 4), scaled(r_cnt, 4), qctx.p, scaled(q_off, 4), scaled(q_cnt, 4));
+        xms += xt.stop();
+        for (uint32_t d = 0; d < W; ++d)
+            if (qn[d]) W2R_LAUNCH(c, k_apply_ghost_ctx, grid(qn[d], 256), 256, 0, st, (const uint32_t*)gslot.p + d * qcap, (const uint32_t*)qctx.p + d * qcap, (uint64_t)qn[d]);
+        rreply.release(); qreply.release(); gslot.release(); rctx.release(); qctx.release();
+        // -- successor links; a node whose predecessor is a ghost heads a local piece
+        const uint64_t nn = 2 * st.size();
+        SBuf<uint32_t> next0(c, nn);
+        SBuf<uint8_t> ghead(c, nn); ghead.zero();
+        W2R_TIMED(W2RAP_KT_LINKS, W2R_LAUNCH(c, k_links_sharded, grid(nn, 256), 256, 0, st, next0.p, ghead.p, flags.p));
+        if (d2h_scalar(c, flags.p)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a neighbour k-mer promised by a pruned context is missing (reference: ForceAssert in EdgeBuilder::lookup)");
+        SBuf<RankState> A(c, nn), B(c, nn);
+        RankState* cur = nullptr; RankState* oth = nullptr;
+        SBuf<PieceRec> pieces;             // all pieces of all ranks
+        SBuf<uint32_t> nxt, flip;
+        SBuf<RankState> S;
+        uint64_t np = 0;
+        uint32_t piece0 = 0;
+        uint32_t* lpiece = nullptr;
+        for (int iteration = 0;; ++iteration) {
+            if (iteration > 1) W2R_FAIL(W2RAP_ERR_INTERNAL, "circles left after cutting them");
+            list_ranking(next0, ghead.p, nn, A, B, &cur, &oth);
+            // -- round 2: one record per local chain, gathered on every rank
+            lpiece = reinterpret_cast<uint32_t*>(oth);          // scratch: local piece index per tail node
+            W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_count_piece_heads, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)ghead.p, nn, scal.p);
+            const uint64_t npl = d2h_scalar(c, scal.p);
+            SBuf<PieceRec> lp(c, npl);
+            W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_emit_pieces, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, (const uint8_t*)ghead.p, (const RankState*)cur, me, lp.p, npl, scal.p, lpiece);
+            xt.start();
+            std::vector<uint64_t> poff;
+            allgather_v(lp.p, npl, pieces, poff);
+            xms += xt.stop();
+            np = poff[W]; piece0 = (uint32_t)poff[me];
+            if (np >= (1ull << 32) - 8) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^32 chain pieces");
+            lp.release();
+            uint64_t msz = 64;
+            while (msz < 2 * np) msz <<= 1;
+            SBuf<uint64_t> mkeys(c, msz); mkeys.fill_ff();
+            SBuf<uint32_t> mvals(c, msz);
+            GidMap gm{mkeys.p, mvals.p, msz - 1};
+            nxt.alloc(c, np); flip.alloc(c, np); S.alloc(c, np);
+            if (np) {
+                W2R_LAUNCH(c, k_gidmap_insert, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, np, gm);
+                W2R_LAUNCH(c, k_piece_link, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, np, gm, nxt.p, flip.p, flags.p + 1);
+                W2R_LAUNCH(c, k_piece_rank_init, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, (const uint32_t*)nxt.p, np, S.p);
+            }
+            if (d2h_scalar(c, flags.p + 1)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a chain piece points at a node that heads no piece");
+            unsigned long long un = 0, prev = ~0ull;
+            for (int round = 0; round < 64 && np; ++round) {
+                W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+                W2R_LAUNCH(c, k_piece_rank_step, grid(np, 256), 256, 0, (unsigned long long*)S.p, np, scal.p);
+                un = d2h_scalar(c, scal.p);
+                if (un == 0 || un == prev) break;
+                prev = un;
+            }
+            if (un == 0) break;
+            // -- circles that span ranks (BuildReadQGraph.cc:126-180): rare and small, resolved on the host.  Label every circle by
+            // walking the piece links, gather the circle nodes from all ranks, cut each circle at its minimum canonical k-mer.
+            std::vector<uint32_t> nxt_h(np);
+            std::vector<RankState> S_h(np);
+            W2R_CUDA(cudaMemcpyAsync(nxt_h.data(), nxt.p, np * 4, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaMemcpyAsync(S_h.data(), S.p, np * 8, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_collect_cycle_nodes, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, (const RankState*)cur, (const uint32_t*)lpiece, piece0, (const RankState*)S.p, me,
+                       (CycleNode*)nullptr, (uint64_t)0, scal.p);
+            const uint64_t ncl = d2h_scalar(c, scal.p);
+            SBuf<CycleNode> cyc_local(c, ncl), cyc_all;
+            W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+            W2R_LAUNCH(c, k_collect_cycle_nodes, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, (const RankState*)cur, (const uint32_t*)lpiece, piece0, (const RankState*)S.p, me,
+                       cyc_local.p, ncl, scal.p);
+            std::vector<uint64_t> coff;
+            allgather_v(cyc_local.p, ncl, cyc_all, coff);
+            std::vector<CycleNode> cn(coff[W]);
+            W2R_CUDA(cudaMemcpyAsync(cn.data(), cyc_all.p, cn.size() * sizeof(CycleNode), cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            std::vector<uint32_t> lab(np, NIL);
+            for (uint64_t i = 0; i < np; ++i) {
+                if ((S_h[i].y & RANK_RESOLVED) || lab[i] != NIL) continue;
+                uint32_t mn = (uint32_t)i;
+                for (uint32_t j = nxt_h[i]; j != i; j = nxt_h[j]) mn = std::min(mn, j);
+                lab[i] = mn;
+                for (uint32_t j = nxt_h[i]; j != i; j = nxt_h[j]) lab[j] = mn;
+            }
+            std::sort(cn.begin(), cn.end(), [&](const CycleNode& a, const CycleNode& b) {
+                const uint32_t la = lab[a.piece], lb = lab[b.piece];
+                if (la != lb) return la < lb;
+                if (a.w0 != b.w0) return a.w0 < b.w0;
+                if (a.w1 != b.w1) return a.w1 < b.w1;
+                return a.gid < b.gid;
+            });
+            std::vector<uint64_t> heads_g, tails_g;            // (kmin,+) becomes a head, (kmin,-) a tail
+            for (size_t i = 0; i < cn.size(); ++i) {
+                if (i > 0 && lab[cn[i].piece] == lab[cn[i - 1].piece]) continue;
+                for (size_t j = i; j < cn.size() && lab[cn[j].piece] == lab[cn[i].piece] && cn[j].w0 == cn[i].w0 && cn[j].w1 == cn[i].w1; ++j)
+                    if (cn[j].gid & 1ull) tails_g.push_back(cn[j].gid); else heads_g.push_back(cn[j].gid);
+            }
+            std::sort(heads_g.begin(), heads_g.end()); std::sort(tails_g.begin(), tails_g.end());
+            SBuf<uint64_t> hg(c, heads_g.size() + 1), tg(c, tails_g.size() + 1);
+            W2R_CUDA(cudaMemcpyAsync(hg.p, heads_g.data(), heads_g.size() * 8, cudaMemcpyHostToDevice, c.stream));
+            W2R_CUDA(cudaMemcpyAsync(tg.p, tails_g.data(), tails_g.size() * 8, cudaMemcpyHostToDevice, c.stream));
+            if (ncl) W2R_LAUNCH(c, k_apply_cycle_cuts, grid(ncl, 256), 256, 0, st, next0.p, ghead.p, me, (const CycleNode*)cyc_local.p, ncl, (const uint64_t*)hg.p, (uint32_t)heads_g.size(),
+                                (const uint64_t*)tg.p, (uint32_t)tails_g.size());
+            W2R_CUDA(cudaStreamSynchronize(c.stream));       // heads_g / tails_g leave scope
+        }
+        // -- strands: even lengths from the piece records (every rank computes them), odd lengths by the owner of the middle k-mer
+        PieceView pv{pieces.p, flip.p, S.p, np};
+        SBuf<uint8_t> is_head(c, np + 4), keepp(c, np + 4);
+        SBuf<uint32_t> chain_n(c, np + 1);
+        is_head.zero(); keepp.zero();
+        if (np) W2R_LAUNCH(c, k_chain_tails, grid(np, 256), 256, 0, pv, (const uint32_t*)nxt.p, is_head.p, chain_n.p, keepp.p, flags.p + 2);
+        W2R_LAUNCH(c, k_node_keep_odd, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, pv, (const RankState*)cur, (const uint32_t*)lpiece, piece0, keepp.p);
+        xt.start();
+        if (np) nccl_check(NcclApi::get().AllReduce(keepp.p, keepp.p, np, ncclUint8, ncclMax, comm, c.stream), "all-reduce");
+        xms += xt.stop();
+        if (d2h_scalar(c, flags.p + 2)) W2R_FAIL(W2RAP_ERR_EDGE_TOO_LONG, "an edge is longer than 2^24 k-mers (reference: KDef offset is 24 bits)");
+        // -- edges: kept heads sorted by k-mer (identical on every rank), emission by the owners, all-reduce of the bases
+        SBuf<uint32_t> h_piece(c, np + 1), h_n(c, np + 1);
+        SBuf<uint64_t> h_w0(c, np + 1), h_w1(c, np + 1);
+        W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+        if (np) W2R_LAUNCH(c, k_collect_head_pieces, grid(np, 256), 256, 0, pv, (const uint8_t*)is_head.p, (const uint8_t*)keepp.p, (const uint32_t*)chain_n.p, h_piece.p, h_w0.p, h_w1.p, h_n.p, scal.p, np);
+        E = d2h_scalar(c, scal.p);
+        SBuf<uint32_t> edge_of_piece(c, np + 1); edge_of_piece.fill_ff();
+        edges_from_heads(h_piece, h_n, h_w0, h_w1, edge_of_piece);
+        W2R_TIMED(W2RAP_KT_EMIT_EDGES, W2R_LAUNCH(c, k_emit_edges_sharded, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, pv, (const RankState*)cur, (const uint32_t*)lpiece, piece0,
+                                                   (const uint32_t*)edge_of_piece.p, (const uint64_t*)edge_off.p, edge_bases.p));
+        xt.start();
+        const uint64_t ebw = (edge_bytes + 3) / 4;          // (disjoint bits: a sum of 32-bit words is their OR)
+        if (ebw) nccl_check(NcclApi::get().AllReduce(edge_bases.p, edge_bases.p, ebw, ncclUint32, ncclSum, comm, c.stream), "all-reduce");
+        xchg_bytes += ebw * 4 + np;
+        // -- the finished entries (pruned context, edge, offset) of every rank: the dictionary the reads are pathed against
+        SBuf<SolidSlot> mine(c, n_local + 1), entries;
+        W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+        W2R_LAUNCH(c, k_dump_owned, grid(st.size(), 256), 256, 0, st, mine.p, n_local, scal.p);
+        if (d2h_scalar(c, scal.p) != n_local) W2R_FAIL(W2RAP_ERR_INTERNAL, "owned entries lost in the local table");
+        std::vector<uint64_t> eoff;
+        allgather_v(mine.p, n_local, entries, eoff);
+        xms += xt.stop();
+        const uint64_t n_solid = eoff[W];
+        mine.release(); next0.release(); ghead.release(); A.release(); B.release(); solid_slots.release();
+        const uint64_t fslots = solid_table_slots(n_solid);
+        solid_slots.alloc(c, fslots);
+        solid_slots.fill_ff();
+        st = SolidTable{solid_slots.p, fslots};
+        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(n_solid, 256), 256, 0, (const SolidSlot*)entries.p, n_solid, st));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        out->timings.graph_exchange_ms = xms;
     }
 
     // ---- buildHBVFromEdges (paths/long/HBVFromEdges.cc:76-154)
@@ -823,8 +1059,6 @@ struct Pipeline {
         const unsigned block = 128;
         static const int path_occ_grid = getenv("W2RAP_PATH_OCC") ? std::max(12, atoi(getenv("W2RAP_PATH_OCC"))) : 12;
         const unsigned gr = grid(n, block, path_occ_grid);
-        const uint32_t qstride = (dr.max_len + 15) & ~15u;
-        SBuf<uint8_t> qscratch(c, (size_t)gr * block * std::max<uint32_t>(qstride, 16));
         const uint32_t cap = 24, left_cap = 8;
         SBuf<int32_t> stage(c, n * cap), row_off(c, n);
         SBuf<PathMeta> meta(c, n);
@@ -834,11 +1068,11 @@ struct Pipeline {
         // measured (config 2, path stage): 8 CTAs/SM (64 registers) 96 ms, 10: 105 ms, 12 (40 registers, more spills) 81.5 ms, 14/16: 86 ms
         static const int path_occ = getenv("W2RAP_PATH_OCC") ? atoi(getenv("W2RAP_PATH_OCC")) : 12;
         auto launch_path = [&](unsigned grd, const uint32_t* list, uint64_t rows, int32_t* stg, uint32_t cp, uint32_t lcp, int32_t* roff, PathMeta* mt) {
-            if (path_occ >= 16) W2R_LAUNCH(c, k_path_reads<16>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
-            else if (path_occ >= 14) W2R_LAUNCH(c, k_path_reads<14>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
-            else if (path_occ >= 12) W2R_LAUNCH(c, k_path_reads<12>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
-            else if (path_occ >= 10) W2R_LAUNCH(c, k_path_reads<10>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
-            else W2R_LAUNCH(c, k_path_reads<8>, grd, block, 0, rv, g, list, rows, qscratch.p, qstride, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            if (path_occ >= 16) W2R_LAUNCH(c, k_path_reads<16>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            else if (path_occ >= 14) W2R_LAUNCH(c, k_path_reads<14>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            else if (path_occ >= 12) W2R_LAUNCH(c, k_path_reads<12>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            else if (path_occ >= 10) W2R_LAUNCH(c, k_path_reads<10>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            else W2R_LAUNCH(c, k_path_reads<8>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
         };
         W2R_TIMED(W2RAP_KT_PATH_READS, launch_path(gr, nullptr, n, stage.p, cap, left_cap, row_off.p, meta.p));
         W2R_LAUNCH(c, k_path_lens, grid(n, 256), 256, 0, meta.p, (const uint32_t*)nullptr, n, lens.p, counters.p);
@@ -897,12 +1131,17 @@ struct Pipeline {
         st_t.start(); count_stage();
         out->timings.count_ms = st_t.stop();
         good.release();
-        say(c, "updating adjacencies");
-        st_t.start();
-        W2R_TIMED(W2RAP_KT_ADJACENCY, W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st));
-        out->timings.adjacency_ms = st_t.stop();
-        say(c, "finding edges (unique paths)");
-        st_t.start(); unipath_stage(); out->timings.unipath_ms = st_t.stop();
+        if (world > 1) {
+            say(c, "updating adjacencies, finding edges (unique paths): dictionary sharded over %d GPUs", world);
+            st_t.start(); graph_stage_sharded(cs_solid, n_solid_local_, count_logP_); out->timings.unipath_ms = st_t.stop();
+        } else {
+            say(c, "updating adjacencies");
+            st_t.start();
+            W2R_TIMED(W2RAP_KT_ADJACENCY, W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st));
+            out->timings.adjacency_ms = st_t.stop();
+            say(c, "finding edges (unique paths)");
+            st_t.start(); unipath_stage(); out->timings.unipath_ms = st_t.stop();
+        }
         say(c, "building graph...");
         st_t.start(); hbv_stage(); out->timings.hbv_ms = st_t.stop();
         SBuf<int32_t> d_offset, d_path_edges; SBuf<uint64_t> d_path_off;

@@ -89,6 +89,28 @@ W2R_HD uint32_t pq_good_length(const uint8_t* stream, uint32_t min_qual, uint32_
     return pq_good_length(stream, (const uint8_t*)~(uintptr_t)0, min_qual, n_quals);
 }
 
+// One quality by position, without decoding the vector: walk the block headers (a 250-base read has a handful of blocks) and pull
+// the delta out of its block by bit offset.  Read pathing only needs qualities at the MISMATCHES of an extension overlap
+// (paths/long/ExtendReadPath.cc:15-109), a few per read, so this replaces a full decode into scratch memory.
+W2R_HD uint32_t pq_qual_at(const uint8_t* stream, uint32_t pos) {
+    const uint8_t* p = stream;
+    uint32_t i = 0;
+    for (;;) {
+        const uint32_t nq = *p;
+        if (!nq) return 0;                                     // past the end (callers stay inside the read)
+        const uint32_t hdr = (uint32_t)p[1] | ((uint32_t)p[2] << 8);
+        const uint32_t nbits = hdr & 7u, minq = (hdr >> 3) & 63u;
+        if (pos < i + nq) {
+            if (!nbits) return minq;
+            const uint32_t bit = 9u + (pos - i) * nbits;       // from the byte after the count
+            const uint8_t* b = p + 1 + (bit >> 3);
+            return minq + ((((uint32_t)b[0] | ((uint32_t)b[1] << 8)) >> (bit & 7u)) & ((1u << nbits) - 1u));
+        }
+        p += 1 + ((9u + nq * nbits + 7u) >> 3);
+        i += nq;
+    }
+}
+
 // Decodes up to `cap` quals into out; returns the number of quals in the stream.
 W2R_HD uint32_t pq_decode(const uint8_t* stream, uint8_t* out, uint32_t cap) {
     PQReader r(stream);

@@ -25,15 +25,33 @@ W2R_HD uint32_t kmer_owner(Kmer k, uint32_t logP, uint32_t world) {
 
 // ---- round 1: which neighbours have to be asked for.  emit(owner rank, canonical neighbour k-mer) for every context bit of an
 // owned k-mer whose neighbour lives on another rank (kmers/ReadPather.h:322-342 looks every one of them up).
+// The neighbour shares 45 of its 46 m-mers with k: its minimiser is the smaller of (k's minimum without the m-mer that drops out) and
+// the one new m-mer, so a k-mer costs 46 + (number of neighbours) m-mer hashes instead of 46 per neighbour.
+W2R_HD uint32_t mmer_of_words(uint64_t lo, uint64_t hi, int t) {          // m-mer t of a k-mer in LSB-first words (base i in bits 2i.. of hi:lo)
+    const int bit = 2 * t;
+    const uint64_t w = bit == 0 ? lo : (bit < 64 ? (lo >> bit) | (hi << (64 - bit)) : hi >> (bit - 64));
+    return (uint32_t)w & ((1u << (2 * MINI_M)) - 1u);
+}
 template <class Emit>
 W2R_HD void neighbour_queries(Kmer k, uint32_t c, uint32_t logP, uint32_t world, uint32_t me, Emit& emit) {
+    if (!(c & 0xffu)) return;
+    const uint64_t lo = rev2(k.w0), hi = rev2(k.w1);
+    uint32_t min_wo_first = 0xffffffffu, min_wo_last = 0xffffffffu;
+    for (int t = 0; t < MINI_W; ++t) {
+        const uint32_t h = mmer_hash_of(mmer_of_words(lo, hi, t));
+        if (t > 0 && h < min_wo_first) min_wo_first = h;
+        if (t < MINI_W - 1 && h < min_wo_last) min_wo_last = h;
+    }
     for (uint32_t b = 0; b < 8; ++b) {
         if (!(c & (1u << b))) continue;
-        const Kmer n = b < 4 ? kmer_succ(k, b) : kmer_pred(k, b - 4);
+        const bool succ = b < 4;
+        const Kmer n = succ ? kmer_succ(k, b) : kmer_pred(k, b - 4);
+        const uint32_t hn = mmer_hash_of(mmer_of_words(rev2(n.w0), rev2(n.w1), succ ? MINI_W - 1 : 0));
+        const uint32_t rest = succ ? min_wo_first : min_wo_last;
+        const uint32_t o = owner_of_partition(mini_part(mini_mix(hn < rest ? hn : rest), logP), logP, world);
+        if (o == me) continue;
         const Kmer r = kmer_rc(n);
-        const Kmer cn = kmer_less(r, n) ? r : n;
-        const uint32_t o = kmer_owner(cn, logP, world);
-        if (o != me) emit(o, cn);
+        emit(o, kmer_less(r, n) ? r : n);
     }
 }
 
