@@ -375,14 +375,16 @@ def main():
     b_path = 6 * n_reads + 4 * npe
     alg_bytes_total = 2 * b_in + 34 * I + 48 * S + EB // 2 + b_path                 # SURVEY.md §8(d), per rank
     # per-kernel CUDA-event times (w2rap_timings.kernel_ms) with the SURVEY §8(d) bytes each kernel owns.  The model charges 34 B per
-    # k-mer instance for "written once and read once": the map's store launch owns the write half, the reduce the read half
-    # (the product moves ~2 B per instance: super-k-mer records; the fraction is quoted against the model's bytes all the same).
+    # k-mer instance for "written once and read once": the map owns the write half, the reduce the read half (the product moves
+    # ~2.5 B per instance instead: super-k-mer records; the fractions of these two are quoted against the model's bytes all the
+    # same).  k_scatter_records is charged what it really moves: 32 + 4 B read and 32 B written per record.
     km = {T.KERNEL_NAMES[i]: median([t["kernel_ms"][i] for t in tt]) for i in range(len(T.KERNEL_NAMES))}
     S_rank = S // world
-    alg = {"k_good_len": qbytes + 12 * n_reads, "k_minimizer_map<count>": b_bases + 14 * n_reads, "k_minimizer_map<store>": b_bases + 14 * n_reads + 17 * I,
+    nrec = int(tt[-1]["n_records"])
+    alg = {"k_good_len": qbytes + 12 * n_reads, "k_minimizer_map": b_bases + 14 * n_reads + 17 * I, "k_scatter_records": 72 * nrec,
            "k_count_smem": 17 * I, "k_insert_solid": 48 * S_rank // 2, "k_adjacency": 48 * S_rank // 2, "k_links": 24 * S_rank, "k_splitter_walk": 24 * S_rank, "k_splitter_finish": 24 * S_rank,
            "k_emit_edges": EB // 2 // world + 24 * S_rank, "k_bloom_build": 24 * S, "k_path_reads": b_in + b_path}
-    launches = {"k_minimizer_map<store>": max(1, tt[-1]["count_launches"]), "k_minimizer_map<count>": max(1, tt[-1]["count_launches"]), "k_good_len": max(1, tt[-1]["count_launches"])}
+    launches = {"k_minimizer_map": max(1, tt[-1]["count_launches"]), "k_scatter_records": max(1, tt[-1]["count_launches"]), "k_good_len": max(1, tt[-1]["count_launches"])}
     dom = max(km, key=lambda k: km[k])
     peak, peak_src = peaks()
     traffic = load_ncu_traffic()

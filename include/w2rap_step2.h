@@ -103,7 +103,7 @@ typedef struct w2rap_kmer_rec {
 
 /* indices into w2rap_timings.kernel_ms */
 enum {
-    W2RAP_KT_GOOD_LEN = 0, W2RAP_KT_MAP_COUNT = 1, W2RAP_KT_MAP_STORE = 2, W2RAP_KT_REDUCE = 3, W2RAP_KT_INSERT_SOLID = 4,
+    W2RAP_KT_GOOD_LEN = 0, W2RAP_KT_MAP = 1, W2RAP_KT_SCATTER = 2, W2RAP_KT_REDUCE = 3, W2RAP_KT_INSERT_SOLID = 4,
     W2RAP_KT_ADJACENCY = 5, W2RAP_KT_LINKS = 6, W2RAP_KT_SPLITTER_WALK = 7, W2RAP_KT_SPLITTER_FINISH = 8, W2RAP_KT_EMIT_EDGES = 9,
     W2RAP_KT_BLOOM_BUILD = 10, W2RAP_KT_PATH_READS = 11, W2RAP_KT_COUNT
 };
@@ -111,19 +111,20 @@ enum {
 /* Stage timings, device milliseconds from CUDA events on the stream the kernels run on. */
 typedef struct w2rap_timings {
     float h2d_ms, count_ms, solid_ms, adjacency_ms, unipath_ms, hbv_ms, path_ms, d2h_ms, total_ms;
-    float count_kernel_ms;        /* the map: k_minimizer_map counting launch + scan + store launch, all read batches */
+    float count_kernel_ms;        /* the map: k_minimizer_map + scan + k_scatter_records, all read batches */
     float region_ms;              /* the reduce: k_count_smem + all k_count_region / k_scan_region launches */
     float exchange_ms;            /* multi-GPU only: NCCL all-to-all of k-mer records + all-gather of the solid records */
     float host_pre_ms;            /* host wall time from entry to the first pipeline launch (validation, allocation, copy enqueue) */
     float host_post_ms;           /* host wall time after the pipeline finished (buffer release, stream teardown) */
     float wall_ms;                /* host wall time of the whole call */
-    uint32_t count_launches;      /* store launches of the map kernel */
+    uint32_t count_launches;      /* launches of the map kernel (one per read batch and counting pass) */
     uint32_t kernel_launches;     /* all kernels launched by this call */
     uint32_t count_passes;        /* reduce launches: k_count_smem launches + partition groups that went through the counting region */
     uint32_t reserved;
     float dict_ms;                /* dictionary build (k_insert_solid; sharded: + gather of the records it is built from) */
     float graph_exchange_ms;      /* multi-GPU only: the exchanges of the sharded graph stage (neighbour queries, chain ends, edges) */
     uint64_t exchange_bytes;      /* multi-GPU only: bytes this rank sent over NVLink in the whole step */
+    uint64_t n_records;           /* super-k-mer records this rank's map produced (32 bytes each) */
     /* CUDA-event time of individual kernels (all launches of the kernel in this call), index = W2RAP_KT_*; 0 where not run */
     float kernel_ms[16];
 } w2rap_timings;

@@ -5,7 +5,8 @@
 //   map     k_minimizer_map     : a warp per read computes the MINIMISER partition of every k-mer; runs of consecutive k-mers in
 //                                 the same partition leave as one 32-byte SUPER-K-MER record (extract.cuh: SkmRec, <= 32 k-mers:
 //                                 their shared bases + the two context bases) — ~2 bytes per k-mer instance instead of 16.
-//                                 A counting launch sizes every partition exactly, a scan lays them out, a second launch stores.
+//                                 Records are built once, into a staging area, while partitions are counted; a scan lays the
+//                                 partitions out exactly and a copy kernel (k_scatter_records) moves every record home.
 //   reduce  k_count_smem        : one CTA counts one partition (~20 k k-mer instances, a few thousand distinct k-mers) in a
 //                                 shared-memory hash table.  The partition's records are staged into shared memory by bulk
 //                                 asynchronous copies (cp.async.bulk + mbarrier, double buffered; SASS: UBLKCP/SYNCS), and the
@@ -26,23 +27,23 @@ namespace w2r {
 // Window minima: the hashes of all m-mers of a tile live in registers (8 per lane), five doubling steps of shuffles give the
 // min over 32 consecutive hashes, the 46-wide window is two overlapping 32-wide ones.  The segments of a tile are listed in
 // shared memory and then built one per lane (4 aligned 8-byte loads, 3 funnel shifts, two 16-byte stores).
-// Two launches: COUNT_ONLY sizes every partition exactly (records and k-mers per partition), an exclusive scan turns the
-// record counts into partition bases, and the second launch stores.  Exact sizes mean no capacity guess can overflow,
-// whatever the multiplicity skew of the read set (a repeat with 10^4 copies just makes its partitions long).
 constexpr uint32_t MINI_TILE = 192;                       // k-mers per tile (a 250-base read is one tile)
 constexpr uint32_t MINI_NU = 8;                           // hashes per lane: positions 32u + lane, u < 8, cover the 192 + 45 m-mers of a tile
+constexpr uint32_t MAP_CHUNK = 512;                       // records a warp reserves at a time in the staging area (>= MINI_TILE)
 struct MiniParams {
     uint32_t logP, npass, pass;
-    uint32_t* count;                 // COUNT_ONLY: records per partition
-    uint32_t* kcount;                // COUNT_ONLY: k-mer instances per partition
-    const uint64_t* base;            // store: first record of every partition, relative to *batch_off
-    uint32_t* cursor;                // store: records appended so far
-    SkmRec* recs;
-    const unsigned long long* batch_off;   // store: where this read batch's records start (device scalar: no host round trip)
-    uint64_t recs_cap;               // records the buffer holds (sized from an estimate; the exact need is known after the counting launch)
+    uint32_t* count;                 // records per partition (this read batch)
+    uint32_t* kcount;                // k-mer instances per partition
+    SkmRec* tmp;                     // staging area: records in the order the warps produce them ...
+    uint32_t* tpart;                 // ... with the partition of each (NIL: unused slot)
+    unsigned long long* tmp_cursor;  // slots handed out so far (in chunks of MAP_CHUNK per warp)
+    uint64_t tmp_cap;
     int* overflow;
 };
-template <bool COUNT_ONLY>
+// Launch 1 (the expensive one: minimisers): builds every record ONCE, into a staging area in production order, and counts records
+// and k-mers per partition.  After an exclusive scan of the counts, launch 2 (k_scatter_records: a copy kernel) moves every record
+// to its partition.  Exact sizes mean no capacity guess per partition can overflow, whatever the multiplicity skew of the read set
+// (a repeat with 10^4 copies just makes its partitions long).
 __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t first, uint64_t count, const uint16_t* __restrict__ good, MiniParams mp) {
     __shared__ uint32_t wbuf[8][MINI_TILE];
     __shared__ uint32_t sbuf[8][MINI_TILE];               // segment list of the tile: start | n << 16
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t 
     const uint32_t lane = threadIdx.x & 31u;
     const unsigned upto = (2u << lane) - 1u;                  // lanes 0..lane
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5, end = first + count;
-    const unsigned long long boff = COUNT_ONLY ? 0ull : *mp.batch_off;
+    unsigned long long chunk_pos = 0;                         // this warp's current chunk of the staging area (warp-uniform)
+    uint32_t chunk_left = 0;
     for (uint64_t i = first + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < end; i += nwarps) {
         const uint32_t gl = good[i];
         if (gl <= (uint32_t)K) continue;
@@ -110,20 +112,51 @@ __global__ void __launch_bounds__(256, 6) k_minimizer_map(ReadsView r, uint64_t 
                 nseg += (uint32_t)__popc(heads);
             }
             __syncwarp();
+            if (nseg > chunk_left) {                                      // a new chunk of the staging area (the rest of the old one stays NIL)
+                if (lane == 0) chunk_pos = atomicAdd(mp.tmp_cursor, (unsigned long long)MAP_CHUNK);
+                chunk_pos = __shfl_sync(0xffffffffu, chunk_pos, 0);
+                chunk_left = MAP_CHUNK;
+            }
             for (uint32_t s = lane; s < nseg; s += 32) {                  // one record per lane
                 const uint32_t e = sl[s], jj = e & 0xffffu, n = e >> 16, b = wb[jj];
-                if (COUNT_ONLY) { atomicAdd(mp.count + b, 1u); atomicAdd(mp.kcount + b, n); continue; }
-                const unsigned long long pos = boff + mp.base[b] + atomicAdd(mp.cursor + b, 1u);
-                const SkmRec rec = skm_build(bases, j0 + jj, n, last);
-                if (pos < mp.recs_cap) {
-                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(mp.recs + pos);
+                atomicAdd(mp.count + b, 1u); atomicAdd(mp.kcount + b, n);
+                const unsigned long long pos = chunk_pos + s;
+                if (pos < mp.tmp_cap) {
+                    const SkmRec rec = skm_build(bases, j0 + jj, n, last);
+                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(mp.tmp + pos);
                     dst[0] = make_ulonglong2(rec.q[0], rec.q[1]);
                     dst[1] = make_ulonglong2(rec.q[2], rec.q[3]);
+                    mp.tpart[pos] = b;
                 } else atomicExch(mp.overflow, 1);
             }
+            chunk_pos += nseg; chunk_left -= nseg;
         }
     }
 }
+// Launch 2: staging slots [range[0], range[1]) -> recs[*batch_off + base[partition] + arrival order]
+struct ScatterParams {
+    const SkmRec* tmp; const uint32_t* tpart;
+    const unsigned long long* range;        // device: first and one-past-last staging slot of this read batch
+    const uint64_t* base;                   // first record of every partition, relative to *batch_off
+    uint32_t* cursor;                       // records appended so far
+    SkmRec* recs;
+    const unsigned long long* batch_off;    // where this read batch's records start
+    uint64_t recs_cap, tmp_cap;
+    int* overflow;
+};
+__global__ void __launch_bounds__(256) k_scatter_records(ScatterParams sp) {
+    const unsigned long long t0 = sp.range[0], t1 = sp.range[1] < sp.tmp_cap ? sp.range[1] : sp.tmp_cap, boff = *sp.batch_off;
+    for (unsigned long long i = t0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < t1; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t b = __ldcs(sp.tpart + i);
+        if (b == NIL) continue;
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(sp.tmp + i);
+        const ulonglong2 lo = __ldcs(src), hi = __ldcs(src + 1);
+        const unsigned long long pos = boff + sp.base[b] + atomicAdd(sp.cursor + b, 1u);
+        if (pos < sp.recs_cap) { ulonglong2* dst = reinterpret_cast<ulonglong2*>(sp.recs + pos); dst[0] = lo; dst[1] = hi; }
+        else atomicExch(sp.overflow, 1);
+    }
+}
+__global__ void k_copy_scalar(const unsigned long long* src, unsigned long long* dst) { *dst = *src; }
 
 // batch_off[1] = batch_off[0] + total[0]: chains the record areas of consecutive read batches on the device
 __global__ void k_next_batch_off(unsigned long long* batch_off, const uint64_t* total) { batch_off[1] = batch_off[0] + *total; }

@@ -259,6 +259,8 @@ struct Pipeline {
     // device state of one counting attempt
     struct CountBufs {
         SBuf<SkmRec> recs, xrecs;                      // local record area; sharded: the records this rank owns after the exchange
+        SBuf<SkmRec> tmp; SBuf<uint32_t> tpart;        // staging area of the map: records in production order + the partition of each
+        SBuf<unsigned long long> tmp_cursor, tmp_range;   // slots handed out; [nmap + 1] staging range of every read batch
         SBuf<uint32_t> part_count, part_kcount, cursor;   // [nmap][P]
         SBuf<uint64_t> part_base, batch_total, batch_ktotal;
         SBuf<unsigned long long> batch_off;            // [nmap + 1]
@@ -276,7 +278,7 @@ struct Pipeline {
     bool good_done = false;
     float map_ms = 0, reduce_ms = 0, xchg_ms = 0;
     uint32_t n_groups = 0;
-    uint64_t xchg_bytes = 0;
+    uint64_t xchg_bytes = 0, n_records = 0;
 
     void run_good_len(const Batch& bt) {
         if (bt.ready) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
@@ -299,26 +301,32 @@ struct Pipeline {
         }
         std::vector<cudaEvent_t> ev(2 * pl.nmap, nullptr);                 // the map launches are timed without stalling the queue
         struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); } } evg{ev};
+        W2R_CUDA(cudaMemsetAsync(cb.tmp_cursor.p, 0, 8, c.stream));
+        W2R_CUDA(cudaMemsetAsync(cb.tpart.p, 0xff, cb.tpart.bytes(), c.stream));      // NIL: unused staging slot
         for (uint32_t bi = 0; bi < pl.nmap; ++bi) {
             const Batch& bt = mb[bi];
-            MiniParams mp{pl.logP, pl.npass, pass, cb.part_count.p + bi * P, cb.part_kcount.p + bi * P, cb.part_base.p + bi * P, cb.cursor.p + bi * P, cb.recs.p,
-                          cb.batch_off.p + bi, cb.recs.n, cs_flags.p + 1};
+            MiniParams mp{pl.logP, pl.npass, pass, cb.part_count.p + bi * P, cb.part_kcount.p + bi * P, cb.tmp.p, cb.tpart.p, cb.tmp_cursor.p, cb.tmp.n, cs_flags.p + 1};
+            ScatterParams sp{cb.tmp.p, cb.tpart.p, cb.tmp_range.p + bi, cb.part_base.p + bi * P, cb.cursor.p + bi * P, cb.recs.p, cb.batch_off.p + bi, cb.recs.n, cb.tmp.n, cs_flags.p + 1};
             if (!good_done) run_good_len(bt);
             W2R_CUDA(cudaEventCreate(&ev[2 * bi])); W2R_CUDA(cudaEventCreate(&ev[2 * bi + 1]));
             W2R_CUDA(cudaEventRecord(ev[2 * bi], c.stream));
-            if (bt.count && pl.n_inst_local) W2R_TIMED(W2RAP_KT_MAP_COUNT, W2R_LAUNCH(c, k_minimizer_map<true>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp));
+            W2R_LAUNCH(c, k_copy_scalar, 1, 1, 0, (const unsigned long long*)cb.tmp_cursor.p, cb.tmp_range.p + bi);
+            if (bt.count && pl.n_inst_local) W2R_TIMED(W2RAP_KT_MAP, W2R_LAUNCH(c, k_minimizer_map, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp));
+            W2R_LAUNCH(c, k_copy_scalar, 1, 1, 0, (const unsigned long long*)cb.tmp_cursor.p, cb.tmp_range.p + bi + 1);
             exclusive_scan<uint32_t, uint64_t>(c, cb.part_count.p + bi * P, P, cb.part_base.p + bi * P, cb.batch_total.p + bi);
             W2R_LAUNCH(c, k_next_batch_off, 1, 1, 0, cb.batch_off.p + bi, cb.batch_total.p + bi);
-            if (bt.count && pl.n_inst_local) { W2R_TIMED(W2RAP_KT_MAP_STORE, W2R_LAUNCH(c, k_minimizer_map<false>, grid(bt.count * 32, 256, map_ctas), 256, 0, rv, bt.first, bt.count, good.p, mp)); c.count_launches++; }
+            if (bt.count && pl.n_inst_local) { W2R_TIMED(W2RAP_KT_SCATTER, W2R_LAUNCH(c, k_scatter_records, (unsigned)(c.sm_count * 8), 256, 0, sp)); c.count_launches++; }
             W2R_CUDA(cudaEventRecord(ev[2 * bi + 1], c.stream));
         }
         good_done = true;
-        unsigned long long total = 0;
+        unsigned long long total = 0, staged = 0;
         W2R_CUDA(cudaMemcpyAsync(&total, cb.batch_off.p + pl.nmap, 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaMemcpyAsync(&staged, cb.tmp_cursor.p, 8, cudaMemcpyDeviceToHost, c.stream));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         for (uint32_t bi = 0; bi < pl.nmap; ++bi) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * bi], ev[2 * bi + 1]); map_ms += ms; }
         if (d2h_scalar(c, cs_flags.p)) W2R_FAIL(W2RAP_ERR_BAD_ARG, "a read's quality vector does not have one quality per base");
-        *need = total;
+        n_records += total;
+        *need = std::max(total, staged);       // (the staging area also holds the unused ends of the warps' chunks)
         std::vector<unsigned long long> of = {(unsigned long long)d2h_scalar(c, cs_flags.p + 1)};
         allreduce_u64(of, ncclMax);               // every rank must take the same branch
         if (of[0]) { W2R_CUDA(cudaMemsetAsync(cs_flags.p + 1, 0, sizeof(int), c.stream)); return false; }
@@ -538,7 +546,7 @@ struct Pipeline {
             // with several passes the k-mer space is split by minimiser hash: allow for uneven passes
             const size_t local_recs = std::max<uint64_t>(need_exact + need_exact / 64, (uint64_t)((double)pl.n_inst_local * rec_per_inst / pl.npass * (pl.npass > 1 ? 1.25 : 1.0))) + 1024;
             const size_t solid_est = (size_t)((double)pl.n_inst / world / pl.npass / std::max<uint32_t>(1, prm.min_freq) * 1.3) * sizeof(ulonglong2);
-            const size_t rec_bytes = (local_recs + (world > 1 ? (size_t)((double)pl.n_inst * rec_per_inst / world / pl.npass * 1.25) : 0)) * sizeof(SkmRec);
+            const size_t rec_bytes = (local_recs * 2 + local_recs / 8 + (world > 1 ? (size_t)((double)pl.n_inst * rec_per_inst / world / pl.npass * 1.25) : 0)) * (sizeof(SkmRec) + 4);
             std::vector<unsigned long long> too_big = {(rec_bytes + solid_est + cs_dump.bytes() + (64u << 20) > budget) ? 1ull : 0ull};
             allreduce_u64(too_big, ncclMax);                     // every rank must run the same number of passes
             if (too_big[0] && !prm.force_passes) {
@@ -547,6 +555,11 @@ struct Pipeline {
             }
             CountBufs cb;
             cb.recs.alloc(c, local_recs);
+            {   // staging: the same records plus the unused ends of the chunks the warps reserve
+                const size_t stage_recs = local_recs + local_recs / 8 + (size_t)c.sm_count * 6 * 8 * MAP_CHUNK;
+                cb.tmp.alloc(c, stage_recs); cb.tpart.alloc(c, stage_recs);
+                cb.tmp_cursor.alloc(c, 1); cb.tmp_range.alloc(c, pl.nmap + 1);
+            }
             cb.part_count.alloc(c, pl.nmap * P); cb.part_kcount.alloc(c, pl.nmap * P); cb.cursor.alloc(c, pl.nmap * P);
             cb.part_base.alloc(c, pl.nmap * P); cb.batch_total.alloc(c, pl.nmap); cb.batch_ktotal.alloc(c, pl.nmap);
             cb.batch_off.alloc(c, pl.nmap + 1);
@@ -1208,6 +1221,7 @@ struct Pipeline {
         out->timings.total_ms = total.stop();
         kt_.resolve(out->timings.kernel_ms);
         out->timings.exchange_bytes = xchg_bytes;
+        out->timings.n_records = n_records;
         out->timings.kernel_launches = c.launches;
         out->timings.count_launches = c.count_launches;
         say(c, "%llu edges of total length %llu; %llu vertices", (unsigned long long)E, (unsigned long long)neb, (unsigned long long)nv);
