@@ -105,7 +105,13 @@ typedef struct w2rap_kmer_rec {
 enum {
     W2RAP_KT_GOOD_LEN = 0, W2RAP_KT_MAP = 1, W2RAP_KT_SCATTER = 2, W2RAP_KT_REDUCE = 3, W2RAP_KT_INSERT_SOLID = 4,
     W2RAP_KT_ADJACENCY = 5, W2RAP_KT_LINKS = 6, W2RAP_KT_SPLITTER_WALK = 7, W2RAP_KT_SPLITTER_FINISH = 8, W2RAP_KT_EMIT_EDGES = 9,
-    W2RAP_KT_BLOOM_BUILD = 10, W2RAP_KT_PATH_READS = 11, W2RAP_KT_COUNT
+    W2RAP_KT_BLOOM_BUILD = 10, W2RAP_KT_PATH_READS = 11,
+    /* sharded graph stage, phases (kernels + the exchanges between them) */
+    W2RAP_KT_SG_QUERIES = 12,   /* neighbour queries, answers, ghost entries, ghost contexts (without k_adjacency) */
+    W2RAP_KT_SG_PIECES = 13,    /* chain-end records: emit, all-gather, link, rank */
+    W2RAP_KT_SG_EDGES = 14,     /* strands, edge ids, all-reduce of the edge bases (without k_emit_edges) */
+    W2RAP_KT_SG_DICT = 15,      /* finished entries gathered into the pathing dictionary (without k_insert_solid) */
+    W2RAP_KT_COUNT
 };
 
 /* Stage timings, device milliseconds from CUDA events on the stream the kernels run on. */

@@ -564,12 +564,13 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         const uint32_t kf = chain_keep_even(pv, (uint32_t)i, hp, n);
         if (kf != 2u) keepp[hp] = (uint8_t)kf;
     }
-    for (Rank& me : rk)
-        for (uint64_t x = 0; x < me.next0.size(); ++x) {
-            if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL) continue;
-            const NodePos pos = node_position(pv, me.R.data(), me.lpiece.data(), me.piece0, (uint32_t)x);
-            const int kf = node_keep_odd(me.st, pos, (uint32_t)x);
-            if (kf >= 0) keepp[pos.head_piece] = (uint8_t)kf;
+    std::vector<PieceInfo> pinfo(np);                                          // k_piece_info (replicated)
+    for (uint64_t i = 0; i < np; ++i) pinfo[i] = piece_info(pv, (uint32_t)i);
+    for (uint32_t r = 0; r < world; ++r)                                       // k_piece_keep_odd: every rank over its own pieces
+        for (size_t j = 0; j < rk[r].pieces.size(); ++j) {
+            const uint32_t gi = rk[r].piece0 + (uint32_t)j;
+            const int kf = piece_keep_odd(rk[r].st, rk[r].next0.data(), pinfo[gi], (uint32_t)P[gi].head);
+            if (kf >= 0) keepp[pinfo[gi].head_piece] = (uint8_t)kf;
         }
     // ---- edges: kept heads sorted by k-mer (replicated), emission by the owners, all-reduce of the bases
     struct Head { Kmer k; uint32_t piece; };
@@ -584,12 +585,11 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
     for (uint64_t i = 0; i < E; ++i) { edge_of_piece[heads[i].piece] = (uint32_t)i; es.edge_len[i] = (uint32_t)chain_n[heads[i].piece] + K - 1; es.edge_off[i + 1] = es.edge_off[i] + (es.edge_len[i] + 3) / 4; }
     es.edge_bases.assign(es.edge_off[E] + 32, 0);
     PutBase put{es.edge_bases.data()};
+    for (uint64_t i = 0; i < np; ++i) pinfo[i].head_piece = edge_of_piece[pinfo[i].head_piece];       // k_piece_edges
     for (Rank& me : rk)
         for (uint64_t x = 0; x < me.next0.size(); ++x) {
             if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL) continue;
-            const NodePos pos = node_position(pv, me.R.data(), me.lpiece.data(), me.piece0, (uint32_t)x);
-            const uint32_t e = edge_of_piece[pos.head_piece];
-            if (e != NIL) emit_node_sharded(me.st, pos, e, es.edge_off.data(), (uint32_t)x, put);
+            emit_node_sharded(me.st, me.R.data(), me.lpiece.data(), pinfo.data() + me.piece0, es.edge_off.data(), (uint32_t)x, put);
         }
     // ---- all-gather of the owned entries (with pruned context, edge, offset): the whole dictionary for pathing
     std::vector<SolidSlot> full(table_slots_for(n_solid));

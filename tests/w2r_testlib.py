@@ -42,7 +42,8 @@ class Timings(C.Structure):
 
 
 KERNEL_NAMES = ["k_good_len", "k_minimizer_map", "k_scatter_records", "k_count_smem", "k_insert_solid", "k_adjacency", "k_links",
-                "k_splitter_walk", "k_splitter_finish", "k_emit_edges", "k_bloom_build", "k_path_reads"]
+                "k_splitter_walk", "k_splitter_finish", "k_emit_edges", "k_bloom_build", "k_path_reads",
+                "sharded:queries+ghosts", "sharded:pieces", "sharded:strands+edges", "sharded:gather dictionary"]
 
 
 class KmerRec(C.Structure):

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) k_count_region(const SkmRec* __restrict__
 // shared-memory table, so the per-instance atomics are shared-memory atomics instead of L2 atomics (the L2-resident region count
 // is limited by L2 atomic throughput, about one k-mer per 30 ps chip-wide).  Partitions whose distinct k-mers do not fit are listed
 // in `failed`: they are retried with a larger table and, failing that, go through the region path.
-constexpr uint32_t SMEM_LOG_SLOTS_MAX = 13;                    // 8192 slots: 64 KB w0 + 64 KB w1 + 32 KB count|ctx = 160 KB
+constexpr uint32_t SMEM_LOG_SLOTS_MAX = 13;                    // 8192 slots: 128 KB keys + 32 KB count|ctx = 160 KB
 constexpr uint32_t SMEM_MAX_PROBE = 512;
 constexpr uint32_t COUNT_STOP = 1u << 16;                      // counters stop here (>= 255 is all anyone asks); + one add per racing thread
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // runs (read batches / source ranks) that make up one partition
@@ -283,18 +283,38 @@ __device__ __forceinline__ uint32_t smem_slot_hash(Kmer k) {
     return x;
 }
 
+// 128-bit compare-and-swap on a 16-byte aligned shared-memory slot (ATOMS.CAS.128 on sm_100a): a 120-bit k-mer is claimed whole
+__device__ __forceinline__ U128 cas128_shared(void* addr, uint64_t cmp_lo, uint64_t cmp_hi, uint64_t val_lo, uint64_t val_hi) {
+    U128 old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.shared.relaxed.cta.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.lo), "=l"(old.hi)
+        : "l"(cmp_lo), "l"(cmp_hi), "l"(val_lo), "l"(val_hi), "r"(smem_addr(addr))
+        : "memory");
+    return old;
+}
+__device__ __forceinline__ ulonglong2 lds128_volatile(const void* addr) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(smem_addr(addr)) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t SMEM_SLOTS = 1u << sp.log_slots;
-    unsigned long long* w0s = reinterpret_cast<unsigned long long*>(smem_raw);
-    unsigned long long* w1s = w0s + SMEM_SLOTS;
-    uint32_t* ccs = reinterpret_cast<uint32_t*>(w1s + SMEM_SLOTS);          // count (low 24 bits) | ctx << 24
+    ulonglong2* keys = reinterpret_cast<ulonglong2*>(smem_raw);             // {w0, w1}; empty = all ones (a canonical 60-mer never starts with 32 T's)
+    uint32_t* ccs = reinterpret_cast<uint32_t*>(keys + SMEM_SLOTS);         // count (low 24 bits) | ctx << 24
     SkmRec* stage = reinterpret_cast<SkmRec*>(smem_raw + (size_t)20 * SMEM_SLOTS);   // [2][SKM_CHUNK]
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ unsigned int sh_hist[104];
     __shared__ int sh_fail;
     __shared__ uint32_t sh_tot[2], sh_cnt[2];                   // per staging buffer: records of the whole partition / of the staged chunk
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const unsigned le_mask = (2u << lane) - 1u;                 // lanes 0..lane
     for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
     if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
@@ -323,30 +343,23 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     for (uint32_t pi = blockIdx.x; pi < n_todo; pi += gridDim.x) {
         const uint32_t p = sp.plist ? sp.plist[pi] : pi;
         {   // empty table (16-byte stores)
-            ulonglong2* kw = reinterpret_cast<ulonglong2*>(smem_raw);
             const ulonglong2 ff = make_ulonglong2(~0ull, ~0ull);
-            for (uint32_t j = threadIdx.x; j < SMEM_SLOTS; j += blockDim.x) kw[j] = ff;          // w0s and w1s: 2 * SMEM_SLOTS u64
+            for (uint32_t j = threadIdx.x; j < SMEM_SLOTS; j += blockDim.x) keys[j] = ff;
             uint4* cw = reinterpret_cast<uint4*>(ccs);
             for (uint32_t j = threadIdx.x; j < SMEM_SLOTS / 4; j += blockDim.x) cw[j] = make_uint4(0, 0, 0, 0);
         }
         if (threadIdx.x == 0) sh_fail = 0;
         __syncthreads();
         auto insert = [&](const Kmer k, const uint32_t ctx) {
-            const unsigned long long kw0 = k.w0, kw1 = k.w1;
             uint32_t s = smem_slot_hash(k) >> (32 - sp.log_slots);
             bool done = false;
             for (uint32_t probe = 0; probe < SMEM_MAX_PROBE && !done; ++probe) {
-                unsigned long long k0 = *(volatile unsigned long long*)(w0s + s);
-                bool mine = false;
-                if (k0 == ~0ull) {
-                    const unsigned long long old = atomicCAS(w0s + s, ~0ull, kw0);
-                    if (old == ~0ull) { *(volatile unsigned long long*)(w1s + s) = kw1; __threadfence_block(); mine = true; }
-                    else k0 = old;
-                }
-                if (!mine && k0 == kw0) {                     // same first 32 bases: the owner publishes the second word right after its CAS
-                    unsigned long long w = *(volatile unsigned long long*)(w1s + s);
-                    while (w == ~0ull) w = *(volatile unsigned long long*)(w1s + s);
-                    mine = (w == kw1);
+                ulonglong2 cur = lds128_volatile(keys + s);
+                while (cur.x != ~0ull && cur.y == ~0ull) cur = lds128_volatile(keys + s);      // (a slot caught half-written: no key has an all-ones second word)
+                bool mine = cur.x == k.w0 && cur.y == k.w1;
+                if (!mine && cur.x == ~0ull) {
+                    const U128 old = cas128_shared(keys + s, ~0ull, ~0ull, k.w0, k.w1);
+                    mine = (old.lo == ~0ull && old.hi == ~0ull) || (old.lo == k.w0 && old.hi == k.w1);
                 }
                 if (mine) {
                     // counts saturate at 255 downstream; the 24-bit field must not run into the context bits however many
@@ -368,24 +381,28 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
             if (threadIdx.x == 0) { if (more) issue(pi, c + 1, bf ^ 1u); else if (pi + gridDim.x < n_todo) issue(pi + gridDim.x, 0, bf ^ 1u); }
             const SkmRec* st = stage + (size_t)bf * SKM_CHUNK;
             // groups of 32 records, dealt to the warps; inside a group the k-mers are numbered consecutively across the records and
-            // lane l takes k-mer t + l (binary search over the running sums held one per lane)
+            // lane l takes k-mer t + l.  Which record that is: the records that START inside the 32-k-mer window are ORed into a
+            // bit mask (one REDUX), a population count of the mask below the lane gives the record.
             for (uint32_t g0 = warp * 32u; g0 < cnt; g0 += nwarp * 32u) {
-                const uint32_t nr = g0 + lane < cnt ? skm_n(st[g0 + lane].q[3]) : 0u;
+                const uint64_t hdr = g0 + lane < cnt ? st[g0 + lane].q[3] : 0ull;
+                const uint32_t nr = g0 + lane < cnt ? skm_n(hdr) : 0u;
                 uint32_t incl = nr;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - nr;
+                uint32_t before_window = 0;                      // records that start before the window
                 for (uint32_t t = 0; t < total; t += 32) {
-                    const uint32_t g = t + lane;
-                    uint32_t rr = 0;
-#pragma unroll
-                    for (uint32_t step = 16; step; step >>= 1) { const uint32_t v = __shfl_sync(0xffffffffu, incl, rr + step - 1u); if (v <= g) rr += step; }
-                    const uint32_t before = __shfl_sync(0xffffffffu, incl - nr, rr & 31u);
-                    if (g < total) {
+                    const uint32_t rel = excl - t;               // (unsigned: records that start before the window wrap to huge values)
+                    const unsigned starts = __reduce_or_sync(0xffffffffu, (nr && rel < 32u) ? 1u << rel : 0u);
+                    const uint32_t rr = before_window + (uint32_t)__popc(starts & le_mask) - 1u;
+                    const uint32_t r_excl = __shfl_sync(0xffffffffu, excl, rr & 31u);
+                    const uint64_t r_hdr = __shfl_sync(0xffffffffu, hdr, rr & 31u);
+                    if (t + lane < total) {
                         Kmer k; uint32_t ctx;
-                        skm_kmer_at(st[g0 + rr].q, g - before, &k, &ctx);
+                        skm_kmer_at(st[g0 + rr].q, r_hdr, t + lane - r_excl, &k, &ctx);
                         insert(k, ctx);
                     }
+                    before_window += (uint32_t)__popc(starts);
                 }
             }
             __syncthreads();                                     // chunk consumed (and, after the last one, every insert has landed)
@@ -398,20 +415,21 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
             for (uint32_t base = 0; base < SMEM_SLOTS; base += blockDim.x) {
                 const uint32_t j = base + threadIdx.x;
                 const bool in = j < SMEM_SLOTS;
-                const unsigned long long k0 = in ? w0s[j] : ~0ull;
-                const bool occ = k0 != ~0ull;
+                const ulonglong2 kk = in ? keys[j] : make_ulonglong2(~0ull, ~0ull);
+                const bool occ = kk.x != ~0ull;
                 const uint32_t cc = in ? ccs[j] : 0u;
                 uint32_t c = cc & 0xffffffu; if (c > 255u) c = 255u;
                 const uint32_t ctx = cc >> 24;
-                const uint32_t bin = occ ? (c > 100u ? 100u : c) : 103u;
-                const unsigned peers = __match_any_sync(0xffffffffu, bin);
-                if (occ && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sh_hist[bin], (unsigned)__popc(peers));
+                // histogram: the singletons (sequencing errors: most distinct k-mers) are counted per warp, the rest one by one
+                const unsigned ones = __ballot_sync(0xffffffffu, occ && c == 1u);
+                if (lane == 0 && ones) atomicAdd(&sh_hist[1], (unsigned)__popc(ones));
+                if (occ && c != 1u) atomicAdd(&sh_hist[c > 100u ? 100u : c], 1u);
                 const bool solid = occ && c >= sp.min_freq;
                 const uint64_t pos = warp_append(sp.solid_cursor, solid);
-                if (solid) { if (pos < sp.solid_cap) sp.solid_out[pos] = make_ulonglong2(k0, w1s[j] | ctx); else atomicExch(sp.solid_overflow, 1); }
+                if (solid) { if (pos < sp.solid_cap) sp.solid_out[pos] = make_ulonglong2(kk.x, kk.y | ctx); else atomicExch(sp.solid_overflow, 1); }
                 if (sp.dump_out) {
                     const uint64_t dp = warp_append(sp.dump_cursor, occ);
-                    if (occ) sp.dump_out[dp] = DumpRec{k0, w1s[j], c, ctx, NIL, 0};
+                    if (occ) sp.dump_out[dp] = DumpRec{kk.x, kk.y, c, ctx, NIL, 0};
                 }
             }
         }

@@ -76,8 +76,7 @@ W2R_HD SkmRec skm_build(const uint8_t* bases, uint32_t j_first, uint32_t n, uint
 }
 // K-mer j (< n) of a record: canonical form and context byte, exactly what extract_read_kmers emits for that read position.
 // `q` may point to global, shared or host memory.
-W2R_HD void skm_kmer_at(const uint64_t* q, uint32_t j, Kmer* canon, uint32_t* ctx) {
-    const uint64_t hdr = q[3];
+W2R_HD void skm_kmer_at(const uint64_t* q, uint64_t hdr /* = q[3] */, uint32_t j, Kmer* canon, uint32_t* ctx) {
     const uint32_t n = skm_n(hdr), hp = (uint32_t)(hdr >> 61) & 1u, hs = (uint32_t)(hdr >> 62) & 1u;
     const uint32_t b = 2u * (hp + j), wo = b >> 6, sh = b & 63u;                // b <= 66: wo is 0 or 1
     const uint64_t A = q[wo], B = q[wo + 1], C = wo ? 0ull : q[2];              // wo == 1: C only reaches bits that are masked off
@@ -92,6 +91,7 @@ W2R_HD void skm_kmer_at(const uint64_t* q, uint32_t j, Kmer* canon, uint32_t* ct
     *canon = Kmer{rev ? rc.w0 : f.w0, rev ? rc.w1 : f.w1};
     *ctx = rev ? ctx_rc(c) : c;
 }
+W2R_HD void skm_kmer_at(const uint64_t* q, uint32_t j, Kmer* canon, uint32_t* ctx) { skm_kmer_at(q, q[3], j, canon, ctx); }
 
 // ---------------------------------------------------------------- minimisers (partition key of the single-GPU count)
 // The partition of a k-mer is derived from its MINIMISER: the canonical 15-mer with the smallest hash among the 46 inside the

@@ -806,6 +806,7 @@ struct Pipeline {
         SBuf<int> flags(c, 8); flags.zero();
         SBuf<unsigned long long> scal(c, 8); scal.zero();
         // -- round 1: neighbour queries from the solid records
+        kt_.begin(W2RAP_KT_SG_QUERIES);
         uint64_t qcap = std::max<uint64_t>(1024, n_local / 4);
         SBuf<ulonglong2> qkeys;
         SBuf<unsigned long long> qcount(c, W);
@@ -828,6 +829,7 @@ struct Pipeline {
         }
         uint64_t nq_total = 0;
         for (auto v : qn) nq_total += v;
+        kt_.end();
         // -- the local table: owned entries now, ghosts later
         const uint64_t nslots = solid_table_slots(n_local + nq_total);
         if (nslots > (1ull << 31) - 8) W2R_FAIL(W2RAP_ERR_OOM, "too many solid k-mers per GPU for 32-bit oriented node ids; shard over more GPUs");
@@ -837,6 +839,7 @@ struct Pipeline {
         if (n_local) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_local, 256), 256, 0, (const ulonglong2*)solid.p, n_local, st));
         solid.release();
         // -- keys to the owners, slots back
+        kt_.begin(W2RAP_KT_SG_QUERIES);
         xt.start();
         SBuf<unsigned long long> rcount(c, W);
         alltoall_slabs(qcount.p, rcount.p, sizeof(unsigned long long));
@@ -857,8 +860,10 @@ struct Pipeline {
         for (uint32_t d = 0; d < W; ++d)
             if (qn[d]) W2R_LAUNCH(c, k_insert_ghosts, grid(qn[d], 256), 256, 0, st, (const ulonglong2*)qkeys.p + d * qcap, (const uint32_t*)qreply.p + d * qcap, (uint64_t)qn[d], d, gslot.p + d * qcap);
         qkeys.release();
+        kt_.end();
         // -- adjacency pruning of the owned entries (ghosts only answer membership); then the ghosts' pruned contexts
         W2R_TIMED(W2RAP_KT_ADJACENCY, W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st));
+        kt_.begin(W2RAP_KT_SG_QUERIES);
         xt.start();
         SBuf<uint32_t> rctx(c, nr_total + 1), qctx(c, W * qcap);
         if (nr_total) W2R_LAUNCH(c, k_gather_ctx, grid(nr_total, 256), 256, 0, st, (const uint32_t*)rreply.p, nr_total, rctx.p);
@@ -866,6 +871,7 @@ struct Pipeline {
         xms += xt.stop();
         for (uint32_t d = 0; d < W; ++d)
             if (qn[d]) W2R_LAUNCH(c, k_apply_ghost_ctx, grid(qn[d], 256), 256, 0, st, (const uint32_t*)gslot.p + d * qcap, (const uint32_t*)qctx.p + d * qcap, (uint64_t)qn[d]);
+        kt_.end();
         rreply.release(); qreply.release(); gslot.release(); rctx.release(); qctx.release();
         // -- successor links; a node whose predecessor is a ghost heads a local piece
         const uint64_t nn = 2 * st.size();
@@ -878,13 +884,14 @@ struct Pipeline {
         SBuf<PieceRec> pieces;             // all pieces of all ranks
         SBuf<uint32_t> nxt, flip;
         SBuf<RankState> S;
-        uint64_t np = 0;
+        uint64_t np = 0, npl_last = 0;
         uint32_t piece0 = 0;
         uint32_t* lpiece = nullptr;
         for (int iteration = 0;; ++iteration) {
             if (iteration > 1) W2R_FAIL(W2RAP_ERR_INTERNAL, "circles left after cutting them");
             list_ranking(next0, ghead.p, nn, A, B, &cur, &oth);
             // -- round 2: one record per local chain, gathered on every rank
+            kt_.begin(W2RAP_KT_SG_PIECES);
             lpiece = reinterpret_cast<uint32_t*>(oth);          // scratch: local piece index per tail node
             W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
             W2R_LAUNCH(c, k_count_piece_heads, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)ghead.p, nn, scal.p);
@@ -896,7 +903,7 @@ struct Pipeline {
             std::vector<uint64_t> poff;
             allgather_v(lp.p, npl, pieces, poff);
             xms += xt.stop();
-            np = poff[W]; piece0 = (uint32_t)poff[me];
+            np = poff[W]; piece0 = (uint32_t)poff[me]; npl_last = npl;
             if (np >= (1ull << 32) - 8) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^32 chain pieces");
             lp.release();
             uint64_t msz = 64;
@@ -919,6 +926,7 @@ struct Pipeline {
                 if (un == 0 || un == prev) break;
                 prev = un;
             }
+            kt_.end();
             if (un == 0) break;
             // -- circles that span ranks (BuildReadQGraph.cc:126-180): rare and small, resolved on the host.  Label every circle by
             // walking the piece links, gather the circle nodes from all ranks, cut each circle at its minimum canonical k-mer.
@@ -969,12 +977,15 @@ struct Pipeline {
             W2R_CUDA(cudaStreamSynchronize(c.stream));       // heads_g / tails_g leave scope
         }
         // -- strands: even lengths from the piece records (every rank computes them), odd lengths by the owner of the middle k-mer
+        kt_.begin(W2RAP_KT_SG_EDGES);
         PieceView pv{pieces.p, flip.p, S.p, np};
         SBuf<uint8_t> is_head(c, np + 4), keepp(c, np + 4);
         SBuf<uint32_t> chain_n(c, np + 1);
         is_head.zero(); keepp.zero();
         if (np) W2R_LAUNCH(c, k_chain_tails, grid(np, 256), 256, 0, pv, (const uint32_t*)nxt.p, is_head.p, chain_n.p, keepp.p, flags.p + 2);
-        W2R_LAUNCH(c, k_node_keep_odd, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, pv, (const RankState*)cur, (const uint32_t*)lpiece, piece0, keepp.p);
+        SBuf<PieceInfo> pinfo(c, np + 1);
+        if (np) W2R_LAUNCH(c, k_piece_info, grid(np, 256), 256, 0, pv, pinfo.p);
+        if (npl_last) W2R_LAUNCH(c, k_piece_keep_odd, grid(npl_last, 256), 256, 0, st, (const uint32_t*)next0.p, (const PieceRec*)pieces.p, (const PieceInfo*)pinfo.p, piece0, npl_last, keepp.p);
         xt.start();
         if (np) nccl_check(NcclApi::get().AllReduce(keepp.p, keepp.p, np, ncclUint8, ncclMax, comm, c.stream), "all-reduce");
         xms += xt.stop();
@@ -987,12 +998,17 @@ struct Pipeline {
         E = d2h_scalar(c, scal.p);
         SBuf<uint32_t> edge_of_piece(c, np + 1); edge_of_piece.fill_ff();
         edges_from_heads(h_piece, h_n, h_w0, h_w1, edge_of_piece);
-        W2R_TIMED(W2RAP_KT_EMIT_EDGES, W2R_LAUNCH(c, k_emit_edges_sharded, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, pv, (const RankState*)cur, (const uint32_t*)lpiece, piece0,
-                                                   (const uint32_t*)edge_of_piece.p, (const uint64_t*)edge_off.p, edge_bases.p));
+        if (np) W2R_LAUNCH(c, k_piece_edges, grid(np, 256), 256, 0, pinfo.p, np, (const uint32_t*)edge_of_piece.p);
+        kt_.end();
+        W2R_TIMED(W2RAP_KT_EMIT_EDGES, W2R_LAUNCH(c, k_emit_edges_sharded, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, (const RankState*)cur, (const uint32_t*)lpiece,
+                                                   (const PieceInfo*)pinfo.p + piece0, (const uint64_t*)edge_off.p, edge_bases.p));
+        kt_.begin(W2RAP_KT_SG_EDGES);
         xt.start();
         const uint64_t ebw = (edge_bytes + 3) / 4;          // (disjoint bits: a sum of 32-bit words is their OR)
         if (ebw) nccl_check(NcclApi::get().AllReduce(edge_bases.p, edge_bases.p, ebw, ncclUint32, ncclSum, comm, c.stream), "all-reduce");
         xchg_bytes += ebw * 4 + np;
+        kt_.end();
+        kt_.begin(W2RAP_KT_SG_DICT);
         // -- the finished entries (pruned context, edge, offset) of every rank: the dictionary the reads are pathed against
         SBuf<SolidSlot> mine(c, n_local + 1), entries;
         W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
@@ -1007,6 +1023,7 @@ struct Pipeline {
         solid_slots.alloc(c, fslots);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, fslots};
+        kt_.end();
         if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(n_solid, 256), 256, 0, (const SolidSlot*)entries.p, n_solid, st));
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         out->timings.graph_exchange_ms = xms;

@@ -118,38 +118,45 @@ W2R_HD uint32_t chain_keep_even(const PieceView& pv, uint32_t tail_piece, uint32
     return (kmer_less(hk, ok) || (hk == ok && (pv.rec[head_piece].head & 1ull) == 0)) ? 1u : 0u;
 }
 
-// Global position of an owned node: which chain (its first piece), offset from the chain's first k-mer, chain length.
-struct NodePos { uint32_t head_piece; uint64_t off, dist, n; };
-// lpiece[t] = local piece index of the piece whose tail is node t; piece0 = global index of this rank's first piece.
-W2R_HD NodePos node_position(const PieceView& pv, const RankState* R, const uint32_t* lpiece, uint32_t piece0, uint32_t x) {
-    const RankState a = R[x], f = R[x ^ 1u];
-    const uint32_t pa = piece0 + lpiece[a.x], pf = piece0 + lpiece[f.x];
-    NodePos np;
-    np.dist = (uint64_t)(a.y & ~RANK_RESOLVED) + (pv.S[pa].y & ~RANK_RESOLVED);       // k-mers after x in its chain
-    np.off = (uint64_t)(f.y & ~RANK_RESOLVED) + (pv.S[pf].y & ~RANK_RESOLVED);        // k-mers before x
-    np.n = np.dist + np.off + 1;
-    np.head_piece = pv.flip[pv.S[pf].x];
-    return np;
+// Per piece, once the pieces are ranked: where the piece sits in its chain.
+struct PieceInfo {
+    uint32_t head_piece;    // first piece of the chain; later replaced by the chain's edge id (NIL: the strand is not kept)
+    uint32_t off;           // k-mers of the chain before this piece
+    uint32_t after;         // k-mers of the chain after this piece
+    uint32_t n;             // k-mers in this piece
+};
+W2R_HD PieceInfo piece_info(const PieceView& pv, uint32_t i) {
+    const uint32_t fi = pv.flip[i];
+    return PieceInfo{pv.flip[pv.S[fi].x], pv.S[fi].y & ~RANK_RESOLVED, pv.S[i].y & ~RANK_RESOLVED, pv.rec[i].n};
 }
-// Odd-length edges are oriented by their middle base alone (dna/CanonicalForm.h:34-46); the node that holds it says so.
-// Returns -1 if x is not that node, else the keep flag.
-W2R_HD int node_keep_odd(const SolidTable& t, const NodePos& np, uint32_t x) {
-    const uint64_t L = np.n + K - 1;
+// Odd-length edges are oriented by their middle base alone (dna/CanonicalForm.h:34-46).  The piece that holds the middle k-mer
+// walks to it from its head.  Returns -1 if the chain has even length or its middle lies in another piece, else the keep flag.
+W2R_HD int piece_keep_odd(const SolidTable& t, const uint32_t* next0, const PieceInfo& pi, uint32_t head_node) {
+    const uint64_t n = (uint64_t)pi.off + pi.n + pi.after, L = n + K - 1;
     if (!(L & 1ull)) return -1;
-    const uint64_t m = L / 2, ostar = m < np.n - 1 ? m : np.n - 1;
-    if (np.off != ostar) return -1;
-    return (kmer_base(node_kmer(t, x), (int)(m - np.off)) & 2u) ? 0 : 1;
+    const uint64_t m = L / 2, ostar = m < n - 1 ? m : n - 1;
+    if (ostar < pi.off || ostar >= (uint64_t)pi.off + pi.n) return -1;
+    uint32_t x = head_node;
+    for (uint64_t s = pi.off; s < ostar; ++s) x = next0[x];
+    return (kmer_base(node_kmer(t, x), (int)(m - ostar)) & 2u) ? 0 : 1;
 }
-// Edge emission + KDef back-fill for one owned node (BuildReadQGraph.cc:287-301).  put(edge byte offset, base position, base code).
+// Edge emission + KDef back-fill for one owned node (BuildReadQGraph.cc:287-301).  R[x] = (local tail, distance to it);
+// lpiece[tail] = local index of its piece; pinfo[] = this rank's pieces with head_piece already replaced by the edge id.
+// put(edge byte offset, base position, base code).
 template <class Put>
-W2R_HD void emit_node_sharded(const SolidTable& t, const NodePos& np, uint32_t e, const uint64_t* edge_off, uint32_t x, Put& put) {
+W2R_HD void emit_node_sharded(const SolidTable& t, const RankState* R, const uint32_t* lpiece, const PieceInfo* pinfo, const uint64_t* edge_off, uint32_t x, Put& put) {
+    const RankState a = R[x];
+    const PieceInfo pi = pinfo[lpiece[a.x]];
+    if (pi.head_piece == NIL) return;
+    const uint32_t d = a.y & ~RANK_RESOLVED;
+    const uint64_t off = (uint64_t)pi.off + (pi.n - 1u - d);
     SolidSlot* s = t.slots + (x >> 1);
-    s->edge = e; s->off = (uint32_t)np.off;
+    s->edge = pi.head_piece; s->off = (uint32_t)off;
     const Kmer k = node_kmer(t, x);
-    const uint64_t bo = edge_off[e];
-    put(bo, np.off, kmer_first(k));
-    if (np.dist == 0)
-        for (int i = 1; i < K; ++i) put(bo, np.off + i, kmer_base(k, i));
+    const uint64_t bo = edge_off[pi.head_piece];
+    put(bo, off, kmer_first(k));
+    if (d == 0 && pi.after == 0)
+        for (int i = 1; i < K; ++i) put(bo, off + i, kmer_base(k, i));
 }
 
 // 64-bit key -> u32 value open-addressing map (global piece ids -> piece index).  Keys are unique; EMPTY = ~0.

@@ -191,15 +191,20 @@ __global__ void k_chain_tails(PieceView pv, const uint32_t* __restrict__ nxt, ui
         if (kf != 2u) keepp[hp] = (uint8_t)kf;
     }
 }
-__global__ void k_node_keep_odd(SolidTable st, const uint32_t* __restrict__ next0, PieceView pv, const RankState* __restrict__ R, const uint32_t* __restrict__ lpiece, uint32_t piece0,
-                                uint8_t* __restrict__ keepp) {
-    const uint64_t nn = 2 * st.size();
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nn; x += (uint64_t)gridDim.x * blockDim.x) {
-        if (next0[x] == EMPTY_NODE || next0[x] == GHOST_TAIL) continue;
-        const NodePos pos = node_position(pv, R, lpiece, piece0, (uint32_t)x);
-        const int kf = node_keep_odd(st, pos, (uint32_t)x);
-        if (kf >= 0) keepp[pos.head_piece] = (uint8_t)kf;
+__global__ void k_piece_info(PieceView pv, PieceInfo* __restrict__ pinfo) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pv.n; i += (uint64_t)gridDim.x * blockDim.x) pinfo[i] = piece_info(pv, (uint32_t)i);
+}
+// every rank over ITS pieces [piece0, piece0 + npl): the one that holds the middle k-mer of an odd-length chain decides its strand
+__global__ void k_piece_keep_odd(SolidTable st, const uint32_t* __restrict__ next0, const PieceRec* __restrict__ rec, const PieceInfo* __restrict__ pinfo, uint32_t piece0, uint64_t npl,
+                                 uint8_t* __restrict__ keepp) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < npl; j += (uint64_t)gridDim.x * blockDim.x) {
+        const PieceInfo pi = pinfo[piece0 + j];
+        const int kf = piece_keep_odd(st, next0, pi, (uint32_t)rec[piece0 + j].head);
+        if (kf >= 0) keepp[pi.head_piece] = (uint8_t)kf;
     }
+}
+__global__ void k_piece_edges(PieceInfo* __restrict__ pinfo, uint64_t np, const uint32_t* __restrict__ edge_of_piece) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) pinfo[i].head_piece = edge_of_piece[pinfo[i].head_piece];
 }
 __global__ void k_collect_head_pieces(PieceView pv, const uint8_t* __restrict__ is_head, const uint8_t* __restrict__ keepp, const uint32_t* __restrict__ chain_n, uint32_t* __restrict__ h_piece,
                                       uint64_t* __restrict__ h_w0, uint64_t* __restrict__ h_w1, uint32_t* __restrict__ h_n, unsigned long long* cursor, uint64_t cap) {
@@ -210,15 +215,13 @@ __global__ void k_collect_head_pieces(PieceView pv, const uint8_t* __restrict__ 
         if (want && pos < cap) { h_piece[pos] = (uint32_t)i; h_w0[pos] = pv.rec[i].head_k.w0; h_w1[pos] = pv.rec[i].head_k.w1; h_n[pos] = chain_n[i]; }
     }
 }
-__global__ void k_emit_edges_sharded(SolidTable st, const uint32_t* __restrict__ next0, PieceView pv, const RankState* __restrict__ R, const uint32_t* __restrict__ lpiece, uint32_t piece0,
-                                     const uint32_t* __restrict__ edge_of_piece, const uint64_t* __restrict__ edge_off, uint8_t* __restrict__ edge_bases) {
+__global__ void k_emit_edges_sharded(SolidTable st, const uint32_t* __restrict__ next0, const RankState* __restrict__ R, const uint32_t* __restrict__ lpiece,
+                                     const PieceInfo* __restrict__ my_pinfo, const uint64_t* __restrict__ edge_off, uint8_t* __restrict__ edge_bases) {
     const uint64_t nn = 2 * st.size();
     OrBase put{edge_bases};
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nn; x += (uint64_t)gridDim.x * blockDim.x) {
         if (next0[x] == EMPTY_NODE || next0[x] == GHOST_TAIL) continue;
-        const NodePos pos = node_position(pv, R, lpiece, piece0, (uint32_t)x);
-        const uint32_t e = edge_of_piece[pos.head_piece];
-        if (e != NIL) emit_node_sharded(st, pos, e, edge_off, (uint32_t)x, put);
+        emit_node_sharded(st, R, lpiece, my_pinfo, edge_off, (uint32_t)x, put);
     }
 }
 // owned entries (pruned context, edge, offset) out of the local table, for the all-gather that builds the pathing dictionary
