@@ -288,3 +288,34 @@ def test_standalone_step2_binary(T, tmp_path):
     got = T.run_product(T.read_fastb_qualp(d), T.default_params(apply_fixpaths=1))
     rep = T.compare_with_reference(got, T.graph_from_reference_files(d))
     assert rep["edge_set_equal"] and rep["vertices_equal"] and rep["hist_equal"] and rep["path_mismatches"] == [] and rep["path_ties"] == 0
+
+
+def test_config1_against_the_reference_binary(T, tmp_path):
+    """BASELINE.json configs[0] at full size — E. coli-sized 4.6 Mbp genome, 2x250 PE at 100x, 1.84 M reads — through the UNMODIFIED
+    reference binary (oracle/_ref/w2rap-contigger, all host threads) and through the B200 path, same reads: histogram, edge set,
+    vertices and every read path must agree (modulo the reference's racy edge numbering and its extension ties)."""
+    if not os.path.exists(T.REF_BIN):
+        pytest.skip("oracle/_ref/w2rap-contigger not built (needs /root/reference at build time)")
+    lib = T.product_lib()
+    err = C.create_string_buffer(512)
+    sp = T.SynthParams(4_600_000, 250, 100, 11, 0, 0, 0, 0)
+    h = C.c_void_p()
+    assert lib.w2rap_step2_synth(C.byref(sp), -1, C.byref(h), err, 512) == 0, err.value
+    hr = T.Reads()
+    assert lib.w2rap_step2_download_reads(h, C.byref(hr), err, 512) == 0, err.value
+    assert int(hr.n_reads) == 1_840_000
+    d = str(tmp_path)
+    assert lib.w2rap_write_fastb(os.path.join(d, "frag_reads_orig.fastb").encode(), C.byref(hr), err, 512) == 0, err.value
+    assert lib.w2rap_write_qualp(os.path.join(d, "frag_reads_orig.qualp").encode(), C.byref(hr), err, 512) == 0, err.value
+    lib.w2rap_step2_free_host_reads(C.byref(hr))
+    g = T.Graph()
+    p = T.default_params(apply_fixpaths=1)
+    assert lib.w2rap_step2_run_resident(h, C.byref(p), C.byref(g), err, 512) == 0, err.value
+    got = T.graph_to_dict(g)
+    lib.w2rap_step2_free(C.byref(g))
+    lib.w2rap_step2_release(h)
+    T.run_reference_step2(d, threads=os.cpu_count() or 1)
+    rep = T.compare_with_reference_fast(got, T.graph_from_reference_files(d))
+    assert rep["edge_set_equal"] and rep["hist_equal"] and rep["vertices_equal"], {k: v for k, v in rep.items() if k != "path_mismatches"}
+    assert rep["path_mismatches"] == [] and rep["path_ties"] <= 50, (rep["path_ties"], rep["path_mismatches"][:10])
+    assert got["n_pathed"] > 0.97 * got["n_reads"]

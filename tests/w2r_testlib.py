@@ -591,6 +591,56 @@ def compare_with_reference(d, ref, post_fixpaths=True):
     return rep
 
 
+def compare_with_reference_fast(d, ref):
+    """compare_with_reference for millions of reads: the path comparison is done on flattened arrays; only reads that differ are
+    looked at one by one (tolerated: extension ties between parallel equal-length edges)."""
+    rep = {}
+    seqs, left, right = hbv_view(d)
+    rseqs = [e.tobytes() for e in ref["hbv"]["edges"]]
+    ours = {s: i for i, s in enumerate(seqs)}
+    rep["n_hbv_edges"] = (len(seqs), len(rseqs))
+    rep["edge_set_equal"] = len(ours) == len(seqs) and len(rseqs) == len(seqs) and set(ours) == set(rseqs)
+    rep["hist_equal"] = bool(np.array_equal(d["hist"][1:], ref["hist"][1:]))
+    if not rep["edge_set_equal"]:
+        return rep
+    r2o = np.array([ours[s] for s in rseqs], dtype=np.int64)
+    rep["vertices_equal"] = bool(np.array_equal(left[r2o], ref["left"]) and np.array_equal(right[r2o], ref["right"]))
+    n = len(ref["paths"])
+    rlens = np.fromiter((len(p) for p in ref["paths"]), dtype=np.int64, count=n)
+    rflat = r2o[np.concatenate(ref["paths"]).astype(np.int64)] if rlens.sum() else np.zeros(0, np.int64)
+    po = d["path_off"].astype(np.int64)
+    olens = po[1:] - po[:-1]
+    same_len = (olens == rlens) & (d["path_offset"] == ref["path_offset"])
+    roff = np.concatenate([[0], np.cumsum(rlens)])
+    differs = ~same_len
+    if same_len.any():
+        # element-wise comparison of the reads whose lengths agree
+        idx = np.nonzero(same_len)[0]
+        reps = np.repeat(idx, rlens[idx])
+        within = np.arange(len(reps)) - np.repeat(np.cumsum(rlens[idx]) - rlens[idx], rlens[idx])
+        neq = d["path_edges"][po[reps] + within] != rflat[roff[reps] + within]
+        differs[np.unique(reps[neq])] = True
+    elen = np.array([len(s) for s in seqs])
+    ties, bad = 0, []
+    for r in np.nonzero(differs)[0]:
+        mine = d["path_edges"][po[r]:po[r + 1]]
+        theirs = rflat[roff[r]:roff[r + 1]]
+        ok = len(mine) == len(theirs) and d["path_offset"][r] == ref["path_offset"][r]
+        if ok:
+            for a, b in zip(mine, theirs):
+                if a != b and not (left[a] == left[b] and right[a] == right[b] and elen[a] == elen[b]):
+                    ok = False
+                    break
+        if ok:
+            ties += 1
+        else:
+            bad.append(int(r))
+    rep["path_ties"] = ties
+    rep["path_mismatches"] = bad
+    rep["n_reads"] = n
+    return rep
+
+
 def assert_graph_equal(a, b, what="graph", check_paths=True, check_dump=True):
     """Exact equality of two w2rap_graph dicts (oracle vs product): both use the sorted-by-sequence edge order."""
     for k in ("n_reads", "n_bases", "n_kmer_instances", "n_distinct", "n_solid", "n_edges", "n_edge_bases", "n_vertices",
