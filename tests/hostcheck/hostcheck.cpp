@@ -289,7 +289,7 @@ int finish_graph(const SolidTable& st, EdgeSet& es, uint64_t n_solid, const w2ra
     // k_bloom_build: the negative-lookup filter of the pathing kernel
     std::vector<uint32_t> bloom_words(std::max<uint64_t>(1024, n_solid / 2), 0u);
     KmerBloom bloom{bloom_words.data(), bloom_words.size()};
-    for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) { uint64_t h = kmer_hash(Kmer{slots[i].w0, slots[i].w1}); bloom_words[bloom_word(bloom, h)] |= bloom_mask(h); }
+    for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) { uint32_t h = bloom_hash(Kmer{slots[i].w0, slots[i].w1}); bloom_words[bloom_word(bloom, h)] |= bloom_mask(h); }
     GraphView g{st, bloom, edge_bases.data(), edge_off.data(), edge_len.data(), fwd.data(), rev.data(), hcanon.data(), hleft.data(), hright.data(), from_e.data(), to_e.data(), from_n.data(), to_n.data()};
     const uint64_t n = in->n_reads;
     uint32_t maxlen = 0;

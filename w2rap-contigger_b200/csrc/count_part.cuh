@@ -238,6 +238,7 @@ constexpr uint32_t SMEM_MAX_PROBE = 512;
 constexpr uint32_t COUNT_STOP = 1u << 16;                      // counters stop here (>= 255 is all anyone asks); + one add per racing thread
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // runs (read batches / source ranks) that make up one partition
 constexpr uint32_t SKM_CHUNK = 1024;                           // records per staging buffer (32 KB), two buffers
+constexpr uint32_t SKM_GROUP = 16;                             // records a warp takes at a time (~200 k-mers: 6-7 steps of 32 lanes)
 struct SmemCountParams {
     const SkmRec* recs;
     const uint32_t* cursor;         // [nbatch][P] records of partition p in slab bi
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     __shared__ unsigned int sh_hist[104];
     __shared__ int sh_fail;
     __shared__ uint32_t sh_tot[2], sh_cnt[2];                   // per staging buffer: records of the whole partition / of the staged chunk
+    __shared__ uint32_t sh_next[2];                             // ... and the next record group to hand to a warp
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const unsigned le_mask = (2u << lane) - 1u;                 // lanes 0..lane
     for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
         }
         sh_tot[bf] = acc;
         sh_cnt[bf] = (acc < hi ? acc : hi) - (acc < lo ? acc : lo);
+        sh_next[bf] = 0;
         mbar_arrive(&mbar[bf]);
     };
     uint32_t it = 0;                                             // staged chunks so far: buffer = it & 1, parity = (it >> 1) & 1
@@ -380,16 +383,22 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
             // the other buffer is free: everyone left it at the barrier that ended the previous chunk
             if (threadIdx.x == 0) { if (more) issue(pi, c + 1, bf ^ 1u); else if (pi + gridDim.x < n_todo) issue(pi + gridDim.x, 0, bf ^ 1u); }
             const SkmRec* st = stage + (size_t)bf * SKM_CHUNK;
-            // groups of 32 records, dealt to the warps; inside a group the k-mers are numbered consecutively across the records and
+            // groups of SKM_GROUP records, handed to the warps on demand (a static deal left half the warps waiting at the barrier
+            // below: 24 % of all stall samples).  Inside a group the k-mers are numbered consecutively across the records and
             // lane l takes k-mer t + l.  Which record that is: the records that START inside the 32-k-mer window are ORed into a
             // bit mask (one REDUX), a population count of the mask below the lane gives the record.
-            for (uint32_t g0 = warp * 32u; g0 < cnt; g0 += nwarp * 32u) {
-                const uint64_t hdr = g0 + lane < cnt ? st[g0 + lane].q[3] : 0ull;
-                const uint32_t nr = g0 + lane < cnt ? skm_n(hdr) : 0u;
+            for (;;) {
+                uint32_t g0 = 0;
+                if (lane == 0) g0 = atomicAdd(&sh_next[bf], SKM_GROUP);
+                g0 = __shfl_sync(0xffffffffu, g0, 0);
+                if (g0 >= cnt) break;
+                const bool have = lane < SKM_GROUP && g0 + lane < cnt;
+                const uint64_t hdr = have ? st[g0 + lane].q[3] : 0ull;
+                const uint32_t nr = have ? skm_n(hdr) : 0u;
                 uint32_t incl = nr;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - nr;
+                for (int d = 1; d < (int)SKM_GROUP; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, SKM_GROUP - 1), excl = incl - nr;
                 uint32_t before_window = 0;                      // records that start before the window
                 for (uint32_t t = 0; t < total; t += 32) {
                     const uint32_t rel = excl - t;               // (unsigned: records that start before the window wrap to huge values)

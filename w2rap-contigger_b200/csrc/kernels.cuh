@@ -141,7 +141,7 @@ __global__ void k_bloom_build(SolidTable st, KmerBloom b) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) {
         const SolidSlot* s = st.slots + i;
         if (s->w0 == EMPTY_W0) continue;
-        const uint64_t h = kmer_hash(Kmer{s->w0, s->w1});
+        const uint32_t h = bloom_hash(Kmer{s->w0, s->w1});
         atomicOr(b.words + bloom_word(b, h), bloom_mask(h));
     }
 }
@@ -218,14 +218,19 @@ __global__ void k_count_splitters(const uint32_t* __restrict__ next0, const uint
         if (lane_id() == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
     }
 }
-__global__ void k_splitter_walk(const uint32_t* __restrict__ next0, const uint8_t* __restrict__ ghead, uint64_t nn, RankState* __restrict__ label, RankState* __restrict__ S,
-                                uint32_t* __restrict__ list, uint64_t list_cap, unsigned long long* cursor) {
+// The splitters are listed first and walked from the list: a warp then drives 32 independent chains (walking straight off the node
+// sweep kept ~4 of 32 lanes busy, and this kernel lives on memory-level parallelism: every step is a dependent random fetch).
+__global__ void k_list_splitters(const uint32_t* __restrict__ next0, const uint8_t* __restrict__ ghead, uint64_t nn, uint32_t* __restrict__ list, uint64_t list_cap,
+                                 unsigned long long* cursor) {
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t x = base + threadIdx.x;
         bool sp = x < nn && node_is_splitter(next0, ghead, (uint32_t)x);
         uint64_t pos = warp_append(cursor, sp);
-        if (sp) { if (pos < list_cap) list[pos] = (uint32_t)x; splitter_walk(next0, (uint32_t)x, label, S); }
+        if (sp && pos < list_cap) list[pos] = (uint32_t)x;
     }
+}
+__global__ void k_splitter_walk(const uint32_t* __restrict__ next0, const uint32_t* __restrict__ list, uint64_t n, RankState* __restrict__ label, RankState* __restrict__ S) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) splitter_walk(next0, list[i], label, S);
 }
 __global__ void k_splitter_finish(const uint32_t* __restrict__ next0, uint64_t nn, RankState* __restrict__ label_then_rank, const RankState* __restrict__ S,
                                   unsigned long long* __restrict__ unresolved) {
@@ -415,16 +420,20 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, GraphView g, const uint32_t* __restrict__ list, uint64_t n_rows,
                                                     int32_t* __restrict__ stage, uint32_t cap, uint32_t left_cap, int32_t* __restrict__ out_offset,
                                                     PathMeta* __restrict__ out_meta, uint32_t apply_fixpaths) {
+    // walker state in shared memory, one slot per thread, padded to an odd number of words (no bank conflicts across lanes)
+    struct Slot { PathState st; uint32_t pad[(sizeof(PathState) / 4) % 2 == 0 ? 1 : 2]; };
+    __shared__ Slot slots[128];
+    PathState& ps = slots[threadIdx.x].st;
     const uint32_t lane = lane_id();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t row0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); row0 < n_rows; row0 += stride) {   // warp-uniform trip count
         const uint64_t row = row0 + lane;
         const bool live = row < n_rows;
         const uint64_t i = live ? (list ? list[row] : row) : 0;
-        PathWalker w;
+        PathWalker w(ps);
         w.init(g, r.bases + r.base_off[i], live ? r.len[i] : 0u, stage + (live ? row : 0) * cap, cap, left_cap);
         bool need = w.scan();
-        uint32_t from = w.itr + 1u;                               // first unscreened position of this lane's gap
+        uint32_t from = ps.itr + 1u;                               // first unscreened position of this lane's gap
         for (;;) {
             unsigned m = __ballot_sync(0xffffffffu, need);
             if (!m) break;
@@ -439,12 +448,12 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
                 for (int q = 0; q < PATH_GAP_BATCH; ++q) {
                     word[q] = 0; bits[q] = 1;                     // (word & bits) != bits: not a candidate
                     if (q < n) {
-                        const uint8_t* b = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(w.bases), src[q]));
-                        const uint32_t p = __shfl_sync(0xffffffffu, from, src[q]) + lane, nk = __shfl_sync(0xffffffffu, w.nk, src[q]);
+                        const uint8_t* b = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ps.bases), src[q]));
+                        const uint32_t p = __shfl_sync(0xffffffffu, from, src[q]) + lane, nk = __shfl_sync(0xffffffffu, ps.nk, src[q]);
                         if (p < nk) {
                             Kmer f, rc;
                             kmer_pair_at(b, p, &f, &rc);
-                            const uint64_t hh = kmer_hash(kmer_less(rc, f) ? rc : f);
+                            const uint32_t hh = bloom_hash(kmer_less(rc, f) ? rc : f);
                             if (g.bloom.words) { word[q] = __ldg(g.bloom.words + bloom_word(g.bloom, hh)); bits[q] = bloom_mask(hh); }
                             else { word[q] = 1; bits[q] = 1; }   // no filter (tiny dictionary): every position is a candidate
                         }
@@ -464,16 +473,16 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
                     const uint32_t p = from + (uint32_t)(__ffs((int)cand) - 1);
                     cand &= cand - 1;
                     Kmer f, rc;
-                    kmer_pair_at(w.bases, p, &f, &rc);
+                    kmer_pair_at(ps.bases, p, &f, &rc);
                     const Kmer canon = kmer_less(rc, f) ? rc : f;
                     const int64_t s = solid_find_hashed(g.solid, canon, kmer_hash(canon));
                     if (s >= 0) { w.gap_found(p, s); resolved = true; break; }
                 }
                 if (!resolved) {
                     from += 32;
-                    if (from >= w.nk) { w.gap_found(w.nk, -1); resolved = true; }
+                    if (from >= ps.nk) { w.gap_found(ps.nk, -1); resolved = true; }
                 }
-                if (resolved) { need = w.scan(); from = w.itr + 1u; }
+                if (resolved) { need = w.scan(); from = ps.itr + 1u; }
             }
         }
         if (live) {

@@ -178,7 +178,8 @@ struct SolidTable {
 };
 
 // slots for n keys: load ~0.6 (linear probing: ~1.8 probes per hit, ~3.6 per miss; pathing screens misses with the Bloom filter)
-W2R_HD uint64_t solid_table_slots(uint64_t n) { return n + (n >> 1) + (n >> 3) + 1024; }
+// (beyond 2^29 keys the table is what decides whether a genome fits the device: load ~0.77 there)
+W2R_HD uint64_t solid_table_slots(uint64_t n) { return n < (1ull << 29) ? n + (n >> 1) + (n >> 3) + 1024 : n + (n >> 2) + (n >> 4); }
 
 // Canonical lookup with the k-mer's hash already known; returns slot or -1.
 W2R_HD int64_t solid_find_hashed(const SolidTable& t, Kmer k, uint64_t hh) {
@@ -204,9 +205,18 @@ struct KmerBloom {
     uint32_t* words;        // nullptr = no filter
     uint64_t nwords;
 };
-W2R_HD uint64_t bloom_word(const KmerBloom& b, uint64_t h) { return mulhi64((h << 32) | (h >> 32), b.nwords); }
-W2R_HD uint32_t bloom_mask(uint64_t h) { return (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)); }
-W2R_HD bool bloom_may_contain(const KmerBloom& b, uint64_t h) {
+// The filter has its own cheap 32-bit hash (two multiply-adds per word half): gap screening hashes ~100 k-mers per read, and the
+// 64-bit table hash (four 64-bit multiplies) is only worth computing for the few candidates that pass.
+W2R_HD uint32_t bloom_hash(Kmer k) {
+    uint32_t x = (uint32_t)k.w0 * 0x9e3779b1u + (uint32_t)(k.w0 >> 32) * 0x85ebca77u;
+    x ^= x >> 15;
+    x += (uint32_t)(k.w1 >> 8) * 0xc2b2ae3du + (uint32_t)(k.w1 >> 40) * 0x27d4eb2fu;
+    x ^= x >> 13; x *= 0x165667b1u; x ^= x >> 16;
+    return x;
+}
+W2R_HD uint64_t bloom_word(const KmerBloom& b, uint32_t h) { return ((uint64_t)h * b.nwords) >> 32; }        // nwords < 2^32
+W2R_HD uint32_t bloom_mask(uint32_t h) { const uint32_t y = h * 0x2c1b3c6du; return (1u << (y >> 27)) | (1u << ((y >> 22) & 31u)); }
+W2R_HD bool bloom_may_contain(const KmerBloom& b, uint32_t h) {
     if (!b.words) return true;
     const uint32_t m = bloom_mask(h);
 #if defined(__CUDA_ARCH__)
@@ -217,9 +227,8 @@ W2R_HD bool bloom_may_contain(const KmerBloom& b, uint64_t h) {
 }
 // Canonical lookup through the filter.
 W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer k) {
-    const uint64_t hh = kmer_hash(k);
-    if (!bloom_may_contain(b, hh)) return -1;
-    return solid_find_hashed(t, k, hh);
+    if (!bloom_may_contain(b, bloom_hash(k))) return -1;
+    return solid_find(t, k);
 }
 
 // kmers/ReadPather.h:196-199 findEntry: canonicalise then look up.  *rev = query was in REV form (rc < query).

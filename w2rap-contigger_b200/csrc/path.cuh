@@ -161,11 +161,12 @@ struct PathResult { int32_t offset; uint32_t start, len; bool overflow; };
 // p in (itr, nk) whose k-mer IS in the dictionary — serially (path_one_read below, the host check) or with the whole warp
 // (k_path_reads: 32 positions per step) — and hands it back with gap_found(p, slot) (p = nk, slot = -1 if there is none).
 // finish() applies the tail rules, the quality-aware extensions and FixPaths.
-struct PathWalker {
-    const GraphView* g;
+// The walker's state, kept apart from the handle so that a kernel can place it in SHARED memory (one slot per thread): with the
+// state in registers the path kernel spilled ~350 bytes per thread, and that local-memory traffic was the largest single source
+// of L2/DRAM sectors of the whole kernel (ncu: profiles/r2_ncu_path_reads_c2.txt).
+struct PathState {
     const uint8_t* bases;
-    int32_t* row;
-    uint32_t rlen, nk, left_cap, right_cap;
+    uint32_t rlen, nk;
     PathPart pend[2];
     int npend;
     bool last_kept_valid; uint32_t lk_edge, lk_rc;
@@ -176,23 +177,30 @@ struct PathWalker {
     bool pending_gap; uint32_t gap_len, gap_index;
     uint32_t itr;
     bool overflow, scan_done;
+};
+struct PathWalker {
+    PathState& s;
+    const GraphView* g;
+    int32_t* row;
+    uint32_t left_cap, right_cap;
+    W2R_HD explicit PathWalker(PathState& st) : s(st), g(nullptr), row(nullptr), left_cap(0), right_cap(0) {}
 
     W2R_HD void init(const GraphView& g_, const uint8_t* bases_, uint32_t rlen_, int32_t* row_, uint32_t cap, uint32_t left_cap_) {
-        g = &g_; bases = bases_; row = row_; rlen = rlen_; left_cap = left_cap_; right_cap = cap - left_cap_;
-        nk = rlen >= (uint32_t)K ? rlen - K + 1 : 0;           // :503-506 a read shorter than K is a single gap part: empty path
-        npend = 0; last_kept_valid = false; lk_edge = lk_rc = 0;
-        n_ids = sum_kmers = seeds = nparts = 0;
-        first_is_gap = have_first_hit = false; gap0_len = first_hit_off = 0;
-        last_is_gap = last2_is_gap = false; pending_gap = false; gap_len = gap_index = 0;
-        itr = 0; overflow = false; scan_done = false;
+        g = &g_; s.bases = bases_; row = row_; s.rlen = rlen_; left_cap = left_cap_; right_cap = cap - left_cap_;
+        s.nk = s.rlen >= (uint32_t)K ? s.rlen - K + 1 : 0;           // :503-506 a read shorter than K is a single gap part: empty path
+        s.npend = 0; s.last_kept_valid = false; s.lk_edge = s.lk_rc = 0;
+        s.n_ids = s.sum_kmers = s.seeds = s.nparts = 0;
+        s.first_is_gap = s.have_first_hit = false; s.gap0_len = s.first_hit_off = 0;
+        s.last_is_gap = s.last2_is_gap = false; s.pending_gap = false; s.gap_len = s.gap_index = 0;
+        s.itr = 0; s.overflow = false; s.scan_done = false;
     }
     W2R_HD void commit(const PathPart& h) {                     // :804-815 pathPartsToReadPath, one kept seed
-        if (last_kept_valid && lk_edge == h.edge && lk_rc == h.rc) return;
-        if (n_ids < right_cap) row[left_cap + n_ids] = h.rc ? g->rev_xlat[h.edge] : g->fwd_xlat[h.edge]; else overflow = true;
-        ++n_ids; sum_kmers += h.elen;
-        last_kept_valid = true; lk_edge = h.edge; lk_rc = h.rc;
+        if (s.last_kept_valid && s.lk_edge == h.edge && s.lk_rc == h.rc) return;
+        if (s.n_ids < right_cap) row[left_cap + s.n_ids] = h.rc ? g->rev_xlat[h.edge] : g->fwd_xlat[h.edge]; else s.overflow = true;
+        ++s.n_ids; s.sum_kmers += h.elen;
+        s.last_kept_valid = true; s.lk_edge = h.edge; s.lk_rc = h.rc;
     }
-    // the k-mer at itr is dictionary entry `slot`: extend the match along its edge; false = the path ends here (captured-gap rule)
+    // the k-mer at s.itr is dictionary entry `slot`: extend the match along its edge; false = the path ends here (captured-gap rule)
     W2R_HD bool seed(int64_t slot) {
         const SolidSlot& ss = g->solid.slots[slot];
         PathPart h;
@@ -202,16 +210,16 @@ struct PathWalker {
         const uint8_t* ep = g->edge_bases + g->edge_off[h.edge];
         // dna/CanonicalForm.h:85-92 isRC: the read k-mer is the reverse complement of the edge k-mer at that offset
         Kmer ek = kmer_at(ep, o);
-        h.rc = !(ek == kmer_at(bases, itr));
+        h.rc = !(ek == kmer_at(s.bases, s.itr));
         h.elen = elen - K + 1;
         uint32_t len = 1;
-        // matchLen (:341-350), 32 bases per step: XOR of two packed words, first differing 2-bit group by count-trailing-zeros
+        // matchLen (:341-350), 32 s.bases per step: XOR of two packed words, first differing 2-bit group by count-trailing-zeros
         if (!h.rc) {
-            uint64_t rp = (uint64_t)itr + K, e2 = (uint64_t)o + K;
-            while (rp < rlen && e2 < elen) {
-                uint64_t n = rlen - rp < elen - e2 ? rlen - rp : elen - e2;
+            uint64_t rp = (uint64_t)s.itr + K, e2 = (uint64_t)o + K;
+            while (rp < s.rlen && e2 < elen) {
+                uint64_t n = s.rlen - rp < elen - e2 ? s.rlen - rp : elen - e2;
                 if (n > 32) n = 32;
-                uint64_t x = bases32_at(bases, rp) ^ bases32_at(ep, e2);
+                uint64_t x = bases32_at(s.bases, rp) ^ bases32_at(ep, e2);
                 if (n < 32) x &= (1ull << (2 * n)) - 1;
                 if (x) { len += (uint32_t)(ctz64(x) >> 1); break; }
                 len += (uint32_t)n; rp += n; e2 += n;
@@ -219,13 +227,13 @@ struct PathWalker {
             h.off = o;
         } else {
             uint64_t ro = (uint64_t)elen - o;               // position in rc(edge) just past the k-mer
-            uint64_t rp = (uint64_t)itr + K, e2 = ro;
-            while (rp < rlen && e2 < elen) {
-                uint64_t n = rlen - rp < elen - e2 ? rlen - rp : elen - e2;
+            uint64_t rp = (uint64_t)s.itr + K, e2 = ro;
+            while (rp < s.rlen && e2 < elen) {
+                uint64_t n = s.rlen - rp < elen - e2 ? s.rlen - rp : elen - e2;
                 if (n > 32) n = 32;
                 // rc(edge)[e2 .. e2+n) = reverse complement of edge[elen-e2-n .. elen-e2)
                 uint64_t c = rev2(~bases32_at(ep, (uint64_t)elen - e2 - n)) >> (2 * (32 - n));
-                uint64_t x = bases32_at(bases, rp) ^ c;
+                uint64_t x = bases32_at(s.bases, rp) ^ c;
                 if (n < 32) x &= (1ull << (2 * n)) - 1;
                 if (x) { len += (uint32_t)(ctz64(x) >> 1); break; }
                 len += (uint32_t)n; rp += n; e2 += n;
@@ -233,88 +241,88 @@ struct PathWalker {
             h.off = (uint32_t)(ro - K);
         }
         h.len = len;
-        h.after_gap = pending_gap;
+        h.after_gap = s.pending_gap;
         // :875-898 captured-gap consistency, evaluated when the seed after an interior gap arrives
-        if (pending_gap && gap_index >= 1) {
-            const PathPart& pv = pend[npend - 1];
+        if (s.pending_gap && s.gap_index >= 1) {
+            const PathPart& pv = s.pend[s.npend - 1];
             uint32_t gd = h.off - (pv.off + pv.len);        // :470 unsigned arithmetic
             if (!part_same_edge(pv, h)) gd += pv.elen;
-            int32_t diff = (int32_t)(gap_len - gd);
+            int32_t diff = (int32_t)(s.gap_len - gd);
             uint32_t ad = (uint32_t)(diff < 0 ? -diff : diff);
             if (!(ad <= 3u) || !part_joinable(*g, pv, h)) {
-                if (seeds > 1) { last2_is_gap = pv.after_gap; --npend; }   // drop the seed before the gap and everything after it
-                else { last2_is_gap = false; }                             // the gap absorbs everything after it
-                last_is_gap = true;
+                if (s.seeds > 1) { s.last2_is_gap = pv.after_gap; --s.npend; }   // drop the seed before the gap and everything after it
+                else { s.last2_is_gap = false; }                             // the gap absorbs everything after it
+                s.last_is_gap = true;
                 return false;
             }
         }
-        pending_gap = false;
-        if (npend == 2) { commit(pend[0]); pend[0] = pend[1]; npend = 1; }
-        pend[npend++] = h;
-        ++seeds;
-        if (!have_first_hit) { have_first_hit = true; first_hit_off = h.off; }
-        ++nparts; last2_is_gap = last_is_gap; last_is_gap = false;
-        itr += len;
+        s.pending_gap = false;
+        if (s.npend == 2) { commit(s.pend[0]); s.pend[0] = s.pend[1]; s.npend = 1; }
+        s.pend[s.npend++] = h;
+        ++s.seeds;
+        if (!s.have_first_hit) { s.have_first_hit = true; s.first_hit_off = h.off; }
+        ++s.nparts; s.last2_is_gap = s.last_is_gap; s.last_is_gap = false;
+        s.itr += len;
         return true;
     }
     W2R_HD bool scan() {
-        while (!scan_done && itr < nk) {
-            Kmer f = kmer_at(bases, itr);
+        while (!s.scan_done && s.itr < s.nk) {
+            Kmer f = kmer_at(s.bases, s.itr);
             Kmer r = kmer_rc(f);
             const int64_t slot = solid_find_filtered(g->solid, g->bloom, kmer_less(r, f) ? r : f);
             if (slot < 0) return true;
-            if (!seed(slot)) scan_done = true;
+            if (!seed(slot)) s.scan_done = true;
         }
         return false;
     }
     W2R_HD void gap_found(uint32_t p, int64_t slot) {
-        const uint32_t gl = p - itr;
-        itr = p;
-        if (nparts == 0) { first_is_gap = true; gap0_len = gl; }
-        gap_len = gl; gap_index = nparts; ++nparts;
-        last2_is_gap = last_is_gap; last_is_gap = true;
-        pending_gap = true;
-        if (slot < 0 || !seed(slot)) scan_done = true;
+        const uint32_t gl = p - s.itr;
+        s.itr = p;
+        if (s.nparts == 0) { s.first_is_gap = true; s.gap0_len = gl; }
+        s.gap_len = gl; s.gap_index = s.nparts; ++s.nparts;
+        s.last2_is_gap = s.last_is_gap; s.last_is_gap = true;
+        s.pending_gap = true;
+        if (slot < 0 || !seed(slot)) s.scan_done = true;
     }
     W2R_HD PathResult finish(const uint8_t* qstream, bool apply_fixpaths) {
         PathResult res{0, left_cap, 0, false};
         // :904-918 a trailing seed that only reached <= 5 k-mers into an edge from its very start is dropped
-        if (last_is_gap) {
-            if (nparts > 1 && !last2_is_gap && npend > 0) { const PathPart& l2 = pend[npend - 1]; if (l2.off == 0 && l2.len <= 5) --npend; }
-        } else if (npend > 0) {
-            const PathPart& l = pend[npend - 1];
-            if (l.off == 0 && l.len <= 5) --npend;
+        if (s.last_is_gap) {
+            if (s.nparts > 1 && !s.last2_is_gap && s.npend > 0) { const PathPart& l2 = s.pend[s.npend - 1]; if (l2.off == 0 && l2.len <= 5) --s.npend; }
+        } else if (s.npend > 0) {
+            const PathPart& l = s.pend[s.npend - 1];
+            if (l.off == 0 && l.len <= 5) --s.npend;
         }
-        for (int i = 0; i < npend; ++i) commit(pend[i]);
-        res.overflow = overflow;
-        if (n_ids == 0 || res.overflow) return res;
-        int32_t offset = first_is_gap ? (int32_t)first_hit_off - (int32_t)gap0_len : (int32_t)first_hit_off;   // :816-826
+        for (int i = 0; i < s.npend; ++i) commit(s.pend[i]);
+        res.overflow = s.overflow;
+        if (s.n_ids == 0 || res.overflow) return res;
+        int32_t offset = s.first_is_gap ? (int32_t)s.first_hit_off - (int32_t)s.gap0_len : (int32_t)s.first_hit_off;   // :816-826
 
         // :922-923 quality-aware extension (ExtendReadPath.cc:115-348); all left extensions first, then right
         uint32_t nl = 0;
-        int32_t front = row[left_cap], back = row[left_cap + n_ids - 1];
+        int32_t front = row[left_cap], back = row[left_cap + s.n_ids - 1];
         while (offset < 0 && (uint32_t)(-offset) >= 10u) {
-            int32_t e = choose_extension(*g, g->hleft[front], true, (uint32_t)(-offset), bases, qstream, rlen);
+            int32_t e = choose_extension(*g, g->hleft[front], true, (uint32_t)(-offset), s.bases, qstream, s.rlen);
             if (e < 0) break;
             uint32_t ek = hbv_edge_len(*g, e) - K + 1;
-            offset += (int32_t)ek; sum_kmers += ek;
+            offset += (int32_t)ek; s.sum_kmers += ek;
             if (nl < left_cap) row[left_cap - 1 - nl] = e; else res.overflow = true;
             ++nl; front = e;
         }
         for (;;) {
-            int32_t lastg = (int32_t)rlen + offset - (int32_t)sum_kmers - (K - 1);
+            int32_t lastg = (int32_t)s.rlen + offset - (int32_t)s.sum_kmers - (K - 1);
             if (lastg < 10) break;
             // the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
-            int32_t e = choose_extension(*g, g->hleft[back], false, (uint32_t)lastg, bases, qstream, rlen);
+            int32_t e = choose_extension(*g, g->hleft[back], false, (uint32_t)lastg, s.bases, qstream, s.rlen);
             if (e < 0) break;
-            sum_kmers += hbv_edge_len(*g, e) - K + 1;
-            if (n_ids < right_cap) row[left_cap + n_ids] = e; else res.overflow = true;
-            ++n_ids; back = e;
+            s.sum_kmers += hbv_edge_len(*g, e) - K + 1;
+            if (s.n_ids < right_cap) row[left_cap + s.n_ids] = e; else res.overflow = true;
+            ++s.n_ids; back = e;
         }
         if (res.overflow) return res;
         res.offset = offset;
         res.start = left_cap - nl;
-        res.len = nl + n_ids;
+        res.len = nl + s.n_ids;
         if (apply_fixpaths) {                                    // large/GapToyTools.cc:322-335
             const int32_t* p = row + res.start;
             for (uint32_t i = 0; i + 1 < res.len; ++i)
@@ -328,17 +336,18 @@ struct PathWalker {
 // `row` is this read's staging row of `cap` ints; qualities are looked up in the PQVec stream where an extension needs them.
 W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32_t rlen, const uint8_t* qstream,
                                 int32_t* row, uint32_t cap, uint32_t left_cap, bool apply_fixpaths) {
-    PathWalker w;
+    PathState st;
+    PathWalker w(st);
     w.init(g, bases, rlen, row, cap, left_cap);
     while (w.scan()) {
-        uint32_t p = w.itr + 1;
+        uint32_t p = st.itr + 1;
         int64_t slot = -1;
-        if (p < w.nk) {
+        if (p < st.nk) {
             Kmer f = kmer_at(bases, p), r = kmer_rc(f);
             uint64_t nxt = 0;
             for (uint32_t t = 0;; ++t) {
                 slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
-                if (slot >= 0 || p + 1 >= w.nk) { if (slot < 0) ++p; break; }
+                if (slot >= 0 || p + 1 >= st.nk) { if (slot < 0) ++p; break; }
                 if ((t & 31u) == 0) nxt = bases32_at(bases, (uint64_t)p + K);
                 const uint32_t nb = (uint32_t)nxt & 3u;
                 nxt >>= 2;

@@ -675,7 +675,8 @@ struct Pipeline {
         SBuf<uint32_t> splist(c, nsp);
         W2R_CUDA(cudaMemsetAsync(A.p, 0xff, A.bytes(), c.stream));     // label = {NIL, ...}
         W2R_CUDA(cudaMemsetAsync(scal.p + 3, 0, 8, c.stream));
-        W2R_TIMED(W2RAP_KT_SPLITTER_WALK, W2R_LAUNCH(c, k_splitter_walk, grid(nn, 256), 256, 0, next0.p, ghead, nn, A.p, B.p, splist.p, nsp, scal.p + 3));
+        W2R_LAUNCH(c, k_list_splitters, grid(nn, 256), 256, 0, next0.p, ghead, nn, splist.p, nsp, scal.p + 3);
+        if (nsp) W2R_TIMED(W2RAP_KT_SPLITTER_WALK, W2R_LAUNCH(c, k_splitter_walk, grid(nsp, 256), 256, 0, (const uint32_t*)next0.p, (const uint32_t*)splist.p, nsp, A.p, B.p));
         unsigned long long prev_un = ~0ull;
         if (nsp) {
             for (int round = 0; round < 48; ++round) {
@@ -1010,21 +1011,36 @@ struct Pipeline {
         kt_.end();
         kt_.begin(W2RAP_KT_SG_DICT);
         // -- the finished entries (pruned context, edge, offset) of every rank: the dictionary the reads are pathed against
-        SBuf<SolidSlot> mine(c, n_local + 1), entries;
+        SBuf<SolidSlot> mine(c, n_local + 1);
         W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
         W2R_LAUNCH(c, k_dump_owned, grid(st.size(), 256), 256, 0, st, mine.p, n_local, scal.p);
         if (d2h_scalar(c, scal.p) != n_local) W2R_FAIL(W2RAP_ERR_INTERNAL, "owned entries lost in the local table");
-        std::vector<uint64_t> eoff;
-        allgather_v(mine.p, n_local, entries, eoff);
+        std::vector<unsigned long long> per(W, 0ull);
+        per[me] = n_local;
+        allreduce_u64(per, ncclSum);
+        uint64_t n_solid = 0, per_max = 0;
+        for (auto v : per) { n_solid += v; per_max = std::max<uint64_t>(per_max, v); }
         xms += xt.stop();
-        const uint64_t n_solid = eoff[W];
-        mine.release(); next0.release(); ghead.release(); A.release(); B.release(); solid_slots.release();
+        next0.release(); ghead.release(); A.release(); B.release(); solid_slots.release();
+        pieces.release(); nxt.release(); flip.release(); S.release();
+        kt_.end();
+        // rank by rank through a bounce buffer (a whole-job gather buffer would double the footprint of the dictionary: at 1.5 G
+        // solid k-mers that is the difference between fitting a 180 GB device and not)
         const uint64_t fslots = solid_table_slots(n_solid);
         solid_slots.alloc(c, fslots);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, fslots};
-        kt_.end();
-        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(n_solid, 256), 256, 0, (const SolidSlot*)entries.p, n_solid, st));
+        SBuf<SolidSlot> bounce(c, per_max + 1);
+        for (uint32_t r = 0; r < W; ++r) {
+            if (!per[r]) continue;
+            kt_.begin(W2RAP_KT_SG_DICT);
+            xt.start();
+            nccl_check(NcclApi::get().Broadcast(r == me ? (const void*)mine.p : (const void*)bounce.p, bounce.p, per[r] * sizeof(SolidSlot), ncclUint8, (int)r, comm, c.stream), "broadcast");
+            xms += xt.stop();
+            kt_.end();
+            W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(per[r], 256), 256, 0, (const SolidSlot*)bounce.p, (uint64_t)per[r], st));
+        }
+        xchg_bytes += n_local * sizeof(SolidSlot) * (uint64_t)(W - 1);
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         out->timings.graph_exchange_ms = xms;
     }
