@@ -385,6 +385,8 @@ def main():
            "k_count_smem": 17 * I, "k_insert_solid": 48 * S_rank // 2, "k_adjacency": 48 * S_rank // 2, "k_links": 24 * S_rank, "k_splitter_walk": 24 * S_rank, "k_splitter_finish": 24 * S_rank,
            "k_emit_edges": EB // 2 // world + 24 * S_rank, "k_bloom_build": 24 * S, "k_path_reads": b_in + b_path}
     launches = {"k_minimizer_map": max(1, tt[-1]["count_launches"]), "k_scatter_records": max(1, tt[-1]["count_launches"]), "k_good_len": max(1, tt[-1]["count_launches"])}
+    phases = {k: v for k, v in km.items() if k not in alg}      # phase timers of the sharded graph stage: several kernels + exchanges each
+    km = {k: v for k, v in km.items() if k in alg}
     dom = max(km, key=lambda k: km[k])
     peak, peak_src = peaks()
     traffic = load_ncu_traffic()
@@ -421,7 +423,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic.get(dom, {}).get("dram_bytes_per_launch"), "traffic_source": traffic.get(dom, {}).get("source"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom] / nl, "launches_per_step": nl,
-                     "kernel_ms_per_step": km[dom], "per_kernel": per_kernel,
+                     "kernel_ms_per_step": km[dom], "per_kernel": per_kernel, "sharded_graph_phases_ms": {k: round(v, 3) for k, v in phases.items()} if world > 1 else None,
                      "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9, "whole_step_frac": alg_bytes_total / (dev_ms * 1e-3) / 1e9 / peak},
         "stage_ms": {k: median([t[k] for t in tt]) for k in ("count_ms", "count_kernel_ms", "region_ms", "dict_ms", "exchange_ms", "graph_exchange_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
         "nvlink": ({"bytes_sent_all_ranks_per_step": xbytes_all, "bytes_per_kmer_instance": xbytes_all / max(1, I_all),

@@ -432,9 +432,17 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
         const uint64_t i = live ? (list ? list[row] : row) : 0;
         PathWalker w(ps);
         w.init(g, r.bases + r.base_off[i], live ? r.len[i] : 0u, stage + (live ? row : 0) * cap, cap, left_cap);
-        bool need = w.scan();
-        uint32_t from = ps.itr + 1u;                               // first unscreened position of this lane's gap
+        // scan() and gap_found() have one call site each (the walker's code is large; see PathWalker::scan)
+        bool need = false, run = true, have_gap = false;
+        uint32_t from = 0, found_p = 0;                            // from: first unscreened position of this lane's gap
+        int64_t found_slot = -1;
         for (;;) {
+            if (run) {
+                if (have_gap) w.gap_found(found_p, found_slot);
+                need = w.scan();
+                from = ps.itr + 1u;
+                run = false; have_gap = false;
+            }
             unsigned m = __ballot_sync(0xffffffffu, need);
             if (!m) break;
             uint32_t cand = 0;                                    // candidate mask of positions [from, from + 32)
@@ -468,7 +476,6 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
                 }
             }
             if (need) {
-                bool resolved = false;
                 while (cand) {                                    // candidates in read order; the first one is almost always real
                     const uint32_t p = from + (uint32_t)(__ffs((int)cand) - 1);
                     cand &= cand - 1;
@@ -476,13 +483,12 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
                     kmer_pair_at(ps.bases, p, &f, &rc);
                     const Kmer canon = kmer_less(rc, f) ? rc : f;
                     const int64_t s = solid_find_hashed(g.solid, canon, kmer_hash(canon));
-                    if (s >= 0) { w.gap_found(p, s); resolved = true; break; }
+                    if (s >= 0) { found_p = p; found_slot = s; have_gap = true; run = true; break; }
                 }
-                if (!resolved) {
+                if (!run) {
                     from += 32;
-                    if (from >= ps.nk) { w.gap_found(ps.nk, -1); resolved = true; }
+                    if (from >= ps.nk) { found_p = ps.nk; found_slot = -1; have_gap = true; run = true; }
                 }
-                if (resolved) { need = w.scan(); from = ps.itr + 1u; }
             }
         }
         if (live) {

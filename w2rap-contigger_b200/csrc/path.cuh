@@ -177,6 +177,7 @@ struct PathState {
     bool pending_gap; uint32_t gap_len, gap_index;
     uint32_t itr;
     bool overflow, scan_done;
+    int64_t found_slot;             // dictionary slot of the k-mer at itr, found by the gap screening (-1: not known)
 };
 struct PathWalker {
     PathState& s;
@@ -192,7 +193,7 @@ struct PathWalker {
         s.n_ids = s.sum_kmers = s.seeds = s.nparts = 0;
         s.first_is_gap = s.have_first_hit = false; s.gap0_len = s.first_hit_off = 0;
         s.last_is_gap = s.last2_is_gap = false; s.pending_gap = false; s.gap_len = s.gap_index = 0;
-        s.itr = 0; s.overflow = false; s.scan_done = false;
+        s.itr = 0; s.overflow = false; s.scan_done = false; s.found_slot = -1;
     }
     W2R_HD void commit(const PathPart& h) {                     // :804-815 pathPartsToReadPath, one kept seed
         if (s.last_kept_valid && s.lk_edge == h.edge && s.lk_rc == h.rc) return;
@@ -265,12 +266,18 @@ struct PathWalker {
         s.itr += len;
         return true;
     }
+    // (seed() is large and is inlined exactly once, here: the kernel's instruction footprint matters — divergent warps roam through
+    //  it and instruction-fetch stalls were the second largest stall reason; gap_found() hands its slot over through found_slot)
     W2R_HD bool scan() {
         while (!s.scan_done && s.itr < s.nk) {
-            Kmer f = kmer_at(s.bases, s.itr);
-            Kmer r = kmer_rc(f);
-            const int64_t slot = solid_find_filtered(g->solid, g->bloom, kmer_less(r, f) ? r : f);
-            if (slot < 0) return true;
+            int64_t slot = s.found_slot;
+            s.found_slot = -1;
+            if (slot < 0) {
+                Kmer f = kmer_at(s.bases, s.itr);
+                Kmer r = kmer_rc(f);
+                slot = solid_find_filtered(g->solid, g->bloom, kmer_less(r, f) ? r : f);
+                if (slot < 0) return true;
+            }
             if (!seed(slot)) s.scan_done = true;
         }
         return false;
@@ -282,7 +289,7 @@ struct PathWalker {
         s.gap_len = gl; s.gap_index = s.nparts; ++s.nparts;
         s.last2_is_gap = s.last_is_gap; s.last_is_gap = true;
         s.pending_gap = true;
-        if (slot < 0 || !seed(slot)) s.scan_done = true;
+        if (slot < 0) s.scan_done = true; else s.found_slot = slot;         // scan(), which every caller runs next, seeds from it
     }
     W2R_HD PathResult finish(const uint8_t* qstream, bool apply_fixpaths) {
         PathResult res{0, left_cap, 0, false};
@@ -301,23 +308,25 @@ struct PathWalker {
         // :922-923 quality-aware extension (ExtendReadPath.cc:115-348); all left extensions first, then right
         uint32_t nl = 0;
         int32_t front = row[left_cap], back = row[left_cap + s.n_ids - 1];
-        while (offset < 0 && (uint32_t)(-offset) >= 10u) {
-            int32_t e = choose_extension(*g, g->hleft[front], true, (uint32_t)(-offset), s.bases, qstream, s.rlen);
-            if (e < 0) break;
-            uint32_t ek = hbv_edge_len(*g, e) - K + 1;
-            offset += (int32_t)ek; s.sum_kmers += ek;
-            if (nl < left_cap) row[left_cap - 1 - nl] = e; else res.overflow = true;
-            ++nl; front = e;
-        }
-        for (;;) {
-            int32_t lastg = (int32_t)s.rlen + offset - (int32_t)s.sum_kmers - (K - 1);
-            if (lastg < 10) break;
-            // the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
-            int32_t e = choose_extension(*g, g->hleft[back], false, (uint32_t)lastg, s.bases, qstream, s.rlen);
-            if (e < 0) break;
-            s.sum_kmers += hbv_edge_len(*g, e) - K + 1;
-            if (s.n_ids < right_cap) row[left_cap + s.n_ids] = e; else res.overflow = true;
-            ++s.n_ids; back = e;
+        for (int dir = 0; dir < 2; ++dir) {                      // (one loop, one call site: choose_extension is large)
+            for (;;) {
+                const bool leftward = dir == 0;
+                const int32_t lastg = leftward ? -offset : (int32_t)s.rlen + offset - (int32_t)s.sum_kmers - (K - 1);
+                if (lastg < 10) break;
+                // rightward: the reference hands ToLeft as "to_right" (BuildReadQGraph.cc:836-841): candidates leave the LEFT vertex of the last edge
+                const int32_t e = choose_extension(*g, g->hleft[leftward ? front : back], leftward, (uint32_t)lastg, s.bases, qstream, s.rlen);
+                if (e < 0) break;
+                const uint32_t ek = hbv_edge_len(*g, e) - K + 1;
+                s.sum_kmers += ek;
+                if (leftward) {
+                    offset += (int32_t)ek;
+                    if (nl < left_cap) row[left_cap - 1 - nl] = e; else res.overflow = true;
+                    ++nl; front = e;
+                } else {
+                    if (s.n_ids < right_cap) row[left_cap + s.n_ids] = e; else res.overflow = true;
+                    ++s.n_ids; back = e;
+                }
+            }
         }
         if (res.overflow) return res;
         res.offset = offset;
