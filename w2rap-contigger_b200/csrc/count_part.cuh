@@ -238,7 +238,6 @@ constexpr uint32_t SMEM_MAX_PROBE = 512;
 constexpr uint32_t COUNT_STOP = 1u << 16;                      // counters stop here (>= 255 is all anyone asks); + one add per racing thread
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // runs (read batches / source ranks) that make up one partition
 constexpr uint32_t SKM_CHUNK = 1024;                           // records per staging buffer (32 KB), two buffers
-constexpr uint32_t SKM_GROUP = 16;                             // records a warp takes at a time (~200 k-mers: 6-7 steps of 32 lanes)
 struct SmemCountParams {
     const SkmRec* recs;
     const uint32_t* cursor;         // [nbatch][P] records of partition p in slab bi
@@ -314,35 +313,51 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     __shared__ unsigned int sh_hist[104];
     __shared__ int sh_fail;
     __shared__ uint32_t sh_tot[2], sh_cnt[2];                   // per staging buffer: records of the whole partition / of the staged chunk
-    __shared__ uint32_t sh_next[2];                             // ... and the next record group to hand to a warp
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const unsigned le_mask = (2u << lane) - 1u;                 // lanes 0..lane
     for (int j = threadIdx.x; j < 104; j += blockDim.x) sh_hist[j] = 0;
     if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     const uint32_t n_todo = sp.plist ? sp.nlist : sp.P;
-    // thread 0 stages chunk c of partition index pi into buffer bf: one bulk copy per run that overlaps the chunk
-    auto issue = [&](uint32_t pi, uint32_t c, uint32_t bf) {
-        const uint32_t p = sp.plist ? sp.plist[pi] : pi;
-        const uint32_t lo = c * SKM_CHUNK, hi = lo + SKM_CHUNK;
-        uint32_t acc = 0;
-        for (uint32_t bi = 0; bi < sp.nbatch; ++bi) {
-            const uint32_t cnt = sp.cursor[(uint64_t)bi * sp.P + p];
-            const uint32_t s = acc > lo ? acc : lo, e = acc + cnt < hi ? acc + cnt : hi;
-            if (s < e) {
-                const SkmRec* src = sp.recs + sp.batch_off[bi] + sp.part_base[(uint64_t)bi * sp.P + p] + (s - acc);
-                mbar_expect_tx(&mbar[bf], (e - s) * (uint32_t)sizeof(SkmRec));
-                bulk_g2s(stage + (size_t)bf * SKM_CHUNK + (s - lo), src, (e - s) * (uint32_t)sizeof(SkmRec), &mbar[bf]);
-            }
-            acc += cnt;
+    // Warp 0 stages the records: lane bi owns run bi of a partition (a read batch / source rank).  The run descriptors of the NEXT
+    // partition are loaded a whole partition ahead and sit in registers, so that issuing a chunk is a few shuffles and one bulk copy
+    // per lane (one thread walking the runs with dependent global loads made warp 0 late at every chunk barrier: ~20 % of the
+    // kernel's stall samples).
+    uint32_t cu_cnt = 0, nx_cnt = 0;                             // records of my run in the current / next partition
+    const SkmRec* cu_src = nullptr; const SkmRec* nx_src = nullptr;
+    auto load_desc = [&](uint32_t pi, uint32_t& cnt, const SkmRec*& src) {
+        cnt = 0; src = nullptr;
+        if (pi < n_todo && lane < sp.nbatch) {
+            const uint32_t p = sp.plist ? sp.plist[pi] : pi;
+            cnt = sp.cursor[(uint64_t)lane * sp.P + p];
+            src = sp.recs + sp.batch_off[lane] + sp.part_base[(uint64_t)lane * sp.P + p];
         }
-        sh_tot[bf] = acc;
-        sh_cnt[bf] = (acc < hi ? acc : hi) - (acc < lo ? acc : lo);
-        sh_next[bf] = 0;
-        mbar_arrive(&mbar[bf]);
+    };
+    // all lanes of warp 0: stage chunk c of the partition described by (cnt, src) into buffer bf
+    auto issue = [&](uint32_t cnt, const SkmRec* src, uint32_t c, uint32_t bf) {
+        const uint32_t lo = c * SKM_CHUNK, hi = lo + SKM_CHUNK;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+        const uint32_t acc = incl - cnt, tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t s = acc > lo ? acc : lo, e = acc + cnt < hi ? acc + cnt : hi;
+        if (s < e) {
+            mbar_expect_tx(&mbar[bf], (e - s) * (uint32_t)sizeof(SkmRec));
+            bulk_g2s(stage + (size_t)bf * SKM_CHUNK + (s - lo), src + (s - acc), (e - s) * (uint32_t)sizeof(SkmRec), &mbar[bf]);
+        }
+        __syncwarp();                                            // every expect_tx precedes the arrival
+        if (lane == 0) {
+            sh_tot[bf] = tot;
+            sh_cnt[bf] = (tot < hi ? tot : hi) - (tot < lo ? tot : lo);
+            mbar_arrive(&mbar[bf]);
+        }
     };
     uint32_t it = 0;                                             // staged chunks so far: buffer = it & 1, parity = (it >> 1) & 1
-    if (threadIdx.x == 0 && blockIdx.x < n_todo) issue(blockIdx.x, 0, 0);
+    if (warp == 0) {
+        load_desc(blockIdx.x, cu_cnt, cu_src);
+        load_desc(blockIdx.x + gridDim.x, nx_cnt, nx_src);
+        if (blockIdx.x < n_todo) issue(cu_cnt, cu_src, 0, 0);
+    }
     for (uint32_t pi = blockIdx.x; pi < n_todo; pi += gridDim.x) {
         const uint32_t p = sp.plist ? sp.plist[pi] : pi;
         {   // empty table (16-byte stores)
@@ -381,24 +396,31 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
             const uint32_t tot = sh_tot[bf], cnt = sh_cnt[bf];
             const bool more = (uint64_t)(c + 1) * SKM_CHUNK < tot;
             // the other buffer is free: everyone left it at the barrier that ended the previous chunk
-            if (threadIdx.x == 0) { if (more) issue(pi, c + 1, bf ^ 1u); else if (pi + gridDim.x < n_todo) issue(pi + gridDim.x, 0, bf ^ 1u); }
+            if (warp == 0) {
+                if (more) issue(cu_cnt, cu_src, c + 1, bf ^ 1u);
+                else {
+                    if (pi + gridDim.x < n_todo) issue(nx_cnt, nx_src, 0, bf ^ 1u);
+                    cu_cnt = nx_cnt; cu_src = nx_src;
+                    load_desc(pi + 2 * gridDim.x, nx_cnt, nx_src);   // (in flight while this chunk and the next partition are counted)
+                }
+            }
             const SkmRec* st = stage + (size_t)bf * SKM_CHUNK;
-            // groups of SKM_GROUP records, handed to the warps on demand (a static deal left half the warps waiting at the barrier
-            // below: 24 % of all stall samples).  Inside a group the k-mers are numbered consecutively across the records and
-            // lane l takes k-mer t + l.  Which record that is: the records that START inside the 32-k-mer window are ORed into a
-            // bit mask (one REDUX), a population count of the mask below the lane gives the record.
-            for (;;) {
-                uint32_t g0 = 0;
-                if (lane == 0) g0 = atomicAdd(&sh_next[bf], SKM_GROUP);
-                g0 = __shfl_sync(0xffffffffu, g0, 0);
-                if (g0 >= cnt) break;
-                const bool have = lane < SKM_GROUP && g0 + lane < cnt;
+            // Every warp takes an equal share of the chunk's records, in groups of <= 32 (a fixed deal of 32-record groups left most
+            // warps idle in a partition's short last chunk: 24 % of all stall samples sat at the barrier below).  Inside a group the
+            // k-mers are numbered consecutively across the records and lane l takes k-mer t + l.  Which record that is: the records that
+            // START inside the 32-k-mer window are ORed into a bit mask (one REDUX), a population count of the mask below the lane gives
+            // the record.
+            const uint32_t share = (cnt + nwarp - 1) / nwarp;                       // records per warp
+            const uint32_t w_end = (warp + 1) * share < cnt ? (warp + 1) * share : cnt;
+            for (uint32_t g0 = warp * share; g0 < w_end; g0 += 32u) {
+                const uint32_t gn = w_end - g0 < 32u ? w_end - g0 : 32u;            // records in this group
+                const bool have = lane < gn;
                 const uint64_t hdr = have ? st[g0 + lane].q[3] : 0ull;
                 const uint32_t nr = have ? skm_n(hdr) : 0u;
                 uint32_t incl = nr;
 #pragma unroll
-                for (int d = 1; d < (int)SKM_GROUP; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, SKM_GROUP - 1), excl = incl - nr;
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - nr;
                 uint32_t before_window = 0;                      // records that start before the window
                 for (uint32_t t = 0; t < total; t += 32) {
                     const uint32_t rel = excl - t;               // (unsigned: records that start before the window wrap to huge values)

@@ -1103,7 +1103,7 @@ struct Pipeline {
         GraphView g{st, bloom, edge_bases.p, edge_off.p, edge_len.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, from_e.p, to_e.p, from_n.p, to_n.p};
         const ReadsView rv = dr.view();
         const unsigned block = 128;
-        static const int path_occ_grid = getenv("W2RAP_PATH_OCC") ? std::max(12, atoi(getenv("W2RAP_PATH_OCC"))) : 12;
+        static const int path_occ_grid = getenv("W2RAP_PATH_OCC") ? std::max(6, atoi(getenv("W2RAP_PATH_OCC"))) : 8;
         const unsigned gr = grid(n, block, path_occ_grid);
         const uint32_t cap = 24, left_cap = 8;
         SBuf<int32_t> stage(c, n * cap), row_off(c, n);
@@ -1112,13 +1112,15 @@ struct Pipeline {
         SBuf<unsigned long long> counters(c, 4); counters.zero();
         // resident CTAs per SM the compiler must allow for (register cap): the kernel waits on dependent DRAM fetches, so warps in flight matter
         // measured (config 2, path stage): 8 CTAs/SM (64 registers) 96 ms, 10: 105 ms, 12 (40 registers, more spills) 81.5 ms, 14/16: 86 ms
-        static const int path_occ = getenv("W2RAP_PATH_OCC") ? atoi(getenv("W2RAP_PATH_OCC")) : 12;
+        // round 2 (walker state in shared memory, ~350 B less stack): 12 CTAs/SM 71.8 ms, 10: 59.8 ms, 8 (64 registers): 54.9 ms
+        static const int path_occ = getenv("W2RAP_PATH_OCC") ? atoi(getenv("W2RAP_PATH_OCC")) : 8;
         auto launch_path = [&](unsigned grd, const uint32_t* list, uint64_t rows, int32_t* stg, uint32_t cp, uint32_t lcp, int32_t* roff, PathMeta* mt) {
             if (path_occ >= 16) W2R_LAUNCH(c, k_path_reads<16>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
             else if (path_occ >= 14) W2R_LAUNCH(c, k_path_reads<14>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
             else if (path_occ >= 12) W2R_LAUNCH(c, k_path_reads<12>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
             else if (path_occ >= 10) W2R_LAUNCH(c, k_path_reads<10>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
-            else W2R_LAUNCH(c, k_path_reads<8>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            else if (path_occ >= 8) W2R_LAUNCH(c, k_path_reads<8>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
+            else W2R_LAUNCH(c, k_path_reads<6>, grd, block, 0, rv, g, list, rows, stg, cp, lcp, roff, mt, prm.apply_fixpaths);
         };
         W2R_TIMED(W2RAP_KT_PATH_READS, launch_path(gr, nullptr, n, stage.p, cap, left_cap, row_off.p, meta.p));
         W2R_LAUNCH(c, k_path_lens, grid(n, 256), 256, 0, meta.p, (const uint32_t*)nullptr, n, lens.p, counters.p);
@@ -1134,7 +1136,7 @@ struct Pipeline {
         if (n_ovf) {
             W2R_CUDA(cudaMemsetAsync(counters.p + 3, 0, 8, c.stream));
             W2R_LAUNCH(c, k_collect_overflow, grid(n, 256), 256, 0, meta.p, n, olist.p, counters.p + 3);
-            W2R_TIMED(W2RAP_KT_PATH_READS, launch_path(grid(n_ovf, block, 12), olist.p, n_ovf, stage2.p, cap2, left2, row_off2.p, meta2.p));
+            W2R_TIMED(W2RAP_KT_PATH_READS, launch_path(grid(n_ovf, block, path_occ_grid), olist.p, n_ovf, stage2.p, cap2, left2, row_off2.p, meta2.p));
             W2R_CUDA(cudaMemsetAsync(counters.p + 2, 0, 8, c.stream));
             W2R_LAUNCH(c, k_path_lens, grid(n_ovf, 256), 256, 0, meta2.p, (const uint32_t*)olist.p, n_ovf, lens.p, counters.p);
             W2R_CUDA(cudaMemcpyAsync(cnt, counters.p, 24, cudaMemcpyDeviceToHost, c.stream));
