@@ -139,3 +139,30 @@ def test_sharded_graph_stage_simulated_ranks(T, hc, world, logP):
         d[k] = want[k]
     T.assert_graph_equal(want, d, "sharded hostcheck (world %d) vs oracle" % world)
     assert n_pieces > 2 * want["n_edges"]           # the chains really were cut into pieces at rank boundaries
+
+
+def test_quality_floor_on_random_quality_vectors(T, hc):
+    """pq_good_length (the body of k_good_len: block headers, constant blocks, packed deltas compared with the floor several at a
+    time) against the oracle's end-anchored scan (BuildReadQGraph.cc:962-987) on random quality vectors that use every delta width,
+    both PQVec block partitions and several floors.  Compared through the k-mer instance total, which every good length enters."""
+    rng = np.random.default_rng(5)
+    n, L = 1500, 300
+    codes = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    quals = np.zeros((n, L), np.uint8)
+    for r in range(n):
+        base, spread = rng.integers(2, 41), [1, 3, 7, 20, 40][r % 5]
+        q = np.clip(base + rng.integers(0, spread + 1, L) - spread // 2, 0, 63)
+        for _ in range(rng.integers(0, 4)):
+            a = rng.integers(0, L - 70)
+            q[a:a + rng.integers(40, 120)] = rng.integers(7, 41)
+        quals[r] = q
+    lens = rng.integers(1, L + 1, n).astype(np.uint32)
+    for mode in (0, 1):
+        rs = T.flatten_reads(codes, quals, lens, pq_mode=mode)
+        reads = rs.c()
+        for mq in (0, 7, 10, 20, 41):
+            ptr, nn, ni = C.c_void_p(), C.c_uint64(), C.c_uint64()
+            assert hc.hc_count(C.byref(reads), mq, C.byref(ptr), C.byref(nn), C.byref(ni)) == 0
+            hc.hc_free(ptr)
+            want = T.run_oracle(rs, T.default_params(min_qual=mq, want_paths=0, min_freq=1))
+            assert ni.value == want["n_kmer_instances"], (mode, mq)

@@ -237,7 +237,7 @@ constexpr uint32_t SMEM_LOG_SLOTS_MAX = 13;                    // 8192 slots: 12
 constexpr uint32_t SMEM_MAX_PROBE = 512;
 constexpr uint32_t COUNT_STOP = 1u << 16;                      // counters stop here (>= 255 is all anyone asks); + one add per racing thread
 constexpr uint32_t SMEM_MAX_BATCH = 16;                        // runs (read batches / source ranks) that make up one partition
-constexpr uint32_t SKM_CHUNK = 1024;                           // records per staging buffer (32 KB), two buffers
+constexpr uint32_t SKM_CHUNK = 1024;                           // most records per staging buffer (32 KB), two buffers
 struct SmemCountParams {
     const SkmRec* recs;
     const uint32_t* cursor;         // [nbatch][P] records of partition p in slab bi
@@ -251,6 +251,7 @@ struct SmemCountParams {
     DumpRec* dump_out; unsigned long long* dump_cursor;
     uint32_t* failed; unsigned long long* failed_cursor;       // partitions that did not fit this table size
     uint32_t log_slots;                                        // table size of this launch
+    uint32_t chunk;                                            // records per staging buffer (two buffers); <= SKM_CHUNK
     const uint32_t* plist; uint32_t nlist;                     // if set: only these partitions (the ones a smaller table could not hold)
 };
 
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     const uint32_t SMEM_SLOTS = 1u << sp.log_slots;
     ulonglong2* keys = reinterpret_cast<ulonglong2*>(smem_raw);             // {w0, w1}; empty = all ones (a canonical 60-mer never starts with 32 T's)
     uint32_t* ccs = reinterpret_cast<uint32_t*>(keys + SMEM_SLOTS);         // count (low 24 bits) | ctx << 24
-    SkmRec* stage = reinterpret_cast<SkmRec*>(smem_raw + (size_t)20 * SMEM_SLOTS);   // [2][SKM_CHUNK]
+    SkmRec* stage = reinterpret_cast<SkmRec*>(smem_raw + (size_t)20 * SMEM_SLOTS);   // [2][sp.chunk]
+    const uint32_t CHUNK = sp.chunk;
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ unsigned int sh_hist[104];
     __shared__ int sh_fail;
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
     };
     // all lanes of warp 0: stage chunk c of the partition described by (cnt, src) into buffer bf
     auto issue = [&](uint32_t cnt, const SkmRec* src, uint32_t c, uint32_t bf) {
-        const uint32_t lo = c * SKM_CHUNK, hi = lo + SKM_CHUNK;
+        const uint32_t lo = c * CHUNK, hi = lo + CHUNK;
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
         const uint32_t s = acc > lo ? acc : lo, e = acc + cnt < hi ? acc + cnt : hi;
         if (s < e) {
             mbar_expect_tx(&mbar[bf], (e - s) * (uint32_t)sizeof(SkmRec));
-            bulk_g2s(stage + (size_t)bf * SKM_CHUNK + (s - lo), src + (s - acc), (e - s) * (uint32_t)sizeof(SkmRec), &mbar[bf]);
+            bulk_g2s(stage + (size_t)bf * CHUNK + (s - lo), src + (s - acc), (e - s) * (uint32_t)sizeof(SkmRec), &mbar[bf]);
         }
         __syncwarp();                                            // every expect_tx precedes the arrival
         if (lane == 0) {
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
             const uint32_t bf = it & 1u;
             mbar_wait(&mbar[bf], (it >> 1) & 1u);
             const uint32_t tot = sh_tot[bf], cnt = sh_cnt[bf];
-            const bool more = (uint64_t)(c + 1) * SKM_CHUNK < tot;
+            const bool more = (uint64_t)(c + 1) * CHUNK < tot;
             // the other buffer is free: everyone left it at the barrier that ended the previous chunk
             if (warp == 0) {
                 if (more) issue(cu_cnt, cu_src, c + 1, bf ^ 1u);
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(1024, 1) k_count_smem(SmemCountParams sp) {
                     load_desc(pi + 2 * gridDim.x, nx_cnt, nx_src);   // (in flight while this chunk and the next partition are counted)
                 }
             }
-            const SkmRec* st = stage + (size_t)bf * SKM_CHUNK;
+            const SkmRec* st = stage + (size_t)bf * CHUNK;
             // Every warp takes an equal share of the chunk's records, in groups of <= 32 (a fixed deal of 32-record groups left most
             // warps idle in a partition's short last chunk: 24 % of all stall samples sat at the barrier below).  Inside a group the
             // k-mers are numbered consecutively across the records and lane l takes k-mer t + l.  Which record that is: the records that

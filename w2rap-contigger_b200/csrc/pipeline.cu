@@ -379,16 +379,19 @@ struct Pipeline {
         // the table_slots test hook shrinks the first table as well, so that partitions really take the fallback path
         uint32_t log1 = std::max(2u, std::min(smem_log_env, SMEM_LOG_SLOTS_MAX));
         if (prm.table_slots) log1 = (uint32_t)std::max(2, std::min((int)SMEM_LOG_SLOTS_MAX, (int)cs_logR - 6));
+        // small first table (<= 4096 slots): two CTAs of 512 threads per SM, each with half-size staging buffers
+        const bool two_per_sm = log1 <= 12 && !prm.table_slots;
+        const uint32_t chunk1 = two_per_sm ? SKM_CHUNK / 2 : SKM_CHUNK;
         SmemCountParams sc{xrecs, xcur, runs.part_base, runs.slab_off, nslab, (uint32_t)Pown, prm.min_freq, cs_hist.p, cs_solid.p, cs_scal.p + 1, cs_solid_cap, cs_flags.p + 2,
-                           prm.dump_kmers == 2 ? cs_dump.p : nullptr, cs_scal.p + 2, failed.p, cs_scal.p + 4, log1, nullptr, 0};
+                           prm.dump_kmers == 2 ? cs_dump.p : nullptr, cs_scal.p + 2, failed.p, cs_scal.p + 4, log1, chunk1, nullptr, 0};
         kt_.begin(W2RAP_KT_REDUCE);
-        k_count_smem<<<(unsigned)std::min<uint64_t>(Pown, (uint64_t)c.sm_count), 1024, ((size_t)20u << log1) + stage_bytes, c.stream>>>(sc); c.launches++; ++n_groups;
+        k_count_smem<<<(unsigned)std::min<uint64_t>(Pown, (uint64_t)c.sm_count * (two_per_sm ? 2 : 1)), two_per_sm ? 512 : 1024, ((size_t)20u << log1) + (size_t)2 * chunk1 * sizeof(SkmRec), c.stream>>>(sc); c.launches++; ++n_groups;
         kt_.end();
         W2R_CUDA(cudaGetLastError());
         const uint64_t nfail1 = (log1 < SMEM_LOG_SLOTS_MAX && !prm.table_slots) ? d2h_scalar(c, cs_scal.p + 4) : 0;
         if (nfail1) {
             SmemCountParams sc2 = sc;
-            sc2.failed = failed2.p; sc2.failed_cursor = cs_scal.p + 5; sc2.log_slots = SMEM_LOG_SLOTS_MAX; sc2.plist = failed.p; sc2.nlist = (uint32_t)nfail1;
+            sc2.failed = failed2.p; sc2.failed_cursor = cs_scal.p + 5; sc2.log_slots = SMEM_LOG_SLOTS_MAX; sc2.chunk = SKM_CHUNK; sc2.plist = failed.p; sc2.nlist = (uint32_t)nfail1;
             k_count_smem<<<(unsigned)std::min<uint64_t>(nfail1, (uint64_t)c.sm_count), 1024, ((size_t)20u << SMEM_LOG_SLOTS_MAX) + stage_bytes, c.stream>>>(sc2); c.launches++; ++n_groups;
             W2R_CUDA(cudaGetLastError());
         }

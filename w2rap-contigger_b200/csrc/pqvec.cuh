@@ -43,6 +43,15 @@ struct PQReader {
 // and stops at the first position where K consecutive quals >= minQual have been seen; that is the end of the right-most
 // maximal run of >= K good quals, which a forward scan finds as "the last position at which the current run is >= K".
 // The result is stored in a uint16_t by the reference.  *n_quals receives the number of qualities in the stream.
+// 8 bytes from any address as a little-endian word (two aligned loads + a funnel shift; may touch up to 15 bytes past p: the
+// quality store carries 32 bytes of padding)
+W2R_HD uint64_t pq_load64(const uint8_t* p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint64_t* q = (const uint64_t*)(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+    const uint64_t lo = q[0], hi = q[1];
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+}
 // `end` = one past the last byte of the stream (qual_off[i+1]): a block header or payload that would cross it (a truncated or
 // corrupted .qualp) stops the walk and reports 0xffffffff qualities, which the caller turns into W2RAP_ERR_BAD_ARG.
 W2R_HD uint32_t pq_good_length(const uint8_t* stream, const uint8_t* end, uint32_t min_qual, uint32_t* n_quals) {
@@ -69,18 +78,33 @@ W2R_HD uint32_t pq_good_length(const uint8_t* stream, const uint8_t* end, uint32
             if (run >= (uint32_t)K) good = i;
             continue;
         }
-        uint64_t acc = hdr >> 9;
-        uint32_t have = 7;
-        p += 2;
-        const uint32_t mask = (1u << nbits) - 1u;
-        for (uint32_t k = 0; k < nq; ++k) {
-            while (have < nbits) { acc |= (uint64_t)(*p++) << have; have += 8; }
-            const uint32_t q = minq + ((uint32_t)acc & mask);
-            acc >>= nbits; have -= nbits;
-            ++i;
-            if (q < min_qual) run = 0;
-            else if (++run >= (uint32_t)K) good = i;
+        // Deltas below the floor have to be found: `per` deltas at a time from one 64-bit window, compared with the threshold all at
+        // once (even and odd fields separately, so that each field has its neighbour's bits as carry room); only a window that
+        // holds a low quality is walked value by value.
+        const uint32_t thr = min_qual - minq;                  // quality >= min_qual  <=>  delta >= thr  (thr >= 1 here)
+        const uint32_t nbytes = (9u + nq * nbits + 7u) >> 3;
+        if (thr >> nbits) { run = 0; i += nq; p += nbytes; continue; }     // no delta of this width reaches the floor
+        const uint32_t per = 56u / nbits;                      // fields per window (window start is byte aligned + up to 7 bits)
+        const uint64_t field = (1ull << nbits) - 1ull;
+        uint64_t ones_even = 0;
+        for (uint32_t j = 0; j < per; j += 2) ones_even |= 1ull << (j * nbits);
+        const uint64_t add = ((1ull << nbits) - thr) * ones_even, even_fields = field * ones_even;
+        for (uint32_t k = 0; k < nq; k += per) {
+            const uint32_t n = nq - k < per ? nq - k : per;
+            const uint32_t bit = 9u + k * nbits;
+            const uint64_t x = pq_load64(p + (bit >> 3)) >> (bit & 7u);
+            // bit j*nbits of ge is set iff field j >= thr
+            uint64_t ge = (((x & even_fields) + add) >> nbits) & ones_even;
+            ge |= (((((x >> nbits) & even_fields) + add) >> nbits) & ones_even) << nbits;
+            const uint64_t want = (ones_even | (ones_even << nbits)) & ((1ull << (n * nbits)) - 1ull);      // n * nbits <= 56
+            if ((ge & want) == want) { run += n; i += n; if (run >= (uint32_t)K) good = i; continue; }
+            for (uint32_t j = 0; j < n; ++j) {
+                ++i;
+                if (!((ge >> (j * nbits)) & 1ull)) run = 0;
+                else if (++run >= (uint32_t)K) good = i;
+            }
         }
+        p += nbytes;
     }
     if (n_quals) *n_quals = i;
     return good & 0xffffu;
