@@ -226,9 +226,9 @@ struct PutBase { uint8_t* b; void operator()(uint64_t bo, uint64_t pos, uint32_t
 
 // k_edge_ends .. k_adj_sort, dump level 1, k_path_reads: everything that follows the edges, on the WHOLE dictionary `st`
 // (every solid k-mer with its pruned context, edge and offset).
-int finish_graph(const SolidTable& st, EdgeSet& es, uint64_t n_solid, const w2rap_reads* in, int want_paths, int apply_fixpaths, uint32_t cap, uint32_t left_cap, w2rap_graph* out) {
-    const uint64_t E = es.E, T = st.size();
-    SolidSlot* slots = st.slots;
+int finish_graph(const std::vector<PathSlice>& slices, EdgeSet& es, uint64_t n_solid, const w2rap_reads* in, int want_paths, int apply_fixpaths, uint32_t cap, uint32_t left_cap, w2rap_graph* out) {
+    const uint64_t E = es.E;
+    const uint32_t W = (uint32_t)slices.size();
     std::vector<uint32_t>& edge_len = es.edge_len; std::vector<uint64_t>& edge_off = es.edge_off; std::vector<uint8_t>& edge_bases = es.edge_bases;
     // ---- k_edge_ends .. k_adj_sort
     std::vector<EndKey> keys(4 * E);
@@ -280,17 +280,20 @@ int finish_graph(const SolidTable& st, EdgeSet& es, uint64_t n_solid, const w2ra
     for (uint64_t e = 0; e < E; ++e) out->n_edge_bases += edge_len[e];
     {   // dump level 1
         std::vector<w2rap_kmer_rec> d;
-        for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) d.push_back(w2rap_kmer_rec{slots[i].w0, slots[i].w1, 0, slots[i].ctx & 0xff, slots[i].edge, slots[i].off});
+        for (const PathSlice& sl : slices)
+            for (uint64_t i = 0; i < sl.nslots; ++i) if (sl.tab[i].w0 != EMPTY_W0) d.push_back(w2rap_kmer_rec{sl.tab[i].w0, sl.tab[i].w1, 0, sl.tab[i].ctx & 0xff, sl.tab[i].edge, sl.tab[i].off});
         std::sort(d.begin(), d.end(), [](const w2rap_kmer_rec& a, const w2rap_kmer_rec& b) { return a.w0 < b.w0 || (a.w0 == b.w0 && a.w1 < b.w1); });
         out->n_dump = d.size(); out->dump = dup(d);
     }
     if (!want_paths) return 0;
     // ---- k_path_reads (+ overflow retry), k_path_lens, scan, k_path_gather
     // k_bloom_build: the negative-lookup filter of the pathing kernel
-    std::vector<uint32_t> bloom_words(std::max<uint64_t>(1024, n_solid / 2), 0u);
-    KmerBloom bloom{bloom_words.data(), bloom_words.size()};
-    for (uint64_t i = 0; i < T; ++i) if (slots[i].w0 != EMPTY_W0) { uint32_t h = bloom_hash(Kmer{slots[i].w0, slots[i].w1}); bloom_words[bloom_word(bloom, h)] |= bloom_mask(h); }
-    GraphView g{st, bloom, edge_bases.data(), edge_off.data(), edge_len.data(), fwd.data(), rev.data(), hcanon.data(), hleft.data(), hright.data(), from_e.data(), to_e.data(), from_n.data(), to_n.data()};
+    // k_bloom_build per slice (sharded: every rank builds the filter slice of its own dictionary slice, the slices are all-gathered)
+    const uint32_t slice_words = (uint32_t)std::max<uint64_t>(1024, n_solid / 2 / W);
+    std::vector<uint32_t> bloom_words((size_t)slice_words * W, 0u);
+    for (const PathSlice& sl : slices)
+        for (uint64_t i = 0; i < sl.nslots; ++i) if (sl.tab[i].w0 != EMPTY_W0) { uint32_t h = bloom_hash(Kmer{sl.tab[i].w0, sl.tab[i].w1}); bloom_words[pd_bloom_word(W, slice_words, h)] |= bloom_mask(h); }
+    GraphView g{PathDict{slices.data(), W, bloom_words.data(), slice_words}, edge_bases.data(), edge_off.data(), edge_len.data(), fwd.data(), rev.data(), hcanon.data(), hleft.data(), hright.data(), from_e.data(), to_e.data(), from_n.data(), to_n.data()};
     const uint64_t n = in->n_reads;
     uint32_t maxlen = 0;
     for (uint64_t r = 0; r < n; ++r) maxlen = std::max(maxlen, in->len[r]);
@@ -374,7 +377,7 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     es.edge_bases.assign(es.edge_off[E] + 32, 0);
     PutBase put{es.edge_bases.data()};
     for (uint64_t x = 0; x < nn; ++x) emit_node(st, R, edge_of_head.data(), es.edge_off.data(), (uint32_t)x, put);
-    return finish_graph(st, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
+    return finish_graph(std::vector<PathSlice>{PathSlice{slots.data(), T}}, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
 }
 
 // ---- the SHARDED graph stage (csrc/shardgraph.cuh) with `world` simulated ranks: every rank owns the solid k-mers of its
@@ -591,20 +594,29 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
             if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL) continue;
             emit_node_sharded(me.st, me.R.data(), me.lpiece.data(), pinfo.data() + me.piece0, es.edge_off.data(), (uint32_t)x, put);
         }
-    // ---- all-gather of the owned entries (with pruned context, edge, offset): the whole dictionary for pathing
-    std::vector<SolidSlot> full(table_slots_for(n_solid));
-    memset(full.data(), 0xff, full.size() * sizeof(SolidSlot));
-    SolidTable fst{full.data(), full.size()};
-    for (Rank& me : rk)
-        for (uint64_t i = 0; i < me.st.size(); ++i) {
-            const SolidSlot& sl = me.slots[i];
-            if (sl.w0 == EMPTY_W0 || slot_is_ghost(sl)) continue;
-            uint64_t h = fst.home(Kmer{sl.w0, sl.w1});
-            while (full[h].w0 != EMPTY_W0) h = fst.next(h);
-            full[h] = sl;
-        }
+    // ---- the pathing dictionary: finished entries (pruned context, edge, offset) re-sharded by k-mer hash (all-to-all), slice r built
+    // on rank r; the path kernels of all ranks read all slices (peer memory on the device)
+    std::vector<std::vector<SolidSlot>> stab(world);
+    {
+        std::vector<uint64_t> cnt(world, 0);
+        for (Rank& me : rk)
+            for (uint64_t i = 0; i < me.st.size(); ++i) { const SolidSlot& sl = me.slots[i]; if (sl.w0 != EMPTY_W0 && !slot_is_ghost(sl)) ++cnt[pd_slice_of(world, bloom_hash(Kmer{sl.w0, sl.w1}))]; }
+        for (uint32_t r = 0; r < world; ++r) { stab[r].resize(table_slots_for(cnt[r])); memset(stab[r].data(), 0xff, stab[r].size() * sizeof(SolidSlot)); }
+        for (Rank& me : rk)
+            for (uint64_t i = 0; i < me.st.size(); ++i) {
+                const SolidSlot& sl = me.slots[i];
+                if (sl.w0 == EMPTY_W0 || slot_is_ghost(sl)) continue;
+                std::vector<SolidSlot>& t = stab[pd_slice_of(world, bloom_hash(Kmer{sl.w0, sl.w1}))];
+                SolidTable tt{t.data(), t.size()};
+                uint64_t h = tt.home(Kmer{sl.w0, sl.w1});
+                while (t[h].w0 != EMPTY_W0) h = tt.next(h);
+                t[h] = sl;
+            }
+    }
+    std::vector<PathSlice> slices;
+    for (uint32_t r = 0; r < world; ++r) slices.push_back(PathSlice{stab[r].data(), stab[r].size()});
     const uint32_t keep_passes = out->timings.count_passes, keep_res = out->timings.reserved;
-    const int rc = finish_graph(fst, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
+    const int rc = finish_graph(slices, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
     out->timings.count_passes = keep_passes;
     if (!want_paths) out->timings.reserved = keep_res;
     return rc;

@@ -107,11 +107,13 @@ __global__ void k_dump_solid(SolidTable st, DumpRec* __restrict__ out, unsigned 
 }
 
 // Dictionary build (BuildReadQGraph.cc:1096-1104 insertEntryNoLocking, in parallel): keys are unique, so a successful CAS owns the slot.
-__global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, SolidTable st) {
+// bloom (optional): the pathing filter's bits are set on the way (kmer.cuh: PathDict), which saves a sweep over the finished table.
+__global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, SolidTable st, uint32_t* __restrict__ bloom, uint32_t bloom_W, uint32_t slice_words) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         ulonglong2 rec = __ldcs(recs + i);
         Kmer k{rec.x, rec.y & ~0xffull};
         uint32_t ctx = (uint32_t)rec.y & 0xffu;
+        if (bloom) { const uint32_t bh = bloom_hash(k); atomicOr(bloom + pd_bloom_word(bloom_W, slice_words, bh), bloom_mask(bh)); }
         uint64_t h = st.home(k);
         for (;;) {
             SolidSlot* p = st.slots + h;
@@ -123,9 +125,10 @@ __global__ void k_insert_solid(const ulonglong2* __restrict__ recs, uint64_t n, 
 }
 // The same from whole entries (k-mer, pruned context, edge, offset): the pathing dictionary of a sharded run is built from the
 // entries the owner ranks finished (shardgraph.cuh), gathered from all ranks.
-__global__ void k_insert_entries(const SolidSlot* __restrict__ recs, uint64_t n, SolidTable st) {
+__global__ void k_insert_entries(const SolidSlot* __restrict__ recs, uint64_t n, SolidTable st, uint32_t* __restrict__ bloom, uint32_t bloom_W, uint32_t slice_words) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const SolidSlot e = recs[i];
+        if (bloom) { const uint32_t bh = bloom_hash(Kmer{e.w0, e.w1}); atomicOr(bloom + pd_bloom_word(bloom_W, slice_words, bh), bloom_mask(bh)); }
         uint64_t h = st.home(Kmer{e.w0, e.w1});
         for (;;) {
             SolidSlot* p = st.slots + h;
@@ -136,13 +139,15 @@ __global__ void k_insert_entries(const SolidSlot* __restrict__ recs, uint64_t n,
     }
 }
 
-__global__ void k_bloom_build(SolidTable st, KmerBloom b) {
+// filter bits of the entries of one table (one GPU: the whole dictionary; sharded: this rank's slice, whose keys all select filter
+// slice `me`)
+__global__ void k_bloom_build(SolidTable st, uint32_t* __restrict__ bloom, uint32_t W, uint32_t slice_words) {
     const uint64_t T = st.size();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) {
         const SolidSlot* s = st.slots + i;
         if (s->w0 == EMPTY_W0) continue;
         const uint32_t h = bloom_hash(Kmer{s->w0, s->w1});
-        atomicOr(b.words + bloom_word(b, h), bloom_mask(h));
+        atomicOr(bloom + pd_bloom_word(W, slice_words, h), bloom_mask(h));
     }
 }
 
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
         // scan() and gap_found() have one call site each (the walker's code is large; see PathWalker::scan)
         bool need = false, run = true, have_gap = false;
         uint32_t from = 0, found_p = 0;                            // from: first unscreened position of this lane's gap
-        int64_t found_slot = -1;
+        const SolidSlot* found_slot = nullptr;
         for (;;) {
             if (run) {
                 if (have_gap) w.gap_found(found_p, found_slot);
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
                             Kmer f, rc;
                             kmer_pair_at(b, p, &f, &rc);
                             const uint32_t hh = bloom_hash(kmer_less(rc, f) ? rc : f);
-                            if (g.bloom.words) { word[q] = __ldg(g.bloom.words + bloom_word(g.bloom, hh)); bits[q] = bloom_mask(hh); }
+                            if (g.dict.bloom) { word[q] = __ldg(g.dict.bloom + pd_bloom_word(g.dict.W, g.dict.slice_words, hh)); bits[q] = bloom_mask(hh); }
                             else { word[q] = 1; bits[q] = 1; }   // no filter (tiny dictionary): every position is a candidate
                         }
                     }
@@ -482,12 +487,12 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_path_reads(ReadsView r, Graph
                     Kmer f, rc;
                     kmer_pair_at(ps.bases, p, &f, &rc);
                     const Kmer canon = kmer_less(rc, f) ? rc : f;
-                    const int64_t s = solid_find_hashed(g.solid, canon, kmer_hash(canon));
-                    if (s >= 0) { found_p = p; found_slot = s; have_gap = true; run = true; break; }
+                    const SolidSlot* s = pd_find(g.dict, canon, bloom_hash(canon));
+                    if (s) { found_p = p; found_slot = s; have_gap = true; run = true; break; }
                 }
                 if (!run) {
                     from += 32;
-                    if (from >= ps.nk) { found_p = ps.nk; found_slot = -1; have_gap = true; run = true; }
+                    if (from >= ps.nk) { found_p = ps.nk; found_slot = nullptr; have_gap = true; run = true; }
                 }
             }
         }

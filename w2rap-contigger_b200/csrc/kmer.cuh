@@ -198,15 +198,21 @@ W2R_HD int64_t solid_find_hashed(const SolidTable& t, Kmer k, uint64_t hh) {
     }
 }
 W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) { return solid_find_hashed(t, k, kmer_hash(k)); }
-// Blocked Bloom filter over the dictionary keys (two bits in one 32-bit word per key).  Read pathing looks up every k-mer of
-// a read's error-laden tail, almost all of them absent; the filter is small enough to stay in L2, so a negative lookup costs
-// one L2 hit instead of a random DRAM sector (+ a TLB miss) in the multi-GB table.  No false negatives.
-struct KmerBloom {
-    uint32_t* words;        // nullptr = no filter
-    uint64_t nwords;
-};
+// ---------------------------------------------------------------- the dictionary the reads are pathed against
+// W slices keyed by a hash of the k-mer.  One GPU: one slice = the graph stage's own table.  Sharded: slice r is built and held by
+// GPU r and read by the path kernels of all GPUs through peer-mapped memory (NVLink/NVSwitch P2P loads) — the finished dictionary is
+// never replicated.  In front of it a blocked Bloom filter (two bits in one 32-bit word per key), sliced the same way and small
+// enough to be replicated: read pathing looks up every k-mer of a read's error-laden tail, almost all of them absent, and a negative
+// answer then costs one local sector instead of a (remote) probe chain.  No false negatives.
 // The filter has its own cheap 32-bit hash (two multiply-adds per word half): gap screening hashes ~100 k-mers per read, and the
 // 64-bit table hash (four 64-bit multiplies) is only worth computing for the few candidates that pass.
+struct PathSlice { const SolidSlot* tab; uint64_t nslots; };
+struct PathDict {
+    const PathSlice* slices;   // [W] (device memory)
+    uint32_t W;
+    const uint32_t* bloom;     // W consecutive filter slices of slice_words words; nullptr = no filter
+    uint32_t slice_words;
+};
 W2R_HD uint32_t bloom_hash(Kmer k) {
     uint32_t x = (uint32_t)k.w0 * 0x9e3779b1u + (uint32_t)(k.w0 >> 32) * 0x85ebca77u;
     x ^= x >> 15;
@@ -214,21 +220,42 @@ W2R_HD uint32_t bloom_hash(Kmer k) {
     x ^= x >> 13; x *= 0x165667b1u; x ^= x >> 16;
     return x;
 }
-W2R_HD uint64_t bloom_word(const KmerBloom& b, uint32_t h) { return ((uint64_t)h * b.nwords) >> 32; }        // nwords < 2^32
+W2R_HD uint32_t pd_slice_of(uint32_t W, uint32_t bh) { return W == 1 ? 0u : (uint32_t)(((uint64_t)bh * W) >> 32); }
+W2R_HD uint64_t pd_bloom_word(uint32_t W, uint32_t slice_words, uint32_t bh) {
+    uint32_t y = bh * 0x9e3779b1u; y ^= y >> 15;                               // (re-mixed: the top bits of bh chose the slice)
+    return (uint64_t)pd_slice_of(W, bh) * slice_words + (((uint64_t)y * slice_words) >> 32);
+}
 W2R_HD uint32_t bloom_mask(uint32_t h) { const uint32_t y = h * 0x2c1b3c6du; return (1u << (y >> 27)) | (1u << ((y >> 22) & 31u)); }
-W2R_HD bool bloom_may_contain(const KmerBloom& b, uint32_t h) {
-    if (!b.words) return true;
-    const uint32_t m = bloom_mask(h);
+W2R_HD bool pd_may_contain(const PathDict& d, uint32_t bh) {
+    if (!d.bloom) return true;
+    const uint32_t m = bloom_mask(bh);
 #if defined(__CUDA_ARCH__)
-    return (__ldg(b.words + bloom_word(b, h)) & m) == m;
+    return (__ldg(d.bloom + pd_bloom_word(d.W, d.slice_words, bh)) & m) == m;
 #else
-    return (b.words[bloom_word(b, h)] & m) == m;
+    return (d.bloom[pd_bloom_word(d.W, d.slice_words, bh)] & m) == m;
 #endif
 }
-// Canonical lookup through the filter.
-W2R_HD int64_t solid_find_filtered(const SolidTable& t, const KmerBloom& b, Kmer k) {
-    if (!bloom_may_contain(b, bloom_hash(k))) return -1;
-    return solid_find(t, k);
+// Canonical lookup (bh = bloom_hash(k)); returns the entry or nullptr.  The probe sequence inside a slice is SolidTable's.
+W2R_HD const SolidSlot* pd_find(const PathDict& d, Kmer k, uint32_t bh) {
+    const PathSlice sl = d.slices[pd_slice_of(d.W, bh)];
+    uint64_t h = mulhi64(kmer_hash(k), sl.nslots);
+    for (;;) {
+        const SolidSlot* s = sl.tab + h;
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(s));
+        const uint64_t a = kk.x, b = kk.y;
+#else
+        const uint64_t a = s->w0, b = s->w1;
+#endif
+        if (a == k.w0 && b == k.w1) return s;
+        if (a == EMPTY_W0) return nullptr;
+        h = h + 1 == sl.nslots ? 0 : h + 1;
+    }
+}
+W2R_HD const SolidSlot* pd_find_filtered(const PathDict& d, Kmer k) {
+    const uint32_t bh = bloom_hash(k);
+    if (!pd_may_contain(d, bh)) return nullptr;
+    return pd_find(d, k, bh);
 }
 
 // kmers/ReadPather.h:196-199 findEntry: canonicalise then look up.  *rev = query was in REV form (rc < query).

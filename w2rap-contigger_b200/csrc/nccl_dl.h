@@ -22,6 +22,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -42,6 +43,7 @@ struct NcclApi {
             W2R_NCCL_SYM(CommDestroy, "ncclCommDestroy")
             W2R_NCCL_SYM(AllReduce, "ncclAllReduce")
             W2R_NCCL_SYM(Broadcast, "ncclBroadcast")
+            W2R_NCCL_SYM(AllGather, "ncclAllGather")
             W2R_NCCL_SYM(Send, "ncclSend")
             W2R_NCCL_SYM(Recv, "ncclRecv")
             W2R_NCCL_SYM(GroupStart, "ncclGroupStart")

@@ -12,8 +12,7 @@
 namespace w2r {
 
 struct GraphView {
-    SolidTable solid;
-    KmerBloom bloom;               // negative-lookup filter over the dictionary (may be empty)
+    PathDict dict;                 // the finished dictionary (k-mer -> edge, offset), sliced over the GPUs, + its negative-lookup filter
     const uint8_t* edge_bases;     // canonical edges, bvec packing, byte aligned per edge
     const uint64_t* edge_off;      // byte offsets
     const uint32_t* edge_len;      // bases
@@ -177,7 +176,7 @@ struct PathState {
     bool pending_gap; uint32_t gap_len, gap_index;
     uint32_t itr;
     bool overflow, scan_done;
-    int64_t found_slot;             // dictionary slot of the k-mer at itr, found by the gap screening (-1: not known)
+    const SolidSlot* found_slot;    // dictionary entry of the k-mer at itr, found by the gap screening (nullptr: not known)
 };
 struct PathWalker {
     PathState& s;
@@ -193,7 +192,7 @@ struct PathWalker {
         s.n_ids = s.sum_kmers = s.seeds = s.nparts = 0;
         s.first_is_gap = s.have_first_hit = false; s.gap0_len = s.first_hit_off = 0;
         s.last_is_gap = s.last2_is_gap = false; s.pending_gap = false; s.gap_len = s.gap_index = 0;
-        s.itr = 0; s.overflow = false; s.scan_done = false; s.found_slot = -1;
+        s.itr = 0; s.overflow = false; s.scan_done = false; s.found_slot = nullptr;
     }
     W2R_HD void commit(const PathPart& h) {                     // :804-815 pathPartsToReadPath, one kept seed
         if (s.last_kept_valid && s.lk_edge == h.edge && s.lk_rc == h.rc) return;
@@ -202,8 +201,8 @@ struct PathWalker {
         s.last_kept_valid = true; s.lk_edge = h.edge; s.lk_rc = h.rc;
     }
     // the k-mer at s.itr is dictionary entry `slot`: extend the match along its edge; false = the path ends here (captured-gap rule)
-    W2R_HD bool seed(int64_t slot) {
-        const SolidSlot& ss = g->solid.slots[slot];
+    W2R_HD bool seed(const SolidSlot* slot) {
+        const SolidSlot ss = *slot;
         PathPart h;
         h.edge = ss.edge;
         const uint32_t elen = g->edge_len[h.edge];
@@ -270,26 +269,26 @@ struct PathWalker {
     //  it and instruction-fetch stalls were the second largest stall reason; gap_found() hands its slot over through found_slot)
     W2R_HD bool scan() {
         while (!s.scan_done && s.itr < s.nk) {
-            int64_t slot = s.found_slot;
-            s.found_slot = -1;
-            if (slot < 0) {
+            const SolidSlot* slot = s.found_slot;
+            s.found_slot = nullptr;
+            if (!slot) {
                 Kmer f = kmer_at(s.bases, s.itr);
                 Kmer r = kmer_rc(f);
-                slot = solid_find_filtered(g->solid, g->bloom, kmer_less(r, f) ? r : f);
-                if (slot < 0) return true;
+                slot = pd_find_filtered(g->dict, kmer_less(r, f) ? r : f);
+                if (!slot) return true;
             }
             if (!seed(slot)) s.scan_done = true;
         }
         return false;
     }
-    W2R_HD void gap_found(uint32_t p, int64_t slot) {
+    W2R_HD void gap_found(uint32_t p, const SolidSlot* slot) {
         const uint32_t gl = p - s.itr;
         s.itr = p;
         if (s.nparts == 0) { s.first_is_gap = true; s.gap0_len = gl; }
         s.gap_len = gl; s.gap_index = s.nparts; ++s.nparts;
         s.last2_is_gap = s.last_is_gap; s.last_is_gap = true;
         s.pending_gap = true;
-        if (slot < 0) s.scan_done = true; else s.found_slot = slot;         // scan(), which every caller runs next, seeds from it
+        if (!slot) s.scan_done = true; else s.found_slot = slot;            // scan(), which every caller runs next, seeds from it
     }
     W2R_HD PathResult finish(const uint8_t* qstream, bool apply_fixpaths) {
         PathResult res{0, left_cap, 0, false};
@@ -350,13 +349,13 @@ W2R_HD PathResult path_one_read(const GraphView& g, const uint8_t* bases, uint32
     w.init(g, bases, rlen, row, cap, left_cap);
     while (w.scan()) {
         uint32_t p = st.itr + 1;
-        int64_t slot = -1;
+        const SolidSlot* slot = nullptr;
         if (p < st.nk) {
             Kmer f = kmer_at(bases, p), r = kmer_rc(f);
             uint64_t nxt = 0;
             for (uint32_t t = 0;; ++t) {
-                slot = solid_find_filtered(g.solid, g.bloom, kmer_less(r, f) ? r : f);
-                if (slot >= 0 || p + 1 >= st.nk) { if (slot < 0) ++p; break; }
+                slot = pd_find_filtered(g.dict, kmer_less(r, f) ? r : f);
+                if (slot || p + 1 >= st.nk) { if (!slot) ++p; break; }
                 if ((t & 31u) == 0) nxt = bases32_at(bases, (uint64_t)p + K);
                 const uint32_t nb = (uint32_t)nxt & 3u;
                 nxt >>= 2;

@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <mutex>
 #include <thread>
+#include <unistd.h>
 
 #include "../../include/w2rap_step2.h"
 #include "device_reads.cuh"
@@ -165,6 +166,48 @@ static void say(const Ctx& c, const char* fmt, ...) {
     if (!c.verbose) return;
     va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap); printf("\n"); fflush(stdout);
 }
+
+// The slice of the pathing dictionary this GPU holds in a sharded run is read by the path kernels of the OTHER GPUs through
+// peer-mapped memory.  It is a plain cudaMalloc allocation (stream-ordered pool memory cannot be exported), kept between calls
+// together with the mappings of the peers' slices: exporting/opening a handle costs a driver round trip each.
+struct PeerInfo { cudaIpcMemHandle_t h; unsigned long long ptr, nslots, pid; int dev, pad; };
+struct PeerArena {
+    void* own = nullptr; size_t own_bytes = 0; cudaIpcMemHandle_t own_h;
+    struct Peer { bool open = false; bool ipc = false; cudaIpcMemHandle_t h; void* p = nullptr; } peers[16];
+    static PeerArena& get(int device) { static PeerArena* a = new PeerArena[16]; return a[device & 15]; }
+    // my slice buffer (grow-only); the handle changes only when it is re-allocated
+    void* reserve(size_t bytes) {
+        if (own_bytes < bytes) {
+            if (own) { cudaDeviceSynchronize(); cudaFree(own); own = nullptr; own_bytes = 0; }
+            const size_t want = bytes + bytes / 8;
+            W2R_CUDA(cudaMalloc(&own, want));
+            own_bytes = want;
+            W2R_CUDA(cudaIpcGetMemHandle(&own_h, own));
+        }
+        return own;
+    }
+    // the address at which peer r's slice can be read from this device
+    const void* map(int r, const PeerInfo& pi, int my_device) {
+        Peer& p = peers[r & 15];
+        if (p.open && memcmp(&p.h, &pi.h, sizeof(pi.h)) == 0) return p.p;
+        if (p.open && p.ipc) cudaIpcCloseMemHandle(p.p);
+        p.open = false;
+        if (pi.pid == (unsigned long long)getpid()) {           // ranks driven from threads of one process: enable peer access, use the pointer
+            int can = 0;
+            W2R_CUDA(cudaDeviceCanAccessPeer(&can, my_device, pi.dev));
+            if (!can) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d cannot access the memory of device %d: the sharded pathing dictionary needs peer access", my_device, pi.dev);
+            cudaError_t e = cudaDeviceEnablePeerAccess(pi.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) W2R_CUDA(e);
+            cudaGetLastError();
+            p.p = (void*)(uintptr_t)pi.ptr; p.ipc = false;
+        } else {
+            W2R_CUDA(cudaIpcOpenMemHandle(&p.p, pi.h, cudaIpcMemLazyEnablePeerAccess));
+            p.ipc = true;
+        }
+        p.h = pi.h; p.open = true;
+        return p.p;
+    }
+};
 
 // ---------------------------------------------------------------- the pipeline
 struct Pipeline {
@@ -640,10 +683,27 @@ struct Pipeline {
         build_dictionary(n_solid_local, n_distinct);
     }
 
+    // the pathing filter (kmer.cuh: PathDict): W slices of path_slice_words words, zeroed; its bits are set while the dictionary is built
+    void alloc_path_filter(uint64_t n_solid) {
+        path_slice_words = 0;
+        path_bloom.release();
+        if (n_solid < 4096 || getenv("W2RAP_NO_BLOOM") || !prm.want_paths) return;
+        static const uint64_t bloom_mb = getenv("W2RAP_BLOOM_MB") ? (uint64_t)atoi(getenv("W2RAP_BLOOM_MB")) : 192;
+        const uint64_t bytes = std::min<uint64_t>(bloom_mb << 20, std::max<uint64_t>(4096, n_solid * 2));
+        path_slice_words = (uint32_t)std::max<uint64_t>(64, bytes / 4 / world);
+        path_bloom.alloc(c, (size_t)path_slice_words * world);
+        path_bloom.zero();
+    }
+
     // One GPU: the dictionary (kmers/ReadPather.h:176-349) as an open-addressing table over all solid k-mers.  Sharded: every rank keeps
     // the solid k-mers it counted; graph_stage_sharded() builds its local table from them.
     uint64_t n_solid_local_ = 0;
     uint32_t count_logP_ = 0;
+    // the dictionary the reads are pathed against (kmer.cuh: PathDict)
+    SBuf<PathSlice> path_slices;
+    SBuf<uint32_t> path_bloom;
+    uint32_t path_slice_words = 0;
+    uint64_t n_slice_entries = 0;           // sharded: entries of the dictionary slice this rank holds
     void build_dictionary(uint64_t n_solid_local, uint64_t n_distinct) {
         std::vector<unsigned long long> tot = {n_solid_local};
         allreduce_u64(tot, ncclSum);
@@ -660,7 +720,9 @@ struct Pipeline {
         solid_slots.alloc(c, nslots);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, nslots};
-        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, (const ulonglong2*)cs_solid.p, n_solid, st));
+        alloc_path_filter(n_solid);
+        if (n_solid) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_solid, 256), 256, 0, (const ulonglong2*)cs_solid.p, n_solid, st,
+                                                                   path_slice_words ? path_bloom.p : nullptr, 1u, path_slice_words));
         out->timings.dict_ms = kt.stop();
         cs_solid.release();
     }
@@ -840,7 +902,7 @@ struct Pipeline {
         solid_slots.alloc(c, nslots);
         solid_slots.fill_ff();
         st = SolidTable{solid_slots.p, nslots};
-        if (n_local) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_local, 256), 256, 0, (const ulonglong2*)solid.p, n_local, st));
+        if (n_local) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_local, 256), 256, 0, (const ulonglong2*)solid.p, n_local, st, (uint32_t*)nullptr, 1u, 0u));
         solid.release();
         // -- keys to the owners, slots back
         kt_.begin(W2RAP_KT_SG_QUERIES);
@@ -1013,37 +1075,82 @@ struct Pipeline {
         xchg_bytes += ebw * 4 + np;
         kt_.end();
         kt_.begin(W2RAP_KT_SG_DICT);
-        // -- the finished entries (pruned context, edge, offset) of every rank: the dictionary the reads are pathed against
-        SBuf<SolidSlot> mine(c, n_local + 1);
-        W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
-        W2R_LAUNCH(c, k_dump_owned, grid(st.size(), 256), 256, 0, st, mine.p, n_local, scal.p);
-        if (d2h_scalar(c, scal.p) != n_local) W2R_FAIL(W2RAP_ERR_INTERNAL, "owned entries lost in the local table");
-        std::vector<unsigned long long> per(W, 0ull);
-        per[me] = n_local;
-        allreduce_u64(per, ncclSum);
-        uint64_t n_solid = 0, per_max = 0;
-        for (auto v : per) { n_solid += v; per_max = std::max<uint64_t>(per_max, v); }
+        // -- the finished entries (pruned context, edge, offset) become the dictionary the reads are pathed against: re-sharded by
+        // k-mer hash (all-to-all), slice r built on rank r in peer-mappable memory, filter slices all-gathered (kmer.cuh: PathDict)
         xms += xt.stop();
-        next0.release(); ghead.release(); A.release(); B.release(); solid_slots.release();
+        next0.release(); ghead.release(); A.release(); B.release();
         pieces.release(); nxt.release(); flip.release(); S.release();
-        kt_.end();
-        // rank by rank through a bounce buffer (a whole-job gather buffer would double the footprint of the dictionary: at 1.5 G
-        // solid k-mers that is the difference between fitting a 180 GB device and not)
-        const uint64_t fslots = solid_table_slots(n_solid);
-        solid_slots.alloc(c, fslots);
-        solid_slots.fill_ff();
-        st = SolidTable{solid_slots.p, fslots};
-        SBuf<SolidSlot> bounce(c, per_max + 1);
-        for (uint32_t r = 0; r < W; ++r) {
-            if (!per[r]) continue;
-            kt_.begin(W2RAP_KT_SG_DICT);
-            xt.start();
-            nccl_check(NcclApi::get().Broadcast(r == me ? (const void*)mine.p : (const void*)bounce.p, bounce.p, per[r] * sizeof(SolidSlot), ncclUint8, (int)r, comm, c.stream), "broadcast");
-            xms += xt.stop();
-            kt_.end();
-            W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(per[r], 256), 256, 0, (const SolidSlot*)bounce.p, (uint64_t)per[r], st));
+        uint64_t ecap = std::max<uint64_t>(1024, n_local / W + n_local / (4 * W));
+        SBuf<SolidSlot> ebuck;
+        SBuf<unsigned long long> ecount(c, W);
+        std::vector<unsigned long long> en(W, 0);
+        for (int attempt = 0;; ++attempt) {
+            if (attempt > 2) W2R_FAIL(W2RAP_ERR_INTERNAL, "dictionary slice buffers did not converge");
+            ebuck.alloc(c, W * ecap);
+            ecount.zero();
+            W2R_LAUNCH(c, k_dump_owned_sliced, grid(st.size(), 256), 256, 0, st, W, ebuck.p, ecap, ecount.p);
+            W2R_CUDA(cudaMemcpyAsync(en.data(), ecount.p, W * 8, cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));
+            unsigned long long mx = 0, sum = 0;
+            for (auto v : en) { mx = std::max(mx, v); sum += v; }
+            if (sum != n_local) W2R_FAIL(W2RAP_ERR_INTERNAL, "owned entries lost in the local table");
+            if (mx <= ecap) break;
+            ecap = mx + mx / 64 + 64;
         }
-        xchg_bytes += n_local * sizeof(SolidSlot) * (uint64_t)(W - 1);
+        solid_slots.release();
+        xt.start();
+        SBuf<unsigned long long> ercount(c, W);
+        alltoall_slabs(ecount.p, ercount.p, sizeof(unsigned long long));
+        std::vector<unsigned long long> ern(W, 0);
+        W2R_CUDA(cudaMemcpyAsync(ern.data(), ercount.p, W * 8, cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        std::vector<size_t> es_off(W), es_cnt(W), er_off(W), er_cnt(W);
+        uint64_t n_mine = 0;
+        for (uint32_t d = 0; d < W; ++d) { es_off[d] = d * ecap; es_cnt[d] = en[d]; er_off[d] = n_mine; er_cnt[d] = ern[d]; n_mine += ern[d]; if (d != me) xchg_bytes += en[d] * sizeof(SolidSlot); }
+        SBuf<SolidSlot> erecv(c, n_mine + 1);
+        alltoall_v(ebuck.p, scaled(es_off, sizeof(SolidSlot)), scaled(es_cnt, sizeof(SolidSlot)), erecv.p, scaled(er_off, sizeof(SolidSlot)), scaled(er_cnt, sizeof(SolidSlot)));
+        xms += xt.stop();
+        ebuck.release();
+        kt_.end();
+        // my slice
+        PeerArena& arena = PeerArena::get(c.device);
+        const uint64_t sslots = solid_table_slots(n_mine);
+        SolidSlot* slice = (SolidSlot*)arena.reserve(sslots * sizeof(SolidSlot));
+        W2R_CUDA(cudaMemsetAsync(slice, 0xff, sslots * sizeof(SolidSlot), c.stream));
+        st = SolidTable{slice, sslots};
+        n_slice_entries = n_mine;
+        std::vector<unsigned long long> tot = {n_local};
+        allreduce_u64(tot, ncclSum);
+        const uint64_t n_solid = tot[0];
+        // filter: every rank sets the bits of its own slice while it inserts, the slices are all-gathered in place
+        alloc_path_filter(n_solid);
+        if (n_mine) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(n_mine, 256), 256, 0, (const SolidSlot*)erecv.p, n_mine, st,
+                                                                  path_slice_words ? path_bloom.p : nullptr, W, path_slice_words));
+        erecv.release();
+        kt_.begin(W2RAP_KT_SG_DICT);
+        if (path_slice_words) {
+            xt.start();
+            nccl_check(NcclApi::get().AllGather(path_bloom.p + (size_t)me * path_slice_words, path_bloom.p, (size_t)path_slice_words * 4, ncclUint8, comm, c.stream), "all-gather");
+            xms += xt.stop();
+        }
+        // where every slice can be read from this GPU
+        PeerInfo mine_pi;
+        memset(&mine_pi, 0, sizeof mine_pi);
+        mine_pi.h = arena.own_h; mine_pi.ptr = (unsigned long long)(uintptr_t)slice; mine_pi.nslots = sslots; mine_pi.pid = (unsigned long long)getpid(); mine_pi.dev = c.device;
+        SBuf<PeerInfo> pi_dev(c, 1), pi_all;
+        W2R_CUDA(cudaMemcpyAsync(pi_dev.p, &mine_pi, sizeof mine_pi, cudaMemcpyHostToDevice, c.stream));
+        std::vector<uint64_t> pioff;
+        xt.start();
+        allgather_v(pi_dev.p, 1, pi_all, pioff);                 // (a collective after every rank's inserts: nobody reads a slice before it is complete)
+        xms += xt.stop();
+        std::vector<PeerInfo> pis(W);
+        W2R_CUDA(cudaMemcpyAsync(pis.data(), pi_all.p, W * sizeof(PeerInfo), cudaMemcpyDeviceToHost, c.stream));
+        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        std::vector<PathSlice> sl(W);
+        for (uint32_t r = 0; r < W; ++r) sl[r] = PathSlice{r == me ? slice : (const SolidSlot*)arena.map((int)r, pis[r], c.device), pis[r].nslots};
+        path_slices.alloc(c, W);
+        W2R_CUDA(cudaMemcpyAsync(path_slices.p, sl.data(), W * sizeof(PathSlice), cudaMemcpyHostToDevice, c.stream));
+        kt_.end();
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         out->timings.graph_exchange_ms = xms;
     }
@@ -1088,22 +1195,18 @@ struct Pipeline {
         d_offset.alloc(c, n); d_path_off.alloc(c, n + 1);
         *n_path_edges = 0; *pathed = 0; *multipathed = 0;
         if (!n) { W2R_CUDA(cudaMemsetAsync(d_path_off.p, 0, 8, c.stream)); return; }
-        // negative-lookup filter (kmer.cuh: KmerBloom), with an L2 persistence window for the duration of the pathing kernel.  Its
-        // false-positive rate matters more than full L2 residency: every false positive is a random DRAM fetch in the dictionary.
-        SBuf<uint32_t> bloom_words;
-        KmerBloom bloom{nullptr, 0};
-        if (out->n_solid >= 4096 && !getenv("W2RAP_NO_BLOOM")) {
-            static const uint64_t bloom_mb = getenv("W2RAP_BLOOM_MB") ? (uint64_t)atoi(getenv("W2RAP_BLOOM_MB")) : 192;   // measured (config 2): 40 MB 111 ms, 96 MB 100 ms, 192 MB 97.5 ms
-            uint64_t bytes = std::min<uint64_t>(bloom_mb << 20, std::max<uint64_t>(4096, out->n_solid * 2));
-            if (bytes * 8 >= 2 * out->n_solid) {          // below ~2 bits per key the filter passes most queries: not worth its L2
-                bloom_words.alloc(c, bytes / 4); bloom_words.zero();
-                bloom = KmerBloom{bloom_words.p, bytes / 4};
-                W2R_TIMED(W2RAP_KT_BLOOM_BUILD, W2R_LAUNCH(c, k_bloom_build, grid(st.size(), 256), 256, 0, st, bloom));
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) cudaGetLastError();
-                set_l2_window(bloom_words.p, bytes);
-            }
+        // the dictionary the reads are pathed against (kmer.cuh: PathDict).  One GPU: the graph stage's own table as the only slice and
+        // a filter built here; sharded: graph_stage_sharded() left this rank's slice, the peer-mapped slices of the others and the
+        // all-gathered filter.  (The filter is not pinned in L2: its misses are sectors of a 192 MB array either way, and the
+        // persisting carve-out made no difference once the kernel stopped spilling: 96 / 192 / 384 MB all 47 ms at config 2.)
+        if (world == 1) {
+            const PathSlice one{st.slots, st.nslots};
+            path_slices.alloc(c, 1);
+            W2R_CUDA(cudaMemcpyAsync(path_slices.p, &one, sizeof one, cudaMemcpyHostToDevice, c.stream));
+            W2R_CUDA(cudaStreamSynchronize(c.stream));       // (`one` leaves scope)
         }
-        GraphView g{st, bloom, edge_bases.p, edge_off.p, edge_len.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, from_e.p, to_e.p, from_n.p, to_n.p};
+        const PathDict dict{path_slices.p, (uint32_t)world, path_slice_words ? path_bloom.p : nullptr, path_slice_words};
+        GraphView g{dict, edge_bases.p, edge_off.p, edge_len.p, fwd_xlat.p, rev_xlat.p, hcanon.p, hleft.p, hright.p, from_e.p, to_e.p, from_n.p, to_n.p};
         const ReadsView rv = dr.view();
         const unsigned block = 128;
         static const int path_occ_grid = getenv("W2RAP_PATH_OCC") ? std::max(6, atoi(getenv("W2RAP_PATH_OCC"))) : 8;
@@ -1154,12 +1257,6 @@ struct Pipeline {
         W2R_CUDA(cudaStreamSynchronize(c.stream));
         d_path_edges.alloc(c, *n_path_edges);
         W2R_LAUNCH(c, k_path_gather, grid(n, 256), 256, 0, stage.p, cap, meta.p, (const uint32_t*)nullptr, row_off.p, d_path_off.p, n, d_path_edges.p, d_offset.p);
-        if (bloom.words) {
-            set_l2_window(nullptr, 0);
-            W2R_CUDA(cudaStreamSynchronize(c.stream));
-            if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
-        }
         if (n_ovf) W2R_LAUNCH(c, k_path_gather, grid(n_ovf, 256), 256, 0, stage2.p, cap2, meta2.p, (const uint32_t*)olist.p, row_off2.p, d_path_off.p, n_ovf, d_path_edges.p, d_offset.p);
         W2R_CUDA(cudaStreamSynchronize(c.stream));
     }
@@ -1228,11 +1325,15 @@ struct Pipeline {
             out->path_edges = to_host<int32_t>(d_path_edges.p, npe);
         }
         if (prm.dump_kmers == 1 && out->n_solid) {
-            SBuf<DumpRec> dd(c, out->n_solid);
+            // (sharded: every rank dumps the dictionary slice it holds; the test hook gathers them so that every rank reports the whole)
+            const uint64_t n_mine = world > 1 ? n_slice_entries : out->n_solid;
+            SBuf<DumpRec> dd(c, n_mine + 1), dd_all;
             SBuf<unsigned long long> cur(c, 1); cur.zero();
             W2R_LAUNCH(c, k_dump_solid, grid(st.size(), 256), 256, 0, st, dd.p, cur.p);
+            const DumpRec* src = dd.p;
+            if (world > 1) { std::vector<uint64_t> doff; allgather_v(dd.p, n_mine, dd_all, doff); src = dd_all.p; }
             dump_host.resize(out->n_solid);
-            W2R_CUDA(cudaMemcpyAsync(dump_host.data(), dd.p, out->n_solid * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
+            W2R_CUDA(cudaMemcpyAsync(dump_host.data(), src, out->n_solid * sizeof(DumpRec), cudaMemcpyDeviceToHost, c.stream));
             W2R_CUDA(cudaStreamSynchronize(c.stream));
         }
         W2R_CUDA(cudaStreamSynchronize(c.stream));
@@ -1269,7 +1370,8 @@ struct Pipeline {
         // free stream-ordered buffers before the stream goes away
         good.release(); solid_slots.release(); edge_bases.release(); edge_off.release(); edge_len.release();
         edge_vertices.release(); fwd_xlat.release(); rev_xlat.release(); involution.release(); hleft.release();
-        cs_scal.release(); cs_flags.release(); cs_hist.release(); cs_region.release(); cs_dump.release(); cs_solid.release(); hright.release(); from_e.release(); to_e.release();
+        cs_scal.release(); cs_flags.release(); cs_hist.release(); cs_region.release(); cs_dump.release(); cs_solid.release();
+        path_slices.release(); path_bloom.release(); hright.release(); from_e.release(); to_e.release();
         hcanon.release(); from_n.release(); to_n.release();
         if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
     }

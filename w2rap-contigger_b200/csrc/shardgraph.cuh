@@ -32,27 +32,36 @@ W2R_HD uint32_t mmer_of_words(uint64_t lo, uint64_t hi, int t) {          // m-m
     const uint64_t w = bit == 0 ? lo : (bit < 64 ? (lo >> bit) | (hi << (64 - bit)) : hi >> (bit - 64));
     return (uint32_t)w & ((1u << (2 * MINI_M)) - 1u);
 }
-template <class Emit>
-W2R_HD void neighbour_queries(Kmer k, uint32_t c, uint32_t logP, uint32_t world, uint32_t me, Emit& emit) {
-    if (!(c & 0xffu)) return;
-    const uint64_t lo = rev2(k.w0), hi = rev2(k.w1);
-    uint32_t min_wo_first = 0xffffffffu, min_wo_last = 0xffffffffu;
-    for (int t = 0; t < MINI_W; ++t) {
-        const uint32_t h = mmer_hash_of(mmer_of_words(lo, hi, t));
-        if (t > 0 && h < min_wo_first) min_wo_first = h;
-        if (t < MINI_W - 1 && h < min_wo_last) min_wo_last = h;
+struct NeighbourScan {
+    Kmer k; uint32_t c, logP, world, me, min_wo_first, min_wo_last;
+    W2R_HD NeighbourScan(Kmer k_, uint32_t c_, uint32_t logP_, uint32_t world_, uint32_t me_) : k(k_), c(c_ & 0xffu), logP(logP_), world(world_), me(me_),
+                                                                                                  min_wo_first(0xffffffffu), min_wo_last(0xffffffffu) {
+        if (!c) return;
+        const uint64_t lo = rev2(k.w0), hi = rev2(k.w1);
+        for (int t = 0; t < MINI_W; ++t) {
+            const uint32_t h = mmer_hash_of(mmer_of_words(lo, hi, t));
+            if (t > 0 && h < min_wo_first) min_wo_first = h;
+            if (t < MINI_W - 1 && h < min_wo_last) min_wo_last = h;
+        }
     }
-    for (uint32_t b = 0; b < 8; ++b) {
-        if (!(c & (1u << b))) continue;
+    // context bit b (0-3 successors, 4-7 predecessors): does its neighbour live on another rank?  Then *owner and its canonical form *cn.
+    W2R_HD bool remote(uint32_t b, uint32_t* owner, Kmer* cn) const {
+        if (!(c & (1u << b))) return false;
         const bool succ = b < 4;
         const Kmer n = succ ? kmer_succ(k, b) : kmer_pred(k, b - 4);
         const uint32_t hn = mmer_hash_of(mmer_of_words(rev2(n.w0), rev2(n.w1), succ ? MINI_W - 1 : 0));
         const uint32_t rest = succ ? min_wo_first : min_wo_last;
         const uint32_t o = owner_of_partition(mini_part(mini_mix(hn < rest ? hn : rest), logP), logP, world);
-        if (o == me) continue;
+        if (o == me) return false;
         const Kmer r = kmer_rc(n);
-        emit(o, kmer_less(r, n) ? r : n);
+        *owner = o; *cn = kmer_less(r, n) ? r : n;
+        return true;
     }
+};
+template <class Emit>
+W2R_HD void neighbour_queries(Kmer k, uint32_t c, uint32_t logP, uint32_t world, uint32_t me, Emit& emit) {
+    const NeighbourScan ns(k, c, logP, world, me);
+    for (uint32_t b = 0; b < 8; ++b) { uint32_t o; Kmer cn; if (ns.remote(b, &o, &cn)) emit(o, cn); }
 }
 
 // ---- round 2: pieces (local chains) and their ranking

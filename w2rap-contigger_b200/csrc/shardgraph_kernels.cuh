@@ -13,19 +13,28 @@ struct QueryOut {
     unsigned long long* count;        // [world] queries for destination d (keeps counting past cap: the exact need)
     uint64_t cap;                     // per destination
 };
-struct QueryEmit {
-    const QueryOut& q;
-    __device__ __forceinline__ void operator()(uint32_t o, Kmer k) const {
-        const unsigned long long pos = atomicAdd(q.count + o, 1ull);
-        if (pos < q.cap) q.keys[q.base[o] + pos] = make_ulonglong2(k.w0, k.w1);
-    }
-};
-// over the solid records {w0, w1 | raw ctx} this rank owns
+// over the solid records {w0, w1 | raw ctx} this rank owns.  All lanes step through the 8 context bits together; per step the
+// lanes with a query for the same destination share one cursor atomic (there are only W cursors).
 __global__ void __launch_bounds__(256) k_neighbour_queries(const ulonglong2* __restrict__ recs, uint64_t n, uint32_t logP, uint32_t world, uint32_t me, QueryOut q) {
-    QueryEmit emit{q};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const ulonglong2 r = __ldcs(recs + i);
-        neighbour_queries(Kmer{r.x, r.y & ~0xffull}, (uint32_t)r.y & 0xffu, logP, world, me, emit);
+    const uint32_t lane = lane_id();
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const ulonglong2 r = i < n ? __ldcs(recs + i) : make_ulonglong2(0, 0);
+        const NeighbourScan ns(Kmer{r.x, r.y & ~0xffull}, i < n ? (uint32_t)r.y & 0xffu : 0u, logP, world, me);
+        if (!__any_sync(0xffffffffu, ns.c != 0)) continue;
+        for (uint32_t b = 0; b < 8; ++b) {
+            uint32_t o = 0; Kmer cn{0, 0};
+            const bool want = ns.remote(b, &o, &cn);
+            if (!__any_sync(0xffffffffu, want)) continue;
+            const uint32_t key = want ? o : world + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs((int)peers) - 1;
+            unsigned long long pos0 = 0;
+            if (want && (int)lane == leader) pos0 = atomicAdd(q.count + o, (unsigned long long)__popc(peers));
+            pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+            const unsigned long long pos = pos0 + (unsigned)__popc(peers & ((1u << lane) - 1u));
+            if (want && pos < q.cap) q.keys[q.base[o] + pos] = make_ulonglong2(cn.w0, cn.w1);
+        }
     }
 }
 // owner side: slot of every asked k-mer, or NIL.  Runs before any ghost is inserted: the table holds owned entries only.
@@ -224,14 +233,25 @@ __global__ void k_emit_edges_sharded(SolidTable st, const uint32_t* __restrict__
         emit_node_sharded(st, R, lpiece, my_pinfo, edge_off, (uint32_t)x, put);
     }
 }
-// owned entries (pruned context, edge, offset) out of the local table, for the all-gather that builds the pathing dictionary
-__global__ void k_dump_owned(SolidTable st, SolidSlot* __restrict__ out, uint64_t cap, unsigned long long* cursor) {
+// owned entries (pruned context, edge, offset) out of the local table, bucketed by the dictionary slice (= GPU) that will hold them
+// for pathing: slice = pd_slice_of(W, bloom_hash(k-mer)).  count[] keeps counting past cap: the exact need.
+__global__ void k_dump_owned_sliced(SolidTable st, uint32_t W, SolidSlot* __restrict__ out, uint64_t cap, unsigned long long* __restrict__ count) {
     const uint64_t T = st.size();
+    const uint32_t lane = lane_id();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < T; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
-        const bool want = i < T && st.slots[i].w0 != EMPTY_W0 && !slot_is_ghost(st.slots[i]);
-        const uint64_t pos = warp_append(cursor, want);
-        if (want && pos < cap) out[pos] = st.slots[i];
+        SolidSlot s;
+        bool act = false;
+        if (i < T) { s = st.slots[i]; act = s.w0 != EMPTY_W0 && !slot_is_ghost(s); }
+        // one cursor atomic per destination and warp (W counters only: per-entry atomics would serialise on them)
+        const uint32_t d = act ? pd_slice_of(W, bloom_hash(Kmer{s.w0, s.w1})) : W + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs((int)peers) - 1;
+        unsigned long long pos0 = 0;
+        if (act && (int)lane == leader) pos0 = atomicAdd(count + d, (unsigned long long)__popc(peers));
+        pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+        const unsigned long long pos = pos0 + (unsigned)__popc(peers & ((1u << lane) - 1u));
+        if (act && pos < cap) out[(uint64_t)d * cap + pos] = s;
     }
 }
 
