@@ -139,18 +139,6 @@ __global__ void k_insert_entries(const SolidSlot* __restrict__ recs, uint64_t n,
     }
 }
 
-// filter bits of the entries of one table (one GPU: the whole dictionary; sharded: this rank's slice, whose keys all select filter
-// slice `me`)
-__global__ void k_bloom_build(SolidTable st, uint32_t* __restrict__ bloom, uint32_t W, uint32_t slice_words) {
-    const uint64_t T = st.size();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (uint64_t)gridDim.x * blockDim.x) {
-        const SolidSlot* s = st.slots + i;
-        if (s->w0 == EMPTY_W0) continue;
-        const uint32_t h = bloom_hash(Kmer{s->w0, s->w1});
-        atomicOr(bloom + pd_bloom_word(W, slice_words, h), bloom_mask(h));
-    }
-}
-
 // ================================================================ K3: adjacency pruning (kmers/ReadPather.h:307-346)
 __global__ void k_adjacency(SolidTable st) {
     const uint64_t T = st.size();

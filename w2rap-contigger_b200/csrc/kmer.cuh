@@ -199,11 +199,11 @@ W2R_HD int64_t solid_find_hashed(const SolidTable& t, Kmer k, uint64_t hh) {
 }
 W2R_HD int64_t solid_find(const SolidTable& t, Kmer k) { return solid_find_hashed(t, k, kmer_hash(k)); }
 // ---------------------------------------------------------------- the dictionary the reads are pathed against
-// W slices keyed by a hash of the k-mer.  One GPU: one slice = the graph stage's own table.  Sharded: slice r is built and held by
-// GPU r and read by the path kernels of all GPUs through peer-mapped memory (NVLink/NVSwitch P2P loads) — the finished dictionary is
-// never replicated.  In front of it a blocked Bloom filter (two bits in one 32-bit word per key), sliced the same way and small
-// enough to be replicated: read pathing looks up every k-mer of a read's error-laden tail, almost all of them absent, and a negative
-// answer then costs one local sector instead of a (remote) probe chain.  No false negatives.
+// W slices keyed by a hash of the k-mer.  One GPU: one slice = the graph stage's own table.  Sharded: slice r is BUILT by GPU r (1/W of
+// the insert work each) and the finished slices are replicated with one bulk all-gather, so every path kernel probes local memory.
+// In front of it a blocked Bloom filter (two bits in one 32-bit word per key), sliced and gathered the same way: read pathing
+// looks up every k-mer of a read's error-laden tail, almost all of them absent, and a negative answer then costs one sector instead
+// of a probe chain in the multi-GB table.  No false negatives.
 // The filter has its own cheap 32-bit hash (two multiply-adds per word half): gap screening hashes ~100 k-mers per read, and the
 // 64-bit table hash (four 64-bit multiplies) is only worth computing for the few candidates that pass.
 struct PathSlice { const SolidSlot* tab; uint64_t nslots; };

@@ -14,7 +14,6 @@
 #include <cstdarg>
 #include <mutex>
 #include <thread>
-#include <unistd.h>
 
 #include "../../include/w2rap_step2.h"
 #include "device_reads.cuh"
@@ -166,48 +165,6 @@ static void say(const Ctx& c, const char* fmt, ...) {
     if (!c.verbose) return;
     va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap); printf("\n"); fflush(stdout);
 }
-
-// The slice of the pathing dictionary this GPU holds in a sharded run is read by the path kernels of the OTHER GPUs through
-// peer-mapped memory.  It is a plain cudaMalloc allocation (stream-ordered pool memory cannot be exported), kept between calls
-// together with the mappings of the peers' slices: exporting/opening a handle costs a driver round trip each.
-struct PeerInfo { cudaIpcMemHandle_t h; unsigned long long ptr, nslots, pid; int dev, pad; };
-struct PeerArena {
-    void* own = nullptr; size_t own_bytes = 0; cudaIpcMemHandle_t own_h;
-    struct Peer { bool open = false; bool ipc = false; cudaIpcMemHandle_t h; void* p = nullptr; } peers[16];
-    static PeerArena& get(int device) { static PeerArena* a = new PeerArena[16]; return a[device & 15]; }
-    // my slice buffer (grow-only); the handle changes only when it is re-allocated
-    void* reserve(size_t bytes) {
-        if (own_bytes < bytes) {
-            if (own) { cudaDeviceSynchronize(); cudaFree(own); own = nullptr; own_bytes = 0; }
-            const size_t want = bytes + bytes / 8;
-            W2R_CUDA(cudaMalloc(&own, want));
-            own_bytes = want;
-            W2R_CUDA(cudaIpcGetMemHandle(&own_h, own));
-        }
-        return own;
-    }
-    // the address at which peer r's slice can be read from this device
-    const void* map(int r, const PeerInfo& pi, int my_device) {
-        Peer& p = peers[r & 15];
-        if (p.open && memcmp(&p.h, &pi.h, sizeof(pi.h)) == 0) return p.p;
-        if (p.open && p.ipc) cudaIpcCloseMemHandle(p.p);
-        p.open = false;
-        if (pi.pid == (unsigned long long)getpid()) {           // ranks driven from threads of one process: enable peer access, use the pointer
-            int can = 0;
-            W2R_CUDA(cudaDeviceCanAccessPeer(&can, my_device, pi.dev));
-            if (!can) W2R_FAIL(W2RAP_ERR_NO_DEVICE, "device %d cannot access the memory of device %d: the sharded pathing dictionary needs peer access", my_device, pi.dev);
-            cudaError_t e = cudaDeviceEnablePeerAccess(pi.dev, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) W2R_CUDA(e);
-            cudaGetLastError();
-            p.p = (void*)(uintptr_t)pi.ptr; p.ipc = false;
-        } else {
-            W2R_CUDA(cudaIpcOpenMemHandle(&p.p, pi.h, cudaIpcMemLazyEnablePeerAccess));
-            p.ipc = true;
-        }
-        p.h = pi.h; p.open = true;
-        return p.p;
-    }
-};
 
 // ---------------------------------------------------------------- the pipeline
 struct Pipeline {
@@ -1112,42 +1069,34 @@ struct Pipeline {
         xms += xt.stop();
         ebuck.release();
         kt_.end();
-        // my slice
-        PeerArena& arena = PeerArena::get(c.device);
-        const uint64_t sslots = solid_table_slots(n_mine);
-        SolidSlot* slice = (SolidSlot*)arena.reserve(sslots * sizeof(SolidSlot));
+        // my slice, built in place inside the buffer that will hold all W slices (equal sizes: the all-gather wants them so)
+        std::vector<unsigned long long> mxn = {n_mine}, tot = {n_local};
+        allreduce_u64(mxn, ncclMax);
+        allreduce_u64(tot, ncclSum);
+        const uint64_t n_solid = tot[0];
+        const uint64_t sslots = solid_table_slots(mxn[0]);
+        solid_slots.alloc(c, (size_t)W * sslots);
+        SolidSlot* slice = solid_slots.p + (size_t)me * sslots;
         W2R_CUDA(cudaMemsetAsync(slice, 0xff, sslots * sizeof(SolidSlot), c.stream));
         st = SolidTable{slice, sslots};
         n_slice_entries = n_mine;
-        std::vector<unsigned long long> tot = {n_local};
-        allreduce_u64(tot, ncclSum);
-        const uint64_t n_solid = tot[0];
-        // filter: every rank sets the bits of its own slice while it inserts, the slices are all-gathered in place
+        // filter: every rank sets the bits of its own slice while it inserts; the slices are all-gathered in place
         alloc_path_filter(n_solid);
         if (n_mine) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_entries, grid(n_mine, 256), 256, 0, (const SolidSlot*)erecv.p, n_mine, st,
                                                                   path_slice_words ? path_bloom.p : nullptr, W, path_slice_words));
         erecv.release();
         kt_.begin(W2RAP_KT_SG_DICT);
-        if (path_slice_words) {
-            xt.start();
-            nccl_check(NcclApi::get().AllGather(path_bloom.p + (size_t)me * path_slice_words, path_bloom.p, (size_t)path_slice_words * 4, ncclUint8, comm, c.stream), "all-gather");
-            xms += xt.stop();
-        }
-        // where every slice can be read from this GPU
-        PeerInfo mine_pi;
-        memset(&mine_pi, 0, sizeof mine_pi);
-        mine_pi.h = arena.own_h; mine_pi.ptr = (unsigned long long)(uintptr_t)slice; mine_pi.nslots = sslots; mine_pi.pid = (unsigned long long)getpid(); mine_pi.dev = c.device;
-        SBuf<PeerInfo> pi_dev(c, 1), pi_all;
-        W2R_CUDA(cudaMemcpyAsync(pi_dev.p, &mine_pi, sizeof mine_pi, cudaMemcpyHostToDevice, c.stream));
-        std::vector<uint64_t> pioff;
+        // Every rank paths against ALL slices.  They are replicated with one bulk all-gather of finished table memory (large
+        // contiguous NVLink transfers, no insert work on the receivers).  Tried first: leaving the slices where they were built and
+        // reading them from the path kernels through peer-mapped memory (CUDA IPC) — correct, but fine-grained remote LOADS over NVLink
+        // are latency-serialised: the path kernel went from 24 ms to 426 ms on two GPUs.
         xt.start();
-        allgather_v(pi_dev.p, 1, pi_all, pioff);                 // (a collective after every rank's inserts: nobody reads a slice before it is complete)
+        nccl_check(NcclApi::get().AllGather(slice, solid_slots.p, sslots * sizeof(SolidSlot), ncclUint8, comm, c.stream), "all-gather");
+        if (path_slice_words) nccl_check(NcclApi::get().AllGather(path_bloom.p + (size_t)me * path_slice_words, path_bloom.p, (size_t)path_slice_words * 4, ncclUint8, comm, c.stream), "all-gather");
         xms += xt.stop();
-        std::vector<PeerInfo> pis(W);
-        W2R_CUDA(cudaMemcpyAsync(pis.data(), pi_all.p, W * sizeof(PeerInfo), cudaMemcpyDeviceToHost, c.stream));
-        W2R_CUDA(cudaStreamSynchronize(c.stream));
+        xchg_bytes += (sslots * sizeof(SolidSlot) + (size_t)path_slice_words * 4) * (uint64_t)(W - 1);
         std::vector<PathSlice> sl(W);
-        for (uint32_t r = 0; r < W; ++r) sl[r] = PathSlice{r == me ? slice : (const SolidSlot*)arena.map((int)r, pis[r], c.device), pis[r].nslots};
+        for (uint32_t r = 0; r < W; ++r) sl[r] = PathSlice{solid_slots.p + (size_t)r * sslots, sslots};
         path_slices.alloc(c, W);
         W2R_CUDA(cudaMemcpyAsync(path_slices.p, sl.data(), W * sizeof(PathSlice), cudaMemcpyHostToDevice, c.stream));
         kt_.end();
