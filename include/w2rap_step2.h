@@ -237,6 +237,14 @@ int w2rap_step2_run_sharded_resident(w2rap_device_reads* shard, const w2rap_para
 void w2rap_step2_free(w2rap_graph* out);
 
 /*
+ * Pinned (page-locked) host memory for the flattened read stores.  w2rap_step2_run copies pinned buffers at PCIe speed while the first
+ * read batches are already being processed; pageable buffers go through the driver's staging at a fraction of that.  Blocks come from
+ * a process-wide pool and return to it (the C++ drop-in flattens vecbvec / VecPQVec straight into them).  NULL on failure.
+ */
+void* w2rap_step2_host_alloc(size_t bytes);
+void w2rap_step2_host_free(void* p);
+
+/*
  * File-level drop-in (src/modules/w2rap-contigger.cc:326-327,345-346):
  *   read  <dir>/frag_reads_orig.fastb + .qualp  (feudal files),
  *   write <dir>/<prefix>.small_K.hbv (BINWRITE stream of HyperBasevector, paths/HyperBasevector.cc:121-125),

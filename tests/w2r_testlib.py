@@ -196,7 +196,7 @@ def product_lib():
     return _product
 
 
-ABI_SYMBOLS = ["w2rap_step2_abi_version", "w2rap_step2_build_info", "w2rap_step2_device_count", "w2rap_step2_run",
+ABI_SYMBOLS = ["w2rap_step2_host_alloc", "w2rap_step2_host_free", "w2rap_step2_abi_version", "w2rap_step2_build_info", "w2rap_step2_device_count", "w2rap_step2_run",
                "w2rap_step2_upload", "w2rap_step2_run_resident", "w2rap_step2_release", "w2rap_step2_free",
                "w2rap_step2_run_files", "w2rap_write_hbv", "w2rap_write_paths", "w2rap_write_freqs",
                "w2rap_step2_synth", "w2rap_step2_download_reads", "w2rap_step2_free_host_reads",

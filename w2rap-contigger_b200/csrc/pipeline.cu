@@ -1629,6 +1629,11 @@ int w2rap_step2_run_sharded(const w2rap_reads* shard, const w2rap_params* p, w2r
     W2R_API_END
 }
 
+void* w2rap_step2_host_alloc(size_t bytes) {
+    try { return PinnedPool::get().acquire(bytes); } catch (...) { cudaGetLastError(); return nullptr; }
+}
+void w2rap_step2_host_free(void* p) { if (p) PinnedPool::get().release(p); }
+
 void w2rap_step2_free(w2rap_graph* out) {
     if (!out) return;
     delete (GraphOwner*)out->_owner;

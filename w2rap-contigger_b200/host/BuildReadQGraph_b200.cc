@@ -49,7 +49,9 @@ void buildReadQGraph(vecbvec const& reads, VecPQVec const& quals, bool doFillGap
     const size_t n = reads.size();
     ForceAssertEq(n, quals.size());
 
-    // ---- flatten: per-read packed bases and PQVec streams into two contiguous buffers
+    // ---- flatten: per-read packed bases and PQVec streams into two contiguous PINNED buffers (the library then copies them at PCIe
+    // speed under its first kernels); offsets by a serial scan, bytes by all OpenMP threads
+    const double t_flat0 = WallClockTime();
     std::vector<uint64_t> base_off(n + 1), qual_off(n + 1);
     std::vector<uint32_t> len(n ? n : 1);
     base_off[0] = qual_off[0] = 0;
@@ -59,16 +61,21 @@ void buildReadQGraph(vecbvec const& reads, VecPQVec const& quals, bool doFillGap
         size_t qs = quals[i].size();
         qual_off[i + 1] = qual_off[i] + (qs ? qs : 1);     // an empty PQVec has no buffer: emit the terminator byte
     }
-    std::vector<unsigned char> bases(base_off[n] + 32, 0), qbuf(qual_off[n] + 32, 0);
+    unsigned char* bases = static_cast<unsigned char*>(w2rap_step2_host_alloc(base_off[n] + 32));
+    unsigned char* qbuf = static_cast<unsigned char*>(w2rap_step2_host_alloc(qual_off[n] + 32));
+    if (!bases || !qbuf) FatalErr("buildReadQGraph (B200): cannot allocate pinned host memory for the read stores");
+    std::memset(bases + base_off[n], 0, 32); std::memset(qbuf + qual_off[n], 0, 32);
 #pragma omp parallel for schedule(static, 4096)
     for (size_t i = 0; i < n; ++i) {
-        if (len[i]) std::memcpy(&bases[base_off[i]], static_cast<BvecBytes const&>(reads[i]).bytes(), (len[i] + 3) / 4);
+        if (len[i]) std::memcpy(bases + base_off[i], static_cast<BvecBytes const&>(reads[i]).bytes(), (len[i] + 3) / 4);
         size_t qs = quals[i].size();
-        if (qs) std::memcpy(&qbuf[qual_off[i]], pqvec_bytes(quals[i]), qs);
+        if (qs) std::memcpy(qbuf + qual_off[i], pqvec_bytes(quals[i]), qs);
+        else qbuf[qual_off[i]] = 0;
     }
+    const double t_flat = WallClockTime() - t_flat0;
 
     w2rap_reads in;
-    in.n_reads = n; in.bases = bases.data(); in.base_off = base_off.data(); in.len = len.data(); in.quals = qbuf.data(); in.qual_off = qual_off.data();
+    in.n_reads = n; in.bases = bases; in.base_off = base_off.data(); in.len = len.data(); in.quals = qbuf; in.qual_off = qual_off.data();
     w2rap_params p;
     std::memset(&p, 0, sizeof p);
     p.abi_version = W2RAP_STEP2_ABI_VERSION; p.K = (uint32_t)_K; p.min_qual = minQual; p.min_freq = minFreq;
@@ -76,8 +83,12 @@ void buildReadQGraph(vecbvec const& reads, VecPQVec const& quals, bool doFillGap
     p.device = -1; p.workdir = workdir.empty() ? nullptr : workdir.c_str(); p.verbose = 1;
     w2rap_graph g;
     char err[1024];
+    const double t_run0 = WallClockTime();
     int rc = w2rap_step2_run(&in, &p, &g, err, sizeof err);
+    const double t_run = WallClockTime() - t_run0;
+    w2rap_step2_host_free(bases); w2rap_step2_host_free(qbuf);
     if (rc != W2RAP_OK) FatalErr("buildReadQGraph (B200) failed with status " << rc << ": " << err);
+    const double t_build0 = WallClockTime();
 
     // ---- HyperBasevector, as buildHBVFromEdges does it (HBVFromEdges.cc:79,124-151)
     std::cout << Date() << ": building graph..." << std::endl;
@@ -110,5 +121,8 @@ void buildReadQGraph(vecbvec const& reads, VecPQVec const& quals, bool doFillGap
         }
         std::cout << Date() << ": " << g.n_pathed << " / " << n << " reads pathed, " << g.n_multipathed << " spanning junctions" << std::endl;
     }
+    const double device_s = g.timings.total_ms * 1e-3;
     w2rap_step2_free(&g);
+    std::cout << Date() << ": B200 step 2: flatten " << t_flat << " s, w2rap_step2_run " << t_run << " s (device " << device_s << " s), rebuild "
+              << (WallClockTime() - t_build0) << " s" << std::endl;
 }
