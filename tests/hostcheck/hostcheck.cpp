@@ -396,7 +396,7 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         std::vector<uint32_t> next0;
         std::vector<uint8_t> ghead;
         std::vector<RankState> R;
-        std::vector<uint32_t> lpiece;                // per node: local piece index of the piece whose tail it is
+        std::vector<uint32_t> lpiece, lhead;         // per node: local piece index of the piece whose tail / head it is
         std::vector<PieceRec> pieces;
         uint32_t piece0 = 0;
     };
@@ -474,13 +474,15 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         for (uint32_t r = 0; r < world; ++r) {
             Rank& me = rk[r];
             const uint64_t nn = me.next0.size();
-            me.pieces.clear(); me.lpiece.assign(nn, NIL);
+            me.pieces.clear(); me.lpiece.assign(nn, NIL); me.lhead.assign(nn, NIL);
             for (uint64_t x = 0; x < nn; ++x)
                 if (node_is_piece_head(me.next0.data(), me.ghead.data(), (uint32_t)x)) {
                     const PieceRec p = piece_of_head(me.st, me.next0.data(), me.R.data(), r, (uint32_t)x);
-                    me.lpiece[p.tail] = (uint32_t)me.pieces.size();
+                    me.lpiece[p.flip_local] = (uint32_t)me.pieces.size();          // (flip_local still holds the tail node)
+                    me.lhead[x] = (uint32_t)me.pieces.size();
                     me.pieces.push_back(p);
                 }
+            for (PieceRec& p : me.pieces) p.flip_local = me.lhead[p.flip_local ^ 1u];      // k_piece_flips
             me.piece0 = (uint32_t)P.size();
             P.insert(P.end(), me.pieces.begin(), me.pieces.end());
         }
@@ -492,8 +494,8 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         nxt.assign(np, NIL); flip.assign(np, NIL);
         for (uint64_t i = 0; i < np; ++i) {
             if (P[i].succ != GID_NONE) { nxt[i] = gid_find(gm, P[i].succ); if (nxt[i] == NIL) return 107; }
-            flip[i] = gid_find(gm, gid_make((uint32_t)(P[i].head >> 32), P[i].tail ^ 1u));
-            if (flip[i] == NIL) return 108;
+            flip[i] = rk[P[i].head >> 32].piece0 + P[i].flip_local;
+            if (P[i].flip_local == NIL) return 108;
         }
         S.resize(np);
         for (uint64_t i = 0; i < np; ++i) S[i] = piece_rank_init(P.data(), nxt.data(), (uint32_t)i);

@@ -557,12 +557,9 @@ struct Pipeline {
                 pl.npass *= 2; --attempt; continue;              // (more passes are not a failed attempt)
             }
             CountBufs cb;
-            cb.recs.alloc(c, local_recs);
-            {   // staging: the same records plus the unused ends of the chunks the warps reserve
-                const size_t stage_recs = local_recs + local_recs / 8 + (size_t)c.sm_count * 6 * 8 * MAP_CHUNK;
-                cb.tmp.alloc(c, stage_recs); cb.tpart.alloc(c, stage_recs);
-                cb.tmp_cursor.alloc(c, 1); cb.tmp_range.alloc(c, pl.nmap + 1);
-            }
+            // staging: the same records plus the unused ends of the chunks the warps reserve
+            const size_t stage_recs = local_recs + local_recs / 8 + (size_t)c.sm_count * 6 * 8 * MAP_CHUNK;
+            cb.tmp_cursor.alloc(c, 1); cb.tmp_range.alloc(c, pl.nmap + 1);
             cb.part_count.alloc(c, pl.nmap * P); cb.part_kcount.alloc(c, pl.nmap * P); cb.cursor.alloc(c, pl.nmap * P);
             cb.part_base.alloc(c, pl.nmap * P); cb.batch_total.alloc(c, pl.nmap); cb.batch_ktotal.alloc(c, pl.nmap);
             cb.batch_off.alloc(c, pl.nmap + 1);
@@ -577,13 +574,19 @@ struct Pipeline {
             uint64_t solid_used = 0;
             for (uint32_t pass = 0; pass < pl.npass && !retry; ++pass) {
                 uint64_t need = 0;
-                if (!map_records(pl, cb, batches, pass, &need)) {
+                // the big areas live only as long as they are needed (a 1 Gbp job runs within ~25 % of the device's memory of the
+                // limit, and a pool that has to re-map memory on every step costs hundreds of milliseconds)
+                cb.recs.alloc(c, local_recs);
+                cb.tmp.alloc(c, stage_recs); cb.tpart.alloc(c, stage_recs);
+                const bool mapped = map_records(pl, cb, batches, pass, &need);
+                cb.tmp.release(); cb.tpart.release();
+                if (!mapped) {
                     std::vector<unsigned long long> nd = {need};
                     allreduce_u64(nd, ncclMax);
                     need_exact = std::max<uint64_t>(need_exact, nd[0]);
                     retry = true; break;
                 }
-                if (world > 1) exchange_records(pl, cb);
+                if (world > 1) { exchange_records(pl, cb); cb.recs.release(); }      // (the local area is dead once its records are with their owners)
                 const uint32_t* xcur = world > 1 ? cb.xcount.p : cb.part_count.p;
                 const uint32_t* xkcur = world > 1 ? cb.xkcount.p : cb.part_kcount.p;
                 const SkmRec* xrecs = world > 1 ? cb.xrecs.p : cb.recs.p;
@@ -645,8 +648,11 @@ struct Pipeline {
         path_slice_words = 0;
         path_bloom.release();
         if (n_solid < 4096 || getenv("W2RAP_NO_BLOOM") || !prm.want_paths) return;
+        // ~1.5 bytes per key (false positives ~4 %), at least 4 KB, at most 192 MB unless the dictionary is so large that a capped
+        // filter would pass everything (measured at 1.44 G keys with 192 MB: every screened position probed the dictionary)
         static const uint64_t bloom_mb = getenv("W2RAP_BLOOM_MB") ? (uint64_t)atoi(getenv("W2RAP_BLOOM_MB")) : 192;
-        const uint64_t bytes = std::min<uint64_t>(bloom_mb << 20, std::max<uint64_t>(4096, n_solid * 2));
+        const uint64_t cap = std::max<uint64_t>(bloom_mb << 20, std::min<uint64_t>(n_solid + n_solid / 2, 8ull << 30));
+        const uint64_t bytes = std::min<uint64_t>(cap, std::max<uint64_t>(4096, n_solid * 2));
         path_slice_words = (uint32_t)std::max<uint64_t>(64, bytes / 4 / world);
         path_bloom.alloc(c, (size_t)path_slice_words * world);
         path_bloom.zero();
@@ -915,13 +921,15 @@ struct Pipeline {
             list_ranking(next0, ghead.p, nn, A, B, &cur, &oth);
             // -- round 2: one record per local chain, gathered on every rank
             kt_.begin(W2RAP_KT_SG_PIECES);
-            lpiece = reinterpret_cast<uint32_t*>(oth);          // scratch: local piece index per tail node
+            lpiece = reinterpret_cast<uint32_t*>(oth);          // scratch: local piece index per tail node ...
+            uint32_t* lhead = lpiece + nn;                      // ... and per head node (the 8-byte rank array holds 2 * nn words)
             W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
             W2R_LAUNCH(c, k_count_piece_heads, grid(nn, 256), 256, 0, next0.p, (const uint8_t*)ghead.p, nn, scal.p);
             const uint64_t npl = d2h_scalar(c, scal.p);
             SBuf<PieceRec> lp(c, npl);
             W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
-            W2R_LAUNCH(c, k_emit_pieces, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, (const uint8_t*)ghead.p, (const RankState*)cur, me, lp.p, npl, scal.p, lpiece);
+            W2R_LAUNCH(c, k_emit_pieces, grid(nn, 256), 256, 0, st, (const uint32_t*)next0.p, (const uint8_t*)ghead.p, (const RankState*)cur, me, lp.p, npl, scal.p, lpiece, lhead);
+            if (npl) W2R_LAUNCH(c, k_piece_flips, grid(npl, 256), 256, 0, lp.p, npl, (const uint32_t*)lhead);
             xt.start();
             std::vector<uint64_t> poff;
             allgather_v(lp.p, npl, pieces, poff);
@@ -935,16 +943,20 @@ struct Pipeline {
             SBuf<uint32_t> mvals(c, msz);
             GidMap gm{mkeys.p, mvals.p, msz - 1};
             nxt.alloc(c, np); flip.alloc(c, np); S.alloc(c, np);
+            SBuf<uint64_t> poff_dev(c, W + 1);
+            W2R_CUDA(cudaMemcpyAsync(poff_dev.p, poff.data(), (W + 1) * 8, cudaMemcpyHostToDevice, c.stream));
             if (np) {
                 W2R_LAUNCH(c, k_gidmap_insert, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, np, gm);
-                W2R_LAUNCH(c, k_piece_link, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, np, gm, nxt.p, flip.p, flags.p + 1);
+                W2R_LAUNCH(c, k_piece_link, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, np, gm, (const uint64_t*)poff_dev.p, nxt.p, flip.p, flags.p + 1);
                 W2R_LAUNCH(c, k_piece_rank_init, grid(np, 256), 256, 0, (const PieceRec*)pieces.p, (const uint32_t*)nxt.p, np, S.p);
             }
             if (d2h_scalar(c, flags.p + 1)) W2R_FAIL(W2RAP_ERR_INTERNAL, "a chain piece points at a node that heads no piece");
             unsigned long long un = 0, prev = ~0ull;
             for (int round = 0; round < 64 && np; ++round) {
-                W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
-                W2R_LAUNCH(c, k_piece_rank_step, grid(np, 256), 256, 0, (unsigned long long*)S.p, np, scal.p);
+                for (int sub = 0; sub < 3; ++sub) {           // (three doubling steps per host round trip; the count is of the last)
+                    W2R_CUDA(cudaMemsetAsync(scal.p, 0, 8, c.stream));
+                    W2R_LAUNCH(c, k_piece_rank_step, grid(np, 256), 256, 0, (unsigned long long*)S.p, np, scal.p);
+                }
                 un = d2h_scalar(c, scal.p);
                 if (un == 0 || un == prev) break;
                 prev = un;

@@ -71,7 +71,7 @@ struct PieceRec {
     uint64_t head;          // global id (rank << 32 | oriented node) of the first node
     uint64_t succ;          // global id of the node that follows the last node on another rank, or GID_NONE
     uint32_t n;             // k-mers in the piece
-    uint32_t tail;          // oriented node id (same rank) of the last node
+    uint32_t flip_local;    // index, among the owner rank's pieces, of the piece made of the flipped nodes (its head is the flip of our tail)
     Kmer head_k, tail_k;    // oriented k-mers of the first and the last node
 };
 // Is owned node x the head of a local piece?  (no predecessor at all, or a predecessor on another rank)
@@ -86,7 +86,7 @@ W2R_HD PieceRec piece_of_head(const SolidTable& t, const uint32_t* next0, const 
     const uint32_t tail = R[h].x;
     p.head = gid_make(me, h);
     p.n = (R[h].y & ~RANK_RESOLVED) + 1u;
-    p.tail = tail;
+    p.flip_local = tail;                     // the TAIL NODE for now: k_piece_flips turns it into the flipped piece's index
     const uint32_t nt = next0[tail];
     if (nt == NIL) p.succ = GID_NONE;
     else { const SolidSlot& g = t.slots[nt >> 1]; p.succ = gid_make(g.pad - 1u, 2u * g.edge + (nt & 1u)); }     // the ghost knows its owner and its slot there

@@ -88,7 +88,7 @@ __global__ void k_links_sharded(SolidTable st, uint32_t* __restrict__ next0, uin
 
 // ---- round 2: one record per local chain
 __global__ void k_emit_pieces(SolidTable st, const uint32_t* __restrict__ next0, const uint8_t* __restrict__ ghead, const RankState* __restrict__ R, uint32_t me,
-                              PieceRec* __restrict__ out, uint64_t cap, unsigned long long* cursor, uint32_t* __restrict__ lpiece) {
+                              PieceRec* __restrict__ out, uint64_t cap, unsigned long long* cursor, uint32_t* __restrict__ lpiece, uint32_t* __restrict__ lhead) {
     const uint64_t nn = 2 * st.size();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t x = base + threadIdx.x;
@@ -97,9 +97,14 @@ __global__ void k_emit_pieces(SolidTable st, const uint32_t* __restrict__ next0,
         if (want && pos < cap) {
             const PieceRec p = piece_of_head(st, next0, R, me, (uint32_t)x);
             out[pos] = p;
-            lpiece[p.tail] = (uint32_t)pos;
+            lpiece[p.flip_local] = (uint32_t)pos;         // (flip_local still holds the tail node)
+            lhead[x] = (uint32_t)pos;
         }
     }
+}
+// the flipped piece of a piece is the one headed by the flip of its tail: a local look-up (both live on the same rank)
+__global__ void k_piece_flips(PieceRec* __restrict__ rec, uint64_t npl, const uint32_t* __restrict__ lhead) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < npl; j += (uint64_t)gridDim.x * blockDim.x) rec[j].flip_local = lhead[rec[j].flip_local ^ 1u];
 }
 __global__ void k_count_piece_heads(const uint32_t* __restrict__ next0, const uint8_t* __restrict__ ghead, uint64_t nn, unsigned long long* __restrict__ count) {
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nn; base += (uint64_t)gridDim.x * blockDim.x) {
@@ -116,15 +121,15 @@ __global__ void k_gidmap_insert(const PieceRec* __restrict__ rec, uint64_t np, G
         }
     }
 }
-__global__ void k_piece_link(const PieceRec* __restrict__ rec, uint64_t np, GidMap m, uint32_t* __restrict__ nxt, uint32_t* __restrict__ flip, int* __restrict__ bad) {
+// piece0[r] = global index of rank r's first piece
+__global__ void k_piece_link(const PieceRec* __restrict__ rec, uint64_t np, GidMap m, const uint64_t* __restrict__ piece0, uint32_t* __restrict__ nxt, uint32_t* __restrict__ flip,
+                             int* __restrict__ bad) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
         const PieceRec p = rec[i];
         uint32_t nx = NIL;
         if (p.succ != GID_NONE) { nx = gid_find(m, p.succ); if (nx == NIL) atomicExch(bad, 1); }
         nxt[i] = nx;
-        const uint32_t f = gid_find(m, gid_make((uint32_t)(p.head >> 32), p.tail ^ 1u));
-        if (f == NIL) atomicExch(bad, 1);
-        flip[i] = f;
+        flip[i] = (uint32_t)piece0[p.head >> 32] + p.flip_local;
     }
 }
 __global__ void k_piece_rank_init(const PieceRec* __restrict__ rec, const uint32_t* __restrict__ nxt, uint64_t np, RankState* __restrict__ S) {
