@@ -380,112 +380,101 @@ int hc_graph(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, const
     return finish_graph(std::vector<PathSlice>{PathSlice{slots.data(), T}}, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
 }
 
-// ---- the SHARDED graph stage (csrc/shardgraph.cuh) with `world` simulated ranks: every rank owns the solid k-mers of its
-// minimiser partitions; exchanges are plain copies between the per-rank structures, in the order pipeline.cu issues them.
-// Result: the same graph the single-table path builds.  out->timings.reserved receives the number of ghost entries,
-// out->timings.count_passes the number of pieces (local chains).
-int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, uint32_t world, uint32_t logP, const w2rap_reads* in, int want_paths,
-                     int apply_fixpaths, uint32_t cap, uint32_t left_cap, w2rap_graph* out) {
-    memset(out, 0, sizeof(*out));
-    struct Rank {
-        std::vector<w2rap_kmer_rec> owned;
-        std::vector<std::vector<Kmer>> q;            // q[d] = canonical k-mers asked of rank d
-        std::vector<std::vector<uint32_t>> reply;    // reply[d][i] = slot on d or NIL
-        std::vector<SolidSlot> slots;
-        SolidTable st{nullptr, 0};
-        std::vector<uint32_t> next0;
-        std::vector<uint8_t> ghead;
-        std::vector<RankState> R;
-        std::vector<uint32_t> lpiece, lhead;         // per node: local piece index of the piece whose tail / head it is
-        std::vector<PieceRec> pieces;
-        uint32_t piece0 = 0;
-    };
-    std::vector<Rank> rk(world);
-    uint64_t n_solid = 0;
-    for (uint64_t i = 0; i < n_all; ++i) {
-        if (all[i].count < min_freq) continue;
-        ++n_solid;
-        rk[kmer_owner(Kmer{all[i].w0, all[i].w1}, logP, world)].owned.push_back(all[i]);
-    }
-    out->n_solid = n_solid; out->n_distinct = n_all;
-    // ---- k_neighbour_queries (on the solid records), local tables (k_insert_solid)
-    for (uint32_t r = 0; r < world; ++r) {
-        Rank& me = rk[r];
-        me.q.assign(world, {}); me.reply.assign(world, {});
-        struct Emit { std::vector<std::vector<Kmer>>* q; void operator()(uint32_t o, Kmer k) const { (*q)[o].push_back(k); } } emit{&me.q};
-        uint64_t nq = 0;
-        for (const w2rap_kmer_rec& e : me.owned) neighbour_queries(Kmer{e.w0, e.w1}, e.ctx & 0xffu, logP, world, r, emit);
-        for (auto& v : me.q) nq += v.size();
-        me.slots.resize(table_slots_for(me.owned.size() + nq));
-        memset(me.slots.data(), 0xff, me.slots.size() * sizeof(SolidSlot));
-        me.st = SolidTable{me.slots.data(), me.slots.size()};
-        for (const w2rap_kmer_rec& e : me.owned) {
-            uint64_t h = me.st.home(Kmer{e.w0, e.w1});
-            while (me.slots[h].w0 != EMPTY_W0) h = me.st.next(h);
-            me.slots[h] = SolidSlot{e.w0, e.w1, e.ctx & 0xffu, NIL, 0, 0};
-        }
-    }
-    // ---- all-to-all of the keys, k_answer_queries, all-to-all of the replies, k_insert_ghosts
-    uint64_t n_ghost = 0;
-    for (uint32_t r = 0; r < world; ++r)
-        for (uint32_t d = 0; d < world; ++d) {
-            rk[r].reply[d].resize(rk[r].q[d].size());
-            for (size_t i = 0; i < rk[r].q[d].size(); ++i) { const int64_t s = solid_find(rk[d].st, rk[r].q[d][i]); rk[r].reply[d][i] = s < 0 ? NIL : (uint32_t)s; }
-        }
-    for (uint32_t r = 0; r < world; ++r) {
-        Rank& me = rk[r];
-        for (uint32_t d = 0; d < world; ++d)
-            for (size_t i = 0; i < me.q[d].size(); ++i) {
-                if (me.reply[d][i] == NIL) continue;
-                const Kmer k = me.q[d][i];
-                uint64_t h = me.st.home(k);
-                while (me.slots[h].w0 != EMPTY_W0 && !(me.slots[h].w0 == k.w0 && me.slots[h].w1 == k.w1)) h = me.st.next(h);
-                if (me.slots[h].w0 == EMPTY_W0) { me.slots[h] = SolidSlot{k.w0, k.w1, 0, me.reply[d][i], 0, d + 1u}; ++n_ghost; }
-            }
-    }
-    // ---- k_adjacency on owned entries; then the ghosts' pruned contexts (second query round: slot -> context)
-    for (Rank& me : rk)
-        for (uint64_t i = 0; i < me.st.size(); ++i)
-            if (me.slots[i].w0 != EMPTY_W0 && !slot_is_ghost(me.slots[i])) me.slots[i].ctx = pruned_context(me.st, Kmer{me.slots[i].w0, me.slots[i].w1}, me.slots[i].ctx & 0xff);
-    for (Rank& me : rk)
-        for (uint64_t i = 0; i < me.st.size(); ++i)
-            if (me.slots[i].w0 != EMPTY_W0 && slot_is_ghost(me.slots[i])) me.slots[i].ctx = rk[me.slots[i].pad - 1].slots[me.slots[i].edge].ctx;
-    // ---- k_links (+ ghost-predecessor flags), local list ranking
-    uint64_t ncyc_local = 0;
-    for (Rank& me : rk) {
-        const uint64_t nn = 2 * me.st.size();
-        me.next0.resize(nn); me.ghead.assign(nn, 0);
-        int missing = 0;
-        for (uint64_t x = 0; x < nn; ++x) { bool tg; me.next0[x] = unipath_succ_link(me.st, (uint32_t)x, &missing, &tg); if (tg) me.ghead[x ^ 1u] = 1; }
-        if (missing) return 101;
-    }
-    std::vector<PieceRec> P;
+}  // extern "C"
+
+namespace {
+// ---- one rank of the SHARDED graph stage (csrc/shardgraph.cuh), phase by phase, in the order pipeline.cu: graph_stage_sharded() runs
+// them.  Between the phases the ranks exchange flat buffers: by plain copies in hc_graph_sharded() below (simulated ranks in one
+// process), over torch.distributed/gloo in tests/sharded_gloo_worker.py (one process per rank).
+struct CycleNodeH { uint32_t piece, pad; uint64_t w0, w1, gid; };
+struct SgRank {
+    uint32_t world = 1, me = 0, logP = 0;
+    std::vector<w2rap_kmer_rec> owned;
+    std::vector<std::vector<Kmer>> q;            // q[d] = canonical k-mers asked of rank d
+    std::vector<std::vector<uint32_t>> gslot;    // local slot of every query's ghost
+    std::vector<SolidSlot> slots;
+    SolidTable st{nullptr, 0};
+    std::vector<uint32_t> next0;
+    std::vector<uint8_t> ghead;
+    std::vector<RankState> R;
+    std::vector<uint32_t> lpiece, lhead;
+    std::vector<PieceRec> pieces;                // mine
+    std::vector<PieceRec> P;                     // everybody's (replicated)
+    std::vector<uint64_t> poff;
     std::vector<uint32_t> nxt, flip;
     std::vector<RankState> S;
-    for (int iteration = 0;; ++iteration) {
-        if (iteration > 1) return 106;
-        for (Rank& me : rk) {
-            const int64_t nc = rank_local(me.st, me.next0, me.ghead.data(), me.R);
-            if (nc < 0) return 102;
-            ncyc_local += (uint64_t)nc;
+    std::vector<PieceInfo> pinfo;
+    std::vector<uint8_t> is_head;
+    std::vector<uint64_t> chain_n;
+    std::vector<CycleNodeH> cyc;
+    EdgeSet es;
+    uint64_t n_ghost = 0;
+
+    // phase 1: neighbour queries (k_neighbour_queries) and the local table (k_insert_solid)
+    void start() {
+        q.assign(world, {}); gslot.assign(world, {});
+        struct Emit { std::vector<std::vector<Kmer>>* q; void operator()(uint32_t o, Kmer k) const { (*q)[o].push_back(k); } } emit{&q};
+        uint64_t nq = 0;
+        for (const w2rap_kmer_rec& e : owned) neighbour_queries(Kmer{e.w0, e.w1}, e.ctx & 0xffu, logP, world, me, emit);
+        for (auto& v : q) nq += v.size();
+        slots.resize(table_slots_for(owned.size() + nq));
+        memset(slots.data(), 0xff, slots.size() * sizeof(SolidSlot));
+        st = SolidTable{slots.data(), slots.size()};
+        for (const w2rap_kmer_rec& e : owned) {
+            uint64_t h = st.home(Kmer{e.w0, e.w1});
+            while (slots[h].w0 != EMPTY_W0) h = st.next(h);
+            slots[h] = SolidSlot{e.w0, e.w1, e.ctx & 0xffu, NIL, 0, 0};
         }
-        // ---- k_emit_pieces, all-gather, k_piece_map / k_piece_link, piece ranking
-        P.clear();
-        for (uint32_t r = 0; r < world; ++r) {
-            Rank& me = rk[r];
-            const uint64_t nn = me.next0.size();
-            me.pieces.clear(); me.lpiece.assign(nn, NIL); me.lhead.assign(nn, NIL);
-            for (uint64_t x = 0; x < nn; ++x)
-                if (node_is_piece_head(me.next0.data(), me.ghead.data(), (uint32_t)x)) {
-                    const PieceRec p = piece_of_head(me.st, me.next0.data(), me.R.data(), r, (uint32_t)x);
-                    me.lpiece[p.flip_local] = (uint32_t)me.pieces.size();          // (flip_local still holds the tail node)
-                    me.lhead[x] = (uint32_t)me.pieces.size();
-                    me.pieces.push_back(p);
-                }
-            for (PieceRec& p : me.pieces) p.flip_local = me.lhead[p.flip_local ^ 1u];      // k_piece_flips
-            me.piece0 = (uint32_t)P.size();
-            P.insert(P.end(), me.pieces.begin(), me.pieces.end());
+    }
+    // phase 2 (owner side, before any ghost exists): k_answer_queries
+    void answer(const Kmer* keys, uint64_t n, uint32_t* reply) const {
+        for (uint64_t i = 0; i < n; ++i) { const int64_t sl = solid_find(st, keys[i]); reply[i] = sl < 0 ? NIL : (uint32_t)sl; }
+    }
+    // phase 3: k_insert_ghosts for the replies of rank d, then (after all d) k_adjacency
+    void insert_ghosts(uint32_t d, const uint32_t* reply) {
+        gslot[d].assign(q[d].size(), NIL);
+        for (size_t i = 0; i < q[d].size(); ++i) {
+            if (reply[i] == NIL) continue;
+            const Kmer k = q[d][i];
+            uint64_t h = st.home(k);
+            while (slots[h].w0 != EMPTY_W0 && !(slots[h].w0 == k.w0 && slots[h].w1 == k.w1)) h = st.next(h);
+            if (slots[h].w0 == EMPTY_W0) { slots[h] = SolidSlot{k.w0, k.w1, 0, reply[i], 0, d + 1u}; ++n_ghost; }
+            gslot[d][i] = (uint32_t)h;
         }
+    }
+    void adjacency() {
+        for (uint64_t i = 0; i < st.size(); ++i)
+            if (slots[i].w0 != EMPTY_W0 && !slot_is_ghost(slots[i])) slots[i].ctx = pruned_context(st, Kmer{slots[i].w0, slots[i].w1}, slots[i].ctx & 0xff);
+    }
+    // phase 4 (owner side, after adjacency): k_gather_ctx — the pruned contexts of the slots that were asked for
+    void ctx_answer(const uint32_t* slot, uint64_t n, uint32_t* ctx) const { for (uint64_t i = 0; i < n; ++i) ctx[i] = slot[i] == NIL ? 0u : (slots[slot[i]].ctx & 0xffu); }
+    void apply_ghost_ctx(uint32_t d, const uint32_t* ctx) { for (size_t i = 0; i < gslot[d].size(); ++i) if (gslot[d][i] != NIL) slots[gslot[d][i]].ctx = ctx[i]; }
+    // phase 5: k_links_sharded
+    int links() {
+        const uint64_t nn = 2 * st.size();
+        next0.resize(nn); ghead.assign(nn, 0);
+        int missing = 0;
+        for (uint64_t x = 0; x < nn; ++x) { bool tg; next0[x] = unipath_succ_link(st, (uint32_t)x, &missing, &tg); if (tg) ghead[x ^ 1u] = 1; }
+        return missing;
+    }
+    // phase 6: local list ranking, k_emit_pieces, k_piece_flips
+    int rank_and_pieces() {
+        if (rank_local(st, next0, ghead.data(), R) < 0) return 102;
+        const uint64_t nn = next0.size();
+        pieces.clear(); lpiece.assign(nn, NIL); lhead.assign(nn, NIL);
+        for (uint64_t x = 0; x < nn; ++x)
+            if (node_is_piece_head(next0.data(), ghead.data(), (uint32_t)x)) {
+                const PieceRec p = piece_of_head(st, next0.data(), R.data(), me, (uint32_t)x);
+                lpiece[p.flip_local] = (uint32_t)pieces.size();          // (flip_local still holds the tail node)
+                lhead[x] = (uint32_t)pieces.size();
+                pieces.push_back(p);
+            }
+        for (PieceRec& p : pieces) p.flip_local = lhead[p.flip_local ^ 1u];
+        return 0;
+    }
+    // phase 7 (replicated): all pieces of all ranks -> links, ranks.  Returns the number of unranked pieces (circles), or < 0.
+    int64_t set_pieces(const PieceRec* all, uint64_t n_all, const uint64_t* off /* [world + 1] */) {
+        P.assign(all, all + n_all); poff.assign(off, off + world + 1);
         const uint64_t np = P.size();
         uint64_t msz = 64; while (msz < 2 * np) msz <<= 1;
         std::vector<uint64_t> mkeys(msz, GID_NONE); std::vector<uint32_t> mvals(msz, NIL);
@@ -493,9 +482,9 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
         for (uint64_t i = 0; i < np; ++i) { uint64_t h = gid_hash(P[i].head) & gm.mask; while (mkeys[h] != GID_NONE) h = (h + 1) & gm.mask; mkeys[h] = P[i].head; mvals[h] = (uint32_t)i; }
         nxt.assign(np, NIL); flip.assign(np, NIL);
         for (uint64_t i = 0; i < np; ++i) {
-            if (P[i].succ != GID_NONE) { nxt[i] = gid_find(gm, P[i].succ); if (nxt[i] == NIL) return 107; }
-            flip[i] = rk[P[i].head >> 32].piece0 + P[i].flip_local;
-            if (P[i].flip_local == NIL) return 108;
+            if (P[i].succ != GID_NONE) { nxt[i] = gid_find(gm, P[i].succ); if (nxt[i] == NIL) return -107; }
+            if (P[i].flip_local == NIL) return -108;
+            flip[i] = (uint32_t)poff[P[i].head >> 32] + P[i].flip_local;
         }
         S.resize(np);
         for (uint64_t i = 0; i < np; ++i) S[i] = piece_rank_init(P.data(), nxt.data(), (uint32_t)i);
@@ -506,122 +495,235 @@ int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_fre
             if (un == 0 || un == prev) break;
             prev = un;
         }
-        if (un == 0) break;
-        // ---- circles that span ranks (BuildReadQGraph.cc:126-180): unresolved pieces.  Label every circle (min piece index by
-        // pointer doubling), gather its nodes, find the minimum canonical k-mer per circle, cut there, and rank again.
-        std::vector<uint32_t> lab(np), jmp(np);
-        for (uint64_t i = 0; i < np; ++i) { lab[i] = (uint32_t)i; jmp[i] = nxt[i]; }
-        for (int round = 0; round < 40; ++round) {
-            bool any = false;
-            std::vector<uint32_t> lab2 = lab, jmp2 = jmp;
-            for (uint64_t i = 0; i < np; ++i) if (!(S[i].y & RANK_RESOLVED)) { const uint32_t j = jmp[i]; if (lab[j] < lab2[i]) { lab2[i] = lab[j]; any = true; } jmp2[i] = jmp[j]; }
-            lab.swap(lab2); jmp.swap(jmp2);
-            if (!any) break;
+        return (int64_t)un;
+    }
+    // phase 7b: circles that span ranks (BuildReadQGraph.cc:126-180): my nodes on unranked pieces (k_collect_cycle_nodes) ...
+    void collect_cycle_nodes() {
+        cyc.clear();
+        for (uint64_t x = 0; x < next0.size(); ++x) {
+            if (next0[x] == EMPTY_NODE || next0[x] == GHOST_TAIL) continue;
+            const uint32_t pi = (uint32_t)poff[me] + lpiece[R[x].x];
+            if (S[pi].y & RANK_RESOLVED) continue;
+            const SolidSlot& sl = slots[x >> 1];
+            cyc.push_back(CycleNodeH{pi, 0u, sl.w0, sl.w1, gid_make(me, (uint32_t)x)});
         }
-        struct CNode { uint32_t lab; Kmer canon; uint64_t gid; };
-        std::vector<CNode> cn;
-        for (uint32_t r = 0; r < world; ++r) {
-            Rank& me = rk[r];
-            for (uint64_t x = 0; x < me.next0.size(); ++x) {
-                if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL || !(me.R[x].y & RANK_RESOLVED)) continue;
-                const uint32_t pi = me.piece0 + me.lpiece[me.R[x].x];
-                if (S[pi].y & RANK_RESOLVED) continue;
-                const SolidSlot& sl = me.slots[x >> 1];
-                cn.push_back(CNode{lab[pi], Kmer{sl.w0, sl.w1}, gid_make(r, (uint32_t)x)});
-            }
+    }
+    // ... and, from everybody's (the host part of graph_stage_sharded + k_apply_cycle_cuts): cut every circle at its minimum k-mer
+    void apply_cuts(const CycleNodeH* all, uint64_t n_all) {
+        const uint64_t np = P.size();
+        std::vector<uint32_t> lab(np, NIL);
+        for (uint64_t i = 0; i < np; ++i) {
+            if ((S[i].y & RANK_RESOLVED) || lab[i] != NIL) continue;
+            uint32_t mn = (uint32_t)i;
+            for (uint32_t j = nxt[i]; j != i; j = nxt[j]) mn = std::min(mn, j);
+            lab[i] = mn;
+            for (uint32_t j = nxt[i]; j != i; j = nxt[j]) lab[j] = mn;
         }
-        std::sort(cn.begin(), cn.end(), [](const CNode& a, const CNode& b) { return a.lab != b.lab ? a.lab < b.lab : (kmer_less(a.canon, b.canon) || (a.canon == b.canon && a.gid < b.gid)); });
-        // per circle label: the first entry holds the minimum canonical k-mer.  Both strand circles contain that slot: the one through
-        // (kmin,+) starts there, the one through (kmin,-) ends there.
+        std::vector<CycleNodeH> cn(all, all + n_all);
+        std::sort(cn.begin(), cn.end(), [&](const CycleNodeH& a, const CycleNodeH& b) {
+            const uint32_t la = lab[a.piece], lb = lab[b.piece];
+            if (la != lb) return la < lb;
+            if (a.w0 != b.w0) return a.w0 < b.w0;
+            if (a.w1 != b.w1) return a.w1 < b.w1;
+            return a.gid < b.gid;
+        });
         std::vector<uint64_t> heads_g, tails_g;            // (kmin,+) becomes a head, (kmin,-) a tail
         for (size_t i = 0; i < cn.size(); ++i) {
-            if (i > 0 && cn[i].lab == cn[i - 1].lab) continue;
-            for (size_t j = i; j < cn.size() && cn[j].lab == cn[i].lab && cn[j].canon == cn[i].canon; ++j)      // (a circle that is its own reverse complement holds both)
+            if (i > 0 && lab[cn[i].piece] == lab[cn[i - 1].piece]) continue;
+            for (size_t j = i; j < cn.size() && lab[cn[j].piece] == lab[cn[i].piece] && cn[j].w0 == cn[i].w0 && cn[j].w1 == cn[i].w1; ++j)      // (a circle that is its own reverse complement holds both)
                 if (cn[j].gid & 1ull) tails_g.push_back(cn[j].gid); else heads_g.push_back(cn[j].gid);
         }
-        std::sort(heads_g.begin(), heads_g.end());
-        for (uint32_t r = 0; r < world; ++r) {
-            Rank& me = rk[r];
-            for (uint64_t g : tails_g) if ((uint32_t)(g >> 32) == r) me.next0[(uint32_t)g] = NIL;          // (kmin,-) ends its strand
-            for (uint64_t x = 0; x < me.next0.size(); ++x) {                                              // the predecessor of (kmin,+) ends its strand
-                const uint32_t nx = me.next0[x];
-                if (nx >= GHOST_TAIL) continue;
-                const SolidSlot& sl = me.slots[nx >> 1];
-                const uint64_t g = slot_is_ghost(sl) ? gid_make(sl.pad - 1u, 2u * sl.edge + (nx & 1u)) : gid_make(r, nx);
-                if (std::binary_search(heads_g.begin(), heads_g.end(), g)) me.next0[x] = NIL;
+        std::sort(heads_g.begin(), heads_g.end()); std::sort(tails_g.begin(), tails_g.end());
+        for (const CycleNodeH& c : cyc) {
+            const uint32_t x = (uint32_t)c.gid;
+            if (std::binary_search(heads_g.begin(), heads_g.end(), c.gid)) ghead[x] = 0;
+            const uint32_t nx = next0[x];
+            bool cut = std::binary_search(tails_g.begin(), tails_g.end(), c.gid);
+            if (!cut && nx < GHOST_TAIL) {
+                const SolidSlot& sl = slots[nx >> 1];
+                const uint64_t g = slot_is_ghost(sl) ? gid_make(sl.pad - 1u, 2u * sl.edge + (nx & 1u)) : gid_make(me, nx);
+                cut = std::binary_search(heads_g.begin(), heads_g.end(), g);
             }
-            for (uint64_t g : heads_g) if ((uint32_t)(g >> 32) == r) me.ghead[(uint32_t)g] = 0;
+            if (cut) next0[x] = NIL;
         }
     }
-    out->timings.count_passes = (uint32_t)P.size();
-    out->timings.reserved = (uint32_t)n_ghost;
-    // ---- strands: even lengths from the piece records (replicated), odd lengths by the owner of the middle k-mer (all-reduce max)
-    const uint64_t np = P.size();
-    PieceView pv{P.data(), flip.data(), S.data(), np};
-    std::vector<uint8_t> keepp(np, 0), is_head(np, 0);
-    std::vector<uint64_t> chain_n(np, 0);
-    for (uint64_t i = 0; i < np; ++i) {
-        if (nxt[i] != NIL) continue;
-        uint32_t hp; uint64_t n;
-        chain_of_tail_piece(pv, (uint32_t)i, &hp, &n);
-        if (n > 0x1000000ull) return 103;
-        is_head[hp] = 1; chain_n[hp] = n;
-        const uint32_t kf = chain_keep_even(pv, (uint32_t)i, hp, n);
-        if (kf != 2u) keepp[hp] = (uint8_t)kf;
-    }
-    std::vector<PieceInfo> pinfo(np);                                          // k_piece_info (replicated)
-    for (uint64_t i = 0; i < np; ++i) pinfo[i] = piece_info(pv, (uint32_t)i);
-    for (uint32_t r = 0; r < world; ++r)                                       // k_piece_keep_odd: every rank over its own pieces
-        for (size_t j = 0; j < rk[r].pieces.size(); ++j) {
-            const uint32_t gi = rk[r].piece0 + (uint32_t)j;
-            const int kf = piece_keep_odd(rk[r].st, rk[r].next0.data(), pinfo[gi], (uint32_t)P[gi].head);
+    // phase 8: strands — even lengths from the piece records (k_chain_tails, replicated), odd lengths by the piece that holds the
+    // middle k-mer (k_piece_keep_odd); keepp is then max-reduced over the ranks
+    int strands(uint8_t* keepp) {
+        const uint64_t np = P.size();
+        PieceView pv{P.data(), flip.data(), S.data(), np};
+        is_head.assign(np, 0); chain_n.assign(np, 0);
+        memset(keepp, 0, np);
+        for (uint64_t i = 0; i < np; ++i) {
+            if (nxt[i] != NIL) continue;
+            uint32_t hp; uint64_t n;
+            chain_of_tail_piece(pv, (uint32_t)i, &hp, &n);
+            if (n > 0x1000000ull) return 103;
+            is_head[hp] = 1; chain_n[hp] = n;
+            const uint32_t kf = chain_keep_even(pv, (uint32_t)i, hp, n);
+            if (kf != 2u) keepp[hp] = (uint8_t)kf;
+        }
+        pinfo.resize(np);
+        for (uint64_t i = 0; i < np; ++i) pinfo[i] = piece_info(pv, (uint32_t)i);
+        for (size_t j = 0; j < pieces.size(); ++j) {
+            const uint32_t gi = (uint32_t)poff[me] + (uint32_t)j;
+            const int kf = piece_keep_odd(st, next0.data(), pinfo[gi], (uint32_t)P[gi].head);
             if (kf >= 0) keepp[pinfo[gi].head_piece] = (uint8_t)kf;
         }
-    // ---- edges: kept heads sorted by k-mer (replicated), emission by the owners, all-reduce of the bases
-    struct Head { Kmer k; uint32_t piece; };
-    std::vector<Head> heads;
-    for (uint64_t i = 0; i < np; ++i) if (is_head[i] && keepp[i]) heads.push_back(Head{P[i].head_k, (uint32_t)i});
-    std::sort(heads.begin(), heads.end(), [](const Head& a, const Head& b) { return kmer_less(a.k, b.k); });
-    EdgeSet es;
-    es.E = heads.size();
-    const uint64_t E = es.E;
-    std::vector<uint32_t> edge_of_piece(np, NIL);
-    es.edge_len.resize(E); es.edge_off.assign(E + 1, 0);
-    for (uint64_t i = 0; i < E; ++i) { edge_of_piece[heads[i].piece] = (uint32_t)i; es.edge_len[i] = (uint32_t)chain_n[heads[i].piece] + K - 1; es.edge_off[i + 1] = es.edge_off[i] + (es.edge_len[i] + 3) / 4; }
-    es.edge_bases.assign(es.edge_off[E] + 32, 0);
-    PutBase put{es.edge_bases.data()};
-    for (uint64_t i = 0; i < np; ++i) pinfo[i].head_piece = edge_of_piece[pinfo[i].head_piece];       // k_piece_edges
-    for (Rank& me : rk)
-        for (uint64_t x = 0; x < me.next0.size(); ++x) {
-            if (me.next0[x] == EMPTY_NODE || me.next0[x] == GHOST_TAIL) continue;
-            emit_node_sharded(me.st, me.R.data(), me.lpiece.data(), pinfo.data() + me.piece0, es.edge_off.data(), (uint32_t)x, put);
+        return 0;
+    }
+    // phase 9: edge ids from the kept heads (replicated), my k-mers' bases into a zeroed edge array (k_emit_edges_sharded); the arrays are
+    // then OR-reduced over the ranks
+    void edges(const uint8_t* keepp) {
+        const uint64_t np = P.size();
+        struct Head { Kmer k; uint32_t piece; };
+        std::vector<Head> heads;
+        for (uint64_t i = 0; i < np; ++i) if (is_head[i] && keepp[i]) heads.push_back(Head{P[i].head_k, (uint32_t)i});
+        std::sort(heads.begin(), heads.end(), [](const Head& a, const Head& b) { return kmer_less(a.k, b.k); });
+        es = EdgeSet();
+        es.E = heads.size();
+        const uint64_t E = es.E;
+        std::vector<uint32_t> edge_of_piece(np, NIL);
+        es.edge_len.resize(E); es.edge_off.assign(E + 1, 0);
+        for (uint64_t i = 0; i < E; ++i) { edge_of_piece[heads[i].piece] = (uint32_t)i; es.edge_len[i] = (uint32_t)chain_n[heads[i].piece] + K - 1; es.edge_off[i + 1] = es.edge_off[i] + (es.edge_len[i] + 3) / 4; }
+        es.edge_bases.assign(es.edge_off[E] + 32, 0);
+        PutBase put{es.edge_bases.data()};
+        for (uint64_t i = 0; i < np; ++i) pinfo[i].head_piece = edge_of_piece[pinfo[i].head_piece];       // k_piece_edges
+        for (uint64_t x = 0; x < next0.size(); ++x) {
+            if (next0[x] == EMPTY_NODE || next0[x] == GHOST_TAIL) continue;
+            emit_node_sharded(st, R.data(), lpiece.data(), pinfo.data() + poff[me], es.edge_off.data(), (uint32_t)x, put);
         }
-    // ---- the pathing dictionary: finished entries (pruned context, edge, offset) re-sharded by k-mer hash (all-to-all), slice r built
-    // on rank r; the path kernels of all ranks read all slices (peer memory on the device)
+    }
+    // phase 10: my finished entries for dictionary slice d (k_dump_owned_sliced)
+    void entries_for(uint32_t d, std::vector<SolidSlot>* out) const {
+        for (uint64_t i = 0; i < st.size(); ++i) {
+            const SolidSlot& sl = slots[i];
+            if (sl.w0 != EMPTY_W0 && !slot_is_ghost(sl) && pd_slice_of(world, bloom_hash(Kmer{sl.w0, sl.w1})) == d) out->push_back(sl);
+        }
+    }
+};
+// a dictionary slice from its entries (k_insert_entries)
+std::vector<SolidSlot> build_slice(const SolidSlot* e, uint64_t n) {
+    std::vector<SolidSlot> t(n + n / 3 + 1024);
+    memset(t.data(), 0xff, t.size() * sizeof(SolidSlot));
+    SolidTable tt{t.data(), t.size()};
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t h = tt.home(Kmer{e[i].w0, e[i].w1});
+        while (t[h].w0 != EMPTY_W0) h = tt.next(h);
+        t[h] = e[i];
+    }
+    return t;
+}
+}  // namespace
+
+extern "C" {
+
+// `world` simulated ranks in one process: exchanges are plain copies.  Result: the same graph the single-table path builds.
+// out->timings.reserved receives the number of ghost entries, out->timings.count_passes the number of pieces (local chains).
+int hc_graph_sharded(const w2rap_kmer_rec* all, uint64_t n_all, uint32_t min_freq, uint32_t world, uint32_t logP, const w2rap_reads* in, int want_paths,
+                     int apply_fixpaths, uint32_t cap, uint32_t left_cap, w2rap_graph* out) {
+    memset(out, 0, sizeof(*out));
+    std::vector<SgRank> rk(world);
+    uint64_t n_solid = 0;
+    for (uint32_t r = 0; r < world; ++r) { rk[r].world = world; rk[r].me = r; rk[r].logP = logP; }
+    for (uint64_t i = 0; i < n_all; ++i) {
+        if (all[i].count < min_freq) continue;
+        ++n_solid;
+        rk[kmer_owner(Kmer{all[i].w0, all[i].w1}, logP, world)].owned.push_back(all[i]);
+    }
+    out->n_solid = n_solid; out->n_distinct = n_all;
+    for (SgRank& me : rk) me.start();
+    // all-to-all of the keys, answers, all-to-all of the replies
+    std::vector<std::vector<std::vector<uint32_t>>> reply(world, std::vector<std::vector<uint32_t>>(world));
+    for (uint32_t r = 0; r < world; ++r)
+        for (uint32_t d = 0; d < world; ++d) { reply[r][d].resize(rk[r].q[d].size()); rk[d].answer(rk[r].q[d].data(), rk[r].q[d].size(), reply[r][d].data()); }
+    for (uint32_t r = 0; r < world; ++r) for (uint32_t d = 0; d < world; ++d) rk[r].insert_ghosts(d, reply[r][d].data());
+    for (SgRank& me : rk) me.adjacency();
+    // second round: the owners' pruned contexts of the slots they reported
+    for (uint32_t r = 0; r < world; ++r)
+        for (uint32_t d = 0; d < world; ++d) {
+            std::vector<uint32_t> ctx(reply[r][d].size());
+            rk[d].ctx_answer(reply[r][d].data(), reply[r][d].size(), ctx.data());
+            rk[r].apply_ghost_ctx(d, ctx.data());
+        }
+    for (SgRank& me : rk) if (me.links()) return 101;
+    for (int iteration = 0;; ++iteration) {
+        if (iteration > 1) return 106;
+        for (SgRank& me : rk) { const int rc = me.rank_and_pieces(); if (rc) return rc; }
+        std::vector<PieceRec> P;
+        std::vector<uint64_t> off(world + 1, 0);
+        for (uint32_t r = 0; r < world; ++r) { off[r] = P.size(); P.insert(P.end(), rk[r].pieces.begin(), rk[r].pieces.end()); }
+        off[world] = P.size();
+        int64_t un = 0;
+        for (SgRank& me : rk) { un = me.set_pieces(P.data(), P.size(), off.data()); if (un < 0) return (int)-un; }
+        if (un == 0) break;
+        std::vector<CycleNodeH> cn;
+        for (SgRank& me : rk) { me.collect_cycle_nodes(); cn.insert(cn.end(), me.cyc.begin(), me.cyc.end()); }
+        for (SgRank& me : rk) me.apply_cuts(cn.data(), cn.size());
+    }
+    const uint64_t np = rk[0].P.size();
+    uint64_t n_ghost = 0;
+    for (SgRank& me : rk) n_ghost += me.n_ghost;
+    // strands (all-reduce max of the keep flags), edges (all-reduce OR of the bases)
+    std::vector<uint8_t> keepp(np, 0), mine(np);
+    for (SgRank& me : rk) { const int rc = me.strands(mine.data()); if (rc) return rc; for (uint64_t i = 0; i < np; ++i) keepp[i] = std::max(keepp[i], mine[i]); }
+    for (SgRank& me : rk) me.edges(keepp.data());
+    EdgeSet es = rk[0].es;
+    for (uint32_t r = 1; r < world; ++r) for (size_t i = 0; i < es.edge_bases.size(); ++i) es.edge_bases[i] |= rk[r].es.edge_bases[i];
+    // the pathing dictionary: finished entries re-sharded by k-mer hash (all-to-all), slice r built on rank r, slices all-gathered
     std::vector<std::vector<SolidSlot>> stab(world);
-    {
-        std::vector<uint64_t> cnt(world, 0);
-        for (Rank& me : rk)
-            for (uint64_t i = 0; i < me.st.size(); ++i) { const SolidSlot& sl = me.slots[i]; if (sl.w0 != EMPTY_W0 && !slot_is_ghost(sl)) ++cnt[pd_slice_of(world, bloom_hash(Kmer{sl.w0, sl.w1}))]; }
-        for (uint32_t r = 0; r < world; ++r) { stab[r].resize(table_slots_for(cnt[r])); memset(stab[r].data(), 0xff, stab[r].size() * sizeof(SolidSlot)); }
-        for (Rank& me : rk)
-            for (uint64_t i = 0; i < me.st.size(); ++i) {
-                const SolidSlot& sl = me.slots[i];
-                if (sl.w0 == EMPTY_W0 || slot_is_ghost(sl)) continue;
-                std::vector<SolidSlot>& t = stab[pd_slice_of(world, bloom_hash(Kmer{sl.w0, sl.w1}))];
-                SolidTable tt{t.data(), t.size()};
-                uint64_t h = tt.home(Kmer{sl.w0, sl.w1});
-                while (t[h].w0 != EMPTY_W0) h = tt.next(h);
-                t[h] = sl;
-            }
+    for (uint32_t d = 0; d < world; ++d) {
+        std::vector<SolidSlot> e;
+        for (SgRank& me : rk) me.entries_for(d, &e);
+        stab[d] = build_slice(e.data(), e.size());
     }
     std::vector<PathSlice> slices;
     for (uint32_t r = 0; r < world; ++r) slices.push_back(PathSlice{stab[r].data(), stab[r].size()});
-    const uint32_t keep_passes = out->timings.count_passes, keep_res = out->timings.reserved;
     const int rc = finish_graph(slices, es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
-    out->timings.count_passes = keep_passes;
-    if (!want_paths) out->timings.reserved = keep_res;
+    out->timings.count_passes = (uint32_t)np;
+    if (!want_paths) out->timings.reserved = (uint32_t)n_ghost;
     return rc;
+}
+
+// ---- the same phases for ONE rank of a real multi-process run (tests/sharded_gloo_worker.py drives them over gloo)
+void* sg_new(const w2rap_kmer_rec* owned, uint64_t n, uint32_t world, uint32_t rank, uint32_t logP) {
+    SgRank* r = new SgRank();
+    r->world = world; r->me = rank; r->logP = logP; r->owned.assign(owned, owned + n);
+    r->start();
+    return r;
+}
+void sg_delete(void* h) { delete (SgRank*)h; }
+uint32_t sg_owner(uint64_t w0, uint64_t w1, uint32_t logP, uint32_t world) { return kmer_owner(Kmer{w0, w1}, logP, world); }
+uint64_t sg_queries(void* h, uint32_t d, const void** keys) { SgRank* r = (SgRank*)h; *keys = r->q[d].data(); return r->q[d].size(); }
+void sg_answer(void* h, const void* keys, uint64_t n, uint32_t* reply) { ((SgRank*)h)->answer((const Kmer*)keys, n, reply); }
+void sg_insert_ghosts(void* h, uint32_t d, const uint32_t* reply) { ((SgRank*)h)->insert_ghosts(d, reply); }
+void sg_adjacency(void* h) { ((SgRank*)h)->adjacency(); }
+void sg_ctx_answer(void* h, const uint32_t* slot, uint64_t n, uint32_t* ctx) { ((SgRank*)h)->ctx_answer(slot, n, ctx); }
+void sg_apply_ghost_ctx(void* h, uint32_t d, const uint32_t* ctx) { ((SgRank*)h)->apply_ghost_ctx(d, ctx); }
+int sg_links(void* h) { return ((SgRank*)h)->links(); }
+int sg_rank_and_pieces(void* h, const void** pieces, uint64_t* n) { SgRank* r = (SgRank*)h; const int rc = r->rank_and_pieces(); *pieces = r->pieces.data(); *n = r->pieces.size(); return rc; }
+int64_t sg_set_pieces(void* h, const void* all, uint64_t n_all, const uint64_t* off) { return ((SgRank*)h)->set_pieces((const PieceRec*)all, n_all, off); }
+uint64_t sg_cycle_nodes(void* h, const void** nodes) { SgRank* r = (SgRank*)h; r->collect_cycle_nodes(); *nodes = r->cyc.data(); return r->cyc.size(); }
+void sg_apply_cuts(void* h, const void* all, uint64_t n_all) { ((SgRank*)h)->apply_cuts((const CycleNodeH*)all, n_all); }
+int sg_strands(void* h, uint8_t* keepp) { return ((SgRank*)h)->strands(keepp); }
+uint64_t sg_edges(void* h, const uint8_t* keepp, void** edge_bases) { SgRank* r = (SgRank*)h; r->edges(keepp); *edge_bases = r->es.edge_bases.data(); return r->es.edge_bases.size(); }
+uint64_t sg_entries(void* h, uint32_t d, void** out) {      // caller frees *out with hc_free
+    std::vector<SolidSlot> e;
+    ((SgRank*)h)->entries_for(d, &e);
+    *out = dup(e);
+    return e.size();
+}
+uint32_t sg_sizeof(int what) { return what == 0 ? sizeof(PieceRec) : (what == 1 ? sizeof(CycleNodeH) : sizeof(SolidSlot)); }
+// everything after the graph stage, from the (OR-reduced) edge bases of this rank and the entry lists of ALL dictionary slices
+int sg_finish(void* h, const void* const* slice_entries, const uint64_t* slice_n, uint64_t n_solid, const w2rap_reads* in, int want_paths, int apply_fixpaths, uint32_t cap,
+              uint32_t left_cap, w2rap_graph* out) {
+    SgRank* r = (SgRank*)h;
+    memset(out, 0, sizeof(*out));
+    out->n_solid = n_solid;
+    std::vector<std::vector<SolidSlot>> stab(r->world);
+    std::vector<PathSlice> slices;
+    for (uint32_t d = 0; d < r->world; ++d) { stab[d] = build_slice((const SolidSlot*)slice_entries[d], slice_n[d]); slices.push_back(PathSlice{stab[d].data(), stab[d].size()}); }
+    return finish_graph(slices, r->es, n_solid, in, want_paths, apply_fixpaths, cap, left_cap, out);
 }
 
 void hc_graph_free(w2rap_graph* g) {
