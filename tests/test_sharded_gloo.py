@@ -1,4 +1,6 @@
-"""World-size-2 (and 4) run of the sharded step-2 protocol on CPU over gloo (tests/sharded_gloo_worker.py) against the oracle."""
+"""World-size-2 (and 4) run of the sharded step-2 protocol on CPU over gloo (tests/sharded_gloo_worker.py) against the oracle: record routing
+and counting by owners, then the sharded graph stage (neighbour queries, chain-end records, circles across ranks, strand and edge
+reductions, dictionary slices) with every exchange a real collective."""
 import os
 import subprocess
 import sys
@@ -39,3 +41,5 @@ def test_sharded_protocol_over_gloo(T, tmp_path, world):
         a, b = int(want["path_off"][lo]), int(want["path_off"][hi])
         assert np.array_equal(z["path_edges"], want["path_edges"][a:b])
     assert total_inst == want["n_kmer_instances"]
+    z = np.load(os.path.join(str(tmp_path), "rank0.npz"))
+    assert int(z["n_pieces"]) > 2 * want["n_edges"] and int(z["n_cut_rounds"]) == 1      # chains were cut at rank boundaries; the plasmid circle spans ranks

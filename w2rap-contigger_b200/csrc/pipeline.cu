@@ -667,6 +667,10 @@ struct Pipeline {
     SBuf<uint32_t> path_bloom;
     uint32_t path_slice_words = 0;
     uint64_t n_slice_entries = 0;           // sharded: entries of the dictionary slice this rank holds
+    cudaStream_t dict_stream = nullptr;     // sharded: the all-gather of the dictionary slices runs here, under the HBV stage
+    cudaEvent_t dict_ready = nullptr;
+    bool dict_pending = false;
+    void wait_for_dictionary() { if (dict_pending) { W2R_CUDA(cudaStreamWaitEvent(c.stream, dict_ready, 0)); dict_pending = false; } }
     void build_dictionary(uint64_t n_solid_local, uint64_t n_distinct) {
         std::vector<unsigned long long> tot = {n_solid_local};
         allreduce_u64(tot, ncclSum);
@@ -1102,10 +1106,14 @@ struct Pipeline {
         // contiguous NVLink transfers, no insert work on the receivers).  Tried first: leaving the slices where they were built and
         // reading them from the path kernels through peer-mapped memory (CUDA IPC) — correct, but fine-grained remote LOADS over NVLink
         // are latency-serialised: the path kernel went from 24 ms to 426 ms on two GPUs.
-        xt.start();
-        nccl_check(NcclApi::get().AllGather(slice, solid_slots.p, sslots * sizeof(SolidSlot), ncclUint8, comm, c.stream), "all-gather");
-        if (path_slice_words) nccl_check(NcclApi::get().AllGather(path_bloom.p + (size_t)me * path_slice_words, path_bloom.p, (size_t)path_slice_words * 4, ncclUint8, comm, c.stream), "all-gather");
-        xms += xt.stop();
+        // (on a side stream: the HBV vertices, which only need the edges, are computed under the transfer; path_stage() waits)
+        if (!dict_stream) { W2R_CUDA(cudaStreamCreateWithFlags(&dict_stream, cudaStreamNonBlocking)); W2R_CUDA(cudaEventCreateWithFlags(&dict_ready, cudaEventDisableTiming)); }
+        W2R_CUDA(cudaEventRecord(dict_ready, c.stream));
+        W2R_CUDA(cudaStreamWaitEvent(dict_stream, dict_ready, 0));
+        nccl_check(NcclApi::get().AllGather(slice, solid_slots.p, sslots * sizeof(SolidSlot), ncclUint8, comm, dict_stream), "all-gather");
+        if (path_slice_words) nccl_check(NcclApi::get().AllGather(path_bloom.p + (size_t)me * path_slice_words, path_bloom.p, (size_t)path_slice_words * 4, ncclUint8, comm, dict_stream), "all-gather");
+        W2R_CUDA(cudaEventRecord(dict_ready, dict_stream));
+        dict_pending = true;
         xchg_bytes += (sslots * sizeof(SolidSlot) + (size_t)path_slice_words * 4) * (uint64_t)(W - 1);
         std::vector<PathSlice> sl(W);
         for (uint32_t r = 0; r < W; ++r) sl[r] = PathSlice{solid_slots.p + (size_t)r * sslots, sslots};
@@ -1160,6 +1168,7 @@ struct Pipeline {
         // a filter built here; sharded: graph_stage_sharded() left this rank's slice, the peer-mapped slices of the others and the
         // all-gathered filter.  (The filter is not pinned in L2: its misses are sectors of a 192 MB array either way, and the
         // persisting carve-out made no difference once the kernel stopped spilling: 96 / 192 / 384 MB all 47 ms at config 2.)
+        wait_for_dictionary();
         if (world == 1) {
             const PathSlice one{st.slots, st.nslots};
             path_slices.alloc(c, 1);
@@ -1285,6 +1294,7 @@ struct Pipeline {
             out->path_off = to_host<uint64_t>(d_path_off.p, dr.n + 1);
             out->path_edges = to_host<int32_t>(d_path_edges.p, npe);
         }
+        wait_for_dictionary();
         if (prm.dump_kmers == 1 && out->n_solid) {
             // (sharded: every rank dumps the dictionary slice it holds; the test hook gathers them so that every rank reports the whole)
             const uint64_t n_mine = world > 1 ? n_slice_entries : out->n_solid;
@@ -1328,12 +1338,14 @@ struct Pipeline {
     }
 
     ~Pipeline() {
-        // free stream-ordered buffers before the stream goes away
+        // free stream-ordered buffers before the stream goes away (and not under a transfer that still writes into them)
+        if (dict_stream) cudaStreamSynchronize(dict_stream);
         good.release(); solid_slots.release(); edge_bases.release(); edge_off.release(); edge_len.release();
         edge_vertices.release(); fwd_xlat.release(); rev_xlat.release(); involution.release(); hleft.release();
         cs_scal.release(); cs_flags.release(); cs_hist.release(); cs_region.release(); cs_dump.release(); cs_solid.release();
         path_slices.release(); path_bloom.release(); hright.release(); from_e.release(); to_e.release();
         hcanon.release(); from_n.release(); to_n.release();
+        if (dict_stream) { cudaStreamSynchronize(dict_stream); cudaStreamDestroy(dict_stream); cudaEventDestroy(dict_ready); }
         if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
     }
 };
