@@ -604,7 +604,7 @@ struct SgRank {
 };
 // a dictionary slice from its entries (k_insert_entries)
 std::vector<SolidSlot> build_slice(const SolidSlot* e, uint64_t n) {
-    std::vector<SolidSlot> t(n + n / 3 + 1024);
+    std::vector<SolidSlot> t(table_slots_for(n));
     memset(t.data(), 0xff, t.size() * sizeof(SolidSlot));
     SolidTable tt{t.data(), t.size()};
     for (uint64_t i = 0; i < n; ++i) {

@@ -1090,7 +1090,7 @@ struct Pipeline {
         allreduce_u64(mxn, ncclMax);
         allreduce_u64(tot, ncclSum);
         const uint64_t n_solid = tot[0];
-        const uint64_t sslots = mxn[0] + mxn[0] / 3 + 1024;          // load 0.75: these tables cross NVLink whole, and pathing screens its misses with the filter
+        const uint64_t sslots = solid_table_slots(mxn[0]);            // (load 0.75 would save a fifth of the transfer, but cost the path kernel 25 %: measured)
         solid_slots.alloc(c, (size_t)W * sslots);
         SolidSlot* slice = solid_slots.p + (size_t)me * sslots;
         W2R_CUDA(cudaMemsetAsync(slice, 0xff, sslots * sizeof(SolidSlot), c.stream));
