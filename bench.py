@@ -425,6 +425,7 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom] / nl, "launches_per_step": nl,
                      "kernel_ms_per_step": km[dom], "per_kernel": per_kernel, "sharded_graph_phases_ms": {k: round(v, 3) for k, v in phases.items()} if world > 1 else None,
                      "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9, "whole_step_frac": alg_bytes_total / (dev_ms * 1e-3) / 1e9 / peak},
+        "alloc_host_ms": [round(t["alloc_host_ms"], 1) for t in tt],
         "stage_ms": {k: median([t[k] for t in tt]) for k in ("count_ms", "count_kernel_ms", "region_ms", "dict_ms", "exchange_ms", "graph_exchange_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
         "nvlink": ({"bytes_sent_all_ranks_per_step": xbytes_all, "bytes_per_kmer_instance": xbytes_all / max(1, I_all),
                     "count_exchange_GBps_per_gpu": (xbytes_all / world) / max(1e-9, median([t["exchange_ms"] for t in tt]) * 1e-3) / 1e9} if world > 1 else None),

@@ -133,6 +133,9 @@ typedef struct w2rap_timings {
     uint64_t n_records;           /* super-k-mer records this rank's map produced (32 bytes each) */
     /* CUDA-event time of individual kernels (all launches of the kernel in this call), index = W2RAP_KT_*; 0 where not run */
     float kernel_ms[16];
+    float alloc_host_ms;          /* host time spent inside the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync) during this call:
+                                     ~0 when the pool serves every request from cached memory, large when it has to grow, trim or re-map */
+    uint32_t reserved2;
 } w2rap_timings;
 
 /*

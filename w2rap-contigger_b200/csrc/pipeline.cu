@@ -12,8 +12,13 @@
 #include <cmath>
 #include <chrono>
 #include <cstdarg>
+#include <exception>
+#include <map>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
+
+#include <cuda.h>
 
 #include "../../include/w2rap_step2.h"
 #include "device_reads.cuh"
@@ -26,6 +31,7 @@
 namespace w2r {
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static thread_local double g_alloc_host_ms = 0;      // host time inside the stream-ordered allocator (this thread = this rank's call)
 
 // Output arrays live in pinned host memory.  cudaMallocHost is slow (it maps and locks pages), so blocks are kept in a
 // process-wide pool and reused by later calls: steady-state steps pay no allocation.
@@ -95,30 +101,192 @@ static void check_device(int device, Ctx& c) {
     });
 }
 
-// stream-ordered device buffer (memory comes back from the pool on the next call, so steady-state steps do not hit the driver)
+// ---------------------------------------------------------------- device memory
+// Large buffers come from ONE contiguous virtual range per device whose physical backing grows on demand (CUDA virtual memory
+// management: cuMemAddressReserve / cuMemCreate / cuMemMap) and is kept between calls.  A free list with coalescing hands out
+// pieces of it, lowest address first.  Why not cudaMallocAsync for everything: its pool cannot merge freed blocks that came from
+// different growth steps, so a job near the device's capacity (BASELINE config 3: ~60 GB of counting areas freed, then one 60 GB
+// pathing dictionary) made the pool unmap and re-map tens of GB on every call — more than a second of host time per step.
+// One call at a time holds the slab of a device (SlabLease); everything it allocates is used on its one stream (side streams are
+// joined before a buffer is released — the same rule cudaFreeAsync imposes), so host-order reuse is stream-order reuse.  A
+// concurrent call on the same device, small buffers (< 1 MB) and W2RAP_NO_SLAB=1 (compute-sanitizer runs: it checks bounds per
+// allocation) use cudaMallocAsync.
+struct DriverVmm {
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    bool ok = false;
+    DriverVmm() {
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult st;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess && *fn;
+        };
+        ok = get("cuMemAddressReserve", (void**)&AddressReserve) && get("cuMemCreate", (void**)&Create) && get("cuMemMap", (void**)&Map) &&
+             get("cuMemSetAccess", (void**)&SetAccess) && get("cuMemGetAllocationGranularity", (void**)&GetGranularity) && get("cuMemRelease", (void**)&Release);
+        if (!ok) cudaGetLastError();
+    }
+    static DriverVmm& get() { static DriverVmm* v = new DriverVmm(); return *v; }
+};
+
+struct DeviceSlab {
+    static constexpr size_t MIN_BYTES = 1u << 20;        // smaller requests stay with cudaMallocAsync
+    static constexpr size_t ALIGN = 4096;
+    std::mutex lease;                                    // held by the one call that uses the slab
+    int device = -1;
+    bool disabled = false;
+    CUdeviceptr base = 0;
+    size_t va_bytes = 0, mapped = 0, gran = 0, used = 0;
+    std::map<size_t, size_t> free_;                      // offset -> bytes; disjoint, coalesced, all below `mapped`
+    std::unordered_map<size_t, size_t> live_;            // offset -> bytes
+
+    static DeviceSlab& get(int device) { static DeviceSlab* s = new DeviceSlab[16]; return s[device & 15]; }   // leaked on purpose (see PinnedPool)
+    bool contains(const void* p) const { return base && (CUdeviceptr)p >= base && (CUdeviceptr)p < base + va_bytes; }
+    size_t idle_bytes() const { return mapped - used; }
+
+    bool init(int dev) {
+        if (disabled) return false;
+        if (base) return true;
+        DriverVmm& v = DriverVmm::get();
+        static const bool off = getenv("W2RAP_NO_SLAB") != nullptr;
+        size_t fr = 0, tot = 0;
+        if (off || !v.ok || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); disabled = true; return false; }
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = dev;
+        if (v.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !gran) { disabled = true; return false; }
+        va_bytes = (tot + gran - 1) / gran * gran;
+        if (v.AddressReserve(&base, va_bytes, gran, 0, 0) != CUDA_SUCCESS) { base = 0; disabled = true; return false; }
+        device = dev;
+        return true;
+    }
+    // physical backing for [mapped, mapped + bytes): one cuMemCreate per growth step
+    bool grow(size_t need) {
+        DriverVmm& v = DriverVmm::get();
+        size_t want = std::max<size_t>(need, 256u << 20);
+        want = (want + gran - 1) / gran * gran;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return false; }
+            const size_t margin = 512u << 20;            // NCCL, the pool's small buffers, the CUDA context
+            size_t can = fr > margin ? (fr - margin) / gran * gran : 0;
+            size_t take = std::min(want, can);
+            if (take >= (need + gran - 1) / gran * gran && mapped + take <= va_bytes) {
+                CUmemAllocationProp prop = {};
+                prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = device;
+                CUmemGenericAllocationHandle h;
+                if (v.Create(&h, take, &prop, 0) == CUDA_SUCCESS) {
+                    CUmemAccessDesc acc = {};
+                    acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+                    if (v.Map(base + mapped, take, 0, h, 0) == CUDA_SUCCESS && v.SetAccess(base + mapped, take, &acc, 1) == CUDA_SUCCESS) {
+                        v.Release(h);                    // the mapping keeps the memory alive
+                        add_free(mapped, take);
+                        mapped += take;
+                        return true;
+                    }
+                    v.Release(h);
+                    return false;
+                }
+            }
+            // memory cached by the stream-ordered pool may be what is missing: give it back and try once more
+            cudaMemPool_t pool;
+            if (attempt == 0 && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); } else break;
+        }
+        return false;
+    }
+    void add_free(size_t off, size_t bytes) {
+        auto nx = free_.lower_bound(off);
+        if (nx != free_.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second == off) { off = pv->first; bytes += pv->second; free_.erase(pv); } }
+        if (nx != free_.end() && off + bytes == nx->first) { bytes += nx->second; free_.erase(nx); }
+        free_[off] = bytes;
+    }
+    void* acquire(size_t bytes) {
+        bytes = (bytes + ALIGN - 1) / ALIGN * ALIGN;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            for (auto it = free_.begin(); it != free_.end(); ++it) {
+                if (it->second < bytes) continue;
+                const size_t off = it->first, len = it->second;
+                free_.erase(it);
+                if (len > bytes) free_[off + bytes] = len - bytes;
+                live_[off] = bytes; used += bytes;
+                return (void*)(base + off);
+            }
+            // nothing fits: extend the top (only by what the free range touching it lacks)
+            size_t tail = 0;
+            if (!free_.empty()) { auto last = std::prev(free_.end()); if (last->first + last->second == mapped) tail = last->second; }
+            if (attempt || !grow(bytes - tail)) return nullptr;
+        }
+        return nullptr;
+    }
+    void release(void* p) {
+        const size_t off = (size_t)((CUdeviceptr)p - base);
+        auto it = live_.find(off);
+        if (it == live_.end()) return;
+        const size_t bytes = it->second;
+        live_.erase(it); used -= bytes;
+        add_free(off, bytes);
+    }
+};
+// one call holds a device's slab from its first buffer to its last; a failed call drains the device before handing it on
+struct SlabLease {
+    DeviceSlab* slab = nullptr;
+    explicit SlabLease(int device) {
+        DeviceSlab& s = DeviceSlab::get(device);
+        if (s.lease.try_lock()) { if (s.init(device)) slab = &s; else s.lease.unlock(); }
+    }
+    ~SlabLease() {
+        if (!slab) return;
+        if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
+        slab->lease.unlock();
+    }
+    SlabLease(const SlabLease&) = delete;
+    SlabLease& operator=(const SlabLease&) = delete;
+};
+
+// device buffer with stream-ordered lifetime: from the leased slab when it is large, else from CUDA's pool (which caches too)
 template <class T>
 struct SBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    DeviceSlab* slab = nullptr;
     SBuf() {}
     SBuf(Ctx& c, size_t n_) { alloc(c, n_); }
     SBuf(const SBuf&) = delete;
     SBuf& operator=(const SBuf&) = delete;
-    SBuf(SBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
-    SBuf& operator=(SBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; } return *this; }
+    SBuf(SBuf&& o) noexcept : p(o.p), n(o.n), s(o.s), slab(o.slab) { o.p = nullptr; o.n = 0; o.slab = nullptr; }
+    SBuf& operator=(SBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; s = o.s; slab = o.slab; o.p = nullptr; o.n = 0; o.slab = nullptr; } return *this; }
     ~SBuf() { release(); }
     void alloc(Ctx& c, size_t n_) {
         release();
         s = c.stream; n = n_;
-        if (n) W2R_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+        if (!n) return;
+        const double t0 = now_ms();
+        const size_t bytes = n * sizeof(T);
+        DeviceSlab* sl = (DeviceSlab*)c.slab;
+        if (sl && bytes >= DeviceSlab::MIN_BYTES) { p = (T*)sl->acquire(bytes); if (p) slab = sl; }
+        cudaError_t e = cudaSuccess;
+        if (!p) e = cudaMallocAsync((void**)&p, bytes, s);
+        const double dt = now_ms() - t0;
+        g_alloc_host_ms += dt;
+        if (dt > 20.0 && getenv("W2RAP_TRACE")) fprintf(stderr, "[w2rap] device allocation of %.2f GB took %.1f ms on the host\n", bytes / 1e9, dt);
+        W2R_CUDA(e);
     }
-    void release() { if (p) cudaFreeAsync(p, s); p = nullptr; n = 0; }
+    void release() {
+        if (p) {
+            const double t0 = now_ms();
+            if (slab) slab->release(p); else cudaFreeAsync(p, s);
+            g_alloc_host_ms += now_ms() - t0;
+        }
+        p = nullptr; n = 0; slab = nullptr;
+    }
     size_t bytes() const { return n * sizeof(T); }
     void zero() { if (n) W2R_CUDA(cudaMemsetAsync(p, 0, bytes(), s)); }
     void fill_ff() { if (n) W2R_CUDA(cudaMemsetAsync(p, 0xff, bytes(), s)); }
 };
 
+// what a call may still allocate: free device memory + what the pool and the slab hold idle
 static size_t device_budget(const Ctx& c) {
     size_t fr = 0, tot = 0;
     W2R_CUDA(cudaMemGetInfo(&fr, &tot));
@@ -129,6 +297,7 @@ static size_t device_budget(const Ctx& c) {
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
         if (reserved > used) fr += (size_t)(reserved - used);
     }
+    if (c.slab) fr += ((const DeviceSlab*)c.slab)->idle_bytes();
     return fr;
 }
 
@@ -175,6 +344,17 @@ struct Pipeline {
     GraphOwner* owner;
     std::vector<DumpRec> dump_host;
     KernelTimers kt_;
+
+    // W2RAP_TRACE: wall-clock of the phases (drains the stream at every mark, so the totals of a traced run are not a measurement)
+    double trace_t0 = 0;
+    void trace_mark(const char* what) {
+        static const bool on = getenv("W2RAP_TRACE") != nullptr;
+        if (!on) return;
+        cudaStreamSynchronize(c.stream);
+        const double t = now_ms();
+        if (trace_t0 && rank == 0) fprintf(stderr, "[w2rap] %-28s %8.1f ms   (allocator so far %.1f ms)\n", what, t - trace_t0, g_alloc_host_ms);
+        trace_t0 = t;
+    }
 
     // persistent device state between stages
     SBuf<uint16_t> good;
@@ -578,7 +758,9 @@ struct Pipeline {
                 // limit, and a pool that has to re-map memory on every step costs hundreds of milliseconds)
                 cb.recs.alloc(c, local_recs);
                 cb.tmp.alloc(c, stage_recs); cb.tpart.alloc(c, stage_recs);
+                trace_mark("count: buffers");
                 const bool mapped = map_records(pl, cb, batches, pass, &need);
+                trace_mark("count: map+scatter");
                 cb.tmp.release(); cb.tpart.release();
                 if (!mapped) {
                     std::vector<unsigned long long> nd = {need};
@@ -587,6 +769,7 @@ struct Pipeline {
                     retry = true; break;
                 }
                 if (world > 1) { exchange_records(pl, cb); cb.recs.release(); }      // (the local area is dead once its records are with their owners)
+                trace_mark("count: exchange");
                 const uint32_t* xcur = world > 1 ? cb.xcount.p : cb.part_count.p;
                 const uint32_t* xkcur = world > 1 ? cb.xkcount.p : cb.part_kcount.p;
                 const SkmRec* xrecs = world > 1 ? cb.xrecs.p : cb.recs.p;
@@ -607,7 +790,9 @@ struct Pipeline {
                         cs_solid_cap = cs_solid.n;
                     }
                 }
+                trace_mark("count: solid staging");
                 reduce_records(pl, xrecs, xcur, xkcur, runs, s2, ev_fork, ev_join);
+                trace_mark("count: reduce");
                 solid_used = d2h_scalar(c, cs_scal.p + 1);
                 if (world > 1) cb.xrecs.release();
             }
@@ -838,6 +1023,7 @@ struct Pipeline {
         const uint32_t me = (uint32_t)rank, W = (uint32_t)world;
         SBuf<int> flags(c, 8); flags.zero();
         SBuf<unsigned long long> scal(c, 8); scal.zero();
+        trace_mark("(before graph stage)");
         // -- round 1: neighbour queries from the solid records
         kt_.begin(W2RAP_KT_SG_QUERIES);
         uint64_t qcap = std::max<uint64_t>(1024, n_local / 4);
@@ -863,6 +1049,7 @@ struct Pipeline {
         uint64_t nq_total = 0;
         for (auto v : qn) nq_total += v;
         kt_.end();
+        trace_mark("graph: queries");
         // -- the local table: owned entries now, ghosts later
         const uint64_t nslots = solid_table_slots(n_local + nq_total);
         if (nslots > (1ull << 31) - 8) W2R_FAIL(W2RAP_ERR_OOM, "too many solid k-mers per GPU for 32-bit oriented node ids; shard over more GPUs");
@@ -871,6 +1058,7 @@ struct Pipeline {
         st = SolidTable{solid_slots.p, nslots};
         if (n_local) W2R_TIMED(W2RAP_KT_INSERT_SOLID, W2R_LAUNCH(c, k_insert_solid, grid(n_local, 256), 256, 0, (const ulonglong2*)solid.p, n_local, st, (uint32_t*)nullptr, 1u, 0u));
         solid.release();
+        trace_mark("graph: local table");
         // -- keys to the owners, slots back
         kt_.begin(W2RAP_KT_SG_QUERIES);
         xt.start();
@@ -894,6 +1082,7 @@ struct Pipeline {
             if (qn[d]) W2R_LAUNCH(c, k_insert_ghosts, grid(qn[d], 256), 256, 0, st, (const ulonglong2*)qkeys.p + d * qcap, (const uint32_t*)qreply.p + d * qcap, (uint64_t)qn[d], d, gslot.p + d * qcap);
         qkeys.release();
         kt_.end();
+        trace_mark("graph: ghosts");
         // -- adjacency pruning of the owned entries (ghosts only answer membership); then the ghosts' pruned contexts
         W2R_TIMED(W2RAP_KT_ADJACENCY, W2R_LAUNCH(c, k_adjacency, grid(st.size(), 256), 256, 0, st));
         kt_.begin(W2RAP_KT_SG_QUERIES);
@@ -906,6 +1095,7 @@ struct Pipeline {
             if (qn[d]) W2R_LAUNCH(c, k_apply_ghost_ctx, grid(qn[d], 256), 256, 0, st, (const uint32_t*)gslot.p + d * qcap, (const uint32_t*)qctx.p + d * qcap, (uint64_t)qn[d]);
         kt_.end();
         rreply.release(); qreply.release(); gslot.release(); rctx.release(); qctx.release();
+        trace_mark("graph: adjacency");
         // -- successor links; a node whose predecessor is a ghost heads a local piece
         const uint64_t nn = 2 * st.size();
         SBuf<uint32_t> next0(c, nn);
@@ -923,6 +1113,7 @@ struct Pipeline {
         for (int iteration = 0;; ++iteration) {
             if (iteration > 1) W2R_FAIL(W2RAP_ERR_INTERNAL, "circles left after cutting them");
             list_ranking(next0, ghead.p, nn, A, B, &cur, &oth);
+            trace_mark("graph: links+list ranking");
             // -- round 2: one record per local chain, gathered on every rank
             kt_.begin(W2RAP_KT_SG_PIECES);
             lpiece = reinterpret_cast<uint32_t*>(oth);          // scratch: local piece index per tail node ...
@@ -939,6 +1130,7 @@ struct Pipeline {
             allgather_v(lp.p, npl, pieces, poff);
             xms += xt.stop();
             np = poff[W]; piece0 = (uint32_t)poff[me]; npl_last = npl;
+            trace_mark("graph: pieces gathered");
             if (np >= (1ull << 32) - 8) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^32 chain pieces");
             lp.release();
             uint64_t msz = 64;
@@ -1015,6 +1207,7 @@ struct Pipeline {
                                 (const uint64_t*)tg.p, (uint32_t)tails_g.size());
             W2R_CUDA(cudaStreamSynchronize(c.stream));       // heads_g / tails_g leave scope
         }
+        trace_mark("graph: pieces ranked");
         // -- strands: even lengths from the piece records (every rank computes them), odd lengths by the owner of the middle k-mer
         kt_.begin(W2RAP_KT_SG_EDGES);
         PieceView pv{pieces.p, flip.p, S.p, np};
@@ -1029,6 +1222,7 @@ struct Pipeline {
         if (np) nccl_check(NcclApi::get().AllReduce(keepp.p, keepp.p, np, ncclUint8, ncclMax, comm, c.stream), "all-reduce");
         xms += xt.stop();
         if (d2h_scalar(c, flags.p + 2)) W2R_FAIL(W2RAP_ERR_EDGE_TOO_LONG, "an edge is longer than 2^24 k-mers (reference: KDef offset is 24 bits)");
+        trace_mark("graph: strands");
         // -- edges: kept heads sorted by k-mer (identical on every rank), emission by the owners, all-reduce of the bases
         SBuf<uint32_t> h_piece(c, np + 1), h_n(c, np + 1);
         SBuf<uint64_t> h_w0(c, np + 1), h_w1(c, np + 1);
@@ -1048,6 +1242,7 @@ struct Pipeline {
         xchg_bytes += ebw * 4 + np;
         kt_.end();
         kt_.begin(W2RAP_KT_SG_DICT);
+        trace_mark("graph: edges");
         // -- the finished entries (pruned context, edge, offset) become the dictionary the reads are pathed against: re-sharded by
         // k-mer hash (all-to-all), slice r built on rank r in peer-mappable memory, filter slices all-gathered (kmer.cuh: PathDict)
         xms += xt.stop();
@@ -1102,6 +1297,7 @@ struct Pipeline {
                                                                   path_slice_words ? path_bloom.p : nullptr, W, path_slice_words));
         erecv.release();
         kt_.begin(W2RAP_KT_SG_DICT);
+        trace_mark("graph: my dictionary slice");
         // Every rank paths against ALL slices.  They are replicated with one bulk all-gather of finished table memory (large
         // contiguous NVLink transfers, no insert work on the receivers).  Tried first: leaving the slices where they were built and
         // reading them from the path kernels through peer-mapped memory (CUDA IPC) — correct, but fine-grained remote LOADS over NVLink
@@ -1240,6 +1436,7 @@ struct Pipeline {
 
     void run() {
         W2R_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        g_alloc_host_ms = 0;
         kt_.s = c.stream;
         c.verbose = prm.verbose != 0;
         StageTimer total(c), st_t(c);
@@ -1330,6 +1527,7 @@ struct Pipeline {
         }
         out->timings.total_ms = total.stop();
         kt_.resolve(out->timings.kernel_ms);
+        out->timings.alloc_host_ms = (float)g_alloc_host_ms;
         out->timings.exchange_bytes = xchg_bytes;
         out->timings.n_records = n_records;
         out->timings.kernel_launches = c.launches;
@@ -1481,9 +1679,12 @@ static void run_on_device(DeviceReads& dr, const w2rap_params* p, w2rap_graph* o
     memset(out, 0, sizeof(*out));
     out->_owner = owner;
     try {
+        { Ctx probe; check_device(dr.device, probe); }
+        SlabLease lease(dr.device);                  // declared before the pipeline: its buffers go back before the lease does
         Pipeline pl(dr, *p, out, owner);
         if (cm) { pl.world = cm->world; pl.rank = cm->rank; pl.comm = cm->comm; }
         check_device(dr.device, pl.c);
+        pl.c.slab = lease.slab;
         const double t_run = now_ms();
         pl.run();
         out->timings.h2d_ms = h2d_ms;

@@ -42,6 +42,7 @@ struct Ctx {
     uint32_t launches = 0;
     uint32_t count_launches = 0;
     bool verbose = false;
+    void* slab = nullptr;       // DeviceSlab leased to this call (pipeline.cu), or null: large buffers then come from CUDA's pool
 };
 
 template <class T>
