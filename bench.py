@@ -357,11 +357,11 @@ def main():
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         dev_ms, e2e_max, full_ms = [float(x) for x in v.tolist()]
         e2e_ms = e2e_max if do_e2e else None
-        nb = torch.tensor([n_bases, int(tt[-1]["exchange_bytes"])], device="cuda", dtype=torch.int64)
+        nb = torch.tensor([n_bases, int(tt[-1]["exchange_bytes"]), int(tt[-1]["count_exchange_bytes"])], device="cuda", dtype=torch.int64)
         dist.all_reduce(nb)
-        total_bases, xbytes_all = int(nb[0].item()), int(nb[1].item())
+        total_bases, xbytes_all, xbytes_count = int(nb[0].item()), int(nb[1].item()), int(nb[2].item())
     else:
-        xbytes_all = 0
+        xbytes_all = xbytes_count = 0
     if rank != 0:
         if world > 1:
             lib.w2rap_step2_comm_destroy(comm)
@@ -383,9 +383,9 @@ def main():
     nrec = int(tt[-1]["n_records"])
     alg = {"k_good_len": qbytes + 12 * n_reads, "k_minimizer_map": b_bases + 14 * n_reads + 17 * I, "k_scatter_records": 72 * nrec,
            "k_count_smem": 17 * I, "k_insert_solid": 48 * S_rank // 2, "k_adjacency": 48 * S_rank // 2, "k_links": 24 * S_rank, "k_splitter_walk": 24 * S_rank, "k_splitter_finish": 24 * S_rank,
-           "k_emit_edges": EB // 2 // world + 24 * S_rank, "k_bloom_build": 24 * S, "k_path_reads": b_in + b_path}
+           "k_emit_edges": EB // 2 // world + 24 * S_rank, "k_path_reads": b_in + b_path}
     launches = {"k_minimizer_map": max(1, tt[-1]["count_launches"]), "k_scatter_records": max(1, tt[-1]["count_launches"]), "k_good_len": max(1, tt[-1]["count_launches"])}
-    phases = {k: v for k, v in km.items() if k not in alg}      # phase timers of the sharded graph stage: several kernels + exchanges each
+    phases = {k: v for k, v in km.items() if k not in alg and not k.startswith("unused")}      # phase timers of the sharded graph stage: several kernels + exchanges each
     km = {k: v for k, v in km.items() if k in alg}
     dom = max(km, key=lambda k: km[k])
     peak, peak_src = peaks()
@@ -427,8 +427,11 @@ def main():
                      "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9, "whole_step_frac": alg_bytes_total / (dev_ms * 1e-3) / 1e9 / peak},
         "alloc_host_ms": [round(t["alloc_host_ms"], 1) for t in tt],
         "stage_ms": {k: median([t[k] for t in tt]) for k in ("count_ms", "count_kernel_ms", "region_ms", "dict_ms", "exchange_ms", "graph_exchange_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
-        "nvlink": ({"bytes_sent_all_ranks_per_step": xbytes_all, "bytes_per_kmer_instance": xbytes_all / max(1, I_all),
-                    "count_exchange_GBps_per_gpu": (xbytes_all / world) / max(1e-9, median([t["exchange_ms"] for t in tt]) * 1e-3) / 1e9} if world > 1 else None),
+        "nvlink": ({"bytes_delivered_all_ranks_per_step": xbytes_all, "of_which_count_records": xbytes_count,
+                    "of_which_graph_and_dictionary": xbytes_all - xbytes_count,
+                    "count_record_bytes_per_kmer_instance": xbytes_count / max(1, I_all),
+                    "count_exchange_GBps_per_gpu": (xbytes_count / world) / max(1e-9, median([t["exchange_ms"] for t in tt]) * 1e-3) / 1e9,
+                    "note": "bytes each rank sends to the other ranks (an all-gathered slice counts once per receiver)"} if world > 1 else None),
         "result_digest": digest,
         "clocks": summarize_clocks(samples),
         "per_step": {"resident_ms": [round(t["total_ms"] - t["d2h_ms"], 2) for t in tt], "resident_count_ms": [round(t["count_ms"], 2) for t in tt],

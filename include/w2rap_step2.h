@@ -105,7 +105,7 @@ typedef struct w2rap_kmer_rec {
 enum {
     W2RAP_KT_GOOD_LEN = 0, W2RAP_KT_MAP = 1, W2RAP_KT_SCATTER = 2, W2RAP_KT_REDUCE = 3, W2RAP_KT_INSERT_SOLID = 4,
     W2RAP_KT_ADJACENCY = 5, W2RAP_KT_LINKS = 6, W2RAP_KT_SPLITTER_WALK = 7, W2RAP_KT_SPLITTER_FINISH = 8, W2RAP_KT_EMIT_EDGES = 9,
-    W2RAP_KT_BLOOM_BUILD = 10, W2RAP_KT_PATH_READS = 11,
+    W2RAP_KT_UNUSED_10 = 10 /* (was the separate filter build; the filter bits are now set by k_insert_solid) */, W2RAP_KT_PATH_READS = 11,
     /* sharded graph stage, phases (kernels + the exchanges between them) */
     W2RAP_KT_SG_QUERIES = 12,   /* neighbour queries, answers, ghost entries, ghost contexts (without k_adjacency) */
     W2RAP_KT_SG_PIECES = 13,    /* chain-end records: emit, all-gather, link, rank */
@@ -136,6 +136,7 @@ typedef struct w2rap_timings {
     float alloc_host_ms;          /* host time spent inside the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync) during this call:
                                      ~0 when the pool serves every request from cached memory, large when it has to grow, trim or re-map */
     uint32_t reserved2;
+    uint64_t count_exchange_bytes; /* of exchange_bytes, the super-k-mer records of the counting stage (what exchange_ms moved) */
 } w2rap_timings;
 
 /*

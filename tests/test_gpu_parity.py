@@ -69,6 +69,15 @@ def test_partitions_that_do_not_fit_shared_memory(fine_recs, smem_log):
     assert passes >= 2, "the fallback path did not run"
 
 
+def test_vertex_sort_long_path():
+    """HBV vertices: the product sorts the edge ends by their 64-bit hash word and proves the order by a neighbour check; the
+    23-pass sort over hash + bases only runs after a hash collision.  W2RAP_HBV_FULL_SORT forces it: same graph."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, W2RAP_HBV_FULL_SORT="1", PYTHONPATH=here)
+    r = subprocess.run([sys.executable, os.path.join(here, "env_case_runner.py"), "100000", "60", "22"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 @pytest.mark.parametrize("case", ["circ", "rich", "long"])
 def test_golden_reference_outputs(T, case):
     """Straight against the files the UNMODIFIED reference wrote (tests/golden): modulo its racy edge numbering."""

@@ -38,11 +38,11 @@ class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "count_ms", "solid_ms", "adjacency_ms", "unipath_ms", "hbv_ms",
                                          "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms", "exchange_ms", "host_pre_ms", "host_post_ms", "wall_ms")] + \
                [(n, C.c_uint32) for n in ("count_launches", "kernel_launches", "count_passes", "reserved")] + \
-               [("dict_ms", C.c_float), ("graph_exchange_ms", C.c_float), ("exchange_bytes", C.c_uint64), ("n_records", C.c_uint64), ("kernel_ms", C.c_float * 16), ("alloc_host_ms", C.c_float), ("reserved2", C.c_uint32)]
+               [("dict_ms", C.c_float), ("graph_exchange_ms", C.c_float), ("exchange_bytes", C.c_uint64), ("n_records", C.c_uint64), ("kernel_ms", C.c_float * 16), ("alloc_host_ms", C.c_float), ("reserved2", C.c_uint32), ("count_exchange_bytes", C.c_uint64)]
 
 
 KERNEL_NAMES = ["k_good_len", "k_minimizer_map", "k_scatter_records", "k_count_smem", "k_insert_solid", "k_adjacency", "k_links",
-                "k_splitter_walk", "k_splitter_finish", "k_emit_edges", "k_bloom_build", "k_path_reads",
+                "k_splitter_walk", "k_splitter_finish", "k_emit_edges", "unused:10", "k_path_reads",
                 "sharded:queries+ghosts", "sharded:pieces", "sharded:strands+edges", "sharded:gather dictionary"]
 
 

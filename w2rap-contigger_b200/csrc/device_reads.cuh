@@ -16,6 +16,7 @@ struct DeviceReads {
     uint64_t* qual_off = nullptr;
     uint32_t* len = nullptr;
     uint64_t n_inst_upper = 0;      // sum of max(0, len - 59): an upper bound of the k-mer instances, known without the qualities
+    uint64_t n_kreads = 0;          // reads with at least one k-mer (len >= 60): each yields at least one super-k-mer record
     // host-buffer entry points upload in batches on a copy stream; batch b = reads [batch_first[b], batch_first[b+1]) is on the
     // device once batch_ready[b] has fired, so extraction of batch b overlaps the transfer of batch b+1
     std::vector<cudaEvent_t> batch_ready;

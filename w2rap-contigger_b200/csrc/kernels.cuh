@@ -315,6 +315,17 @@ __global__ void k_emit_edges(SolidTable st, const RankState* __restrict__ R, con
     for (uint64_t xi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; xi < nn; xi += (uint64_t)gridDim.x * blockDim.x) emit_node(st, R, edge_of_head, edge_off, (uint32_t)xi, put);
 }
 
+// Device -> pinned host memory by stores over PCIe instead of the copy engine: the D2H engine is shared by every stream, and the
+// small scalar read-backs of the pathing stage would queue behind a gigabyte of graph arrays on it.  A few CTAs are enough to
+// keep the link busy.  Both pointers 16-byte aligned.
+__global__ void k_copy_to_host(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t bytes) {
+    const size_t n16 = bytes / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 15)) dst[n16 * 16 + threadIdx.x] = src[n16 * 16 + threadIdx.x];
+}
+
 // ================================================================ K5: HBV vertices (paths/long/HBVFromEdges.cc:76-154)
 // End w of edge e: 0 fwd-left, 1 fwd-right, 2 rc-left, 3 rc-right.  Key = (FNV-1a 64 over the 59 base codes as bytes
 // (math/Hash.h:26-35), then the bases) — the order EdgeEnd::operator< defines (:34-38).
@@ -340,6 +351,15 @@ __global__ void k_vertex_flags(const uint32_t* __restrict__ perm, uint64_t n4, c
             else { uint32_t q = perm[i - 1]; fl = (kh[q] != kh[j] || k0[q] != k0[j] || k1[q] != k1[j]) ? 1u : 0u; }
         }
         flag[i] = fl;
+    }
+}
+// After sorting by the hash word alone: do two neighbours share a hash but not the bases?  (Then the order inside that run is
+// not EdgeEnd's and the caller sorts by all three words.)
+__global__ void k_hash_order_check(const uint32_t* __restrict__ perm, uint64_t n4, const uint64_t* __restrict__ kh, const uint64_t* __restrict__ k0,
+                                   const uint64_t* __restrict__ k1, unsigned long long* __restrict__ collisions) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = perm[i], q = perm[i - 1];
+        if (kh[q] == kh[j] && (k0[q] != k0[j] || k1[q] != k1[j])) atomicAdd(collisions, 1ull);
     }
 }
 __global__ void k_scatter_vids(const uint32_t* __restrict__ perm, uint64_t n4, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ excl,

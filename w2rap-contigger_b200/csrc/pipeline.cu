@@ -458,7 +458,7 @@ struct Pipeline {
     bool good_done = false;
     float map_ms = 0, reduce_ms = 0, xchg_ms = 0;
     uint32_t n_groups = 0;
-    uint64_t xchg_bytes = 0, n_records = 0;
+    uint64_t xchg_bytes = 0, xchg_count_bytes = 0, n_records = 0;
 
     void run_good_len(const Batch& bt) {
         if (bt.ready) W2R_CUDA(cudaStreamWaitEvent(c.stream, bt.ready, 0));
@@ -537,7 +537,7 @@ struct Pipeline {
         for (int d = 0; d < world; ++d) {
             soff[d] = sbeg[d] * sizeof(SkmRec); scnt[d] = (sbeg[d + 1] - sbeg[d]) * sizeof(SkmRec);
             roff[d] = racc * sizeof(SkmRec); rcnt[d] = rtot[d] * sizeof(SkmRec); racc += rtot[d];
-            if (d != rank) xchg_bytes += scnt[d];
+            if (d != rank) { xchg_bytes += scnt[d]; xchg_count_bytes += scnt[d]; }
         }
         cb.xrecs.alloc(c, racc + 1);
         alltoall_v(cb.recs.p, soff, scnt, cb.xrecs.p, roff, rcnt);
@@ -720,7 +720,11 @@ struct Pipeline {
 
         // Records per k-mer instance: ~1/13 on 250-base reads; short reads approach 1.  The area is sized from an estimate and, if
         // the store launch reports an overflow, re-sized to the exact need the counting launch computed.
-        double rec_per_inst = 1.0 / 6.0;
+        // Expected: one record per read, one per minimiser change (2 / (window + 1) per k-mer for a random order) and one per cut at
+        // 32 k-mers (1/32 at most): 1 + 0.074 n for a read of n k-mers — 15.1 for n = 191, measured 14.7.  +15 % margin.
+        std::vector<unsigned long long> rk = {dr.n_kreads};
+        allreduce_u64(rk, ncclSum);
+        double rec_per_inst = pl.n_inst ? std::min(1.0, 1.15 * ((double)rk[0] + 0.074 * (double)pl.n_inst) / (double)pl.n_inst) : 1.0;
         uint64_t need_exact = 0;
         pl.npass = prm.force_passes ? prm.force_passes : 1u;
         for (int attempt = 0;; ++attempt) {
@@ -1331,8 +1335,20 @@ struct Pipeline {
         W2R_LAUNCH(c, k_edge_ends, grid(n4, 128), 128, 0, edge_bases.p, edge_off.p, edge_len.p, E, kh.p, k0.p, k1.p, is_pal.p);
         SBuf<uint32_t> perm(c, n4), tmp(c, n4);
         W2R_LAUNCH(c, k_rs_iota, grid(n4, 256), 256, 0, perm.p, (uint32_t)n4);
+        // EdgeEnd order = (64-bit hash, bases).  Distinct (K-1)-mers sharing a hash are a ~n^2/2^65 event, so the 8 digit passes over
+        // the hash word nearly always ARE the order (ends with equal keys may come in any order: they get the same vertex); a check
+        // of neighbours proves it, and if it ever fails the 23-pass sort over all three words runs instead.
         SortWord words[3] = {{k1.p, 10, 64}, {k0.p, 0, 64}, {kh.p, 0, 64}};
-        radix_sort_perm(c, perm.p, tmp.p, (uint32_t)n4, words, 3);
+        static const bool full_sort = getenv("W2RAP_HBV_FULL_SORT") != nullptr;       // (test hook: keeps the long path exercised)
+        SBuf<unsigned long long> coll(c, 1); coll.zero();
+        if (!full_sort) {
+            radix_sort_perm(c, perm.p, tmp.p, (uint32_t)n4, words + 2, 1);
+            W2R_LAUNCH(c, k_hash_order_check, grid(n4, 256), 256, 0, (const uint32_t*)perm.p, n4, (const uint64_t*)kh.p, (const uint64_t*)k0.p, (const uint64_t*)k1.p, coll.p);
+        }
+        if (full_sort || d2h_scalar(c, coll.p)) {
+            W2R_LAUNCH(c, k_rs_iota, grid(n4, 256), 256, 0, perm.p, (uint32_t)n4);
+            radix_sort_perm(c, perm.p, tmp.p, (uint32_t)n4, words, 3);
+        }
         SBuf<uint32_t> flag(c, n4), excl(c, n4), tot(c, 1);
         W2R_LAUNCH(c, k_vertex_flags, grid(n4, 256), 256, 0, perm.p, n4, kh.p, k0.p, k1.p, flag.p);
         exclusive_scan<uint32_t, uint32_t>(c, flag.p, n4, excl.p, tot.p);
@@ -1428,11 +1444,19 @@ struct Pipeline {
     }
 
     template <class T>
-    T* to_host(const T* dptr, size_t n) {
+    T* to_host(const T* dptr, size_t n, cudaStream_t s = nullptr) {
         T* h = out_alloc<T>(owner, n);
-        if (n) W2R_CUDA(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+        if (!n) return h;
+        if (s && ((uintptr_t)h & 15) == 0 && ((uintptr_t)dptr & 15) == 0) {      // side stream: by stores, leaving the copy engine to the main stream
+            k_copy_to_host<<<32, 512, 0, s>>>((const uint8_t*)dptr, (uint8_t*)h, n * sizeof(T));
+            W2R_CUDA(cudaGetLastError());
+            c.launches++;
+        } else {
+            W2R_CUDA(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, s ? s : c.stream));
+        }
         return h;
     }
+    cudaStream_t copy_stream = nullptr;     // the graph travels to the host while the reads are pathed
 
     void run() {
         W2R_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -1459,6 +1483,16 @@ struct Pipeline {
         }
         say(c, "building graph...");
         st_t.start(); hbv_stage(); out->timings.hbv_ms = st_t.stop();
+        // ---- the graph is final: its arrays go to the host on a second stream, under the pathing kernels
+        out->n_edges = E; out->n_vertices = nv; out->n_hbv_edges = nh;
+        W2R_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));     // (hbv_stage ended with a drained stream: st_t.stop())
+        out->edge_off = to_host<uint64_t>(edge_off.p, E + 1, copy_stream);
+        out->edge_len = to_host<uint32_t>(edge_len.p, E, copy_stream);
+        out->edge_bases = to_host<uint8_t>(edge_bases.p, edge_bytes, copy_stream);
+        out->edge_vertices = to_host<int32_t>(edge_vertices.p, 4 * E, copy_stream);
+        out->fwd_xlat = to_host<int32_t>(fwd_xlat.p, E, copy_stream);
+        out->rev_xlat = to_host<int32_t>(rev_xlat.p, E, copy_stream);
+        out->involution = to_host<int32_t>(involution.p, nh, copy_stream);
         SBuf<int32_t> d_offset, d_path_edges; SBuf<uint64_t> d_path_off;
         uint64_t npe = 0; unsigned long long pathed = 0, multi = 0;
         if (prm.want_paths) {
@@ -1468,14 +1502,6 @@ struct Pipeline {
         }
         // ---- results to the host
         st_t.start();
-        out->n_edges = E; out->n_vertices = nv; out->n_hbv_edges = nh;
-        out->edge_off = to_host<uint64_t>(edge_off.p, E + 1);
-        out->edge_len = to_host<uint32_t>(edge_len.p, E);
-        out->edge_bases = to_host<uint8_t>(edge_bases.p, edge_bytes);
-        out->edge_vertices = to_host<int32_t>(edge_vertices.p, 4 * E);
-        out->fwd_xlat = to_host<int32_t>(fwd_xlat.p, E);
-        out->rev_xlat = to_host<int32_t>(rev_xlat.p, E);
-        out->involution = to_host<int32_t>(involution.p, nh);
         SBuf<unsigned long long> dig(c, 2); dig.zero();
         {   // digest of the graph: every array at its own salt
             struct Part { const void* p; size_t bytes; } parts[] = {{edge_len.p, E * 4}, {edge_bases.p, edge_bytes}, {edge_vertices.p, 4 * E * 4}, {fwd_xlat.p, E * 4}, {rev_xlat.p, E * 4}};
@@ -1505,6 +1531,7 @@ struct Pipeline {
             W2R_CUDA(cudaStreamSynchronize(c.stream));
         }
         W2R_CUDA(cudaStreamSynchronize(c.stream));
+        W2R_CUDA(cudaStreamSynchronize(copy_stream));
         out->timings.d2h_ms = st_t.stop();
         if (E == 0 && out->edge_off) out->edge_off[0] = 0;
         uint64_t neb = 0;
@@ -1529,6 +1556,7 @@ struct Pipeline {
         kt_.resolve(out->timings.kernel_ms);
         out->timings.alloc_host_ms = (float)g_alloc_host_ms;
         out->timings.exchange_bytes = xchg_bytes;
+        out->timings.count_exchange_bytes = xchg_count_bytes;
         out->timings.n_records = n_records;
         out->timings.kernel_launches = c.launches;
         out->timings.count_launches = c.count_launches;
@@ -1538,6 +1566,7 @@ struct Pipeline {
     ~Pipeline() {
         // free stream-ordered buffers before the stream goes away (and not under a transfer that still writes into them)
         if (dict_stream) cudaStreamSynchronize(dict_stream);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         good.release(); solid_slots.release(); edge_bases.release(); edge_off.release(); edge_len.release();
         edge_vertices.release(); fwd_xlat.release(); rev_xlat.release(); involution.release(); hleft.release();
         cs_scal.release(); cs_flags.release(); cs_hist.release(); cs_region.release(); cs_dump.release(); cs_solid.release();
@@ -1592,31 +1621,32 @@ static void upload(const w2rap_reads* in, int device, DeviceReads* d, cudaStream
     const double t0 = now_ms();
     {   // one pass over the offsets/lengths, on a few host threads
         const unsigned nt = n > (1u << 20) ? 8u : 1u;
-        std::vector<uint64_t> t_nb(nt, 0), t_inst(nt, 0), t_bad(nt, ~0ull);
+        std::vector<uint64_t> t_nb(nt, 0), t_inst(nt, 0), t_bad(nt, ~0ull), t_kr(nt, 0);
         std::vector<uint32_t> t_mx(nt, 0), t_kind(nt, 0);
         auto work = [&](unsigned t) {
-            uint64_t lo = n * t / nt, hi = n * (t + 1) / nt, nb = 0, inst = 0; uint32_t mx = 0;
+            uint64_t lo = n * t / nt, hi = n * (t + 1) / nt, nb = 0, inst = 0, kr = 0; uint32_t mx = 0;
             for (uint64_t i = lo; i < hi; ++i) {
                 uint32_t L = in->len[i];
                 nb += L; if (L > mx) mx = L;
-                if (L > 59) inst += L - 59;
+                if (L > 59) { inst += L - 59; ++kr; }
                 if (in->base_off[i + 1] < in->base_off[i] || in->base_off[i + 1] - in->base_off[i] < (uint64_t)(L + 3) / 4) { t_bad[t] = i; t_kind[t] = 1; break; }
                 if (in->qual_off[i + 1] <= in->qual_off[i]) { t_bad[t] = i; t_kind[t] = 2; break; }
             }
-            t_nb[t] = nb; t_inst[t] = inst; t_mx[t] = mx;
+            t_nb[t] = nb; t_inst[t] = inst; t_mx[t] = mx; t_kr[t] = kr;
         };
         std::vector<std::thread> th;
         for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
         work(0);
         for (auto& x : th) x.join();
-        uint64_t nb = 0, inst = 0; uint32_t mx = 0;
+        uint64_t nb = 0, inst = 0, kr = 0; uint32_t mx = 0;
         for (unsigned t = 0; t < nt; ++t) {
+            kr += t_kr[t];
             if (t_kind[t] == 1) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: base offsets do not hold its bases", (unsigned long long)t_bad[t]);
             if (t_kind[t] == 2) W2R_FAIL(W2RAP_ERR_BAD_ARG, "read %llu: empty quality stream (at least the terminator byte is required)", (unsigned long long)t_bad[t]);
             nb += t_nb[t]; inst += t_inst[t]; mx = std::max(mx, t_mx[t]);
         }
         if (mx > 65535u) W2R_FAIL(W2RAP_ERR_BAD_ARG, "reads longer than 65535 bases are not supported (the reference stores good lengths in uint16_t)");
-        d->n_bases = nb; d->max_len = mx; d->n_inst_upper = inst;
+        d->n_bases = nb; d->max_len = mx; d->n_inst_upper = inst; d->n_kreads = kr;
     }
     const double t1 = now_ms();
     // +32 bytes of padding: packed bases are read with aligned 8-byte loads that may touch a few bytes past a read

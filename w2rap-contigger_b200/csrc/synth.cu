@@ -189,7 +189,7 @@ int w2rap_step2_synth(const w2rap_synth_params* sp, int device, w2rap_device_rea
         w2rap_device_reads* h = new w2rap_device_reads();
         DeviceReads& d = h->d;
         try {
-            d.device = device; d.n = nr; d.n_bases = nr * L; d.max_len = L; d.n_inst_upper = nr * (uint64_t)(L - 59);
+            d.device = device; d.n = nr; d.n_bases = nr * L; d.max_len = L; d.n_inst_upper = nr * (uint64_t)(L - 59); d.n_kreads = nr;
             const uint64_t nbb = (L + 3) / 4;
             d.bases_bytes = nr * nbb;
             W2R_CUDA(cudaMalloc((void**)&d.bases, d.bases_bytes + 32));
