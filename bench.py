@@ -263,7 +263,7 @@ def main():
             raise SystemExit("comm init failed: " + err.value.decode())
     if lib.w2rap_step2_synth(C.byref(sp), local, C.byref(h), err, 1024):
         raise SystemExit("synth failed: " + err.value.decode())
-    p = T.default_params(apply_fixpaths=1, device=local)
+    p = T.default_params(apply_fixpaths=1, device=local, graph_on_root_only=1 if world > 1 else 0)      # (the graph arrays go to the one process that would write the .hbv)
     hr = T.Reads()
     do_e2e = not args.no_e2e
     if do_e2e and lib.w2rap_step2_download_reads(h, C.byref(hr), err, 1024):

@@ -90,6 +90,11 @@ typedef struct w2rap_params {
     uint32_t verbose;        /* 1: reference-style progress lines on stdout */
     uint32_t force_passes;   /* test hook: 0 = auto; n > 0 = count in exactly n hash-range passes (the replacement of the
                                 reference's disk batches, BuildReadQGraph.cc:1120-1250; normally chosen from free device memory) */
+    uint32_t graph_on_root_only; /* sharded runs: 0 = every rank receives the graph arrays; 1 = only rank 0 does (the process that
+                                writes the .hbv): the other ranks get the counters, edge_len, digests and their own paths, with
+                                edge_off/edge_bases/edge_vertices/fwd_xlat/rev_xlat/involution null.  Eight identical copies of a
+                                1 Gbp graph (1.3 GB each) otherwise share the host's PCIe uplinks with the path arrays. */
+    uint32_t reserved;
 } w2rap_params;
 
 /* One record of the optional k-mer dump (sorted by k-mer). */

@@ -84,3 +84,20 @@ def test_sharded_small_region_and_skew(T):
     res, _ = run_sharded(T, rs, 2, dump_kmers=1, table_slots=256)
     for got in res:
         T.assert_graph_equal(want, dict(got, n_reads=want["n_reads"], n_bases=want["n_bases"]), "small region", check_paths=False)
+
+
+def test_graph_on_root_only(T):
+    """graph_on_root_only: rank 0 receives the whole graph, the other ranks the counters, edge lengths, digests and their own paths."""
+    rs = T.rich_set(seed=16, genome=40000, cov=40, families=3, palindromes=2, plasmid=900)
+    want = T.run_oracle(rs, T.default_params(apply_fixpaths=1))
+    res, bounds = run_sharded(T, rs, 2, apply_fixpaths=1, graph_on_root_only=1)
+    T.assert_graph_equal(want, dict(res[0], n_reads=want["n_reads"], n_bases=want["n_bases"]), "rank 0 graph", check_paths=False, check_dump=False)
+    other = res[1]
+    assert other["n_edges"] == want["n_edges"] and other["n_vertices"] == want["n_vertices"] and other["n_edge_bases"] == want["n_edge_bases"]
+    assert np.array_equal(other["edge_len"], want["edge_len"])
+    assert other["edge_bases"].size == 0 and other["edge_vertices"].size == 0 and other["fwd_xlat"].size == 0 and other["involution"].size == 0
+    assert other["digest_graph"] == res[0]["digest_graph"] and other["digest_paths"] == res[0]["digest_paths"]
+    lo, hi = bounds[1], bounds[2]
+    assert np.array_equal(other["path_offset"], want["path_offset"][lo:hi])
+    a, b = int(want["path_off"][lo]), int(want["path_off"][hi])
+    assert np.array_equal(other["path_edges"], want["path_edges"][a:b])

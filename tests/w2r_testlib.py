@@ -31,7 +31,7 @@ class Params(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("K", C.c_uint32), ("min_qual", C.c_uint32), ("min_freq", C.c_uint32),
                 ("want_paths", C.c_uint32), ("apply_fixpaths", C.c_uint32), ("dump_kmers", C.c_uint32),
                 ("device", C.c_int32), ("workdir", C.c_char_p), ("table_slots", C.c_uint64), ("verbose", C.c_uint32),
-                ("force_passes", C.c_uint32)]
+                ("force_passes", C.c_uint32), ("graph_on_root_only", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Timings(C.Structure):
@@ -78,9 +78,9 @@ ABI_VERSION = 2
 
 
 def default_params(min_qual=7, min_freq=4, want_paths=1, apply_fixpaths=0, dump_kmers=0, workdir=None,
-                   table_slots=0, device=-1, verbose=0, force_passes=0):
+                   table_slots=0, device=-1, verbose=0, force_passes=0, graph_on_root_only=0):
     return Params(ABI_VERSION, K, min_qual, min_freq, want_paths, apply_fixpaths, dump_kmers, device,
-                  workdir.encode() if workdir else None, table_slots, verbose, force_passes)
+                  workdir.encode() if workdir else None, table_slots, verbose, force_passes, graph_on_root_only, 0)
 
 
 def _arr(ptr, n, dtype):
@@ -96,14 +96,14 @@ def _arr(ptr, n, dtype):
 def graph_to_dict(g):
     """Convert a filled w2rap_graph into plain numpy data (copies; safe to free the graph afterwards)."""
     ne, npth = int(g.n_edges), int(g.n_paths)
-    edge_off = _arr(g.edge_off, ne + 1, "<u8")
+    edge_off = _arr(g.edge_off, ne + 1, "<u8") if g.edge_off else np.zeros(1, dtype="<u8")       # (null: graph_on_root_only on another rank)
     d = dict(
         n_reads=int(g.n_reads), n_bases=int(g.n_bases), n_kmer_instances=int(g.n_kmer_instances),
         n_distinct=int(g.n_distinct), n_solid=int(g.n_solid), hist=np.array(list(g.hist), dtype=np.uint64),
         n_edges=ne, n_edge_bases=int(g.n_edge_bases), edge_off=edge_off, edge_len=_arr(g.edge_len, ne, "<u4"),
-        edge_bases=_arr(g.edge_bases, int(edge_off[-1]) if ne else 0, "u1"),
+        edge_bases=_arr(g.edge_bases, int(edge_off[-1]) if ne and g.edge_off else 0, "u1"),
         n_vertices=int(g.n_vertices), n_hbv_edges=int(g.n_hbv_edges),
-        edge_vertices=_arr(g.edge_vertices, 4 * ne, "<i4").reshape(-1, 4),
+        edge_vertices=_arr(g.edge_vertices, 4 * ne if g.edge_vertices else 0, "<i4").reshape(-1, 4),
         fwd_xlat=_arr(g.fwd_xlat, ne, "<i4"), rev_xlat=_arr(g.rev_xlat, ne, "<i4"),
         involution=_arr(g.involution, g.n_hbv_edges, "<i4"), digest_graph=int(g.digest_graph), digest_paths=int(g.digest_paths),
         n_paths=npth, n_path_edges=int(g.n_path_edges), path_offset=_arr(g.path_offset, npth, "<i4"),

@@ -1486,13 +1486,15 @@ struct Pipeline {
         // ---- the graph is final: its arrays go to the host on a second stream, under the pathing kernels
         out->n_edges = E; out->n_vertices = nv; out->n_hbv_edges = nh;
         W2R_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));     // (hbv_stage ended with a drained stream: st_t.stop())
-        out->edge_off = to_host<uint64_t>(edge_off.p, E + 1, copy_stream);
         out->edge_len = to_host<uint32_t>(edge_len.p, E, copy_stream);
-        out->edge_bases = to_host<uint8_t>(edge_bases.p, edge_bytes, copy_stream);
-        out->edge_vertices = to_host<int32_t>(edge_vertices.p, 4 * E, copy_stream);
-        out->fwd_xlat = to_host<int32_t>(fwd_xlat.p, E, copy_stream);
-        out->rev_xlat = to_host<int32_t>(rev_xlat.p, E, copy_stream);
-        out->involution = to_host<int32_t>(involution.p, nh, copy_stream);
+        if (!(world > 1 && prm.graph_on_root_only && rank != 0)) {
+            out->edge_off = to_host<uint64_t>(edge_off.p, E + 1, copy_stream);
+            out->edge_bases = to_host<uint8_t>(edge_bases.p, edge_bytes, copy_stream);
+            out->edge_vertices = to_host<int32_t>(edge_vertices.p, 4 * E, copy_stream);
+            out->fwd_xlat = to_host<int32_t>(fwd_xlat.p, E, copy_stream);
+            out->rev_xlat = to_host<int32_t>(rev_xlat.p, E, copy_stream);
+            out->involution = to_host<int32_t>(involution.p, nh, copy_stream);
+        }
         SBuf<int32_t> d_offset, d_path_edges; SBuf<uint64_t> d_path_off;
         uint64_t npe = 0; unsigned long long pathed = 0, multi = 0;
         if (prm.want_paths) {
