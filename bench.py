@@ -414,7 +414,7 @@ def main():
                    "cache": "inputs (%.1f GB) and dictionary larger than the 126 MB L2" % (b_in / 1e9),
                    "statistic": "median over the timed steps",
                    "kmer_instances": I_all, "distinct": D, "solid": S, "edges": E, "reads_pathed": pathed,
-                   "parallelism": "one process per GPU; reads sharded by index; super-k-mer records routed to the owner GPU of their minimiser partition (NCCL all-to-all of exactly sized runs); dictionary, adjacency and unipaths sharded by the same owners (neighbour queries + chain-end records exchanged); pathing dictionary built in hash slices (one per GPU) and replicated by one all-gather of table memory; reads pathed by shard"},
+                   "parallelism": "one process per GPU; reads sharded by index; super-k-mer records routed to the owner GPU of their minimiser partition (NCCL all-to-all of exactly sized runs); dictionary, adjacency and unipaths sharded by the same owners (neighbour queries + chain-end records exchanged); pathing dictionary built in hash slices (one per GPU) and replicated by one all-gather of table memory; reads pathed by shard; graph arrays returned to rank 0 (graph_on_root_only), paths to the rank of their reads"},
         "e2e": ({"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": b_in, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms, "host_memory": "pinned",
                  "inside": {k: median([t[k] for t in e2e_t]) for k in ("h2d_ms", "total_ms", "count_ms", "count_kernel_ms", "region_ms", "path_ms", "d2h_ms", "host_pre_ms", "host_post_ms", "wall_ms")}}
                 if do_e2e else {"value": None, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "--no-e2e"}),

@@ -227,11 +227,13 @@ int w2rap_step2_run_resident(w2rap_device_reads* handle, const w2rap_params* p, 
 void w2rap_step2_release(w2rap_device_reads* handle);
 
 /*
- * Multi-GPU (one process or thread per GPU, NCCL over NVLink/NVSwitch; SURVEY.md §8e).  Reads are sharded by index by the
- * caller; every k-mer record is routed to the rank that owns its hash partition with one all-to-all (the reference's
- * MapReduceEngine "swizzle", MapReduceEngine.h:337-358); owners count; the solid records are all-gathered so that every rank
- * builds the same graph; each rank paths its own shard.  On return every rank holds the WHOLE graph (identical on all
- * ranks: edges, vertices, xlat, histogram, counters of the whole job) and the paths of ITS shard (n_paths = shard reads).
+ * Multi-GPU (one process or thread per GPU, NCCL over NVLink/NVSwitch; SURVEY.md §8e, X1).  Reads are sharded by index by the
+ * caller; every super-k-mer record is routed to the rank that owns its minimiser partition with one all-to-all (the reference's
+ * MapReduceEngine "swizzle", MapReduceEngine.h:337-358); owners count.  The dictionary, adjacency pruning and the unipath walk stay
+ * sharded by the same owners (neighbour queries and one record per local chain are exchanged); only the finished
+ * dictionary is replicated, for pathing; each rank paths its own shard.  On return every rank holds the WHOLE graph (identical on
+ * all ranks: edges, vertices, xlat, histogram, n_kmer_instances / n_distinct / n_solid and the digests of the whole job) — unless
+ * graph_on_root_only — and the paths of ITS shard; n_reads, n_bases, n_paths, n_pathed and n_multipathed count the shard.
  * world must be a power of two.  Rank 0 creates the id and hands the 128 bytes to the others (any transport).
  */
 typedef struct w2rap_comm w2rap_comm;

@@ -21,6 +21,7 @@
 #include "../../w2rap-contigger_b200/csrc/pqvec.cuh"
 #include "../../w2rap-contigger_b200/csrc/unipath.cuh"
 #include "../../w2rap-contigger_b200/csrc/shardgraph.cuh"
+#include "../../w2rap-contigger_b200/csrc/slab_freelist.h"
 
 using namespace w2r;
 
@@ -733,3 +734,60 @@ void hc_graph_free(w2rap_graph* g) {
 }
 
 }  // extern "C"
+
+
+// ---- the device slab's free list (csrc/slab_freelist.h) against a byte-map model: random takes, give-backs and growth steps.
+// Checks after every operation: pieces never overlap and lie inside the range, a take returns the LOWEST address that fits,
+// free ranges are disjoint and fully coalesced, and `used` matches.  Returns 0, or the number of the first failed check.
+extern "C" int hc_slab_freelist_fuzz(uint64_t seed, uint32_t ops) {
+    w2r::SlabFreeList fl;
+    std::vector<uint8_t> model;                 // 1 = in use, per unit (units keep the model small; sizes are multiples of it)
+    const size_t unit = 4096;
+    std::vector<std::pair<size_t, size_t>> live;
+    uint64_t x = seed * 0x9e3779b97f4a7c15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    auto check = [&]() -> int {
+        size_t used = 0, runs = 0;
+        for (size_t i = 0; i < model.size(); ++i) { used += model[i]; if (!model[i] && (i == 0 || model[i - 1])) ++runs; }
+        if (used * unit != fl.used) return 1;
+        if (runs != fl.free_.size()) return 2;                               // not coalesced (or a range lost)
+        size_t prev_end = 0; bool first = true;
+        for (auto& kv : fl.free_) {
+            if (kv.first % unit || kv.second % unit || kv.second == 0) return 3;
+            if (!first && kv.first <= prev_end) return 4;                    // overlapping or touching ranges
+            for (size_t i = kv.first / unit; i < (kv.first + kv.second) / unit; ++i) if (i >= model.size() || model[i]) return 5;
+            prev_end = kv.first + kv.second; first = false;
+        }
+        return 0;
+    };
+    for (uint32_t op = 0; op < ops; ++op) {
+        const uint64_t r = rnd();
+        if (r % 8 == 0 || model.empty()) {                                   // growth: new backing at the top
+            const size_t add = (1 + rnd() % 64) * unit;
+            fl.add_free(model.size() * unit, add);
+            model.resize(model.size() + add / unit, 0);
+        } else if (r % 8 < 5) {                                              // take
+            const size_t want = (1 + rnd() % 48) * unit;
+            size_t expect = w2r::SlabFreeList::NONE, run = 0;
+            for (size_t i = 0; i < model.size(); ++i) { run = model[i] ? 0 : run + 1; if (run * unit >= want) { expect = (i + 1 - run) * unit; break; } }
+            if (expect != w2r::SlabFreeList::NONE) {                         // (lowest run that fits; its start, not the first fitting position inside it)
+                size_t st = expect / unit; while (st > 0 && !model[st - 1]) --st; expect = st * unit;
+            }
+            const size_t got = fl.take(want);
+            if (got != expect) return 10;
+            if (got != w2r::SlabFreeList::NONE) { for (size_t i = got / unit; i < (got + want) / unit; ++i) { if (model[i]) return 11; model[i] = 1; } live.push_back({got, want}); }
+            else if (fl.free_tail(model.size() * unit) >= want) return 12;
+        } else if (!live.empty()) {                                          // give back
+            const size_t k = rnd() % live.size();
+            if (fl.give_back(live[k].first) != live[k].second) return 20;
+            if (fl.give_back(live[k].first) != 0) return 21;                 // twice: refused
+            for (size_t i = live[k].first / unit; i < (live[k].first + live[k].second) / unit; ++i) model[i] = 0;
+            live[k] = live.back(); live.pop_back();
+        }
+        if (int c = check()) return 100 + c;
+    }
+    // everything back: one free range covering the whole slab
+    for (auto& pc : live) if (fl.give_back(pc.first) != pc.second) return 30;
+    if (!(fl.used == 0 && fl.free_.size() == (model.empty() ? 0u : 1u) && (model.empty() || (fl.free_.begin()->first == 0 && fl.free_.begin()->second == model.size() * unit)))) return 31;
+    return 0;
+}

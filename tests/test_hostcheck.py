@@ -19,7 +19,7 @@ SO = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
 @pytest.fixture(scope="session")
 def hc(T):
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh", "shard.cuh", "shardgraph.cuh")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
+    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh", "shard.cuh", "shardgraph.cuh", "slab_freelist.h")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, src], check=True)
@@ -166,3 +166,12 @@ def test_quality_floor_on_random_quality_vectors(T, hc):
             hc.hc_free(ptr)
             want = T.run_oracle(rs, T.default_params(min_qual=mq, want_paths=0, min_freq=1))
             assert ni.value == want["n_kmer_instances"], (mode, mq)
+
+
+def test_device_slab_free_list(hc):
+    """The bookkeeping of the device slab (csrc/slab_freelist.h: lowest-address first fit, coalescing free ranges) fuzzed against a
+    byte-map model: thousands of random takes, give-backs and growth steps, invariants checked after every one."""
+    hc.hc_slab_freelist_fuzz.restype = C.c_int
+    hc.hc_slab_freelist_fuzz.argtypes = [C.c_uint64, C.c_uint32]
+    for seed in range(1, 9):
+        assert hc.hc_slab_freelist_fuzz(seed, 4000) == 0

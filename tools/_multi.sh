@@ -12,5 +12,3 @@ P
 timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu 2>&1 | tail -3
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --config c3 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/r2_c3_final.log 2> gpurun_out/r2_c3_final.err
 summ gpurun_out/r2_c3_final.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_n8_final.log 2> gpurun_out/r2_n8_final.err
-summ gpurun_out/r2_n8_final.log

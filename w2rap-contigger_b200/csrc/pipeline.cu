@@ -27,6 +27,7 @@
 #include "shardgraph_kernels.cuh"
 #include "nccl_dl.h"
 #include "prims.cuh"
+#include "slab_freelist.h"
 
 namespace w2r {
 
@@ -138,13 +139,12 @@ struct DeviceSlab {
     int device = -1;
     bool disabled = false;
     CUdeviceptr base = 0;
-    size_t va_bytes = 0, mapped = 0, gran = 0, used = 0;
-    std::map<size_t, size_t> free_;                      // offset -> bytes; disjoint, coalesced, all below `mapped`
-    std::unordered_map<size_t, size_t> live_;            // offset -> bytes
+    size_t va_bytes = 0, mapped = 0, gran = 0;
+    SlabFreeList fl;                                     // which pieces of [0, mapped) are in use (slab_freelist.h)
 
     static DeviceSlab& get(int device) { static DeviceSlab* s = new DeviceSlab[16]; return s[device & 15]; }   // leaked on purpose (see PinnedPool)
     bool contains(const void* p) const { return base && (CUdeviceptr)p >= base && (CUdeviceptr)p < base + va_bytes; }
-    size_t idle_bytes() const { return mapped - used; }
+    size_t idle_bytes() const { return mapped - fl.used; }
 
     bool init(int dev) {
         if (disabled) return false;
@@ -181,7 +181,7 @@ struct DeviceSlab {
                     acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
                     if (v.Map(base + mapped, take, 0, h, 0) == CUDA_SUCCESS && v.SetAccess(base + mapped, take, &acc, 1) == CUDA_SUCCESS) {
                         v.Release(h);                    // the mapping keeps the memory alive
-                        add_free(mapped, take);
+                        fl.add_free(mapped, take);
                         mapped += take;
                         return true;
                     }
@@ -195,38 +195,18 @@ struct DeviceSlab {
         }
         return false;
     }
-    void add_free(size_t off, size_t bytes) {
-        auto nx = free_.lower_bound(off);
-        if (nx != free_.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second == off) { off = pv->first; bytes += pv->second; free_.erase(pv); } }
-        if (nx != free_.end() && off + bytes == nx->first) { bytes += nx->second; free_.erase(nx); }
-        free_[off] = bytes;
-    }
     void* acquire(size_t bytes) {
         bytes = (bytes + ALIGN - 1) / ALIGN * ALIGN;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            for (auto it = free_.begin(); it != free_.end(); ++it) {
-                if (it->second < bytes) continue;
-                const size_t off = it->first, len = it->second;
-                free_.erase(it);
-                if (len > bytes) free_[off + bytes] = len - bytes;
-                live_[off] = bytes; used += bytes;
-                return (void*)(base + off);
-            }
+        size_t off = fl.take(bytes);
+        if (off == SlabFreeList::NONE) {
             // nothing fits: extend the top (only by what the free range touching it lacks)
-            size_t tail = 0;
-            if (!free_.empty()) { auto last = std::prev(free_.end()); if (last->first + last->second == mapped) tail = last->second; }
-            if (attempt || !grow(bytes - tail)) return nullptr;
+            if (!grow(bytes - fl.free_tail(mapped))) return nullptr;
+            off = fl.take(bytes);
+            if (off == SlabFreeList::NONE) return nullptr;
         }
-        return nullptr;
+        return (void*)(base + off);
     }
-    void release(void* p) {
-        const size_t off = (size_t)((CUdeviceptr)p - base);
-        auto it = live_.find(off);
-        if (it == live_.end()) return;
-        const size_t bytes = it->second;
-        live_.erase(it); used -= bytes;
-        add_free(off, bytes);
-    }
+    void release(void* p) { fl.give_back((size_t)((CUdeviceptr)p - base)); }
 };
 // one call holds a device's slab from its first buffer to its last; a failed call drains the device before handing it on
 struct SlabLease {
@@ -841,7 +821,9 @@ struct Pipeline {
         // filter would pass everything (measured at 1.44 G keys with 192 MB: every screened position probed the dictionary)
         static const uint64_t bloom_mb = getenv("W2RAP_BLOOM_MB") ? (uint64_t)atoi(getenv("W2RAP_BLOOM_MB")) : 192;
         const uint64_t cap = std::max<uint64_t>(bloom_mb << 20, std::min<uint64_t>(n_solid + n_solid / 2, 8ull << 30));
-        const uint64_t bytes = std::min<uint64_t>(cap, std::max<uint64_t>(4096, n_solid * 2));
+        uint64_t bytes = std::min<uint64_t>(cap, std::max<uint64_t>(4096, n_solid * 2));
+        static const uint64_t exact_mb = getenv("W2RAP_BLOOM_EXACT_MB") ? (uint64_t)atoi(getenv("W2RAP_BLOOM_EXACT_MB")) : 0;      // (diagnostic sweep)
+        if (exact_mb) bytes = exact_mb << 20;
         path_slice_words = (uint32_t)std::max<uint64_t>(64, bytes / 4 / world);
         path_bloom.alloc(c, (size_t)path_slice_words * world);
         path_bloom.zero();
