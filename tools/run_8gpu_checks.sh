@@ -1,3 +1,4 @@
+# what the round-2 8-GPU numbers in profiles/ came from: sharded tests, then config 3 on 8 B200s (run under gpurun --gpus 8)
 summ() { python - "$1" <<'P'
 import json,sys
 for l in open(sys.argv[1]):
