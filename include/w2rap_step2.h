@@ -94,7 +94,9 @@ typedef struct w2rap_params {
                                 writes the .hbv): the other ranks get the counters, edge_len, digests and their own paths, with
                                 edge_off/edge_bases/edge_vertices/fwd_xlat/rev_xlat/involution null.  Eight identical copies of a
                                 1 Gbp graph (1.3 GB each) otherwise share the host's PCIe uplinks with the path arrays. */
-    uint32_t reserved;
+    uint32_t places_K2;      /* 0 = off; otherwise also build step 3's "places" for large K = places_K2 (w2rap-contigger -K, default
+                                200) from the finished paths: RepathInMemory's first block (paths/long/large/Repath.cc:46-72).  Needs
+                                want_paths and apply_fixpaths (step 3 reads the paths as main() left them, after FixPaths). */
 } w2rap_params;
 
 /* One record of the optional k-mer dump (sorted by k-mer). */
@@ -142,6 +144,8 @@ typedef struct w2rap_timings {
                                      ~0 when the pool serves every request from cached memory, large when it has to grow, trim or re-map */
     uint32_t reserved2;
     uint64_t count_exchange_bytes; /* of exchange_bytes, the super-k-mer records of the counting stage (what exchange_ms moved) */
+    float places_ms;              /* params.places_K2: construction + unique sort of the places */
+    uint32_t reserved3;
 } w2rap_timings;
 
 /*
@@ -197,6 +201,16 @@ typedef struct w2rap_graph {
 
     uint64_t n_dump;
     w2rap_kmer_rec* dump;       /* sorted by (w0,w1); null unless params.dump_kmers */
+
+    /* Step-3 input (params.places_K2): every read path that implies at least K2 bases, replaced by its inverse (reversed, each edge
+     * by its involution) if that is smaller, then sorted lexicographically and made unique — `places` of RepathInMemory
+     * (paths/long/large/Repath.cc:46-72; std::vector<int> order: element by element, a proper prefix first).  In a sharded run the
+     * places of all ranks are merged: every rank receives the same list. */
+    uint64_t n_places_kept;     /* paths that passed the K2 test ("sorting N places" in the reference's log) */
+    uint64_t n_places;          /* unique places ("N unique places") */
+    uint64_t n_place_edges;
+    uint64_t* place_off;        /* n_places+1 */
+    int32_t* place_edges;       /* hbv edge ids */
 
     w2rap_timings timings;
     void* _owner;               /* library-private */

@@ -515,6 +515,15 @@ static void pack_bases(const uint8_t* codes, uint64_t n, uint8_t* out) {
     for (uint64_t i = 0; i < n; ++i) out[i >> 2] |= (uint8_t)(codes[i] << ((i & 3) * 2));
 }
 
+/* a place: a vector of hbv edge ids; order = std::vector<int>::operator< (element by element, a proper prefix first) */
+typedef struct { const int32_t* p; size_t n; } place_t;
+static int place_cmp(const void* a_, const void* b_) {
+    const place_t* a = (const place_t*)a_; const place_t* b = (const place_t*)b_;
+    const size_t n = a->n < b->n ? a->n : b->n;
+    for (size_t i = 0; i < n; ++i) if (a->p[i] != b->p[i]) return a->p[i] < b->p[i] ? -1 : 1;
+    return a->n < b->n ? -1 : (a->n > b->n ? 1 : 0);
+}
+
 int oracle_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* out) {
     if (!in || !p || !out || p->K != KK) return W2RAP_ERR_BAD_ARG;
     memset(out, 0, sizeof(*out));
@@ -749,6 +758,38 @@ int oracle_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* 
         free(parts); free(np); free(rp.e);
     }
 
+    /* ---- step-3 input: RepathInMemory's `places` (paths/long/large/Repath.cc:46-72).  Per path x: nkmers = sum of
+     * edges[x[j]].size() - (K-1) (:57-59); dropped if nkmers + (K-1) < K2 (:60); y = reversed x with every edge replaced by its
+     * involution (:61-62); the smaller of x and y is the place (:63); then sort + unique (:69-71). */
+    if (p->places_K2 && p->want_paths) {
+        place_t* pl = (place_t*)xmalloc(sizeof(place_t) * (n_reads + 1));
+        int32_t* store = (int32_t*)xmalloc(sizeof(int32_t) * (out->n_path_edges + 1));
+        size_t npl = 0, used = 0;
+        for (uint64_t r = 0; r < n_reads; ++r) {
+            const int32_t* x = out->path_edges + out->path_off[r];
+            const size_t n = (size_t)(out->path_off[r + 1] - out->path_off[r]);
+            int nkmers = 0;
+            for (size_t j = 0; j < n; ++j) nkmers += (int)h.elen[x[j]] - (KK - 1);
+            if (nkmers + (KK - 1) < (int)p->places_K2) continue;
+            int32_t* dst = store + used;
+            int flip = 0;                                         /* is y < x ? */
+            for (size_t j = 0; j < n; ++j) { int32_t yj = out->involution[x[n - 1 - j]]; if (yj != x[j]) { flip = yj < x[j]; break; } }
+            for (size_t j = 0; j < n; ++j) dst[j] = flip ? out->involution[x[n - 1 - j]] : x[j];
+            pl[npl].p = dst; pl[npl].n = n; ++npl; used += n;
+        }
+        out->n_places_kept = npl;
+        qsort(pl, npl, sizeof(place_t), place_cmp);
+        size_t nu = 0, ne = 0;
+        for (size_t i = 0; i < npl; ++i) if (i == 0 || place_cmp(&pl[i - 1], &pl[i]) != 0) { pl[nu++] = pl[i]; ne += pl[i].n; }
+        out->n_places = nu; out->n_place_edges = ne;
+        out->place_off = (uint64_t*)xmalloc(sizeof(uint64_t) * (nu + 1));
+        out->place_edges = (int32_t*)xmalloc(sizeof(int32_t) * (ne + 1));
+        size_t at = 0;
+        for (size_t i = 0; i < nu; ++i) { out->place_off[i] = at; memcpy(out->place_edges + at, pl[i].p, pl[i].n * sizeof(int32_t)); at += pl[i].n; }
+        out->place_off[nu] = at;
+        free(pl); free(store);
+    }
+
     for (size_t e = 0; e < el.n; ++e) { free(el.e[e].seq); free(el.e[e].ents); }
     free(el.e); free(epal);
     free(h.left); free(h.right); free(h.elen); free(h.canon); free(h.is_rc);
@@ -761,7 +802,7 @@ int oracle_step2_run(const w2rap_reads* in, const w2rap_params* p, w2rap_graph* 
 void oracle_step2_free(w2rap_graph* g) {
     if (!g) return;
     free(g->edge_off); free(g->edge_len); free(g->edge_bases); free(g->edge_vertices); free(g->fwd_xlat); free(g->rev_xlat); free(g->involution);
-    free(g->path_offset); free(g->path_off); free(g->path_edges); free(g->dump);
+    free(g->path_offset); free(g->path_off); free(g->path_edges); free(g->dump); free(g->place_off); free(g->place_edges);
     memset(g, 0, sizeof(*g));
 }
 

@@ -22,6 +22,7 @@
 #include "../../w2rap-contigger_b200/csrc/unipath.cuh"
 #include "../../w2rap-contigger_b200/csrc/shardgraph.cuh"
 #include "../../w2rap-contigger_b200/csrc/slab_freelist.h"
+#include "../../w2rap-contigger_b200/csrc/places.cuh"
 
 using namespace w2r;
 
@@ -789,5 +790,64 @@ extern "C" int hc_slab_freelist_fuzz(uint64_t seed, uint32_t ops) {
     // everything back: one free range covering the whole slab
     for (auto& pc : live) if (fl.give_back(pc.first) != pc.second) return 30;
     if (!(fl.used == 0 && fl.free_.size() == (model.empty() ? 0u : 1u) && (model.empty() || (fl.free_.begin()->first == 0 && fl.free_.begin()->second == model.size() * unit)))) return 31;
+    return 0;
+}
+
+
+// ---- step-3 places (csrc/places.cuh) through the device functions, in the order pipeline.cu: places_stage()/unique_places() runs them:
+// measure + fill, hash, sort by hash, neighbour comparison (collisions counted), representatives, stable LSD sort over element
+// positions.  `g` is a finished graph with paths (oracle or product); the result goes to malloc'ed arrays the caller frees with hc_free.
+extern "C" int hc_places(const w2rap_graph* g, uint32_t K2, uint64_t salt, uint64_t* n_kept, uint64_t* n_places, uint64_t** place_off, int32_t** place_edges,
+                         uint64_t* n_collisions) {
+    using namespace w2r;
+    const uint64_t n = g->n_paths, nh = g->n_hbv_edges;
+    std::vector<uint32_t> hcanon(nh ? nh : 1);
+    for (uint64_t i = 0; i < g->n_edges; ++i) { hcanon[g->fwd_xlat[i]] = (uint32_t)(i << 1); if (g->rev_xlat[i] != g->fwd_xlat[i]) hcanon[g->rev_xlat[i]] = (uint32_t)(i << 1) | 1u; }   // (k_hbv_edges' encoding)
+    // measure + fill
+    std::vector<uint64_t> off(1, 0);
+    std::vector<int32_t> edges;
+    for (uint64_t r = 0; r < n; ++r) {
+        const int32_t* x = g->path_edges + g->path_off[r];
+        const uint64_t len = g->path_off[r + 1] - g->path_off[r];
+        bool flip;
+        const uint32_t pl = place_measure(x, len, hcanon.data(), g->edge_len, g->involution, K2, &flip);
+        if (!pl) continue;
+        for (uint32_t j = 0; j < pl; ++j) edges.push_back(place_element(x, len, g->involution, flip, j));
+        off.push_back(edges.size());
+    }
+    const uint64_t M = off.size() - 1;
+    *n_kept = M;
+    edges.push_back(0);
+    PlacesView s{off.data(), edges.data(), M};
+    std::vector<uint64_t> h(M);
+    for (uint64_t i = 0; i < M; ++i) h[i] = place_hash(s.edges + s.off[i], s.off[i + 1] - s.off[i], salt);
+    std::vector<uint32_t> perm(M);
+    for (uint64_t i = 0; i < M; ++i) perm[i] = (uint32_t)i;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return h[a] < h[b]; });
+    std::vector<uint32_t> rep;
+    uint64_t coll = 0; uint32_t maxlen = 0;
+    for (uint64_t i = 0; i < M; ++i) {
+        bool first = true;
+        if (i) { if (place_equal(s, perm[i], perm[i - 1])) first = false; else if (h[perm[i]] == h[perm[i - 1]]) ++coll; }
+        if (first) { rep.push_back(perm[i]); maxlen = std::max<uint32_t>(maxlen, (uint32_t)(s.off[perm[i] + 1] - s.off[perm[i]])); }
+    }
+    *n_collisions = coll;
+    const uint64_t U = rep.size();
+    std::vector<uint32_t> order(U);
+    for (uint64_t u = 0; u < U; ++u) order[u] = (uint32_t)u;
+    for (uint32_t pos = maxlen; pos-- > 0;)
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return place_key(s, rep[a], pos) < place_key(s, rep[b], pos); });
+    *n_places = U;
+    uint64_t ne = 0;
+    for (uint64_t u = 0; u < U; ++u) ne += s.off[rep[u] + 1] - s.off[rep[u]];
+    *place_off = (uint64_t*)malloc(sizeof(uint64_t) * (U + 1));
+    *place_edges = (int32_t*)malloc(sizeof(int32_t) * (ne + 1));
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < U; ++i) {
+        const uint32_t a = rep[order[i]];
+        (*place_off)[i] = at;
+        for (uint64_t j = s.off[a]; j < s.off[a + 1]; ++j) (*place_edges)[at++] = s.edges[j];
+    }
+    (*place_off)[U] = at;
     return 0;
 }

@@ -328,3 +328,38 @@ def test_config1_against_the_reference_binary(T, tmp_path):
     assert rep["edge_set_equal"] and rep["hist_equal"] and rep["vertices_equal"], {k: v for k, v in rep.items() if k != "path_mismatches"}
     assert rep["path_mismatches"] == [] and rep["path_ties"] <= 50, (rep["path_ties"], rep["path_mismatches"][:10])
     assert got["n_pathed"] > 0.97 * got["n_reads"]
+
+
+@pytest.mark.parametrize("K2", [100, 200])
+def test_places_for_step3(T, K2):
+    """RepathInMemory's places (paths/long/large/Repath.cc:46-72) built on the device from the finished paths, against
+    the oracle (whose restatement reproduces the reference's logged counts, tests/test_oracle_golden.py)."""
+    rs = T.rich_set(seed=33, genome=120000, cov=60, families=6, palindromes=3, plasmid=2500)
+    want = T.run_oracle(rs, T.default_params(apply_fixpaths=1, places_K2=K2))
+    got = T.run_product(rs, T.default_params(apply_fixpaths=1, places_K2=K2))
+    assert want["n_places"] > 500 and want["n_places_kept"] > want["n_places"] + 1000
+    T.assert_graph_equal(want, got, check_dump=False)
+    # sorted in std::vector<int> order and unique
+    pl = [tuple(int(e) for e in got["place_edges"][int(got["place_off"][i]):int(got["place_off"][i + 1])]) for i in range(got["n_places"])]
+    assert pl == sorted(set(pl))
+
+
+@pytest.mark.parametrize("case", ["circ", "rich", "long"])
+def test_places_counts_of_the_reference_on_golden_cases(T, case):
+    """The reference prints how many paths pass the K2 test and how many unique places remain (tests/golden/<case>/
+    reference_step3_places.txt, from the unmodified binary run on its own step-2 files): the product's counts on the same reads may
+    differ only by the <= 3 extension ties its paths differ by."""
+    d = os.path.join(GOLD, case)
+    rs = T.read_fastb_qualp(d)
+    for line in open(os.path.join(d, "reference_step3_places.txt")).read().splitlines():
+        K2, n_paths, kept, unique = (int(x) for x in line.split())
+        got = T.run_product(rs, T.default_params(apply_fixpaths=1, places_K2=K2))
+        assert got["n_paths"] == n_paths
+        assert abs(got["n_places_kept"] - kept) <= 3 and abs(got["n_places"] - unique) <= 3, (K2, got["n_places_kept"], got["n_places"], kept, unique)
+
+
+def test_places_parameter_checks(T):
+    rs = T.smoke_set()
+    for bad in (dict(apply_fixpaths=0, places_K2=200), dict(apply_fixpaths=1, want_paths=0, places_K2=200), dict(apply_fixpaths=1, places_K2=40)):
+        with pytest.raises(RuntimeError, match="places_K2"):
+            T.run_product(rs, T.default_params(**bad))

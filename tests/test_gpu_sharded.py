@@ -101,3 +101,15 @@ def test_graph_on_root_only(T):
     assert np.array_equal(other["path_offset"], want["path_offset"][lo:hi])
     a, b = int(want["path_off"][lo]), int(want["path_off"][hi])
     assert np.array_equal(other["path_edges"], want["path_edges"][a:b])
+
+
+def test_sharded_places(T):
+    """Step-3 places in a sharded run: every rank removes the duplicates of its shard, the unique places are all-gathered and merged;
+    every rank returns the list of the whole job."""
+    rs = T.rich_set(seed=17, genome=60000, cov=50, families=4, palindromes=2, plasmid=1200)
+    want = T.run_oracle(rs, T.default_params(apply_fixpaths=1, places_K2=200))
+    res, _ = run_sharded(T, rs, 2, apply_fixpaths=1, places_K2=200)
+    assert want["n_places"] > 200
+    for got in res:
+        assert (got["n_places_kept"], got["n_places"]) == (want["n_places_kept"], want["n_places"])
+        assert np.array_equal(got["place_off"], want["place_off"]) and np.array_equal(got["place_edges"], want["place_edges"])

@@ -19,7 +19,7 @@ SO = os.path.join(ROOT, "oracle", "_build", "libhostcheck.so")
 @pytest.fixture(scope="session")
 def hc(T):
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh", "shard.cuh", "shardgraph.cuh", "slab_freelist.h")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
+    deps = [src] + [os.path.join(ROOT, "w2rap-contigger_b200", "csrc", f) for f in ("kmer.cuh", "pqvec.cuh", "extract.cuh", "unipath.cuh", "path.cuh", "shard.cuh", "shardgraph.cuh", "slab_freelist.h", "places.cuh")] + [os.path.join(ROOT, "include", "w2rap_step2.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, src], check=True)
@@ -175,3 +175,29 @@ def test_device_slab_free_list(hc):
     hc.hc_slab_freelist_fuzz.argtypes = [C.c_uint64, C.c_uint32]
     for seed in range(1, 9):
         assert hc.hc_slab_freelist_fuzz(seed, 4000) == 0
+
+
+@pytest.mark.parametrize("K2", [100, 200, 320])
+def test_places_device_functions(T, hc, K2):
+    """Step-3 places through the functions the kernels call, in the pipeline's order (hash sort -> neighbour
+    comparison -> stable LSD sort over element positions), against the oracle's qsort + unique (pinned on the reference's log in
+    test_oracle_golden.py).  Built on the ORACLE's graph, so only the places logic is under test."""
+    rs = T.rich_set(seed=31, genome=60000, cov=50, families=4, palindromes=2, plasmid=1200)
+    lib = T.oracle_lib()
+    g = T.Graph()
+    p = T.default_params(apply_fixpaths=1, places_K2=K2)
+    assert lib.oracle_step2_run(C.byref(rs.c()), C.byref(p), C.byref(g)) == 0
+    try:
+        want = T.graph_to_dict(g)
+        hc.hc_places.argtypes = [C.POINTER(T.Graph), C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        nk, npl, po, pe, coll = C.c_uint64(), C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        assert hc.hc_places(C.byref(g), K2, 7, C.byref(nk), C.byref(npl), C.byref(po), C.byref(pe), C.byref(coll)) == 0
+        off = T._arr(po.value, npl.value + 1, "<u8")
+        edges = T._arr(pe.value, int(off[-1]), "<i4")
+        hc.hc_free(po); hc.hc_free(pe)
+    finally:
+        lib.oracle_step2_free(C.byref(g))
+    assert coll.value == 0
+    assert want["n_places"] > 100 and want["n_places_kept"] > want["n_places"]
+    assert (nk.value, npl.value) == (want["n_places_kept"], want["n_places"])
+    assert np.array_equal(off, want["place_off"]) and np.array_equal(edges, want["place_edges"])

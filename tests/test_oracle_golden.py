@@ -102,3 +102,51 @@ def test_oracle_edge_cases(T):
     inst = (250 - 59) * 35 + 2
     assert o["n_kmer_instances"] == inst
     assert o["n_paths"] == 40 and o["path_off"][1] == o["path_off"][0]   # read 0 has no path
+
+
+def places_from(paths, hlen, inv, K2):
+    """RepathInMemory's `places` (paths/long/large/Repath.cc:46-72) restated in Python: paths = per read a list of hbv edge ids,
+    hlen = bases per hbv edge, inv = the involution.  Returns (paths that passed the K2 test, sorted unique places)."""
+    kept = []
+    for x in paths:
+        x = [int(e) for e in x]
+        if sum(int(hlen[e]) - 59 for e in x) + 59 < K2:          # :57-60 (an empty path has 0 k-mers and is dropped too)
+            continue
+        y = [int(inv[e]) for e in reversed(x)]                   # :61-62
+        kept.append(tuple(x if x < y else y))                    # :63
+    return len(kept), sorted(set(kept))                          # :69-71
+
+
+def places_of_result(o, K2):
+    hlen = np.zeros(o["n_hbv_edges"], np.int64)
+    hlen[o["fwd_xlat"]] = o["edge_len"]
+    hlen[o["rev_xlat"]] = o["edge_len"]
+    paths = [o["path_edges"][int(o["path_off"][r]):int(o["path_off"][r + 1])] for r in range(o["n_paths"])]
+    return places_from(paths, hlen, o["involution"], K2)
+
+
+@pytest.mark.parametrize("case", ["circ", "rich", "long"])
+def test_places_against_the_reference_log(T, case):
+    """Step-3 input.  The reference never writes its places; it prints how many paths passed the K2 test and how many
+    unique places remain (tests/golden/<case>/reference_step3_places.txt, made by make_golden_places.py from the reference binary run
+    on its own step-2 files, for six values of K2).  (1) The Python restatement applied to THOSE files must reproduce both counts
+    exactly; (2) the C oracle's list must be the restatement's on the oracle's own graph; (3) the oracle's counts can differ from the
+    log only by the extension ties its paths differ by (<= 3 reads, see test_oracle_matches_reference_files)."""
+    d = os.path.join(GOLD, case)
+    rows = [tuple(int(x) for x in l.split()) for l in open(os.path.join(d, "reference_step3_places.txt")).read().splitlines() if l.strip()]
+    assert len(rows) >= 5
+    ref = T.graph_from_reference_files(d)
+    seqs = [e.tobytes() for e in ref["hbv"]["edges"]]
+    ids = {s: i for i, s in enumerate(seqs)}
+    inv = np.array([ids[T.revcomp(e).tobytes()] for e in ref["hbv"]["edges"]], np.int64)      # hbv.Involution (HyperBasevector.cc:648-660)
+    hlen = np.array([len(e) for e in ref["hbv"]["edges"]], np.int64)
+    rs = T.read_fastb_qualp(d)
+    for K2, n_paths, kept, unique in rows:
+        assert len(ref["paths"]) == n_paths
+        nk, places = places_from(ref["paths"], hlen, inv, K2)
+        assert (nk, len(places)) == (kept, unique), (K2, nk, len(places), kept, unique)
+        o = T.run_oracle(rs, T.default_params(apply_fixpaths=1, places_K2=K2))
+        nk2, want = places_of_result(o, K2)
+        got = [tuple(int(e) for e in o["place_edges"][int(o["place_off"][i]):int(o["place_off"][i + 1])]) for i in range(o["n_places"])]
+        assert o["n_places_kept"] == nk2 and got == want
+        assert abs(o["n_places_kept"] - kept) <= 3 and abs(o["n_places"] - unique) <= 3

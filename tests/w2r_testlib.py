@@ -31,14 +31,15 @@ class Params(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("K", C.c_uint32), ("min_qual", C.c_uint32), ("min_freq", C.c_uint32),
                 ("want_paths", C.c_uint32), ("apply_fixpaths", C.c_uint32), ("dump_kmers", C.c_uint32),
                 ("device", C.c_int32), ("workdir", C.c_char_p), ("table_slots", C.c_uint64), ("verbose", C.c_uint32),
-                ("force_passes", C.c_uint32), ("graph_on_root_only", C.c_uint32), ("reserved", C.c_uint32)]
+                ("force_passes", C.c_uint32), ("graph_on_root_only", C.c_uint32), ("places_K2", C.c_uint32)]
 
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "count_ms", "solid_ms", "adjacency_ms", "unipath_ms", "hbv_ms",
                                          "path_ms", "d2h_ms", "total_ms", "count_kernel_ms", "region_ms", "exchange_ms", "host_pre_ms", "host_post_ms", "wall_ms")] + \
                [(n, C.c_uint32) for n in ("count_launches", "kernel_launches", "count_passes", "reserved")] + \
-               [("dict_ms", C.c_float), ("graph_exchange_ms", C.c_float), ("exchange_bytes", C.c_uint64), ("n_records", C.c_uint64), ("kernel_ms", C.c_float * 16), ("alloc_host_ms", C.c_float), ("reserved2", C.c_uint32), ("count_exchange_bytes", C.c_uint64)]
+               [("dict_ms", C.c_float), ("graph_exchange_ms", C.c_float), ("exchange_bytes", C.c_uint64), ("n_records", C.c_uint64), ("kernel_ms", C.c_float * 16), ("alloc_host_ms", C.c_float), ("reserved2", C.c_uint32), ("count_exchange_bytes", C.c_uint64),
+                ("places_ms", C.c_float), ("reserved3", C.c_uint32)]
 
 
 KERNEL_NAMES = ["k_good_len", "k_minimizer_map", "k_scatter_records", "k_count_smem", "k_insert_solid", "k_adjacency", "k_links",
@@ -66,6 +67,7 @@ class Graph(C.Structure):
                 ("path_off", C.c_void_p), ("path_edges", C.c_void_p), ("n_pathed", C.c_uint64),
                 ("n_multipathed", C.c_uint64), ("digest_graph", C.c_uint64), ("digest_paths", C.c_uint64),
                 ("n_dump", C.c_uint64), ("dump", C.c_void_p),
+                ("n_places_kept", C.c_uint64), ("n_places", C.c_uint64), ("n_place_edges", C.c_uint64), ("place_off", C.c_void_p), ("place_edges", C.c_void_p),
                 ("timings", Timings), ("_owner", C.c_void_p)]
 
 
@@ -78,9 +80,9 @@ ABI_VERSION = 2
 
 
 def default_params(min_qual=7, min_freq=4, want_paths=1, apply_fixpaths=0, dump_kmers=0, workdir=None,
-                   table_slots=0, device=-1, verbose=0, force_passes=0, graph_on_root_only=0):
+                   table_slots=0, device=-1, verbose=0, force_passes=0, graph_on_root_only=0, places_K2=0):
     return Params(ABI_VERSION, K, min_qual, min_freq, want_paths, apply_fixpaths, dump_kmers, device,
-                  workdir.encode() if workdir else None, table_slots, verbose, force_passes, graph_on_root_only, 0)
+                  workdir.encode() if workdir else None, table_slots, verbose, force_passes, graph_on_root_only, places_K2)
 
 
 def _arr(ptr, n, dtype):
@@ -110,6 +112,8 @@ def graph_to_dict(g):
         path_off=_arr(g.path_off, npth + 1 if npth else 0, "<u8"), path_edges=_arr(g.path_edges, g.n_path_edges, "<i4"),
         n_pathed=int(g.n_pathed), n_multipathed=int(g.n_multipathed),
         dump=_arr(g.dump, g.n_dump, KMER_REC_DTYPE),
+        n_places_kept=int(g.n_places_kept), n_places=int(g.n_places), place_off=_arr(g.place_off, g.n_places + 1 if g.place_off else 0, "<u8"),
+        place_edges=_arr(g.place_edges, g.n_place_edges, "<i4"),
         timings={n: (list(getattr(g.timings, n)) if n == "kernel_ms" else getattr(g.timings, n)) for n, _ in Timings._fields_},
     )
     return d
@@ -659,6 +663,11 @@ def assert_graph_equal(a, b, what="graph", check_paths=True, check_dump=True):
             if not np.array_equal(a[k], b[k]):
                 bad = np.nonzero(a["path_offset"] != b["path_offset"])[0]
                 raise AssertionError("%s: array %s differs (first offset mismatch at reads %s)" % (what, k, bad[:5]))
+        # step-3 places (params.places_K2): counts, then the lists
+        for k in ("n_places_kept", "n_places"):
+            assert a[k] == b[k], "%s: %s differs: %s vs %s" % (what, k, a[k], b[k])
+        for k in ("place_off", "place_edges"):
+            assert np.array_equal(a[k], b[k]), "%s: array %s differs" % (what, k)
 
 
 if __name__ == "__main__":

@@ -28,6 +28,7 @@
 #include "nccl_dl.h"
 #include "prims.cuh"
 #include "slab_freelist.h"
+#include "places.cuh"
 
 namespace w2r {
 
@@ -1425,6 +1426,105 @@ struct Pipeline {
         W2R_CUDA(cudaStreamSynchronize(c.stream));
     }
 
+    // ---- step-3 input: RepathInMemory's places (paths/long/large/Repath.cc:46-72; kernels and rules in places.cuh)
+    struct PlaceSet { SBuf<uint64_t> off; SBuf<int32_t> edges; uint64_t n = 0, n_edges = 0; };
+    // `in` without its duplicates, in std::vector<int> order if `sorted` (else in hash order)
+    void unique_places(PlaceSet& in, PlaceSet& res, bool sorted) {
+        const uint64_t M = in.n;
+        res.n = res.n_edges = 0;
+        if (M == 0) { res.off.alloc(c, 1); res.off.zero(); res.edges.alloc(c, 1); return; }
+        if (M >= (1ull << 32) - 8) W2R_FAIL(W2RAP_ERR_OOM, "more than 2^32 places");
+        PlacesView s{in.off.p, in.edges.p, M};
+        SBuf<uint64_t> h(c, M);
+        SBuf<uint32_t> perm(c, M), tmp(c, M), first(c, M), excl(c, M), tot(c, 1);
+        SBuf<unsigned long long> coll(c, 1);
+        for (int attempt = 0;; ++attempt) {
+            W2R_LAUNCH(c, k_place_hash, grid(M, 256), 256, 0, s, 0x1234567ull + 0x9e3779b97f4a7c15ull * (uint64_t)attempt, h.p);
+            W2R_LAUNCH(c, k_rs_iota, grid(M, 256), 256, 0, perm.p, (uint32_t)M);
+            SortWord w{h.p, 0, 64};
+            radix_sort_perm(c, perm.p, tmp.p, (uint32_t)M, &w, 1);
+            coll.zero();
+            W2R_LAUNCH(c, k_place_first, grid(M, 256), 256, 0, s, (const uint32_t*)perm.p, (const uint64_t*)h.p, first.p, coll.p);
+            if (!d2h_scalar(c, coll.p)) break;                 // no two different places share a hash: equal places are neighbours
+            if (attempt == 3) W2R_FAIL(W2RAP_ERR_INTERNAL, "place hashes collide under four salts");
+        }
+        exclusive_scan<uint32_t, uint32_t>(c, first.p, M, excl.p, tot.p);
+        const uint64_t U = d2h_scalar(c, tot.p);
+        SBuf<uint32_t> rep(c, U), order;
+        SBuf<unsigned int> maxlen(c, 1); maxlen.zero();
+        W2R_LAUNCH(c, k_place_select, grid(M, 256), 256, 0, s, (const uint32_t*)perm.p, (const uint32_t*)first.p, (const uint32_t*)excl.p, rep.p, maxlen.p);
+        if (sorted && U > 1) {
+            const uint32_t ml = d2h_scalar(c, maxlen.p);
+            order.alloc(c, U);
+            SBuf<uint32_t> tmp2(c, U);
+            SBuf<uint64_t> key(c, U);
+            W2R_LAUNCH(c, k_rs_iota, grid(U, 256), 256, 0, order.p, (uint32_t)U);
+            int bits = 1;
+            while ((1ull << bits) < nh + 2) ++bits;            // keys are hbv id + 1 (0 = the vector has ended)
+            for (uint32_t pos = ml; pos-- > 0;) {              // stable LSD: last element position first
+                W2R_LAUNCH(c, k_place_key, grid(U, 256), 256, 0, s, (const uint32_t*)rep.p, U, pos, key.p);
+                SortWord w{key.p, 0, bits};
+                radix_sort_perm(c, order.p, tmp2.p, (uint32_t)U, &w, 1);
+            }
+        }
+        SBuf<uint32_t> olen(c, U);
+        SBuf<uint64_t> tote(c, 1);
+        W2R_LAUNCH(c, k_place_out_len, grid(U, 256), 256, 0, s, (const uint32_t*)rep.p, (const uint32_t*)order.p, U, olen.p);
+        res.off.alloc(c, U + 1);
+        exclusive_scan<uint32_t, uint64_t>(c, olen.p, U, res.off.p, tote.p);
+        W2R_CUDA(cudaMemcpyAsync(res.off.p + U, tote.p, 8, cudaMemcpyDeviceToDevice, c.stream));
+        const uint64_t ne = d2h_scalar(c, tote.p);
+        res.edges.alloc(c, ne + 1);
+        W2R_LAUNCH(c, k_place_gather, grid(U, 256), 256, 0, s, (const uint32_t*)rep.p, (const uint32_t*)order.p, U, (const uint64_t*)res.off.p, res.edges.p);
+        res.n = U; res.n_edges = ne;
+    }
+    void places_stage(SBuf<uint64_t>& d_path_off, SBuf<int32_t>& d_path_edges) {
+        const uint64_t n = dr.n;
+        PlaceSet local, uniq;
+        {
+            PathsView pv{d_path_off.p, d_path_edges.p, n};
+            SBuf<uint32_t> plen(c, n + 1), kept(c, n + 1), pidx(c, n + 1), totk(c, 1);
+            SBuf<uint8_t> flip(c, n + 1);
+            SBuf<uint64_t> poff(c, n + 1), tote(c, 1);
+            if (n) W2R_LAUNCH(c, k_place_measure, grid(n, 256), 256, 0, pv, (const uint32_t*)hcanon.p, (const uint32_t*)edge_len.p, (const int32_t*)involution.p, prm.places_K2, plen.p, kept.p, flip.p);
+            exclusive_scan<uint32_t, uint32_t>(c, kept.p, n, pidx.p, totk.p);
+            exclusive_scan<uint32_t, uint64_t>(c, plen.p, n, poff.p, tote.p);
+            local.n = d2h_scalar(c, totk.p);
+            local.n_edges = d2h_scalar(c, tote.p);
+            local.off.alloc(c, local.n + 1); local.edges.alloc(c, local.n_edges + 1);
+            if (n) W2R_LAUNCH(c, k_place_fill, grid(n, 256), 256, 0, pv, (const int32_t*)involution.p, (const uint32_t*)plen.p, (const uint8_t*)flip.p, (const uint32_t*)pidx.p,
+                              (const uint64_t*)poff.p, local.off.p, local.edges.p);
+            W2R_CUDA(cudaMemcpyAsync(local.off.p + local.n, tote.p, 8, cudaMemcpyDeviceToDevice, c.stream));
+        }
+        std::vector<unsigned long long> kt = {local.n};
+        allreduce_u64(kt, ncclSum);
+        out->n_places_kept = kt[0];
+        if (world == 1) {
+            unique_places(local, uniq, true);
+        } else {                                               // every rank removes its own duplicates, the rest is merged on all ranks
+            PlaceSet mine, merged;
+            unique_places(local, mine, false);
+            local.off.release(); local.edges.release();
+            SBuf<uint32_t> mylen(c, mine.n + 1), all_len;
+            SBuf<uint64_t> tot(c, 1);
+            if (mine.n) W2R_LAUNCH(c, k_place_lens, grid(mine.n, 256), 256, 0, (const uint64_t*)mine.off.p, mine.n, mylen.p);
+            std::vector<uint64_t> loff, eoff;
+            allgather_v(mylen.p, mine.n, all_len, loff);
+            allgather_v(mine.edges.p, mine.n_edges, merged.edges, eoff);
+            merged.n = loff[world]; merged.n_edges = eoff[world];
+            merged.off.alloc(c, merged.n + 1);
+            exclusive_scan<uint32_t, uint64_t>(c, all_len.p, merged.n, merged.off.p, tot.p);
+            W2R_CUDA(cudaMemcpyAsync(merged.off.p + merged.n, tot.p, 8, cudaMemcpyDeviceToDevice, c.stream));
+            unique_places(merged, uniq, true);
+        }
+        out->n_places = uniq.n; out->n_place_edges = uniq.n_edges;
+        if (!(world > 1 && prm.graph_on_root_only && rank != 0)) {
+            out->place_off = to_host<uint64_t>(uniq.off.p, uniq.n + 1);
+            out->place_edges = to_host<int32_t>(uniq.edges.p, uniq.n_edges);
+        }
+        W2R_CUDA(cudaStreamSynchronize(c.stream));             // (the sets leave scope)
+    }
+
     template <class T>
     T* to_host(const T* dptr, size_t n, cudaStream_t s = nullptr) {
         T* h = out_alloc<T>(owner, n);
@@ -1483,6 +1583,12 @@ struct Pipeline {
             say(c, "pathing reads into graph...");
             st_t.start(); path_stage(d_offset, d_path_off, d_path_edges, &npe, &pathed, &multi); out->timings.path_ms = st_t.stop();
             say(c, "%llu / %llu reads pathed, %llu spanning junctions", pathed, (unsigned long long)dr.n, multi);
+        }
+        if (prm.places_K2) {
+            say(c, "constructing places from %llu paths", (unsigned long long)dr.n);
+            st_t.start(); places_stage(d_path_off, d_path_edges); out->timings.places_ms = st_t.stop();
+            say(c, "sorting %llu places", (unsigned long long)out->n_places_kept);
+            say(c, "%llu unique places", (unsigned long long)out->n_places);
         }
         // ---- results to the host
         st_t.start();
@@ -1681,6 +1787,8 @@ static void check_params(const w2rap_params* p) {
     if (p->K != W2RAP_K) W2R_FAIL(W2RAP_ERR_BAD_ARG, "K=%u: only K=60 is built (the reference hard-wires it, BuildReadQGraph.cc:51)", p->K);
     if (p->min_freq == 0 || p->min_freq > 255) W2R_FAIL(W2RAP_ERR_BAD_ARG, "min_freq must be in 1..255 (counts saturate at 255)");
     if (p->force_passes > 4096) W2R_FAIL(W2RAP_ERR_BAD_ARG, "force_passes must be <= 4096");
+    if (p->places_K2 && (p->places_K2 < W2RAP_K || !p->want_paths || !p->apply_fixpaths))
+        W2R_FAIL(W2RAP_ERR_BAD_ARG, "places_K2 needs want_paths and apply_fixpaths (step 3 reads the paths after FixPaths) and K2 >= 60");
 }
 
 }  // namespace w2r
