@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--read-len", type=int, default=250)
     ap.add_argument("--het", type=int, default=None, help="SNPs per 10,000 bases on the second haplotype")
     ap.add_argument("--ref-genome-mbp", type=float, default=2.0, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--places", type=int, default=0, help="also build step 3's places for this large K inside the timed step (SURVEY N1; off by default: not part of the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) legs: for workloads whose reads do not fit pinned host memory")
     args = ap.parse_args()
@@ -263,7 +264,7 @@ def main():
             raise SystemExit("comm init failed: " + err.value.decode())
     if lib.w2rap_step2_synth(C.byref(sp), local, C.byref(h), err, 1024):
         raise SystemExit("synth failed: " + err.value.decode())
-    p = T.default_params(apply_fixpaths=1, device=local, graph_on_root_only=1 if world > 1 else 0)      # (the graph arrays go to the one process that would write the .hbv)
+    p = T.default_params(apply_fixpaths=1, device=local, graph_on_root_only=1 if world > 1 else 0, places_K2=args.places)      # (the graph arrays go to the one process that would write the .hbv)
     hr = T.Reads()
     do_e2e = not args.no_e2e
     if do_e2e and lib.w2rap_step2_download_reads(h, C.byref(hr), err, 1024):
@@ -284,6 +285,7 @@ def main():
         if rc:
             raise SystemExit("run failed: " + err.value.decode())
         t = timings_of(g)
+        t["n_places_kept"], t["n_places"] = int(g.n_places_kept), int(g.n_places)
         info = (int(g.n_kmer_instances), int(g.n_distinct), int(g.n_solid), int(g.n_edges), int(g.n_edge_bases), int(g.n_pathed), int(g.n_path_edges), int(g.digest_graph), int(g.digest_paths))
         lib.w2rap_step2_free(C.byref(g))
         return t, info
@@ -426,6 +428,7 @@ def main():
                      "kernel_ms_per_step": km[dom], "per_kernel": per_kernel, "sharded_graph_phases_ms": {k: round(v, 3) for k, v in phases.items()} if world > 1 else None,
                      "whole_step_algorithmic_GBps": alg_bytes_total / (dev_ms * 1e-3) / 1e9, "whole_step_frac": alg_bytes_total / (dev_ms * 1e-3) / 1e9 / peak},
         "alloc_host_ms": [round(t["alloc_host_ms"], 1) for t in tt],
+        "places": ({"K2": args.places, "ms": median([t["places_ms"] for t in tt]), "paths_kept": tt[-1].get("n_places_kept"), "unique_places": tt[-1].get("n_places"), "note": "inside ms_per_step; RepathInMemory's places built on the device (paths/long/large/Repath.cc:46-72)"} if args.places else None),
         "stage_ms": {k: median([t[k] for t in tt]) for k in ("count_ms", "count_kernel_ms", "region_ms", "dict_ms", "exchange_ms", "graph_exchange_ms", "adjacency_ms", "unipath_ms", "hbv_ms", "path_ms", "d2h_ms", "total_ms")},
         "nvlink": ({"bytes_delivered_all_ranks_per_step": xbytes_all, "of_which_count_records": xbytes_count,
                     "of_which_graph_and_dictionary": xbytes_all - xbytes_count,
