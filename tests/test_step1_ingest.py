@@ -221,3 +221,22 @@ def test_empty_files(T, s1, tmp_path):
     rc, err, p, r, st = ingest(T, s1, a, b)
     assert rc == 0 and r.n_reads == 0 and st.n_pairs == 0
     s1.w2rap_step1_free(C.byref(p), C.byref(r))
+
+
+def test_fastq_to_step_files_program(T, s1, tmp_path):
+    """host/step12_main.cc: FASTQ pair -> frag_reads_orig.* (step 1) -> step 2 on the B200.  Here (no device) it must write the
+    step-1 files, identical to the library's, and then stop loudly at step 2: there is no CPU path."""
+    exe = os.path.join(ROOT, "w2rap-contigger_b200", "step12")
+    if not os.path.exists(exe):
+        pytest.skip("step12 not built (run __graft_entry__.build())")
+    seqs, quals = golden_fastq(T, tmp_path)
+    fq1, fq2 = write_fastq_pair(str(tmp_path), seqs, quals)
+    out = tmp_path / "out"; out.mkdir()
+    r = subprocess.run([exe, fq1, fq2, str(out), "x", "--stores-only"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for f in ("frag_reads_orig.fastb", "frag_reads_orig.qualp"):
+        assert open(str(out / f), "rb").read() == open(os.path.join(HERE, "golden", "step1", f), "rb").read(), f
+    if T.product_lib().w2rap_step2_device_count() == 0:
+        r = subprocess.run([exe, fq1, fq2, str(out), "x"], capture_output=True, text=True)
+        assert r.returncode == 1 and "step 2 failed (2)" in r.stderr and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+        assert not os.path.exists(str(out / "x.small_K.hbv"))
