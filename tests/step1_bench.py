@@ -12,7 +12,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))      # (this script lives in tests/: it runs the reference binary under oracle/_ref as the comparison arm)
 import w2r_testlib as T  # noqa: E402
 from test_step1_ingest import S1Params, S1Stats  # noqa: E402
 
